@@ -160,6 +160,8 @@ def test_vec_dot_live_vs_reference_simd_and_generic(t, wfn, cpu_fn, port_fn, qfn
             vd(k, C.byref(s), 0, w[r].ctypes.data, 0, q.ctypes.data, 0, 1)
             mine = getattr(qf.port(), port_fn)(k, w[r].ctypes.data, q.ctypes.data)
             if variant.endswith("_generic"):
-                assert mine == s.value          # same scalar association -> bit-exact
+                # same scalar association; the reference object is built with -mfma, so gcc contracts
+                # `sums[l] += d*aux32[l]` into FMAs while the port is -ffp-contract=off: <= a few ulp
+                assert abs(mine - s.value) <= 2e-6 * max(1e-3, abs(s.value))
             else:
                 assert abs(mine - s.value) <= 2e-5 * max(1e-3, abs(s.value)) + 1e-6
