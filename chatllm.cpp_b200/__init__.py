@@ -1,0 +1,56 @@
+"""chatllm.cpp_b200 — B200-native (sm_100a) implementation of chatllm.cpp's quantized-matmul decode hot path.
+
+This Python package is only the host-side mirror used by tests and bench.py: it loads the in-tree C-ABI library
+(lib/libchatllm_b200.so, built from csrc/ by csrc/Makefile) with ctypes and wraps its entry points over torch
+tensors (torch is used for device memory / streams only).  The product is the CUDA code in csrc/ and the ggml
+backend plugin lib/libggml-cuda.so.  There is NO CPU fallback: if the extension is missing or no GPU is present
+the calls raise.
+"""
+import ctypes as C
+import os
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_DIR = os.path.join(PKG_DIR, "lib")
+LIB_PATH = os.path.join(LIB_DIR, "libchatllm_b200.so")
+PLUGIN_PATH = os.path.join(LIB_DIR, "libggml-cuda.so")
+
+# ggml type ids (reference ggml/include/ggml.h:389-405)
+F32, F16, Q4_0, Q8_0, Q4_K = 0, 1, 2, 8, 12
+
+_lib = None
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+def lib():
+    """ctypes handle to libchatllm_b200.so; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise B200Error(f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                            "or `make -C chatllm.cpp_b200/csrc`")
+        L = C.CDLL(LIB_PATH)
+        vp, i64, i32, f32 = C.c_void_p, C.c_int64, C.c_int, C.c_float
+        L.b200_abi_version.restype = i32
+        L.b200_device_sm_count.restype = i32
+        L.b200_repack_weights.argtypes = [i32, vp, vp, i64, i64, i64, i32, vp]
+        L.b200_qact_col_bytes.argtypes = [i32, i64]; L.b200_qact_col_bytes.restype = C.c_size_t
+        L.b200_quantize_act.argtypes = [i32, vp, i64, i64, i64, vp, vp]
+        L.b200_mul_mat_q.argtypes = [i32, vp, i64, i64, vp, i64, vp, i64, vp, vp]
+        L.b200_mul_mat.argtypes = [i32, vp, i64, i64, vp, i64, i64, vp, i64, vp, vp]
+        L.b200_gemv_set_tuning.argtypes = [i32] * 5
+        L.b200_rms_norm.argtypes = [vp, vp, vp, i64, i64, f32, vp]
+        L.b200_add.argtypes = [vp, vp, vp, i64, vp]
+        L.b200_silu_mul.argtypes = [vp, vp, vp, i64, vp]
+        L.b200_rope.argtypes = [vp, vp, vp, vp, i64, i64, i64, i64, i64, i64, i64, i32, i32, i32] + [f32] * 6 + [vp]
+        L.b200_soft_max.argtypes = [vp, vp, vp, i64, i64, f32, vp]
+        L.b200_get_rows.argtypes = [i32, vp, i64, vp, i64, vp, vp]
+        _lib = L
+    return _lib
+
+
+EXPORTS = ["b200_abi_version", "b200_device_sm_count", "b200_repack_weights", "b200_qact_col_bytes", "b200_quantize_act",
+           "b200_mul_mat_q", "b200_mul_mat", "b200_gemv_set_tuning", "b200_rms_norm", "b200_add", "b200_silu_mul", "b200_rope",
+           "b200_soft_max", "b200_get_rows"]

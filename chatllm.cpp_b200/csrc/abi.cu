@@ -1,0 +1,97 @@
+// abi.cu — extern "C" entry points declared in include/chatllm_b200.h
+#include "../../include/chatllm_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+#include <mutex>
+
+using namespace b200;
+
+static GemvTuning g_tune = {0, 0, 0, 0, 0};
+
+// per-device scratch for the convenience entry point (grown on demand; serialised by the stream it is used on)
+static void * g_scratch[16] = {nullptr};
+static size_t g_scratch_bytes[16] = {0};
+static std::mutex g_mu;
+
+static void * scratch(size_t bytes) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_scratch_bytes[dev] < bytes) {
+        if (g_scratch[dev]) { cudaDeviceSynchronize(); cudaFree(g_scratch[dev]); }
+        size_t nb = bytes < (1u << 20) ? (1u << 20) : bytes;
+        if (cudaMalloc(&g_scratch[dev], nb) != cudaSuccess) { g_scratch[dev] = nullptr; g_scratch_bytes[dev] = 0; return nullptr; }
+        g_scratch_bytes[dev] = nb;
+    }
+    return g_scratch[dev];
+}
+
+extern "C" {
+
+int b200_abi_version(void) { return 1; }
+int b200_device_sm_count(void) { return sm_count(); }
+
+int b200_repack_weights(int wtype, void * native, void * dev_tensor, int64_t tensor_off, int64_t nbytes, int64_t k, int inverse, void * stream) {
+    cudaStream_t st = (cudaStream_t) stream;
+    if (wtype == B200_TYPE_Q4_0 || wtype == B200_TYPE_Q8_0) {
+        if (k % 256) return B200_ERR_UNSUPPORTED;
+        return repack_window(wtype, native, dev_tensor, tensor_off, nbytes, k, inverse != 0, st);
+    }
+    if (inverse) return (int) cudaMemcpyAsync(native, (uint8_t *) dev_tensor + tensor_off, (size_t) nbytes, cudaMemcpyDeviceToDevice, st);
+    return (int) cudaMemcpyAsync((uint8_t *) dev_tensor + tensor_off, native, (size_t) nbytes, cudaMemcpyDeviceToDevice, st);
+}
+
+size_t b200_qact_col_bytes(int wtype, int64_t k) { return qact_col_bytes(wtype, k); }
+
+int b200_quantize_act(int wtype, const float * x, int64_t x_col_stride, int64_t k, int64_t n, void * qact, void * stream) {
+    return quantize_act(wtype, x, x_col_stride, k, n, qact, (cudaStream_t) stream);
+}
+
+int b200_mul_mat_q(int wtype, const void * W, int64_t k, int64_t m, const void * qact, int64_t n, float * y, int64_t ldy, const float * bias,
+                   void * stream) {
+    return mul_mat_q(wtype, W, k, m, qact, n, y, ldy, bias, &g_tune, (cudaStream_t) stream);
+}
+
+int b200_mul_mat(int wtype, const void * W, int64_t k, int64_t m, const float * x, int64_t x_col_stride, int64_t n, float * y, int64_t ldy,
+                 const float * bias, void * stream) {
+    if (n <= 0) return B200_OK;
+    const size_t cb = qact_col_bytes(wtype, k);
+    // process in column batches so the scratch stays small for prefill-sized n
+    const int64_t batch = 64;
+    void * q = scratch(cb * (size_t) (n < batch ? n : batch));
+    if (!q) return (int) cudaErrorMemoryAllocation;
+    for (int64_t c0 = 0; c0 < n; c0 += batch) {
+        const int64_t nc = (n - c0) < batch ? (n - c0) : batch;
+        int rc = quantize_act(wtype, x + c0 * x_col_stride, x_col_stride, k, nc, q, (cudaStream_t) stream);
+        if (rc) return rc;
+        rc = mul_mat_q(wtype, W, k, m, q, nc, y + c0 * ldy, ldy, bias, &g_tune, (cudaStream_t) stream);
+        if (rc) return rc;
+    }
+    return B200_OK;
+}
+
+int b200_gemv_set_tuning(int ks, int stages, int warps, int rg, int grid) {
+    g_tune.ks = ks; g_tune.stages = stages; g_tune.warps = warps; g_tune.rg = rg; g_tune.grid = grid;
+    return B200_OK;
+}
+
+int b200_rms_norm(const float * x, const float * w, float * y, int64_t ne0, int64_t nrows, float eps, void * stream) {
+    return rms_norm_mul(x, w, y, ne0, nrows, eps, (cudaStream_t) stream);
+}
+int b200_add(const float * a, const float * b, float * y, int64_t n, void * stream) { return add_f32(a, b, y, n, (cudaStream_t) stream); }
+int b200_silu_mul(const float * gate, const float * up, float * y, int64_t n, void * stream) { return silu_mul(gate, up, y, n, (cudaStream_t) stream); }
+int b200_rope(const float * x, float * y, const int32_t * pos, const float * freq_factors, int64_t ne0, int64_t n_heads, int64_t n_tokens,
+              int64_t xs_h, int64_t xs_t, int64_t ys_h, int64_t ys_t, int n_dims, int mode, int n_ctx_orig, float freq_base, float freq_scale,
+              float ext_factor, float attn_factor, float beta_fast, float beta_slow, void * stream) {
+    return rope_f32(x, y, pos, freq_factors, ne0, n_heads, n_tokens, xs_h, xs_t, ys_h, ys_t, n_dims, mode, n_ctx_orig, freq_base, freq_scale,
+                    ext_factor, attn_factor, beta_fast, beta_slow, (cudaStream_t) stream);
+}
+int b200_soft_max(const float * x, const float * mask, float * y, int64_t ne0, int64_t nrows, float scale, void * stream) {
+    return soft_max_f32(x, mask, y, ne0, nrows, scale, (cudaStream_t) stream);
+}
+int b200_get_rows(int type, const void * table, int64_t k, const int32_t * ids, int64_t n, float * y, void * stream) {
+    return get_rows_q(type, table, k, ids, n, y, (cudaStream_t) stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,39 @@
+// kernels.h — internal C++ interface between the .cu translation units and the C ABI (abi.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace b200 {
+
+// ---- quantize.cu
+size_t qact_col_bytes(int wtype, int64_t k);
+int quantize_act(int wtype, const float * x, int64_t x_col_stride, int64_t k, int64_t n, void * qact, cudaStream_t st);
+int repack_window(int wtype, const void * native_window, void * dev_tensor, int64_t tensor_off, int64_t nbytes, int64_t k, bool inverse,
+                  cudaStream_t st);
+
+// ---- gemv.cu
+struct GemvTuning {
+    int ks;      // k-units (256 elements) per pipeline stage
+    int stages;  // pipeline depth per warp
+    int warps;   // consumer warps per CTA
+    int rg;      // rows per row-group (1, 2 or 4)
+    int grid;    // CTAs (0 = auto)
+};
+// epilogue selectors for mul_mat_q
+enum : int { EPI_NONE = 0, EPI_BIAS = 1 };
+int mul_mat_q(int wtype, const void * W, int64_t k, int64_t m, const void * qact, int64_t n, float * y, int64_t ldy, const float * bias,
+              const GemvTuning * tune, cudaStream_t st);
+int sm_count();
+
+// ---- ops.cu
+int rms_norm_mul(const float * x, const float * w, float * y, int64_t ne0, int64_t nrows, float eps, cudaStream_t st);
+int add_f32(const float * a, const float * b, float * y, int64_t n, cudaStream_t st);
+int silu_mul(const float * gate, const float * up, float * y, int64_t n, cudaStream_t st);
+int rope_f32(const float * x, float * y, const int32_t * pos, const float * freq_factors, int64_t ne0, int64_t n_heads, int64_t n_tokens,
+             int64_t x_head_stride, int64_t x_tok_stride, int64_t y_head_stride, int64_t y_tok_stride, int n_dims, int mode, int n_ctx_orig,
+             float freq_base, float freq_scale, float ext_factor, float attn_factor, float beta_fast, float beta_slow, cudaStream_t st);
+int soft_max_f32(const float * x, const float * mask, float * y, int64_t ne0, int64_t nrows, float scale, cudaStream_t st);
+int get_rows_q(int type, const void * table, int64_t k, const int32_t * ids, int64_t n, float * y, cudaStream_t st);
+
+}  // namespace b200

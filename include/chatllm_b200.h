@@ -1,0 +1,87 @@
+/* chatllm_b200.h — kernel-level C ABI of libchatllm_b200.so (sm_100a).
+ *
+ * Plain C, device pointers and sizes only.  Every entry point returns 0 on success, a positive cudaError_t
+ * value on a CUDA failure, or a negative B200_ERR_* code; nothing here falls back to the CPU.
+ * `stream` is a cudaStream_t passed as void* (NULL = default stream).  All calls are asynchronous on it.
+ *
+ * This is the layer the ggml backend plugin (include/ggml_b200_backend.h, libggml-cuda.so) is built on; each
+ * function names the reference routine it replaces (paths relative to the reference tree).
+ *
+ * Weight layouts in device memory
+ *   Q4_K : native ggml block_q4_K stream (ggml/src/ggml-common.h:288-306), rows contiguous.
+ *   Q4_0 / Q8_0 : per-row SoA  "qs[nb][16|32] then fp16 d[nb]"  (same byte count and row stride as the native
+ *          AoS blocks, ggml-common.h:170-176 / :219-224).  Convert with b200_repack_weights(); the plugin does this
+ *          inside buffer.set_tensor / get_tensor so the host application never sees it.
+ *   k (= ne00) must be a multiple of 256 for the quantized matmul entry points.
+ */
+#ifndef CHATLLM_B200_H
+#define CHATLLM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_TYPE_F32_ 0
+#define B200_TYPE_F16_ 1
+#define B200_TYPE_Q4_0_ 2
+#define B200_TYPE_Q8_0_ 8
+#define B200_TYPE_Q4_K_ 12
+
+/* library / device info */
+int b200_abi_version(void);                 /* = 1 */
+int b200_device_sm_count(void);
+
+/* ---- weight layout ------------------------------------------------------------------------------------ */
+/* Convert a window [tensor_off, tensor_off+nbytes) of a tensor given in the NATIVE ggml layout (`native`, device
+ * memory) into the device layout inside `dev_tensor` (inverse=0), or back (inverse=1: `native` is written).
+ * Q4_K: plain copy.  Replaces nothing in the reference (the reference CUDA backend keeps AoS blocks); it is what
+ * ggml_backend_buffer_i.set_tensor / get_tensor (ggml/src/ggml-backend-impl.h:46-51) do in our plugin. */
+int b200_repack_weights(int wtype, void * native, void * dev_tensor, int64_t tensor_off, int64_t nbytes, int64_t k,
+                        int inverse, void * stream);
+
+/* ---- activation quantization ---------------------------------------------------------------------------- */
+/* bytes of one quantized activation column for a weight type (Q4_K -> Q8_K codes, Q4_0/Q8_0 -> Q8_0 codes) */
+size_t b200_qact_col_bytes(int wtype, int64_t k);
+/* x: n columns of k floats, column stride x_col_stride floats -> qact (n * b200_qact_col_bytes).
+ * Reproduces bit-for-bit quantize_row_q8_K_ref (ggml/src/ggml-quants.c:2555-2592) resp. the x86
+ * quantize_row_q8_0 (ggml/src/ggml-cpu/arch/x86/quants.c:290-384) the CPU backend applies to src1
+ * (ggml/src/ggml-cpu/ggml-cpu.c:1291-1326). */
+int b200_quantize_act(int wtype, const float * x, int64_t x_col_stride, int64_t k, int64_t n, void * qact, void * stream);
+
+/* ---- quantized matmul (decode GEMV / skinny GEMM, n <= 8 fast; larger n loops column groups) -------------- */
+/* y[c*ldy + i] = sum_k W[i,k] * x_c[k]  (+ bias[i]),  i < m, c < n.  Replaces ggml_compute_forward_mul_mat
+ * (ggml/src/ggml-cpu/ggml-cpu.c:1229-1421) / mul_mat_vec_q (ggml/src/ggml-cuda/mmvq.cu:140-356) for
+ * src0 in {Q4_K, Q4_0, Q8_0}. */
+int b200_mul_mat_q(int wtype, const void * W, int64_t k, int64_t m, const void * qact, int64_t n, float * y, int64_t ldy,
+                   const float * bias, void * stream);
+/* convenience: quantize x into an internal per-device scratch, then b200_mul_mat_q */
+int b200_mul_mat(int wtype, const void * W, int64_t k, int64_t m, const float * x, int64_t x_col_stride, int64_t n, float * y,
+                 int64_t ldy, const float * bias, void * stream);
+/* override the pipeline shape of the GEMV kernel (0 = keep default): units(256 elts)/stage, stages, warps/CTA,
+ * rows/group, grid */
+int b200_gemv_set_tuning(int ks, int stages, int warps, int rg, int grid);
+
+/* ---- fp32 glue ops ----------------------------------------------------------------------------------------- */
+/* y = rms_norm(x) * w   (w may be NULL).  ggml/src/ggml-cpu/ops.cpp:3710-3758 + src/layers.cpp:2216-2225 */
+int b200_rms_norm(const float * x, const float * w, float * y, int64_t ne0, int64_t nrows, float eps, void * stream);
+int b200_add(const float * a, const float * b, float * y, int64_t n, void * stream);
+/* y = silu(gate) * up.  src/layers.cpp:2475-2483 */
+int b200_silu_mul(const float * gate, const float * up, float * y, int64_t n, void * stream);
+/* RoPE on x[ne0, n_heads, n_tokens] (strides in floats), mode 0 = NORMAL, 2 = NEOX.
+ * ggml/src/ggml-cpu/ops.cpp:5587-5865 */
+int b200_rope(const float * x, float * y, const int32_t * pos, const float * freq_factors, int64_t ne0, int64_t n_heads,
+              int64_t n_tokens, int64_t x_head_stride, int64_t x_tok_stride, int64_t y_head_stride, int64_t y_tok_stride,
+              int n_dims, int mode, int n_ctx_orig, float freq_base, float freq_scale, float ext_factor, float attn_factor,
+              float beta_fast, float beta_slow, void * stream);
+/* y = softmax(x*scale + mask) over rows of ne0.  ggml/src/ggml-cpu/ops.cpp:5225-5335 */
+int b200_soft_max(const float * x, const float * mask, float * y, int64_t ne0, int64_t nrows, float scale, void * stream);
+/* y[i, :] = dequant(table[ids[i], :]).  ggml/src/ggml-cpu/ops.cpp:4820 */
+int b200_get_rows(int type, const void * table, int64_t k, const int32_t * ids, int64_t n, float * y, void * stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CHATLLM_B200_H */

@@ -1,0 +1,227 @@
+"""GPU parity tests (run with -m gpu on the B200): the CUDA path, called through the C ABI
+(include/chatllm_b200.h), against the oracle port (pinned in test_oracle_pin.py) and the committed golden vectors
+produced by executing the reference.  Integer results bit-exact; fp32 results within the stated tolerance
+(north star: logits within 1e-3 relative — per-op we hold 2e-5)."""
+import os
+
+import numpy as np
+import pytest
+
+import qformats as qf
+
+pytestmark = pytest.mark.gpu
+
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_vectors.npz"))
+
+
+@pytest.fixture(scope="module")
+def K():
+    import torch
+    import __graft_entry__ as ge
+    pkg = ge.load_package()
+    pkg.lib()  # raises if the extension is missing — no fallback
+    from chatllm_cpp_b200 import kernels
+    assert torch.cuda.is_available()
+    return kernels
+
+
+def _t(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _acts(rng, n, k, heavy=True):
+    x = rng.standard_normal((n, k)).astype(np.float32)
+    if heavy:
+        x[rng.random((n, k)) < 1e-3] *= 20.0
+    return x
+
+
+def _decode_qact(q, wtype, k):
+    """device qact column bytes -> (qs int8[k], d float32[k/G], bs int32[k/32])"""
+    Gs = 256 if wtype == qf.Q4_K else 32
+    a16 = lambda v: (v + 15) & ~15
+    o1 = a16(k); o2 = o1 + a16(k // Gs * 4)
+    qs = q[:, :k].view(np.int8)
+    d = q[:, o1:o1 + k // Gs * 4].copy().view(np.float32)
+    bs = q[:, o2:o2 + k // 32 * 4].copy().view(np.int32)
+    return qs, d, bs
+
+
+@pytest.mark.parametrize("k", [256, 4096, 14336])
+def test_quantize_q8_K_bit_exact(K, k):
+    rng = np.random.default_rng(k)
+    x = _acts(rng, 5, k)
+    x[1, :256] = 0.0                      # all-zero block
+    x[2, 3] = 7.5; x[2, 200] = -7.5       # +/- tie on |max|: the FIRST occurrence decides the sign of the scale
+    x[3, 10] = -9.25; x[3, 11] = 9.25
+    q = K.quantize_act(qf.Q4_K, _t(x)).cpu().numpy()
+    qs, d, bs = _decode_qact(q, qf.Q4_K, k)
+    ref = np.zeros((5, k // 256 * 292), dtype=np.uint8)
+    for r in range(5):
+        qf.port().oq_quantize_row_q8_K_ref(x[r].ctypes.data, ref[r].ctypes.data, k)
+    rb = ref.reshape(5, k // 256, 292)
+    assert np.array_equal(d, rb[:, :, 0:4].copy().view(np.float32).reshape(5, -1))
+    assert np.array_equal(qs, rb[:, :, 4:260].view(np.int8).reshape(5, k))
+    bsum16 = rb[:, :, 260:].copy().view(np.int16).reshape(5, k // 256, 8, 2).astype(np.int32).sum(-1).reshape(5, -1)
+    assert np.array_equal(bs, bsum16)
+
+
+@pytest.mark.parametrize("wtype", [qf.Q4_0, qf.Q8_0])
+@pytest.mark.parametrize("k", [256, 2048, 18944])
+def test_quantize_q8_0_bit_exact(K, wtype, k):
+    rng = np.random.default_rng(k + wtype)
+    x = _acts(rng, 3, k)
+    x[0, :32] = 0.0
+    x[1, 0:32] = (np.arange(32, dtype=np.float32) + 0.5) * np.where(np.arange(32) % 2 == 0, 1.0, -1.0); x[1, 0] = 127.0  # RNE ties
+    q = K.quantize_act(wtype, _t(x)).cpu().numpy()
+    qs, d, bs = _decode_qact(q, wtype, k)
+    ref = np.zeros((3, k // 32 * 34), dtype=np.uint8)
+    for r in range(3):
+        qf.port().oq_quantize_row_q8_0_x86(x[r].ctypes.data, ref[r].ctypes.data, k)
+    rb = ref.reshape(3, k // 32, 34)
+    assert np.array_equal(qs, rb[:, :, 2:].view(np.int8).reshape(3, k))
+    assert np.array_equal(d, rb[:, :, 0:2].copy().view(np.float16).astype(np.float32).reshape(3, -1))
+    assert np.array_equal(bs, rb[:, :, 2:].view(np.int8).astype(np.int32).sum(-1))
+
+
+@pytest.mark.parametrize("wtype", [qf.Q4_0, qf.Q8_0, qf.Q4_K])
+def test_repack_round_trip_and_windows(K, wtype):
+    import torch
+    rng = np.random.default_rng(3)
+    k, m = 1024, 37
+    w = qf.random_blocks(wtype, m, k, rng=rng)
+    dev = K.upload_weights(wtype, w, k, m)
+    back = K.download_weights(wtype, dev, k).cpu().numpy().reshape(w.shape)
+    assert np.array_equal(back, w)
+    # windowed upload at odd offsets (ggml_backend_tensor_set writes 1 MiB chunks, src/chat.cpp:1322-1338)
+    import chatllm_cpp_b200 as pkg
+    flat = torch.from_numpy(w.reshape(-1)).cuda()
+    dst = torch.zeros_like(flat)
+    cuts = [0, 7, 1000, 1001, 20011, flat.numel()]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        chunk = flat[a:b].clone()
+        assert pkg.lib().b200_repack_weights(wtype, chunk.data_ptr(), dst.data_ptr(), a, b - a, k, 0, 0) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(dst, dev)
+
+
+SHAPES = [(256, 1), (512, 33), (1024, 48), (4096, 300), (5632, 64), (2048, 257)]
+
+
+@pytest.mark.parametrize("wtype", [qf.Q4_0, qf.Q8_0, qf.Q4_K])
+@pytest.mark.parametrize("k,m", SHAPES)
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 8])
+def test_mul_mat_vs_oracle(K, wtype, k, m, n):
+    rng = np.random.default_rng(k * 7 + m + n)
+    w = qf.random_blocks(wtype, m, k, rng=rng)
+    x = _acts(rng, n, k)
+    bias = rng.standard_normal(m).astype(np.float32) if (m + n) % 2 else None
+    y = K.mul_mat(wtype, K.upload_weights(wtype, w, k, m), k, m, _t(x), bias=None if bias is None else _t(bias)).cpu().numpy()
+    ref = qf.port_mul_mat(wtype, w, k, m, x, variant=1)
+    if bias is not None:
+        ref = ref + bias[None, :]
+    assert np.abs(y - ref).max() <= 2e-5 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("wtype", [qf.Q4_0, qf.Q8_0, qf.Q4_K])
+@pytest.mark.parametrize("n", [1, 3, 8])
+def test_mul_mat_vs_reference_golden(K, wtype, n):
+    """fixtures produced by the reference CPU backend itself (tests/golden/make_golden.py)"""
+    w = G[f"mm_{qf.NAMES[wtype]}_w"]; x = G[f"mm_{qf.NAMES[wtype]}_n{n}_x"]; ref = G[f"mm_{qf.NAMES[wtype]}_n{n}_y"]
+    k, m = x.shape[1], w.shape[0]
+    y = K.mul_mat(wtype, K.upload_weights(wtype, w, k, m), k, m, _t(x)).cpu().numpy()
+    assert np.abs(y - ref).max() <= 2e-5 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("wtype,k,m", [(qf.Q4_K, 4096, 14336), (qf.Q4_K, 14336, 4096), (qf.Q4_0, 3584, 18944), (qf.Q8_0, 2048, 5632),
+                                       (qf.Q4_K, 4096, 128256)])
+def test_mul_mat_full_size_semantics(K, wtype, k, m):
+    """BASELINE.json's real shapes: result == dequant(W) . dequant(Q(x)) (the oracle's definition, pinned in
+    test_oracle_pin.py) evaluated in float64 with the vectorized numpy dequantizers."""
+    rng = np.random.default_rng(k + m)
+    w = qf.random_blocks(wtype, m, k, rng=rng)
+    x = _acts(rng, 1, k)
+    y = K.mul_mat(wtype, K.upload_weights(wtype, w, k, m), k, m, _t(x)).cpu().numpy()[0]
+    if wtype == qf.Q4_K:
+        q = np.zeros((1, k // 256 * 292), dtype=np.uint8)
+        qf.port().oq_quantize_row_q8_K_ref(x.ctypes.data, q.ctypes.data, k)
+        qb = q.reshape(k // 256, 292)
+        xd = (qb[:, 4:260].view(np.int8).astype(np.float64) * qb[:, 0:4].copy().view(np.float32).astype(np.float64)).reshape(k)
+    else:
+        q = np.zeros((1, k // 32 * 34), dtype=np.uint8)
+        qf.port().oq_quantize_row_q8_0_x86(x.ctypes.data, q.ctypes.data, k)
+        xd = qf.dequant_np(qf.Q8_0, q, k)[0].astype(np.float64)
+    ref = np.empty(m)
+    for r0 in range(0, m, 8192):
+        ref[r0:r0 + 8192] = qf.dequant_np(wtype, w[r0:r0 + 8192], k).astype(np.float64) @ xd
+    assert np.abs(y - ref).max() <= 2e-5 * np.abs(ref).max()
+    # spot-check 64 rows against the scalar oracle port as well
+    idx = rng.choice(m, 64, replace=False)
+    ref2 = qf.port_mul_mat(wtype, w[idx], k, 64, x, variant=1)[0]
+    assert np.abs(y[idx] - ref2).max() <= 2e-5 * np.abs(ref).max()
+
+
+def test_rms_norm(K):
+    x, w, ref = G["rms_x"], G["rms_w"], G["rms_y"]
+    y = K.rms_norm(_t(x), _t(w), 1e-5).cpu().numpy()
+    assert np.abs(y - ref).max() <= 2e-6 * np.abs(ref).max()
+    rng = np.random.default_rng(0)
+    for ne0 in (64, 4096, 5120):
+        x = _acts(rng, 7, ne0); w = rng.standard_normal(ne0).astype(np.float32)
+        y = K.rms_norm(_t(x), _t(w), 1e-6).cpu().numpy()
+        r = np.zeros_like(x); qf.port().oq_rms_norm(x.ctypes.data, w.ctypes.data, r.ctypes.data, ne0, 7, 1e-6)
+        assert np.abs(y - r).max() <= 2e-6 * np.abs(r).max()
+
+
+def test_soft_max(K):
+    x, ref = G["sm_x"], G["sm_y"]
+    y = K.soft_max(_t(x), 0.088388).cpu().numpy()
+    assert np.abs(y - ref).max() <= 1e-6
+    rng = np.random.default_rng(1)
+    x = (_acts(rng, 32, 4097) * 4).astype(np.float32)
+    mask = np.where(rng.random((32, 4097)) < 0.1, -np.inf, 0.0).astype(np.float32)
+    y = K.soft_max(_t(x), 0.125, mask=_t(mask)).cpu().numpy()
+    r = np.zeros_like(x); qf.port().oq_soft_max(x.ctypes.data, mask.ctypes.data, r.ctypes.data, 4097, 32, 0.125)
+    assert np.abs(y - r).max() <= 1e-6
+    assert np.all(y[mask == -np.inf] == 0)
+
+
+@pytest.mark.parametrize("mode,nm", [(0, "norm"), (2, "neox")])
+@pytest.mark.parametrize("use_ff", [0, 1])
+def test_rope(K, mode, nm, use_ff):
+    x, pos, ff, ref = G[f"rope_{nm}_x"], G[f"rope_{nm}_pos"], G[f"rope_{nm}_ff"], G[f"rope_{nm}_ff{use_ff}_y"]
+    y = K.rope(_t(x), _t(pos), 128, mode, 500000.0, ff=_t(ff) if use_ff else None).cpu().numpy()
+    # the angle is the same fp32 recurrence as the CPU's; device cosf/sinf differ from glibc by <= 2 ulp
+    assert np.abs(y - ref).max() <= 4e-6 * np.abs(ref).max()
+    y2 = K.rope(_t(x).clone(), _t(pos), 128, mode, 500000.0, ff=_t(ff) if use_ff else None, inplace=True).cpu().numpy()
+    assert np.array_equal(y, y2)
+
+
+def test_rope_partial_dims_and_yarn(K):
+    rng = np.random.default_rng(2)
+    x = _acts(rng, 5 * 3, 96, heavy=False).reshape(5, 3, 96)
+    pos = np.array([0, 1, 100, 4095, 8000], dtype=np.int32)
+    for mode in (0, 2):
+        y = K.rope(_t(x), _t(pos), 64, mode, 10000.0, n_ctx_orig=4096, freq_scale=0.25, ext=1.0, attn=1.1).cpu().numpy()
+        r = np.zeros_like(x)
+        qf.port().oq_rope(x.ctypes.data, r.ctypes.data, pos.ctypes.data, None, 96, 3, 5, 64, mode, 4096, 10000.0, 0.25, 1.0, 1.1, 32.0, 1.0)
+        assert np.abs(y - r).max() <= 4e-6 * np.abs(r).max()
+
+
+def test_silu_mul_and_add(K):
+    g, u, ref = G["silu_g"], G["silu_u"], G["silu_y"]
+    y = K.silu_mul(_t(g), _t(u)).cpu().numpy()
+    assert np.abs(y - ref).max() <= 2e-6 * np.abs(ref).max()
+    assert np.array_equal(K.add(_t(g), _t(u)).cpu().numpy(), g + u)
+
+
+@pytest.mark.parametrize("wtype", [qf.Q4_0, qf.Q8_0, qf.Q4_K])
+def test_get_rows(K, wtype):
+    rng = np.random.default_rng(4)
+    k, rows = 1024, 50
+    w = qf.random_blocks(wtype, rows, k, rng=rng)
+    ids = np.array([0, 49, 7, 7, 13], dtype=np.int32)
+    y = K.get_rows(wtype, K.upload_weights(wtype, w, k, rows), k, _t(ids)).cpu().numpy()
+    ref = qf.dequant_np(wtype, w[ids], k)
+    assert np.abs(y - ref).max() <= 1e-6 * np.abs(ref).max()
