@@ -13,20 +13,22 @@
 //     barriers in the main loop, no producer/consumer hand-off, perfectly even byte split over all SMs
 //     (rows_per_warp differs by at most one row).
 //   * activations are pre-quantized exactly like the reference (quantize.cu) and live in shared memory for the whole
-//     kernel; integer dot products use dp4a (u8 x s8); RG rows share each activation fetch.
+//     kernel in a chunk-permuted layout (actlayout.cuh) so that every 16-byte lane load is bank-conflict free;
+//     integer dot products use dp4a (u8 x s8) / dp2a; RG rows share each activation fetch.
 //   * weights are read from HBM exactly once with an L2 evict-first policy (they are not re-used within a token).
+//   * launched with programmatic dependent launch: the weight prefetch of kernel N+1 overlaps the tail of kernel N;
+//     only the activation read waits (griddepcontrol.wait).
 //
 // Weight layouts in HBM: Q4_K native ggml blocks (144 B, 16-byte aligned).  Q4_0 / Q8_0 per-row SoA
 // ("qs[nb][QB] then d[nb]", see quantize.cu repack_window) because 18 / 34-byte AoS blocks cannot be read with
 // aligned 16-byte shared-memory loads.
+#include "actlayout.cuh"
 #include "common.cuh"
 #include "kernels.h"
 
 #include <cstdlib>
 
 namespace b200 {
-
-__host__ __device__ inline int64_t a16(int64_t x) { return (x + 15) & ~(int64_t) 15; }
 
 __device__ __forceinline__ int dp4a_us(uint32_t a_u8x4, uint32_t b_s8x4, int c) {
     int d;
@@ -38,68 +40,75 @@ __device__ __forceinline__ int dp4a_ss(uint32_t a_s8x4, uint32_t b_s8x4, int c) 
     asm("dp4a.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a_s8x4), "r"(b_s8x4), "r"(c));
     return d;
 }
+// a = 2 x s16, b = 4 x u8 (lo: bytes 0,1 ; hi: bytes 2,3)
+__device__ __forceinline__ int dp2a_lo_su(uint32_t a_s16x2, uint32_t b_u8x4, int c) {
+    int d;
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a_s16x2), "r"(b_u8x4), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int dp2a_hi_su(uint32_t a_s16x2, uint32_t b_u8x4, int c) {
+    int d;
+    asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a_s16x2), "r"(b_u8x4), "r"(c));
+    return d;
+}
 __device__ __forceinline__ uint4 lds128(const void * p) { return *reinterpret_cast<const uint4 *>(p); }
-
-// view of one quantized activation column in shared memory (layout: quantize.cu)
-struct ActView {
-    const int8_t * qs;
-    const float * d;
-    const int * bs;
-};
+__device__ __forceinline__ int byte_of(uint32_t x, int i) { return (int) __byte_perm(x, 0, 0x4440 + i); }
 
 // ======================================================================================================
-// Format traits.  A "unit" is 256 consecutive k-elements for every format.
-//   stage layout in smem: region A = RG rows x (KS units x A_UNIT bytes), region B = RG rows x (KS units x B_UNIT bytes)
+// Format traits.  A "unit" is 256 consecutive k-elements for every format; LPU lanes cooperate on a unit.
 // ======================================================================================================
 struct FmtQ4K {
     static constexpr int A_UNIT = 144;  // one native block_q4_K per unit
     static constexpr int B_UNIT = 0;
-    static constexpr int ACT_G = 256;  // activation scale granularity (Q8_K)
-    static constexpr int LANES_PER_UNIT = 4;  // each lane handles 64 elements (one 32-byte qs group = sub-blocks 2g, 2g+1)
-    __device__ static __forceinline__ const uint8_t * rowA(const uint8_t * W, int64_t row, int64_t nunits) { return W + row * nunits * 144; }
-    __device__ static __forceinline__ const uint8_t * rowB(const uint8_t * W, int64_t row, int64_t nunits) { return nullptr; }
+    static constexpr bool Q8K = true;
+    static constexpr int LPU = 2;  // lane h owns qs bytes [64h, 64h+64) = sub-blocks 4h .. 4h+3 (128 elements)
+    struct Act { uint32_t a[32]; uint32_t bs01, bs23; float dx; };
+    struct Wt { uint32_t w[16]; uint32_t sc4, mn4; float d, dmin; };
 
-    // one row, one unit, one lane-group g: returns this lane's contribution
-    template <int NC>
-    __device__ static __forceinline__ void dot(const uint8_t * a_row, const uint8_t * /*b_row*/, int u, int g, int64_t gu, const ActView * act,
-                                               float * acc /*[NC]*/) {
+    __device__ static __forceinline__ void load_act(const uint8_t * col, const ActLayout & L, int64_t gu, int h, Act & A) {
+        const uint8_t * p = col + (gu >> 2) * 1024 + (gu & 3) * 32 + h * 16;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint4 v = lds128(p + j * 128);
+            A.a[4 * j + 0] = v.x; A.a[4 * j + 1] = v.y; A.a[4 * j + 2] = v.z; A.a[4 * j + 3] = v.w;
+        }
+        const uint2 b = *reinterpret_cast<const uint2 *>(col + L.bs_off + (gu * 8 + 4 * h) * 2);
+        A.bs01 = b.x; A.bs23 = b.y;
+        A.dx = *reinterpret_cast<const float *>(col + L.d_off + gu * 4);
+    }
+    __device__ static __forceinline__ void load_w(const uint8_t * a_row, const uint8_t *, int u, int h, Wt & W) {
         const uint8_t * blk = a_row + u * 144;
         const uint4 hdr = lds128(blk);
-        const uint4 q0 = lds128(blk + 16 + g * 32);
-        const uint4 q1 = lds128(blk + 32 + g * 32);
-        const float d = half_bits_to_float(hdr.x & 0xffffu);
-        const float dmin = half_bits_to_float(hdr.x >> 16);
-        // 6-bit scales / mins (reference get_scale_min_k4, ggml/src/ggml-quants.c:703-711), 4 at a time
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint4 v = lds128(blk + 16 + h * 64 + j * 16);
+            W.w[4 * j + 0] = v.x; W.w[4 * j + 1] = v.y; W.w[4 * j + 2] = v.z; W.w[4 * j + 3] = v.w;
+        }
+        W.d = half_bits_to_float(hdr.x & 0xffffu);
+        W.dmin = half_bits_to_float(hdr.x >> 16);
+        // 6-bit scales / mins (reference get_scale_min_k4, ggml/src/ggml-quants.c:703-711), four at a time
         const uint32_t sc_a = hdr.y & 0x3f3f3f3fu;
         const uint32_t sc_b = (hdr.w & 0x0f0f0f0fu) | (((hdr.y >> 6) & 0x03030303u) << 4);
         const uint32_t mn_a = hdr.z & 0x3f3f3f3fu;
         const uint32_t mn_b = ((hdr.w >> 4) & 0x0f0f0f0fu) | (((hdr.z >> 6) & 0x03030303u) << 4);
-        const uint32_t scw = (g < 2) ? sc_a : sc_b;
-        const uint32_t mnw = (g < 2) ? mn_a : mn_b;
-        const int sh = (g & 1) * 16;
-        const int sc0 = (scw >> sh) & 0xff, sc1 = (scw >> (sh + 8)) & 0xff;
-        const int mn0 = (mnw >> sh) & 0xff, mn1 = (mnw >> (sh + 8)) & 0xff;
-        const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+        W.sc4 = h ? sc_b : sc_a;
+        W.mn4 = h ? mn_b : mn_a;
+    }
+    __device__ static __forceinline__ float dot(const Wt & W, const Act & A, float acc) {
+        int s0 = 0, s1 = 0, s2 = 0, s3 = 0;
 #pragma unroll
-        for (int c = 0; c < NC; ++c) {
-            const int8_t * aq = act[c].qs + gu * 256 + g * 64;
-            const uint4 a0 = lds128(aq), a1 = lds128(aq + 16), a2 = lds128(aq + 32), a3 = lds128(aq + 48);
-            const uint32_t al[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-            const uint32_t ah[8] = {a2.x, a2.y, a2.z, a2.w, a3.x, a3.y, a3.z, a3.w};
-            int slo = 0, shi = 0;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                slo = dp4a_us(w[i] & 0x0f0f0f0fu, al[i], slo);
-                shi = dp4a_us(w[i] & 0xf0f0f0f0u, ah[i], shi);  // = 16 * sum(hi nibble * a)
-            }
-            const int2 bs = *reinterpret_cast<const int2 *>(act[c].bs + gu * 8 + g * 2);
-            const int t = ((sc0 * slo) << 4) + sc1 * shi;  // 16 * sum_j sc_j * isum_j
-            const int ms = mn0 * bs.x + mn1 * bs.y;
-            const float dx = act[c].d[gu];
-            // reference association (arch/x86/quants.c:1764-1815): d = y.d * fp16(x.d); dmin = y.d * fp16(x.dmin)
-            acc[c] = fmaf(dx * d * 0.0625f, (float) t, acc[c]);
-            acc[c] = fmaf(-(dx * dmin), (float) ms, acc[c]);
+        for (int i = 0; i < 8; ++i) {
+            s0 = dp4a_us(W.w[i] & 0x0f0f0f0fu, A.a[i], s0);
+            s1 = dp4a_us(W.w[i] & 0xf0f0f0f0u, A.a[8 + i], s1);       // 16 x
+            s2 = dp4a_us(W.w[8 + i] & 0x0f0f0f0fu, A.a[16 + i], s2);
+            s3 = dp4a_us(W.w[8 + i] & 0xf0f0f0f0u, A.a[24 + i], s3);  // 16 x
         }
+        const int t = ((byte_of(W.sc4, 0) * s0 + byte_of(W.sc4, 2) * s2) << 4) + byte_of(W.sc4, 1) * s1 + byte_of(W.sc4, 3) * s3;
+        const int ms = dp2a_hi_su(A.bs23, W.mn4, dp2a_lo_su(A.bs01, W.mn4, 0));
+        // reference association (arch/x86/quants.c:1764-1815): d = y.d * fp16(x.d); dmin = y.d * fp16(x.dmin)
+        acc = fmaf(A.dx * W.d * 0.0625f, (float) t, acc);
+        acc = fmaf(-(A.dx * W.dmin), (float) ms, acc);
+        return acc;
     }
 };
 
@@ -107,35 +116,32 @@ struct FmtQ4K {
 struct FmtQ40 {
     static constexpr int A_UNIT = 128;
     static constexpr int B_UNIT = 16;
-    static constexpr int ACT_G = 32;
-    static constexpr int LANES_PER_UNIT = 8;  // one 32-element block per lane
-    __device__ static __forceinline__ const uint8_t * rowA(const uint8_t * W, int64_t row, int64_t nunits) { return W + row * nunits * 144; }
-    __device__ static __forceinline__ const uint8_t * rowB(const uint8_t * W, int64_t row, int64_t nunits) {
-        return W + row * nunits * 144 + nunits * 128;
+    static constexpr bool Q8K = false;
+    static constexpr int LPU = 8;  // one 32-element block per lane
+    struct Act { uint32_t a[8]; int bs; float dx; };
+    struct Wt { uint32_t w[4]; float d; };
+    __device__ static __forceinline__ void load_act(const uint8_t * col, const ActLayout & L, int64_t gu, int g, Act & A) {
+        const uint8_t * p = col + gu * 256 + g * 16;
+        const uint4 v0 = lds128(p), v1 = lds128(p + 128);
+        A.a[0] = v0.x; A.a[1] = v0.y; A.a[2] = v0.z; A.a[3] = v0.w;
+        A.a[4] = v1.x; A.a[5] = v1.y; A.a[6] = v1.z; A.a[7] = v1.w;
+        A.bs = *reinterpret_cast<const int *>(col + L.bs_off + (gu * 8 + g) * 4);
+        A.dx = *reinterpret_cast<const float *>(col + L.d_off + (gu * 8 + g) * 4);
     }
-    template <int NC>
-    __device__ static __forceinline__ void dot(const uint8_t * a_row, const uint8_t * b_row, int u, int g, int64_t gu, const ActView * act,
-                                               float * acc) {
+    __device__ static __forceinline__ void load_w(const uint8_t * a_row, const uint8_t * b_row, int u, int g, Wt & W) {
         const uint4 q = lds128(a_row + u * 128 + g * 16);
-        const float d = half_bits_to_float(*reinterpret_cast<const unsigned short *>(b_row + u * 16 + g * 2));
-        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+        W.w[0] = q.x; W.w[1] = q.y; W.w[2] = q.z; W.w[3] = q.w;
+        W.d = half_bits_to_float(*reinterpret_cast<const unsigned short *>(b_row + u * 16 + g * 2));
+    }
+    __device__ static __forceinline__ float dot(const Wt & W, const Act & A, float acc) {
+        int slo = 0, shi = 0;
 #pragma unroll
-        for (int c = 0; c < NC; ++c) {
-            const int64_t gb = gu * 8 + g;  // global 32-block index
-            const int8_t * aq = act[c].qs + gb * 32;
-            const uint4 a0 = lds128(aq), a1 = lds128(aq + 16);
-            const uint32_t al[4] = {a0.x, a0.y, a0.z, a0.w};
-            const uint32_t ah[4] = {a1.x, a1.y, a1.z, a1.w};
-            int slo = 0, shi = 0;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                slo = dp4a_us(w[i] & 0x0f0f0f0fu, al[i], slo);   // elements 0..15  (low nibbles, ggml-quants.c:307-325)
-                shi = dp4a_us(w[i] & 0xf0f0f0f0u, ah[i], shi);   // 16 * elements 16..31 (high nibbles)
-            }
-            // sum (q-8)*a = sum q*a - 8*sum a
-            const int t = (slo << 4) + shi - (act[c].bs[gb] << 7);
-            acc[c] = fmaf(d * act[c].d[gb] * 0.0625f, (float) t, acc[c]);
+        for (int i = 0; i < 4; ++i) {
+            slo = dp4a_us(W.w[i] & 0x0f0f0f0fu, A.a[i], slo);      // elements 0..15 (low nibbles, ggml-quants.c:307-325)
+            shi = dp4a_us(W.w[i] & 0xf0f0f0f0u, A.a[4 + i], shi);  // 16 x elements 16..31 (high nibbles)
         }
+        const int t = (slo << 4) + shi - (A.bs << 7);  // 16 * sum (q-8)*a
+        return fmaf(W.d * A.dx * 0.0625f, (float) t, acc);
     }
 };
 
@@ -143,30 +149,29 @@ struct FmtQ40 {
 struct FmtQ80 {
     static constexpr int A_UNIT = 256;
     static constexpr int B_UNIT = 16;
-    static constexpr int ACT_G = 32;
-    static constexpr int LANES_PER_UNIT = 8;
-    __device__ static __forceinline__ const uint8_t * rowA(const uint8_t * W, int64_t row, int64_t nunits) { return W + row * nunits * 272; }
-    __device__ static __forceinline__ const uint8_t * rowB(const uint8_t * W, int64_t row, int64_t nunits) {
-        return W + row * nunits * 272 + nunits * 256;
+    static constexpr bool Q8K = false;
+    static constexpr int LPU = 8;
+    struct Act { uint32_t a[8]; float dx; };
+    struct Wt { uint32_t w[8]; float d; };
+    __device__ static __forceinline__ void load_act(const uint8_t * col, const ActLayout & L, int64_t gu, int g, Act & A) {
+        const uint8_t * p = col + gu * 256 + g * 16;
+        const uint4 v0 = lds128(p), v1 = lds128(p + 128);
+        A.a[0] = v0.x; A.a[1] = v0.y; A.a[2] = v0.z; A.a[3] = v0.w;
+        A.a[4] = v1.x; A.a[5] = v1.y; A.a[6] = v1.z; A.a[7] = v1.w;
+        A.dx = *reinterpret_cast<const float *>(col + L.d_off + (gu * 8 + g) * 4);
     }
-    template <int NC>
-    __device__ static __forceinline__ void dot(const uint8_t * a_row, const uint8_t * b_row, int u, int g, int64_t gu, const ActView * act,
-                                               float * acc) {
+    __device__ static __forceinline__ void load_w(const uint8_t * a_row, const uint8_t * b_row, int u, int g, Wt & W) {
         const uint4 q0 = lds128(a_row + u * 256 + g * 32);
         const uint4 q1 = lds128(a_row + u * 256 + g * 32 + 16);
-        const float d = half_bits_to_float(*reinterpret_cast<const unsigned short *>(b_row + u * 16 + g * 2));
-        const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+        W.w[0] = q0.x; W.w[1] = q0.y; W.w[2] = q0.z; W.w[3] = q0.w;
+        W.w[4] = q1.x; W.w[5] = q1.y; W.w[6] = q1.z; W.w[7] = q1.w;
+        W.d = half_bits_to_float(*reinterpret_cast<const unsigned short *>(b_row + u * 16 + g * 2));
+    }
+    __device__ static __forceinline__ float dot(const Wt & W, const Act & A, float acc) {
+        int s = 0;
 #pragma unroll
-        for (int c = 0; c < NC; ++c) {
-            const int64_t gb = gu * 8 + g;
-            const int8_t * aq = act[c].qs + gb * 32;
-            const uint4 a0 = lds128(aq), a1 = lds128(aq + 16);
-            const uint32_t a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-            int s = 0;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) s = dp4a_ss(w[i], a[i], s);
-            acc[c] = fmaf(d * act[c].d[gb], (float) s, acc[c]);
-        }
+        for (int i = 0; i < 8; ++i) s = dp4a_ss(W.w[i], A.a[i], s);
+        return fmaf(W.d * A.dx, (float) s, acc);
     }
 };
 
@@ -175,13 +180,13 @@ struct FmtQ80 {
 // ======================================================================================================
 struct GemvParams {
     const uint8_t * W;
-    const uint8_t * qact;  // global, n columns
+    const uint8_t * qact;  // global, NC columns back to back
     float * y;
     const float * bias;
     int64_t k, m, ldy;
-    int n;
-    int nunits;     // k / 256
-    int ks;         // units per stage
+    int n;       // valid columns (<= NC)
+    int nunits;  // k / 256
+    int ks;      // units per stage (== nunits -> whole rows per stage, one bulk copy)
     int stages;
     uint32_t act_col_bytes;
 };
@@ -193,14 +198,18 @@ __global__ void __launch_bounds__(512) gemv_q_kernel(const GemvParams p) {
     const int warp = threadIdx.x >> 5;
     const int nwarps = blockDim.x >> 5;
 
-    // ---- shared memory carve-up: [activations][per-warp: barriers | stages]
-    const uint32_t act_bytes = (uint32_t) a16((int64_t) p.act_col_bytes * NC);
-    const uint32_t stageA = (uint32_t) RG * p.ks * F::A_UNIT;
-    const uint32_t stageB = (uint32_t) RG * p.ks * F::B_UNIT;
-    const uint32_t stage_bytes = stageA + stageB;
+    constexpr int UNIT = F::A_UNIT + F::B_UNIT;
+    const bool whole = (p.ks == p.nunits);
+    const uint32_t act_bytes = (uint32_t) al16((int64_t) p.act_col_bytes * NC);
+    const uint32_t stage_bytes = (uint32_t) RG * p.ks * UNIT;
+    // row r of a stage: A part at st + r*rsA, B part at st + offB + r*rsB
+    const uint32_t rsA = whole ? p.ks * UNIT : p.ks * F::A_UNIT;
+    const uint32_t rsB = whole ? p.ks * UNIT : p.ks * F::B_UNIT;
+    const uint32_t offB = whole ? p.ks * F::A_UNIT : RG * p.ks * F::A_UNIT;
+
     uint8_t * act_s = smem;
     uint64_t * bars = reinterpret_cast<uint64_t *>(smem + act_bytes) + (size_t) warp * p.stages;
-    uint8_t * ring = smem + act_bytes + a16((int64_t) nwarps * p.stages * 8) + (size_t) warp * p.stages * stage_bytes;
+    uint8_t * ring = smem + act_bytes + al16((int64_t) nwarps * p.stages * 8) + (size_t) warp * p.stages * stage_bytes;
 
     // ---- this warp's rows and work items (row-group x k-segment)
     const int64_t gw = (int64_t) blockIdx.x * nwarps + warp;
@@ -209,6 +218,7 @@ __global__ void __launch_bounds__(512) gemv_q_kernel(const GemvParams p) {
     const int nseg = (p.nunits + p.ks - 1) / p.ks;
     const int ngroups = (int) ((r1 - r0 + RG - 1) / RG);
     const int nitems = ngroups * nseg;
+    const int64_t row_bytes = (int64_t) p.nunits * UNIT;
 
     if (lane == 0) {
         for (int s = 0; s < p.stages; ++s) mbar_init(&bars[s], 1);
@@ -224,16 +234,22 @@ __global__ void __launch_bounds__(512) gemv_q_kernel(const GemvParams p) {
         const int grp = it / nseg, seg = it - grp * nseg;
         const int64_t row0 = r0 + (int64_t) grp * RG;
         const int nr = (int) min((int64_t) RG, r1 - row0);
-        const int u0 = seg * p.ks;
-        const int nu = min(p.ks, p.nunits - u0);
         uint8_t * st = ring + (size_t) s * stage_bytes;
-        mbar_arrive_expect_tx(&bars[s], (uint32_t) nr * nu * (F::A_UNIT + F::B_UNIT));
-        for (int r = 0; r < nr; ++r) {
-            bulk_g2s_hint(st + (size_t) r * p.ks * F::A_UNIT, F::rowA(p.W, row0 + r, p.nunits) + (size_t) u0 * F::A_UNIT, (uint32_t) nu * F::A_UNIT,
-                          &bars[s], pol);
-            if (F::B_UNIT)
-                bulk_g2s_hint(st + stageA + (size_t) r * p.ks * F::B_UNIT, F::rowB(p.W, row0 + r, p.nunits) + (size_t) u0 * F::B_UNIT,
-                              (uint32_t) nu * F::B_UNIT, &bars[s], pol);
+        if (whole) {
+            const uint32_t bytes = (uint32_t) (nr * row_bytes);
+            mbar_arrive_expect_tx(&bars[s], bytes);
+            bulk_g2s_hint(st, p.W + row0 * row_bytes, bytes, &bars[s], pol);
+        } else {
+            const int u0 = seg * p.ks;
+            const int nu = min(p.ks, p.nunits - u0);
+            mbar_arrive_expect_tx(&bars[s], (uint32_t) nr * nu * UNIT);
+            for (int r = 0; r < nr; ++r) {
+                const uint8_t * grow = p.W + (row0 + r) * row_bytes;
+                bulk_g2s_hint(st + (size_t) r * rsA, grow + (size_t) u0 * F::A_UNIT, (uint32_t) nu * F::A_UNIT, &bars[s], pol);
+                if (F::B_UNIT)
+                    bulk_g2s_hint(st + offB + (size_t) r * rsB, grow + (size_t) p.nunits * F::A_UNIT + (size_t) u0 * F::B_UNIT,
+                                  (uint32_t) nu * F::B_UNIT, &bars[s], pol);
+            }
         }
     };
 
@@ -254,16 +270,8 @@ __global__ void __launch_bounds__(512) gemv_q_kernel(const GemvParams p) {
     __syncthreads();
     pdl_launch_dependents();
 
-    ActView act[NC];
-#pragma unroll
-    for (int c = 0; c < NC; ++c) {
-        const uint8_t * b = act_s + (size_t) c * p.act_col_bytes;
-        act[c].qs = reinterpret_cast<const int8_t *>(b);
-        act[c].d = reinterpret_cast<const float *>(b + a16(p.k));
-        act[c].bs = reinterpret_cast<const int *>(b + a16(p.k) + a16(p.k / F::ACT_G * 4));
-    }
-
-    constexpr int LPU = F::LANES_PER_UNIT;
+    const ActLayout L = act_layout(F::Q8K, p.k);
+    constexpr int LPU = F::LPU;
     constexpr int UPS = 32 / LPU;  // units per warp step
     const int g = lane % LPU;
     const int ul = lane / LPU;
@@ -286,9 +294,31 @@ __global__ void __launch_bounds__(512) gemv_q_kernel(const GemvParams p) {
         mbar_wait(&bars[s], parity);
         const uint8_t * st = ring + (size_t) s * stage_bytes;
         for (int u = ul; u < nu; u += UPS) {
+            if constexpr (NC == 1) {
+                typename F::Act A;
+                F::load_act(act_s, L, u0 + u, g, A);
 #pragma unroll
-            for (int r = 0; r < RG; ++r) {
-                if (r < nr) F::template dot<NC>(st + (size_t) r * p.ks * F::A_UNIT, st + stageA + (size_t) r * p.ks * F::B_UNIT, u, g, u0 + u, act, acc[r]);
+                for (int r = 0; r < RG; ++r) {
+                    if (r < nr) {
+                        typename F::Wt Wr;
+                        F::load_w(st + (size_t) r * rsA, st + offB + (size_t) r * rsB, u, g, Wr);
+                        acc[r][0] = F::dot(Wr, A, acc[r][0]);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < RG; ++r) {
+                    if (r < nr) {
+                        typename F::Wt Wr;
+                        F::load_w(st + (size_t) r * rsA, st + offB + (size_t) r * rsB, u, g, Wr);
+#pragma unroll
+                        for (int c = 0; c < NC; ++c) {
+                            typename F::Act A;
+                            F::load_act(act_s + (size_t) c * p.act_col_bytes, L, u0 + u, g, A);
+                            acc[r][c] = F::dot(Wr, A, acc[r][c]);
+                        }
+                    }
+                }
             }
         }
         __syncwarp();
@@ -372,34 +402,44 @@ static int launch_rg(const GemvParams & p, int rg, int nc, int warps, int grid, 
     }
 }
 
-// y[c*ldy + i] = sum_k W[i,k] * x_c[k]   for c < n (n <= 8 handled in column groups of <= 4)
+static int launch_fmt(int wtype, const GemvParams & p, int rg, int nc, int warps, int grid, size_t smem, cudaStream_t st) {
+    switch (wtype) {
+        case B200_TYPE_Q4_K: return launch_rg<FmtQ4K>(p, rg, nc, warps, grid, smem, st);
+        case B200_TYPE_Q4_0: return launch_rg<FmtQ40>(p, rg, nc, warps, grid, smem, st);
+        case B200_TYPE_Q8_0: return launch_rg<FmtQ80>(p, rg, nc, warps, grid, smem, st);
+        default: return B200_ERR_UNSUPPORTED;
+    }
+}
+
+// y[c*ldy + i] = sum_k W[i,k] * x_c[k]   for c < n (processed in column groups of 4 / 2 / 1)
 int mul_mat_q(int wtype, const void * W, int64_t k, int64_t m, const void * qact, int64_t n, float * y, int64_t ldy, const float * bias,
               const GemvTuning * tune, cudaStream_t st) {
     if (k <= 0 || m <= 0 || n <= 0) return B200_OK;
     if (k % 256) return B200_ERR_UNSUPPORTED;
-    int a_unit, b_unit;
+    int unit;
     switch (wtype) {
-        case B200_TYPE_Q4_K: a_unit = FmtQ4K::A_UNIT; b_unit = FmtQ4K::B_UNIT; break;
-        case B200_TYPE_Q4_0: a_unit = FmtQ40::A_UNIT; b_unit = FmtQ40::B_UNIT; break;
-        case B200_TYPE_Q8_0: a_unit = FmtQ80::A_UNIT; b_unit = FmtQ80::B_UNIT; break;
+        case B200_TYPE_Q4_K: unit = FmtQ4K::A_UNIT + FmtQ4K::B_UNIT; break;
+        case B200_TYPE_Q4_0: unit = FmtQ40::A_UNIT + FmtQ40::B_UNIT; break;
+        case B200_TYPE_Q8_0: unit = FmtQ80::A_UNIT + FmtQ80::B_UNIT; break;
         default: return B200_ERR_UNSUPPORTED;
     }
     const size_t acb = qact_col_bytes(wtype, k);
     const int nunits = (int) (k / 256);
     const int sms = sm_count();
 
-    for (int64_t c0 = 0; c0 < n; c0 += 4) {
-        const int ncols = (int) ((n - c0) < 4 ? (n - c0) : 4);
-        const int nc = ncols == 3 ? 4 : ncols;  // template width (1, 2, 4); the 4th column of a 3-wide group is masked
+    int64_t c0 = 0;
+    while (c0 < n) {
+        const int64_t left = n - c0;
+        const int nc = left >= 4 ? 4 : (left >= 2 ? 2 : 1);
 
         GemvTuning t;
-        t.rg = tune && tune->rg ? tune->rg : env_int("B200_GEMV_RG", 4);
+        t.rg = tune && tune->rg ? tune->rg : env_int("B200_GEMV_RG", 2);
         t.warps = tune && tune->warps ? tune->warps : env_int("B200_GEMV_WARPS", 8);
         t.stages = tune && tune->stages ? tune->stages : env_int("B200_GEMV_STAGES", 4);
-        t.ks = tune && tune->ks ? tune->ks : env_int("B200_GEMV_KS", 8);
+        t.ks = tune && tune->ks ? tune->ks : env_int("B200_GEMV_KS", 16);
         t.grid = tune && tune->grid ? tune->grid : env_int("B200_GEMV_GRID", 0);
         if (t.ks > nunits) t.ks = nunits;
-        // few rows: keep at least one full row-group per warp
+        // few rows: keep at least one row-group per warp
         while (t.rg > 1 && m < (int64_t) sms * t.warps * t.rg / 2) t.rg >>= 1;
         int grid = t.grid > 0 ? t.grid : sms;
         {
@@ -407,57 +447,32 @@ int mul_mat_q(int wtype, const void * W, int64_t k, int64_t m, const void * qact
             const int64_t max_grid = (max_warps + t.warps - 1) / t.warps;
             if (grid > max_grid) grid = (int) max_grid;
         }
-        const size_t act_bytes = (size_t) a16((int64_t) acb * nc);
+        const size_t act_bytes = (size_t) al16((int64_t) acb * nc);
         auto smem_for = [&](const GemvTuning & q) {
-            return act_bytes + (size_t) a16((int64_t) q.warps * q.stages * 8) + (size_t) q.warps * q.stages * q.rg * q.ks * (a_unit + b_unit);
+            return act_bytes + (size_t) al16((int64_t) q.warps * q.stages * 8) + (size_t) q.warps * q.stages * q.rg * q.ks * unit;
         };
         const size_t limit = 227 * 1024;
+        while (smem_for(t) > limit && t.stages > 3) t.stages--;
+        while (smem_for(t) > limit && t.ks > 4) t.ks = (t.ks + 1) / 2;
         while (smem_for(t) > limit && t.stages > 2) t.stages--;
-        while (smem_for(t) > limit && t.ks > 1) t.ks = (t.ks + 1) / 2;
         while (smem_for(t) > limit && t.warps > 1) t.warps >>= 1;
+        while (smem_for(t) > limit && t.ks > 1) t.ks = (t.ks + 1) / 2;
         if (smem_for(t) > limit) return B200_ERR_UNSUPPORTED;
 
         GemvParams p;
         p.W = (const uint8_t *) W;
-        // a 3-wide group reads one column past the end of qact: the caller's buffer always holds >= n columns; the
-        // extra column (if any) is garbage-in and masked at the store (c < p.n).  For the very last group we must not
-        // read out of bounds, so narrow to what exists.
         p.qact = (const uint8_t *) qact + (size_t) c0 * acb;
         p.y = y + c0 * ldy;
         p.bias = bias;
         p.k = k; p.m = m; p.ldy = ldy;
-        p.n = ncols;
+        p.n = nc;
         p.nunits = nunits;
         p.ks = t.ks;
         p.stages = t.stages;
         p.act_col_bytes = (uint32_t) acb;
-        int rc;
-        if (ncols == 3) {
-            // run as 2 + 1 to stay inside the qact buffer
-            GemvParams p2 = p; p2.n = 2;
-            const size_t s2 = (size_t) a16((int64_t) acb * 2) + (smem_for(t) - act_bytes);
-            switch (wtype) {
-                case B200_TYPE_Q4_K: rc = launch_rg<FmtQ4K>(p2, t.rg, 2, t.warps, grid, s2, st); break;
-                case B200_TYPE_Q4_0: rc = launch_rg<FmtQ40>(p2, t.rg, 2, t.warps, grid, s2, st); break;
-                default: rc = launch_rg<FmtQ80>(p2, t.rg, 2, t.warps, grid, s2, st); break;
-            }
-            if (rc) return rc;
-            GemvParams p1 = p; p1.n = 1; p1.qact += 2 * acb; p1.y += 2 * ldy;
-            const size_t s1 = (size_t) a16((int64_t) acb) + (smem_for(t) - act_bytes);
-            switch (wtype) {
-                case B200_TYPE_Q4_K: rc = launch_rg<FmtQ4K>(p1, t.rg, 1, t.warps, grid, s1, st); break;
-                case B200_TYPE_Q4_0: rc = launch_rg<FmtQ40>(p1, t.rg, 1, t.warps, grid, s1, st); break;
-                default: rc = launch_rg<FmtQ80>(p1, t.rg, 1, t.warps, grid, s1, st); break;
-            }
-            if (rc) return rc;
-            continue;
-        }
-        switch (wtype) {
-            case B200_TYPE_Q4_K: rc = launch_rg<FmtQ4K>(p, t.rg, nc, t.warps, grid, smem_for(t), st); break;
-            case B200_TYPE_Q4_0: rc = launch_rg<FmtQ40>(p, t.rg, nc, t.warps, grid, smem_for(t), st); break;
-            default: rc = launch_rg<FmtQ80>(p, t.rg, nc, t.warps, grid, smem_for(t), st); break;
-        }
+        const int rc = launch_fmt(wtype, p, t.rg, nc, t.warps, grid, smem_for(t), st);
         if (rc) return rc;
+        c0 += nc;
     }
     return B200_OK;
 }

@@ -6,22 +6,15 @@
 //   Q4_0 / Q8_0 weights    -> Q8_0 activations: x86 quantize_row_q8_0 (ggml/src/ggml-cpu/arch/x86/quants.c:290-384)
 // Matching the integer codes exactly makes the integer dot products exact; only fp32 summation order differs.
 //
-// Device layout of one quantized activation column ("qact", ours — not the reference's AoS blocks):
-//   int8  qs[k]            k bytes (k % 32 == 0 -> 16-byte multiple)
-//   float d [k / G]        G = 256 (Q8_K) or 32 (Q8_0; value already rounded through fp16 like block_q8_0.d)
-//   int   bs[k / 32]       sum of qs over each 32-element group (Q8_K's bsums, pairwise-added)
+// Device layout of one quantized activation column ("qact", ours — not the reference's AoS blocks): actlayout.cuh.
 // Columns are laid out back to back with stride qact_col_bytes().
+#include "actlayout.cuh"
 #include "common.cuh"
 #include "kernels.h"
 
 namespace b200 {
 
-__host__ __device__ inline int64_t align16(int64_t x) { return (x + 15) & ~(int64_t) 15; }
-
-size_t qact_col_bytes(int wtype, int64_t k) {
-    const int64_t G = (wtype == B200_TYPE_Q4_K) ? 256 : 32;
-    return (size_t) (align16(k) + align16(k / G * 4) + align16(k / 32 * 4));
-}
+size_t qact_col_bytes(int wtype, int64_t k) { return (size_t) act_layout(wtype == B200_TYPE_Q4_K, k).col_bytes; }
 
 // ---- Q8_K: one warp-group of 256 threads per 256-element block ----------------------------------------
 // max = the element with the largest |x| (FIRST occurrence on ties, ggml-quants.c:2563-2567), iscale = -127/max,
@@ -61,10 +54,11 @@ __global__ void __launch_bounds__(256) quantize_q8_K_kernel(const float * __rest
     __syncthreads();
     const float mx = s_max;
 
+    const ActLayout L = act_layout(true, k);
     uint8_t * base = qact + (size_t) col * col_bytes;
     int8_t * qs = (int8_t *) base;
-    float * d = (float *) (base + align16(k));
-    int * bs = (int *) (base + align16(k) + align16(k / 256 * 4));
+    float * d = (float *) (base + L.d_off);
+    int16_t * bs = (int16_t *) (base + L.bs_off);
 
     int q = 0;
     float dd = 0.0f;
@@ -73,12 +67,16 @@ __global__ void __launch_bounds__(256) quantize_q8_K_kernel(const float * __rest
         q = min(127, __float2int_rn(__fmul_rn(iscale, v)));
         dd = __fdiv_rn(1.0f, iscale);
     }
-    qs[(int64_t) blk * 256 + tid] = (int8_t) q;
+    qs[act_qs_off_q8k((int64_t) blk * 256 + tid)] = (int8_t) q;
     int s = q;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if ((tid & 31) == 0) bs[blk * 8 + (tid >> 5)] = s;
+    if ((tid & 31) == 0) bs[blk * 8 + (tid >> 5)] = (int16_t) s;
     if (tid == 0) d[blk] = dd;
+    // zero the padding chunks of the last (partial) 1024-element group so the GEMV can read them blindly
+    if (blk == (int) (k / 256) - 1) {
+        for (int64_t e = k + tid; e < L.qs_bytes; e += 256) qs[act_qs_off_q8k(e)] = 0;
+    }
 }
 
 // ---- Q8_0 (x86 variant): one warp per 32-element block --------------------------------------------------
@@ -96,11 +94,12 @@ __global__ void __launch_bounds__(256) quantize_q8_0_kernel(const float * __rest
     const float id = (amax != 0.0f) ? __fdiv_rn(127.f, amax) : 0.0f;
     const int q = __float2int_rn(__fmul_rn(v, id));
 
+    const ActLayout L = act_layout(false, k);
     uint8_t * base = qact + (size_t) col * col_bytes;
     int8_t * qs = (int8_t *) base;
-    float * d = (float *) (base + align16(k));
-    int * bs = (int *) (base + align16(k) + align16(k / 32 * 4));
-    qs[blk * 32 + lane] = (int8_t) q;
+    float * d = (float *) (base + L.d_off);
+    int * bs = (int *) (base + L.bs_off);
+    qs[act_qs_off_q80(blk * 32 + lane)] = (int8_t) q;
     int s = q;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);

@@ -38,13 +38,23 @@ def _acts(rng, n, k, heavy=True):
 
 
 def _decode_qact(q, wtype, k):
-    """device qact column bytes -> (qs int8[k], d float32[k/G], bs int32[k/32])"""
-    Gs = 256 if wtype == qf.Q4_K else 32
+    """device qact column bytes (layout: chatllm.cpp_b200/csrc/actlayout.cuh) -> (qs int8[k], d float32[k/G], bs int[k/32])"""
     a16 = lambda v: (v + 15) & ~15
-    o1 = a16(k); o2 = o1 + a16(k // Gs * 4)
-    qs = q[:, :k].view(np.int8)
-    d = q[:, o1:o1 + k // Gs * 4].copy().view(np.float32)
-    bs = q[:, o2:o2 + k // 32 * 4].copy().view(np.int32)
+    e = np.arange(k)
+    if wtype == qf.Q4_K:
+        qs_bytes = (k + 1023) // 1024 * 1024
+        u, h, j, b = e >> 8, (e >> 7) & 1, (e >> 4) & 7, e & 15
+        off = (u >> 2) * 1024 + j * 128 + (u & 3) * 32 + h * 16 + b
+        o1 = qs_bytes; o2 = o1 + a16(k // 256 * 4)
+        d = q[:, o1:o1 + k // 256 * 4].copy().view(np.float32)
+        bs = q[:, o2:o2 + k // 32 * 2].copy().view(np.int16).astype(np.int32)
+    else:
+        blk, j, b = e >> 5, (e >> 4) & 1, e & 15
+        off = (blk >> 3) * 256 + j * 128 + (blk & 7) * 16 + b
+        o1 = a16(k); o2 = o1 + a16(k // 32 * 4)
+        d = q[:, o1:o1 + k // 32 * 4].copy().view(np.float32)
+        bs = q[:, o2:o2 + k // 32 * 4].copy().view(np.int32)
+    qs = q[:, off].view(np.int8)
     return qs, d, bs
 
 
@@ -206,7 +216,9 @@ def test_rope_partial_dims_and_yarn(K):
         y = K.rope(_t(x), _t(pos), 64, mode, 10000.0, n_ctx_orig=4096, freq_scale=0.25, ext=1.0, attn=1.1).cpu().numpy()
         r = np.zeros_like(x)
         qf.port().oq_rope(x.ctypes.data, r.ctypes.data, pos.ctypes.data, None, 96, 3, 5, 64, mode, 4096, 10000.0, 0.25, 1.0, 1.1, 32.0, 1.0)
-        assert np.abs(y - r).max() <= 4e-6 * np.abs(r).max()
+        # the YaRN mix theta_interp*(1-ramp) + theta_extrap*ramp is FMA-contracted by nvcc (and by gcc in the reference
+        # build) but not in the -ffp-contract=off port: 1 ulp of a ~1e3 rad angle is ~6e-5 rad -> tolerance 1e-4
+        assert np.abs(y - r).max() <= 1e-4 * np.abs(r).max()
 
 
 def test_silu_mul_and_add(K):

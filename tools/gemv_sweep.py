@@ -37,10 +37,17 @@ def bench(t, k, m, n=1, iters=50, min_bytes=600e6):
     for i in range(3):
         K.mul_mat_q(t, ws[i % copies], k, m, q, n, out=y)
     torch.cuda.synchronize()
+    # capture the launches in a CUDA graph so Python/ctypes launch overhead is not what we time
+    stream = torch.cuda.Stream()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(stream):
+        with torch.cuda.graph(graph, stream=stream):
+            for i in range(iters):
+                K.mul_mat_q(t, ws[i % copies], k, m, q, n, out=y)
+    graph.replay(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(iters):
-        K.mul_mat_q(t, ws[i % copies], k, m, q, n, out=y)
+    graph.replay()
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
     return ms, gemv_bytes(t, k, m) / ms / 1e6
