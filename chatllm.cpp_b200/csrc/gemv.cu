@@ -378,7 +378,8 @@ static int launch(const GemvParams & p, int warps, int grid, size_t smem_bytes, 
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    static const int no_pdl = env_int("B200_NO_PDL", 0);
+    cfg.numAttrs = no_pdl ? 0 : 1;
     return (int) cudaLaunchKernelEx(&cfg, kern, p);
 }
 
