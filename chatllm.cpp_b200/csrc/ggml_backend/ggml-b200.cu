@@ -1,0 +1,584 @@
+// ggml-b200.cu — the drop-in boundary: a ggml backend module (libggml-cuda.so) for chatllm.cpp, written from
+// scratch for sm_100a on top of the kernels in ../ (no code from ggml-cuda).
+//
+// What it replaces in the reference (file:line under /root/reference):
+//   ggml/src/ggml-cuda/ggml-cuda.cu   buffer iface :568-683, buffer-type iface :685-751, backend iface :4375-4390,
+//                                     device iface :5057-5073, reg iface :5175-5228, GGML_BACKEND_DL_IMPL (last line)
+// against the plugin ABI of ggml/src/ggml-backend-impl.h:11-255 (GGML_BACKEND_API_VERSION 2).
+// The host application (chatllm `main`, src/backend.cpp:277-302, :677-778) loads it through
+// ggml_backend_load_all_from_path -> ggml_backend_load_best("cuda") (ggml/src/ggml-backend-reg.cpp:549-570): the
+// file name libggml-cuda.so is what puts this module in the "cuda" slot, i.e. registered before the CPU backend.
+//
+// Compiled against the host SDK headers in place (-I$REF/ggml/include -I$REF/ggml/src); nothing is copied.
+// There is no CPU fallback in here: an op is either computed by our CUDA kernels or reported as unsupported.
+#include "ggml.h"
+#include "ggml-backend.h"
+#include "ggml-backend-impl.h"
+#include "ggml-impl.h"
+
+#include "../common.cuh"
+#include "../kernels.h"
+
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+using namespace b200;
+
+#define B200_MAX_DEVICES 16
+#define B200_ALIGN 256
+
+#define CUDA_OK(expr)                                                                                       \
+    do {                                                                                                    \
+        cudaError_t _e = (expr);                                                                            \
+        if (_e != cudaSuccess) {                                                                            \
+            GGML_LOG_ERROR("b200: CUDA error %s at %s:%d: %s\n", cudaGetErrorString(_e), __FILE__, __LINE__, #expr); \
+            GGML_ABORT("b200: CUDA error");                                                                 \
+        }                                                                                                   \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------------------
+// contexts
+// ------------------------------------------------------------------------------------------------------------
+struct b200_device_ctx {
+    int device;
+    std::string name, desc;
+    ggml_backend_buffer_type buft;
+    ggml_backend_buffer_type host_buft;
+    // staging buffer for layout conversion in set_tensor / get_tensor
+    std::mutex mu;
+    void * staging = nullptr;
+    size_t staging_bytes = 0;
+    cudaStream_t xfer = nullptr;
+};
+
+struct b200_buffer_ctx {
+    int device;
+    void * base;
+};
+
+struct b200_backend_ctx {
+    int device;
+    cudaStream_t stream;
+    void * qact = nullptr;
+    size_t qact_bytes = 0;
+    long long launches = 0;
+};
+
+static ggml_backend_device g_devices[B200_MAX_DEVICES];
+static b200_device_ctx g_dev_ctx[B200_MAX_DEVICES];
+static int g_n_devices = -1;
+
+static bool is_repacked(const ggml_tensor * t) {
+    return (t->type == GGML_TYPE_Q4_0 || t->type == GGML_TYPE_Q8_0) && t->ne[0] % 256 == 0;
+}
+
+static void * dev_staging(b200_device_ctx * dc, size_t bytes) {
+    if (dc->staging_bytes < bytes) {
+        if (dc->staging) CUDA_OK(cudaFree(dc->staging));
+        size_t nb = bytes < (4u << 20) ? (4u << 20) : bytes;
+        CUDA_OK(cudaMalloc(&dc->staging, nb));
+        dc->staging_bytes = nb;
+    }
+    return dc->staging;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// buffer  (ggml_backend_buffer_i, ggml-backend-impl.h:41-66)
+// ------------------------------------------------------------------------------------------------------------
+static void b200_buffer_free(ggml_backend_buffer_t buffer) {
+    b200_buffer_ctx * c = (b200_buffer_ctx *) buffer->context;
+    cudaSetDevice(c->device);
+    cudaFree(c->base);
+    delete c;
+}
+static void * b200_buffer_get_base(ggml_backend_buffer_t buffer) { return ((b200_buffer_ctx *) buffer->context)->base; }
+
+static void b200_buffer_memset_tensor(ggml_backend_buffer_t buffer, ggml_tensor * tensor, uint8_t value, size_t offset, size_t size) {
+    b200_buffer_ctx * c = (b200_buffer_ctx *) buffer->context;
+    CUDA_OK(cudaSetDevice(c->device));
+    b200_device_ctx * dc = &g_dev_ctx[c->device];
+    CUDA_OK(cudaMemsetAsync((char *) tensor->data + offset, value, size, dc->xfer));
+    CUDA_OK(cudaStreamSynchronize(dc->xfer));
+}
+
+// host (native ggml layout) -> device.  Q4_0 / Q8_0 tensors are converted to the per-row SoA device layout
+// window by window (the loader writes 1 MiB chunks at arbitrary offsets, src/chat.cpp:1322-1338).
+static void b200_buffer_set_tensor(ggml_backend_buffer_t buffer, ggml_tensor * tensor, const void * data, size_t offset, size_t size) {
+    b200_buffer_ctx * c = (b200_buffer_ctx *) buffer->context;
+    CUDA_OK(cudaSetDevice(c->device));
+    b200_device_ctx * dc = &g_dev_ctx[c->device];
+    if (is_repacked(tensor)) {
+        std::lock_guard<std::mutex> lk(dc->mu);
+        void * stg = dev_staging(dc, size);
+        CUDA_OK(cudaMemcpyAsync(stg, data, size, cudaMemcpyHostToDevice, dc->xfer));
+        int rc = repack_window(tensor->type, stg, tensor->data, (int64_t) offset, (int64_t) size, tensor->ne[0], false, dc->xfer);
+        GGML_ASSERT(rc == 0);
+        CUDA_OK(cudaStreamSynchronize(dc->xfer));
+    } else {
+        CUDA_OK(cudaMemcpyAsync((char *) tensor->data + offset, data, size, cudaMemcpyHostToDevice, dc->xfer));
+        CUDA_OK(cudaStreamSynchronize(dc->xfer));
+    }
+}
+static void b200_buffer_get_tensor(ggml_backend_buffer_t buffer, const ggml_tensor * tensor, void * data, size_t offset, size_t size) {
+    b200_buffer_ctx * c = (b200_buffer_ctx *) buffer->context;
+    CUDA_OK(cudaSetDevice(c->device));
+    b200_device_ctx * dc = &g_dev_ctx[c->device];
+    if (is_repacked(tensor)) {
+        std::lock_guard<std::mutex> lk(dc->mu);
+        void * stg = dev_staging(dc, size);
+        int rc = repack_window(tensor->type, stg, tensor->data, (int64_t) offset, (int64_t) size, tensor->ne[0], true, dc->xfer);
+        GGML_ASSERT(rc == 0);
+        CUDA_OK(cudaMemcpyAsync(data, stg, size, cudaMemcpyDeviceToHost, dc->xfer));
+        CUDA_OK(cudaStreamSynchronize(dc->xfer));
+    } else {
+        CUDA_OK(cudaMemcpyAsync(data, (const char *) tensor->data + offset, size, cudaMemcpyDeviceToHost, dc->xfer));
+        CUDA_OK(cudaStreamSynchronize(dc->xfer));
+    }
+}
+
+static bool b200_buffer_is_ours(ggml_backend_buffer_t b);
+
+// dst is in this buffer; src may live in another buffer of ours (same layout conventions on every device)
+static bool b200_buffer_cpy_tensor(ggml_backend_buffer_t buffer, const ggml_tensor * src, ggml_tensor * dst) {
+    if (!src->buffer || !b200_buffer_is_ours(src->buffer)) return false;
+    b200_buffer_ctx * dc = (b200_buffer_ctx *) buffer->context;
+    b200_buffer_ctx * sc = (b200_buffer_ctx *) (src->view_src ? src->view_src->buffer : src->buffer)->context;
+    if (!ggml_is_contiguous(src) || !ggml_is_contiguous(dst) || ggml_nbytes(src) != ggml_nbytes(dst)) return false;
+    CUDA_OK(cudaSetDevice(dc->device));
+    if (sc->device == dc->device) CUDA_OK(cudaMemcpyAsync(dst->data, src->data, ggml_nbytes(src), cudaMemcpyDeviceToDevice, g_dev_ctx[dc->device].xfer));
+    else CUDA_OK(cudaMemcpyPeerAsync(dst->data, dc->device, src->data, sc->device, ggml_nbytes(src), g_dev_ctx[dc->device].xfer));
+    CUDA_OK(cudaStreamSynchronize(g_dev_ctx[dc->device].xfer));
+    return true;
+}
+static void b200_buffer_clear(ggml_backend_buffer_t buffer, uint8_t value) {
+    b200_buffer_ctx * c = (b200_buffer_ctx *) buffer->context;
+    CUDA_OK(cudaSetDevice(c->device));
+    CUDA_OK(cudaMemsetAsync(c->base, value, buffer->size, g_dev_ctx[c->device].xfer));
+    CUDA_OK(cudaStreamSynchronize(g_dev_ctx[c->device].xfer));
+}
+
+static const ggml_backend_buffer_i b200_buffer_iface = {
+    /* .free_buffer   = */ b200_buffer_free,
+    /* .get_base      = */ b200_buffer_get_base,
+    /* .init_tensor   = */ nullptr,
+    /* .memset_tensor = */ b200_buffer_memset_tensor,
+    /* .set_tensor    = */ b200_buffer_set_tensor,
+    /* .get_tensor    = */ b200_buffer_get_tensor,
+    /* .cpy_tensor    = */ b200_buffer_cpy_tensor,
+    /* .clear         = */ b200_buffer_clear,
+    /* .reset         = */ nullptr,
+};
+static bool b200_buffer_is_ours(ggml_backend_buffer_t b) { return b->iface.free_buffer == b200_buffer_free; }
+
+// ------------------------------------------------------------------------------------------------------------
+// buffer type  (ggml_backend_buffer_type_i, ggml-backend-impl.h:17-35)
+// ------------------------------------------------------------------------------------------------------------
+static const char * b200_buft_name(ggml_backend_buffer_type_t buft) { return ((b200_device_ctx *) buft->context)->name.c_str(); }
+static ggml_backend_buffer_t b200_buft_alloc(ggml_backend_buffer_type_t buft, size_t size) {
+    b200_device_ctx * dc = (b200_device_ctx *) buft->context;
+    if (cudaSetDevice(dc->device) != cudaSuccess) return nullptr;
+    void * p = nullptr;
+    size_t sz = size ? size : 1;
+    cudaError_t e = cudaMalloc(&p, sz);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        GGML_LOG_ERROR("b200: cudaMalloc(%zu) on device %d failed: %s\n", sz, dc->device, cudaGetErrorString(e));
+        return nullptr;  // caller CHATLLM_CHECKs (src/backend.cpp:105-107)
+    }
+    b200_buffer_ctx * c = new b200_buffer_ctx{dc->device, p};
+    return ggml_backend_buffer_init(buft, b200_buffer_iface, c, size);
+}
+static size_t b200_buft_alignment(ggml_backend_buffer_type_t) { return B200_ALIGN; }
+static bool b200_buft_is_host(ggml_backend_buffer_type_t) { return false; }
+static const ggml_backend_buffer_type_i b200_buft_iface = {
+    /* .get_name       = */ b200_buft_name,
+    /* .alloc_buffer   = */ b200_buft_alloc,
+    /* .get_alignment  = */ b200_buft_alignment,
+    /* .get_max_size   = */ nullptr,
+    /* .get_alloc_size = */ nullptr,
+    /* .is_host        = */ b200_buft_is_host,
+};
+
+// pinned host buffer type (chatllm asks ggml_backend_dev_host_buffer_type(dev 0/1), src/backend.cpp:319-334)
+static void b200_host_buffer_free(ggml_backend_buffer_t buffer) { cudaFreeHost(buffer->context); }
+static const char * b200_host_buft_name(ggml_backend_buffer_type_t) { return "B200_Host"; }
+static ggml_backend_buffer_t b200_host_buft_alloc(ggml_backend_buffer_type_t buft, size_t size) {
+    void * p = nullptr;
+    if (cudaMallocHost(&p, size ? size : 1) != cudaSuccess) {
+        cudaGetLastError();
+        return ggml_backend_buft_alloc_buffer(ggml_backend_cpu_buffer_type(), size);  // plain host memory
+    }
+    ggml_backend_buffer_t b = ggml_backend_cpu_buffer_from_ptr(p, size);
+    b->buft = buft;
+    b->iface.free_buffer = b200_host_buffer_free;
+    return b;
+}
+static size_t b200_host_buft_alignment(ggml_backend_buffer_type_t) { return 64; }
+static bool b200_host_buft_is_host(ggml_backend_buffer_type_t) { return true; }
+static const ggml_backend_buffer_type_i b200_host_buft_iface = {
+    /* .get_name       = */ b200_host_buft_name,
+    /* .alloc_buffer   = */ b200_host_buft_alloc,
+    /* .get_alignment  = */ b200_host_buft_alignment,
+    /* .get_max_size   = */ nullptr,
+    /* .get_alloc_size = */ nullptr,
+    /* .is_host        = */ b200_host_buft_is_host,
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// op dispatch
+// ------------------------------------------------------------------------------------------------------------
+static TV tv(const ggml_tensor * t) {
+    TV v;
+    v.data = t->data;
+    v.type = (int) t->type;
+    for (int i = 0; i < 4; ++i) { v.ne[i] = t->ne[i]; v.nb[i] = (int64_t) t->nb[i]; }
+    return v;
+}
+static bool is_view_op(enum ggml_op op) {
+    return op == GGML_OP_NONE || op == GGML_OP_RESHAPE || op == GGML_OP_VIEW || op == GGML_OP_PERMUTE || op == GGML_OP_TRANSPOSE;
+}
+static bool qtype_ok(const ggml_tensor * w) {
+    if (w->type == GGML_TYPE_Q4_K) return true;
+    if (w->type == GGML_TYPE_Q4_0 || w->type == GGML_TYPE_Q8_0) return w->ne[0] % 256 == 0;
+    return false;
+}
+static bool f32c(const ggml_tensor * t) { return t && t->type == GGML_TYPE_F32 && ggml_is_contiguous(t); }
+
+static bool b200_supports_op(ggml_backend_dev_t, const ggml_tensor * op) {
+    const ggml_tensor * s0 = op->src[0];
+    const ggml_tensor * s1 = op->src[1];
+    switch (op->op) {
+        case GGML_OP_NONE:
+        case GGML_OP_RESHAPE:
+        case GGML_OP_VIEW:
+        case GGML_OP_PERMUTE:
+        case GGML_OP_TRANSPOSE:
+            return true;
+        case GGML_OP_GET_ROWS:
+            if (op->type != GGML_TYPE_F32 || s1->type != GGML_TYPE_I32) return false;
+            if (s0->type == GGML_TYPE_F32 || s0->type == GGML_TYPE_F16) return s0->nb[0] == ggml_type_size(s0->type);
+            return qtype_ok(s0) && ggml_is_contiguous(s0) && ggml_is_contiguous(s1) && ggml_is_contiguous(op) && s0->ne[2] == 1 && s0->ne[3] == 1;
+        case GGML_OP_RMS_NORM:
+            return s0->type == GGML_TYPE_F32 && s0->nb[0] == 4 && op->type == GGML_TYPE_F32 && op->nb[0] == 4;
+        case GGML_OP_ADD:
+        case GGML_OP_MUL:
+        case GGML_OP_DIV:
+            return s0->type == GGML_TYPE_F32 && s1->type == GGML_TYPE_F32 && op->type == GGML_TYPE_F32 && ggml_are_same_shape(s0, op) &&
+                   ggml_can_repeat(s1, s0);
+        case GGML_OP_MUL_MAT:
+            if (op->type != GGML_TYPE_F32 || s1->type != GGML_TYPE_F32) return false;
+            if (ggml_is_quantized(s0->type)) {
+                return qtype_ok(s0) && s0->ne[0] % 256 == 0 && ggml_is_contiguous(s0) && s0->ne[2] == 1 && s0->ne[3] == 1 && s1->ne[2] == 1 &&
+                       s1->ne[3] == 1 && s1->nb[0] == 4 && op->nb[0] == 4 && ggml_is_contiguous(op);
+            }
+            if (s0->type == GGML_TYPE_F16 || s0->type == GGML_TYPE_F32)
+                return s0->nb[0] == ggml_type_size(s0->type) && op->nb[0] == 4 && s1->ne[2] % s0->ne[2] == 0 && s1->ne[3] % s0->ne[3] == 0;
+            return false;
+        case GGML_OP_ROPE: {
+            const int mode = op->op_params[2];
+            return s0->type == GGML_TYPE_F32 && op->type == GGML_TYPE_F32 && s0->nb[0] == 4 && op->nb[0] == 4 && s1->type == GGML_TYPE_I32 &&
+                   (mode == 0 || mode == GGML_ROPE_TYPE_NEOX) && (!op->src[2] || op->src[2]->type == GGML_TYPE_F32);
+        }
+        case GGML_OP_SET_ROWS:
+            return s0->type == GGML_TYPE_F32 && (s1->type == GGML_TYPE_I32 || s1->type == GGML_TYPE_I64) &&
+                   (op->type == GGML_TYPE_F16 || op->type == GGML_TYPE_F32);
+        case GGML_OP_CPY:
+        case GGML_OP_DUP:
+        case GGML_OP_CONT: {
+            const ggml_type a = s0->type, b = op->type;
+            const bool ok = (a == GGML_TYPE_F32 && (b == GGML_TYPE_F32 || b == GGML_TYPE_F16)) ||
+                            (a == GGML_TYPE_F16 && (b == GGML_TYPE_F32 || b == GGML_TYPE_F16)) || (a == GGML_TYPE_I32 && b == GGML_TYPE_I32);
+            return ok && ggml_nelements(s0) == ggml_nelements(op);
+        }
+        case GGML_OP_SCALE:
+        case GGML_OP_CLAMP:
+        case GGML_OP_DIAG_MASK_INF:
+            return f32c(s0) && f32c(op);
+        case GGML_OP_UNARY:
+            return ggml_get_unary_op(op) == GGML_UNARY_OP_SILU && f32c(s0) && f32c(op);
+        case GGML_OP_SOFT_MAX: {
+            float max_bias;
+            memcpy(&max_bias, (const float *) op->op_params + 1, sizeof(float));
+            if (max_bias != 0.0f || op->src[2]) return false;
+            if (s1 && s1->type != GGML_TYPE_F32 && s1->type != GGML_TYPE_F16) return false;
+            if (s1 && (s1->nb[0] != ggml_type_size(s1->type) || s1->ne[0] < s0->ne[0])) return false;
+            return s0->type == GGML_TYPE_F32 && s0->nb[0] == 4 && op->nb[0] == 4;
+        }
+        case GGML_OP_SUM_ROWS:
+            return s0->type == GGML_TYPE_F32 && s0->nb[0] == 4;
+        case GGML_OP_REPEAT:
+            return s0->type == GGML_TYPE_F32 && op->type == GGML_TYPE_F32;
+        case GGML_OP_ARGSORT:
+        case GGML_OP_TOP_K:
+            return s0->type == GGML_TYPE_F32 && s0->nb[0] == 4 && s0->ne[0] <= 8192;
+        default:
+            return false;
+    }
+}
+
+static void * ensure_qact(b200_backend_ctx * bc, size_t bytes) {
+    if (bc->qact_bytes < bytes) {
+        CUDA_OK(cudaStreamSynchronize(bc->stream));
+        if (bc->qact) CUDA_OK(cudaFree(bc->qact));
+        size_t nb = bytes < (1u << 20) ? (1u << 20) : bytes;
+        CUDA_OK(cudaMalloc(&bc->qact, nb));
+        bc->qact_bytes = nb;
+    }
+    return bc->qact;
+}
+
+static int compute_node(b200_backend_ctx * bc, ggml_tensor * node) {
+    cudaStream_t st = bc->stream;
+    const ggml_tensor * s0 = node->src[0];
+    const ggml_tensor * s1 = node->src[1];
+    switch (node->op) {
+        case GGML_OP_GET_ROWS:
+            if (s0->type == GGML_TYPE_F32 || s0->type == GGML_TYPE_F16) return op_get_rows_f(tv(s0), tv(s1), tv(node), st);
+            return get_rows_q((int) s0->type, s0->data, s0->ne[0], (const int32_t *) s1->data, ggml_nelements(s1), (float *) node->data, st);
+        case GGML_OP_RMS_NORM: {
+            float eps;
+            memcpy(&eps, node->op_params, sizeof(float));
+            if (ggml_is_contiguous(s0) && ggml_is_contiguous(node))
+                return rms_norm_mul((const float *) s0->data, nullptr, (float *) node->data, s0->ne[0], ggml_nrows(s0), eps, st);
+            return op_rms_norm(tv(s0), tv(node), eps, st);
+        }
+        case GGML_OP_ADD: return op_bin(0, tv(s0), tv(s1), tv(node), st);
+        case GGML_OP_MUL: return op_bin(1, tv(s0), tv(s1), tv(node), st);
+        case GGML_OP_DIV: return op_bin(2, tv(s0), tv(s1), tv(node), st);
+        case GGML_OP_MUL_MAT: {
+            if (ggml_is_quantized(s0->type)) {
+                const int64_t k = s0->ne[0], m = s0->ne[1], n = s1->ne[1];
+                const size_t cb = qact_col_bytes((int) s0->type, k);
+                const int64_t batch = 64;
+                void * q = ensure_qact(bc, cb * (size_t) (n < batch ? n : batch));
+                const int64_t ldx = (int64_t) (s1->nb[1] / 4), ldy = (int64_t) (node->nb[1] / 4);
+                for (int64_t c0 = 0; c0 < n; c0 += batch) {
+                    const int64_t nc = (n - c0) < batch ? (n - c0) : batch;
+                    int rc = quantize_act((int) s0->type, (const float *) s1->data + c0 * ldx, ldx, k, nc, q, st);
+                    if (rc) return rc;
+                    rc = mul_mat_q((int) s0->type, s0->data, k, m, q, nc, (float *) node->data + c0 * ldy, ldy, nullptr, nullptr, st);
+                    if (rc) return rc;
+                }
+                return 0;
+            }
+            return op_mul_mat_f(tv(s0), tv(s1), tv(node), st);
+        }
+        case GGML_OP_ROPE: {
+            const int n_dims = node->op_params[1], mode = node->op_params[2], n_ctx_orig = node->op_params[4];
+            float fp[6];
+            memcpy(fp, (const int32_t *) node->op_params + 5, sizeof(fp));
+            for (int64_t i3 = 0; i3 < s0->ne[3]; ++i3) {
+                int rc = rope_f32((const float *) ((const char *) s0->data + i3 * s0->nb[3]), (float *) ((char *) node->data + i3 * node->nb[3]),
+                                  (const int32_t *) s1->data, node->src[2] ? (const float *) node->src[2]->data : nullptr, s0->ne[0], s0->ne[1],
+                                  s0->ne[2], (int64_t) s0->nb[1] / 4, (int64_t) s0->nb[2] / 4, (int64_t) node->nb[1] / 4, (int64_t) node->nb[2] / 4,
+                                  n_dims, mode, n_ctx_orig, fp[0], fp[1], fp[2], fp[3], fp[4], fp[5], st);
+                if (rc) return rc;
+            }
+            return 0;
+        }
+        case GGML_OP_SET_ROWS: return op_set_rows(tv(s0), tv(s1), tv(node), st);
+        case GGML_OP_CPY: return op_cpy(tv(s0), tv(node), st);  // dst tensor is a view of src[1]
+        case GGML_OP_DUP:
+        case GGML_OP_CONT: return op_cpy(tv(s0), tv(node), st);
+        case GGML_OP_SCALE: {
+            float s, b;
+            memcpy(&s, (const float *) node->op_params + 0, sizeof(float));
+            memcpy(&b, (const float *) node->op_params + 1, sizeof(float));
+            return op_scale((const float *) s0->data, (float *) node->data, ggml_nelements(node), s, b, st);
+        }
+        case GGML_OP_CLAMP: {
+            float lo, hi;
+            memcpy(&lo, (const float *) node->op_params + 0, sizeof(float));
+            memcpy(&hi, (const float *) node->op_params + 1, sizeof(float));
+            return op_clamp((const float *) s0->data, (float *) node->data, ggml_nelements(node), lo, hi, st);
+        }
+        case GGML_OP_DIAG_MASK_INF:
+            return op_diag_mask_inf((const float *) s0->data, (float *) node->data, s0->ne[0], s0->ne[1], ggml_nelements(node), node->op_params[0], st);
+        case GGML_OP_UNARY: return op_silu((const float *) s0->data, (float *) node->data, ggml_nelements(node), st);
+        case GGML_OP_SOFT_MAX: {
+            float scale;
+            memcpy(&scale, (const float *) node->op_params + 0, sizeof(float));
+            TV m;
+            if (s1) m = tv(s1);
+            return op_soft_max(tv(s0), s1 ? &m : nullptr, tv(node), scale, st);
+        }
+        case GGML_OP_SUM_ROWS: return op_sum_rows(tv(s0), tv(node), st);
+        case GGML_OP_REPEAT: return op_repeat(tv(s0), tv(node), st);
+        case GGML_OP_ARGSORT: return op_argsort(tv(s0), tv(node), (int) s0->ne[0], node->op_params[0] == GGML_SORT_ORDER_ASC, st);
+        case GGML_OP_TOP_K: return op_argsort(tv(s0), tv(node), (int) node->ne[0], false, st);
+        default: return B200_ERR_UNSUPPORTED;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// backend (stream)  (ggml_backend_i, ggml-backend-impl.h:87-127)
+// ------------------------------------------------------------------------------------------------------------
+static const char * b200_backend_name(ggml_backend_t backend) { return g_dev_ctx[((b200_backend_ctx *) backend->context)->device].name.c_str(); }
+static void b200_backend_free(ggml_backend_t backend) {
+    b200_backend_ctx * bc = (b200_backend_ctx *) backend->context;
+    cudaSetDevice(bc->device);
+    cudaStreamSynchronize(bc->stream);
+    if (bc->qact) cudaFree(bc->qact);
+    cudaStreamDestroy(bc->stream);
+    delete bc;
+    delete backend;
+}
+static void b200_backend_synchronize(ggml_backend_t backend) {
+    b200_backend_ctx * bc = (b200_backend_ctx *) backend->context;
+    CUDA_OK(cudaSetDevice(bc->device));
+    CUDA_OK(cudaStreamSynchronize(bc->stream));
+}
+static enum ggml_status b200_graph_compute(ggml_backend_t backend, ggml_cgraph * cgraph) {
+    b200_backend_ctx * bc = (b200_backend_ctx *) backend->context;
+    CUDA_OK(cudaSetDevice(bc->device));
+    for (int i = 0; i < cgraph->n_nodes; ++i) {
+        ggml_tensor * node = cgraph->nodes[i];
+        if (is_view_op(node->op) || ggml_is_empty(node)) continue;
+        const int rc = compute_node(bc, node);
+        if (rc != 0) {
+            GGML_LOG_ERROR("b200: op %s (%s) failed rc=%d%s\n", ggml_op_name(node->op), node->name, rc,
+                           rc > 0 ? cudaGetErrorString((cudaError_t) rc) : "");
+            return GGML_STATUS_FAILED;
+        }
+        bc->launches++;
+    }
+    return GGML_STATUS_SUCCESS;
+}
+
+static const ggml_backend_i b200_backend_iface = {
+    /* .get_name           = */ b200_backend_name,
+    /* .free               = */ b200_backend_free,
+    /* .set_tensor_async   = */ nullptr,
+    /* .get_tensor_async   = */ nullptr,
+    /* .cpy_tensor_async   = */ nullptr,
+    /* .synchronize        = */ b200_backend_synchronize,
+    /* .graph_plan_create  = */ nullptr,
+    /* .graph_plan_free    = */ nullptr,
+    /* .graph_plan_update  = */ nullptr,
+    /* .graph_plan_compute = */ nullptr,
+    /* .graph_compute      = */ b200_graph_compute,
+    /* .event_record       = */ nullptr,
+    /* .event_wait         = */ nullptr,
+    /* .graph_optimize     = */ nullptr,
+};
+
+static ggml_guid_t b200_guid() {
+    static ggml_guid guid = {0xb2, 0x00, 0x5a, 0x10, 0x0a, 0x43, 0x4c, 0x4d, 0x2e, 0x63, 0x70, 0x70, 0x5f, 0x62, 0x32, 0x30};
+    return &guid;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// device  (ggml_backend_device_i, ggml-backend-impl.h:140-188)
+// ------------------------------------------------------------------------------------------------------------
+static const char * b200_dev_name(ggml_backend_dev_t dev) { return ((b200_device_ctx *) dev->context)->name.c_str(); }
+static const char * b200_dev_desc(ggml_backend_dev_t dev) { return ((b200_device_ctx *) dev->context)->desc.c_str(); }
+static void b200_dev_memory(ggml_backend_dev_t dev, size_t * free, size_t * total) {
+    b200_device_ctx * dc = (b200_device_ctx *) dev->context;
+    cudaSetDevice(dc->device);
+    if (cudaMemGetInfo(free, total) != cudaSuccess) { *free = 0; *total = 0; }
+}
+static enum ggml_backend_dev_type b200_dev_type(ggml_backend_dev_t) { return GGML_BACKEND_DEVICE_TYPE_GPU; }
+static void b200_dev_props(ggml_backend_dev_t dev, ggml_backend_dev_props * props) {
+    props->name = b200_dev_name(dev);
+    props->description = b200_dev_desc(dev);
+    props->type = GGML_BACKEND_DEVICE_TYPE_GPU;
+    props->device_id = nullptr;
+    b200_dev_memory(dev, &props->memory_free, &props->memory_total);
+    props->caps = {/* async */ false, /* host_buffer */ true, /* buffer_from_host_ptr */ false, /* events */ false};
+}
+static ggml_backend_t b200_dev_init_backend(ggml_backend_dev_t dev, const char *) {
+    b200_device_ctx * dc = (b200_device_ctx *) dev->context;
+    if (cudaSetDevice(dc->device) != cudaSuccess) return nullptr;
+    b200_backend_ctx * bc = new b200_backend_ctx;
+    bc->device = dc->device;
+    if (cudaStreamCreateWithFlags(&bc->stream, cudaStreamNonBlocking) != cudaSuccess) { delete bc; return nullptr; }
+    return new ggml_backend{b200_guid(), b200_backend_iface, dev, bc};
+}
+static ggml_backend_buffer_type_t b200_dev_buft(ggml_backend_dev_t dev) { return &((b200_device_ctx *) dev->context)->buft; }
+static ggml_backend_buffer_type_t b200_dev_host_buft(ggml_backend_dev_t dev) { return &((b200_device_ctx *) dev->context)->host_buft; }
+static bool b200_dev_supports_buft(ggml_backend_dev_t dev, ggml_backend_buffer_type_t buft) {
+    b200_device_ctx * dc = (b200_device_ctx *) dev->context;
+    return buft == &dc->buft || buft->iface.get_name == b200_host_buft_name;
+}
+static const ggml_backend_device_i b200_device_iface = {
+    /* .get_name             = */ b200_dev_name,
+    /* .get_description      = */ b200_dev_desc,
+    /* .get_memory           = */ b200_dev_memory,
+    /* .get_type             = */ b200_dev_type,
+    /* .get_props            = */ b200_dev_props,
+    /* .init_backend         = */ b200_dev_init_backend,
+    /* .get_buffer_type      = */ b200_dev_buft,
+    /* .get_host_buffer_type = */ b200_dev_host_buft,
+    /* .buffer_from_host_ptr = */ nullptr,
+    /* .supports_op          = */ b200_supports_op,
+    /* .supports_buft        = */ b200_dev_supports_buft,
+    /* .offload_op           = */ nullptr,
+    /* .event_new            = */ nullptr,
+    /* .event_free           = */ nullptr,
+    /* .event_synchronize    = */ nullptr,
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// registry  (ggml_backend_reg_i, ggml-backend-impl.h:194-210)
+// ------------------------------------------------------------------------------------------------------------
+static int b200_count_devices() {
+    if (g_n_devices >= 0) return g_n_devices;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); n = 0; }
+    int kept = 0;
+    for (int i = 0; i < n && kept < B200_MAX_DEVICES; ++i) {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, i) != cudaSuccess) continue;
+        if (prop.major != 10) {  // sm_100a code only
+            GGML_LOG_WARN("b200: skipping device %d (%s, cc %d.%d): this module contains sm_100a code only\n", i, prop.name, prop.major, prop.minor);
+            continue;
+        }
+        b200_device_ctx * dc = &g_dev_ctx[kept];
+        dc->device = i;
+        dc->name = "CUDA" + std::to_string(kept);
+        dc->desc = std::string(prop.name) + " (chatllm.cpp_b200, sm_100a)";
+        cudaSetDevice(i);
+        cudaStreamCreateWithFlags(&dc->xfer, cudaStreamNonBlocking);
+        kept++;
+    }
+    g_n_devices = kept;
+    return kept;
+}
+static const char * b200_reg_name(ggml_backend_reg_t) { return "CUDA"; }
+static size_t b200_reg_dev_count(ggml_backend_reg_t) { return (size_t) b200_count_devices(); }
+static ggml_backend_dev_t b200_reg_get_dev(ggml_backend_reg_t, size_t i) {
+    GGML_ASSERT((int) i < b200_count_devices());
+    return &g_devices[i];
+}
+static void * b200_reg_proc(ggml_backend_reg_t, const char *) { return nullptr; }
+static const ggml_backend_reg_i b200_reg_iface = {b200_reg_name, b200_reg_dev_count, b200_reg_get_dev, b200_reg_proc};
+
+static ggml_backend_reg_t b200_reg() {
+    static ggml_backend_reg reg;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const int n = b200_count_devices();
+        reg = ggml_backend_reg{GGML_BACKEND_API_VERSION, b200_reg_iface, nullptr};
+        for (int i = 0; i < n; ++i) {
+            g_devices[i] = ggml_backend_device{b200_device_iface, &reg, &g_dev_ctx[i]};
+            g_dev_ctx[i].buft = ggml_backend_buffer_type{b200_buft_iface, &g_devices[i], &g_dev_ctx[i]};
+            g_dev_ctx[i].host_buft = ggml_backend_buffer_type{b200_host_buft_iface, &g_devices[i], &g_dev_ctx[i]};
+        }
+    });
+    return &reg;
+}
+
+extern "C" {
+// the two symbols the host's dlopen loader resolves (ggml/src/ggml-backend-reg.cpp:211-246)
+__attribute__((visibility("default"))) ggml_backend_reg_t ggml_backend_init(void) { return b200_reg(); }
+__attribute__((visibility("default"))) int ggml_backend_score(void) { return b200_count_devices() > 0 ? 100 : 0; }
+// extra introspection hook for tests / bench: launches issued by a backend instance
+__attribute__((visibility("default"))) long long ggml_backend_b200_launch_count(ggml_backend_t backend) {
+    return backend && backend->iface.get_name == b200_backend_name ? ((b200_backend_ctx *) backend->context)->launches : -1;
+}
+}

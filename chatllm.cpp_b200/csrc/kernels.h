@@ -36,4 +36,27 @@ int rope_f32(const float * x, float * y, const int32_t * pos, const float * freq
 int soft_max_f32(const float * x, const float * mask, float * y, int64_t ne0, int64_t nrows, float scale, cudaStream_t st);
 int get_rows_q(int type, const void * table, int64_t k, const int32_t * ids, int64_t n, float * y, cudaStream_t st);
 
+
+// ---- ops_generic.cu: strided / broadcasting ops as ggml graphs present them (ne[0] fastest, nb in bytes)
+struct TV {
+    void * data;
+    int type;  // ggml type id
+    int64_t ne[4];
+    int64_t nb[4];
+};
+int op_bin(int op /*0 add, 1 mul, 2 div*/, const TV & a, const TV & b, const TV & d, cudaStream_t st);
+int op_cpy(const TV & s, const TV & d, cudaStream_t st);
+int op_set_rows(const TV & s, const TV & ids, const TV & d, cudaStream_t st);
+int op_scale(const float * x, float * y, int64_t n, float s, float b, cudaStream_t st);
+int op_clamp(const float * x, float * y, int64_t n, float lo, float hi, cudaStream_t st);
+int op_silu(const float * x, float * y, int64_t n, cudaStream_t st);
+int op_diag_mask_inf(const float * x, float * y, int64_t ne0, int64_t ne1, int64_t n, int n_past, cudaStream_t st);
+int op_soft_max(const TV & x, const TV * mask, const TV & y, float scale, cudaStream_t st);
+int op_rms_norm(const TV & x, const TV & y, float eps, cudaStream_t st);
+int op_mul_mat_f(const TV & a, const TV & b, const TV & d, cudaStream_t st);
+int op_sum_rows(const TV & x, const TV & y, cudaStream_t st);
+int op_repeat(const TV & s, const TV & d, cudaStream_t st);
+int op_argsort(const TV & x, const TV & y, int k_out, bool ascending, cudaStream_t st);
+int op_get_rows_f(const TV & a, const TV & ids, const TV & d, cudaStream_t st);
+
 }  // namespace b200

@@ -1,0 +1,376 @@
+// ops_generic.cu — strided / broadcasting versions of the glue ops, as the ggml graph presents them to the backend
+// (views, permutes, in-place results).  Shapes follow ggml's convention: ne[0] is the fastest dimension, nb[] are
+// byte strides.  Each kernel cites the reference CPU routine whose arithmetic it mirrors.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace b200 {
+
+struct TVd {  // device-side copy of a TV
+    char * data;
+    int64_t ne0, ne1, ne2, ne3;
+    int64_t nb0, nb1, nb2, nb3;
+};
+static inline TVd dv(const TV & t) {
+    TVd d;
+    d.data = (char *) t.data;
+    d.ne0 = t.ne[0]; d.ne1 = t.ne[1]; d.ne2 = t.ne[2]; d.ne3 = t.ne[3];
+    d.nb0 = t.nb[0]; d.nb1 = t.nb[1]; d.nb2 = t.nb[2]; d.nb3 = t.nb[3];
+    return d;
+}
+static inline int64_t nelem(const TV & t) { return t.ne[0] * t.ne[1] * t.ne[2] * t.ne[3]; }
+static inline int64_t nrows(const TV & t) { return t.ne[1] * t.ne[2] * t.ne[3]; }
+
+__device__ __forceinline__ void unravel(int64_t i, const TVd & t, int64_t & i0, int64_t & i1, int64_t & i2, int64_t & i3) {
+    i0 = i % t.ne0; i /= t.ne0;
+    i1 = i % t.ne1; i /= t.ne1;
+    i2 = i % t.ne2;
+    i3 = i / t.ne2;
+}
+__device__ __forceinline__ char * at(const TVd & t, int64_t i0, int64_t i1, int64_t i2, int64_t i3) {
+    return t.data + i0 * t.nb0 + i1 * t.nb1 + i2 * t.nb2 + i3 * t.nb3;
+}
+
+template <typename T> __device__ __forceinline__ float ldf(const char * p);
+template <> __device__ __forceinline__ float ldf<float>(const char * p) { return *(const float *) p; }
+template <> __device__ __forceinline__ float ldf<__half>(const char * p) { return __half2float(*(const __half *) p); }
+template <typename T> __device__ __forceinline__ void stf(char * p, float v);
+template <> __device__ __forceinline__ void stf<float>(char * p, float v) { *(float *) p = v; }
+template <> __device__ __forceinline__ void stf<__half>(char * p, float v) { *(__half *) p = __float2half_rn(v); }  // GGML_FP32_TO_FP16 (RNE)
+
+// ---- ADD / MUL / DIV with ggml broadcasting of src1 (binary-ops.cpp apply_binary_op) --------------------------
+template <int OP>
+__global__ void bin_bcast_kernel(const TVd a, const TVd b, const TVd d, int64_t n) {
+    pdl_wait();
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int64_t i0, i1, i2, i3;
+    unravel(i, d, i0, i1, i2, i3);
+    const float x = *(const float *) at(a, i0, i1, i2, i3);
+    const float y = *(const float *) at(b, i0 % b.ne0, i1 % b.ne1, i2 % b.ne2, i3 % b.ne3);
+    float r;
+    if (OP == 0) r = x + y;
+    else if (OP == 1) r = x * y;
+    else r = x / y;
+    *(float *) at(d, i0, i1, i2, i3) = r;
+}
+int op_bin(int op, const TV & a, const TV & b, const TV & d, cudaStream_t st) {
+    const int64_t n = nelem(d);
+    if (n <= 0) return B200_OK;
+    const unsigned grid = (unsigned) ((n + 255) / 256);
+    switch (op) {
+        case 0: bin_bcast_kernel<0><<<grid, 256, 0, st>>>(dv(a), dv(b), dv(d), n); break;
+        case 1: bin_bcast_kernel<1><<<grid, 256, 0, st>>>(dv(a), dv(b), dv(d), n); break;
+        case 2: bin_bcast_kernel<2><<<grid, 256, 0, st>>>(dv(a), dv(b), dv(d), n); break;
+        default: return B200_ERR_ARG;
+    }
+    return (int) cudaGetLastError();
+}
+
+// ---- CPY / DUP / CONT: same number of elements, arbitrary shapes & strides, optional F32<->F16 conversion
+//      (ggml_compute_forward_dup, ops.cpp:4637: elements are matched by logical (row-major-in-ne) index)
+template <typename TS, typename TD>
+__global__ void cpy_kernel(const TVd s, const TVd d, int64_t n) {
+    pdl_wait();
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int64_t a0, a1, a2, a3, b0, b1, b2, b3;
+    unravel(i, s, a0, a1, a2, a3);
+    unravel(i, d, b0, b1, b2, b3);
+    stf<TD>(at(d, b0, b1, b2, b3), ldf<TS>(at(s, a0, a1, a2, a3)));
+}
+__global__ void cpy_i32_kernel(const TVd s, const TVd d, int64_t n) {
+    pdl_wait();
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int64_t a0, a1, a2, a3, b0, b1, b2, b3;
+    unravel(i, s, a0, a1, a2, a3);
+    unravel(i, d, b0, b1, b2, b3);
+    *(int32_t *) at(d, b0, b1, b2, b3) = *(const int32_t *) at(s, a0, a1, a2, a3);
+}
+int op_cpy(const TV & s, const TV & d, cudaStream_t st) {
+    const int64_t n = nelem(s);
+    if (n != nelem(d)) return B200_ERR_ARG;
+    if (n <= 0) return B200_OK;
+    const unsigned grid = (unsigned) ((n + 255) / 256);
+    if (s.type == B200_TYPE_F32 && d.type == B200_TYPE_F32) cpy_kernel<float, float><<<grid, 256, 0, st>>>(dv(s), dv(d), n);
+    else if (s.type == B200_TYPE_F32 && d.type == B200_TYPE_F16) cpy_kernel<float, __half><<<grid, 256, 0, st>>>(dv(s), dv(d), n);
+    else if (s.type == B200_TYPE_F16 && d.type == B200_TYPE_F16) cpy_kernel<__half, __half><<<grid, 256, 0, st>>>(dv(s), dv(d), n);
+    else if (s.type == B200_TYPE_F16 && d.type == B200_TYPE_F32) cpy_kernel<__half, float><<<grid, 256, 0, st>>>(dv(s), dv(d), n);
+    else if (s.type == 26 && d.type == 26) cpy_i32_kernel<<<grid, 256, 0, st>>>(dv(s), dv(d), n);
+    else return B200_ERR_UNSUPPORTED;
+    return (int) cudaGetLastError();
+}
+
+// ---- SET_ROWS: dst[:, ids[i1, i2 % ne11, i3 % ne12], i2, i3] = convert(src[:, i1, i2, i3])  (ops.cpp:4942)
+template <typename TD, typename TI>
+__global__ void set_rows_kernel(const TVd s, const TVd ids, const TVd d, int64_t n) {
+    pdl_wait();
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int64_t i0, i1, i2, i3;
+    unravel(i, s, i0, i1, i2, i3);
+    const int64_t r = (int64_t) * (const TI *) at(ids, i1, i2 % ids.ne1, i3 % ids.ne2, 0);
+    stf<TD>(at(d, i0, r, i2, i3), *(const float *) at(s, i0, i1, i2, i3));
+}
+int op_set_rows(const TV & s, const TV & ids, const TV & d, cudaStream_t st) {
+    const int64_t n = nelem(s);
+    if (n <= 0) return B200_OK;
+    const unsigned grid = (unsigned) ((n + 255) / 256);
+    const bool i64 = ids.type == 27;
+    if (d.type == B200_TYPE_F16) {
+        if (i64) set_rows_kernel<__half, int64_t><<<grid, 256, 0, st>>>(dv(s), dv(ids), dv(d), n);
+        else set_rows_kernel<__half, int32_t><<<grid, 256, 0, st>>>(dv(s), dv(ids), dv(d), n);
+    } else if (d.type == B200_TYPE_F32) {
+        if (i64) set_rows_kernel<float, int64_t><<<grid, 256, 0, st>>>(dv(s), dv(ids), dv(d), n);
+        else set_rows_kernel<float, int32_t><<<grid, 256, 0, st>>>(dv(s), dv(ids), dv(d), n);
+    } else return B200_ERR_UNSUPPORTED;
+    return (int) cudaGetLastError();
+}
+
+// ---- SCALE (y = x*s + b, ops.cpp:4374), CLAMP, SILU, DIAG_MASK_INF on contiguous tensors -----------------------
+__global__ void scale_kernel(const float * __restrict__ x, float * __restrict__ y, int64_t n, float s, float b) {
+    pdl_wait();
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = (b == 0.0f) ? x[i] * s : fmaf(x[i], s, b);  // ggml_vec_scale_f32 / ggml_vec_mad1_f32
+}
+int op_scale(const float * x, float * y, int64_t n, float s, float b, cudaStream_t st) {
+    if (n <= 0) return B200_OK;
+    scale_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, st>>>(x, y, n, s, b);
+    return (int) cudaGetLastError();
+}
+__global__ void clamp_kernel(const float * __restrict__ x, float * __restrict__ y, int64_t n, float lo, float hi) {
+    pdl_wait();
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = fminf(fmaxf(x[i], lo), hi);
+}
+int op_clamp(const float * x, float * y, int64_t n, float lo, float hi, cudaStream_t st) {
+    if (n <= 0) return B200_OK;
+    clamp_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, st>>>(x, y, n, lo, hi);
+    return (int) cudaGetLastError();
+}
+__global__ void silu_kernel(const float * __restrict__ x, float * __restrict__ y, int64_t n) {
+    pdl_wait();
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { const float v = x[i]; y[i] = v / (1.0f + expf(-v)); }
+}
+int op_silu(const float * x, float * y, int64_t n, cudaStream_t st) {
+    if (n <= 0) return B200_OK;
+    silu_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, st>>>(x, y, n);
+    return (int) cudaGetLastError();
+}
+// ggml_compute_forward_diag_mask_f32: for k in z, j in rows, i >= n_past: if (i > n_past + j) -inf
+__global__ void diag_mask_inf_kernel(const float * __restrict__ x, float * __restrict__ y, int64_t ne0, int64_t ne1, int64_t n, int n_past) {
+    pdl_wait();
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t c = i % ne0, j = (i / ne0) % ne1;
+    y[i] = (c > n_past + j) ? -INFINITY : x[i];
+}
+int op_diag_mask_inf(const float * x, float * y, int64_t ne0, int64_t ne1, int64_t n, int n_past, cudaStream_t st) {
+    if (n <= 0) return B200_OK;
+    diag_mask_inf_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, st>>>(x, y, ne0, ne1, n, n_past);
+    return (int) cudaGetLastError();
+}
+
+// ---- SOFT_MAX with optional F32/F16 mask broadcast over dims 2,3 (ops.cpp:5225-5335; max_bias == 0 only) -------
+template <typename TM>
+__global__ void __launch_bounds__(1024) soft_max_ext_kernel(const TVd x, const TVd m, const TVd y, float scale, bool has_mask) {
+    __shared__ float red[32];
+    pdl_wait();
+    const int64_t row = blockIdx.x;
+    const int64_t i1 = row % x.ne1, i2 = (row / x.ne1) % x.ne2, i3 = row / (x.ne1 * x.ne2);
+    const float * xr = (const float *) at(x, 0, i1, i2, i3);
+    float * yr = (float *) at(y, 0, i1, i2, i3);
+    const char * mr = has_mask ? at(m, 0, i1, i2 % m.ne2, i3 % m.ne3) : nullptr;
+    float mx = -INFINITY;
+    for (int64_t i = threadIdx.x; i < x.ne0; i += blockDim.x) {
+        float v = xr[i] * scale;
+        if (mr) v += ldf<TM>(mr + i * sizeof(TM));
+        mx = fmaxf(mx, v);
+    }
+    // block max
+    mx = warp_max(mx);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    float t = (threadIdx.x < nw) ? red[threadIdx.x] : -INFINITY;
+    if (warp == 0) { t = warp_max(t); if (lane == 0) red[0] = t; }
+    __syncthreads();
+    mx = red[0];
+    __syncthreads();
+    float s = 0.0f;
+    for (int64_t i = threadIdx.x; i < x.ne0; i += blockDim.x) {
+        float v = xr[i] * scale;
+        if (mr) v += ldf<TM>(mr + i * sizeof(TM));
+        const float e = expf(v - mx);
+        yr[i] = e;
+        s += e;
+    }
+    s = warp_sum(s);
+    if (lane == 0) red[warp] = s;
+    __syncthreads();
+    t = (threadIdx.x < nw) ? red[threadIdx.x] : 0.0f;
+    if (warp == 0) { t = warp_sum(t); if (lane == 0) red[0] = t; }
+    __syncthreads();
+    const float inv = 1.0f / red[0];
+    for (int64_t i = threadIdx.x; i < x.ne0; i += blockDim.x) yr[i] *= inv;
+}
+int op_soft_max(const TV & x, const TV * mask, const TV & y, float scale, cudaStream_t st) {
+    const int64_t rows = nrows(x);
+    if (rows <= 0) return B200_OK;
+    const int threads = x.ne[0] >= 2048 ? 1024 : (x.ne[0] >= 512 ? 256 : 128);
+    TVd m = mask ? dv(*mask) : dv(x);
+    if (mask && mask->type == B200_TYPE_F16) soft_max_ext_kernel<__half><<<(unsigned) rows, threads, 0, st>>>(dv(x), m, dv(y), scale, true);
+    else soft_max_ext_kernel<float><<<(unsigned) rows, threads, 0, st>>>(dv(x), m, dv(y), scale, mask != nullptr);
+    return (int) cudaGetLastError();
+}
+
+// ---- RMS_NORM on strided rows (ops.cpp:3710-3758) ----------------------------------------------------------------
+__global__ void __launch_bounds__(1024) rms_norm_strided_kernel(const TVd x, const TVd y, float eps) {
+    __shared__ float red[32];
+    pdl_wait();
+    const int64_t row = blockIdx.x;
+    const int64_t i1 = row % x.ne1, i2 = (row / x.ne1) % x.ne2, i3 = row / (x.ne1 * x.ne2);
+    const float * xr = (const float *) at(x, 0, i1, i2, i3);
+    float * yr = (float *) at(y, 0, i1, i2, i3);
+    float s = 0.0f;
+    for (int64_t i = threadIdx.x; i < x.ne0; i += blockDim.x) { const float v = xr[i]; s = fmaf(v, v, s); }
+    s = warp_sum(s);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    if (lane == 0) red[warp] = s;
+    __syncthreads();
+    float t = (threadIdx.x < nw) ? red[threadIdx.x] : 0.0f;
+    if (warp == 0) { t = warp_sum(t); if (lane == 0) red[0] = t; }
+    __syncthreads();
+    const float mean = red[0] / (float) x.ne0;
+    const float scale = 1.0f / sqrtf(mean + eps);
+    for (int64_t i = threadIdx.x; i < x.ne0; i += blockDim.x) yr[i] = xr[i] * scale;
+}
+int op_rms_norm(const TV & x, const TV & y, float eps, cudaStream_t st) {
+    const int64_t rows = nrows(x);
+    if (rows <= 0) return B200_OK;
+    const int threads = x.ne[0] >= 4096 ? 1024 : (x.ne[0] >= 1024 ? 512 : 256);
+    rms_norm_strided_kernel<<<(unsigned) rows, threads, 0, st>>>(dv(x), dv(y), eps);
+    return (int) cudaGetLastError();
+}
+
+// ---- MUL_MAT with a float src0 (F16 / F32, arbitrary strides except nb00 == element size) ---------------------------
+// dst[i0, i1, i2, i3] = sum_k src0[k, i0, i2/r2, i3/r3] * src1[k, i1, i2, i3]; when src0 is F16 the reference first
+// rounds src1 to F16 (ggml-cpu.c:213-219, :1291-1326) and accumulates in fp32 (vec.cpp:264).  One warp per output.
+template <typename T0>
+__global__ void mul_mat_f_kernel(const TVd a, const TVd b, const TVd d, int64_t nout) {
+    pdl_wait();
+    const int64_t o = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (o >= nout) return;
+    int64_t i0, i1, i2, i3;
+    unravel(o, d, i0, i1, i2, i3);
+    const int64_t r2 = b.ne2 / a.ne2, r3 = b.ne3 / a.ne3;
+    const char * ar = at(a, 0, i0, i2 / r2, i3 / r3);
+    const char * br = at(b, 0, i1, i2, i3);
+    float s = 0.0f;
+    for (int64_t k = lane; k < a.ne0; k += 32) {
+        float bv = *(const float *) (br + k * b.nb0);
+        if (sizeof(T0) == 2) bv = __half2float(__float2half_rn(bv));
+        s = fmaf(ldf<T0>(ar + k * sizeof(T0)), bv, s);
+    }
+    s = warp_sum(s);
+    if (lane == 0) *(float *) at(d, i0, i1, i2, i3) = s;
+}
+int op_mul_mat_f(const TV & a, const TV & b, const TV & d, cudaStream_t st) {
+    const int64_t nout = nelem(d);
+    if (nout <= 0) return B200_OK;
+    const unsigned grid = (unsigned) ((nout * 32 + 255) / 256);
+    if (a.type == B200_TYPE_F16) mul_mat_f_kernel<__half><<<grid, 256, 0, st>>>(dv(a), dv(b), dv(d), nout);
+    else if (a.type == B200_TYPE_F32) mul_mat_f_kernel<float><<<grid, 256, 0, st>>>(dv(a), dv(b), dv(d), nout);
+    else return B200_ERR_UNSUPPORTED;
+    return (int) cudaGetLastError();
+}
+
+// ---- SUM_ROWS, REPEAT -----------------------------------------------------------------------------------------------
+__global__ void sum_rows_kernel(const TVd x, const TVd y) {
+    pdl_wait();
+    const int64_t row = blockIdx.x;
+    const int64_t i1 = row % x.ne1, i2 = (row / x.ne1) % x.ne2, i3 = row / (x.ne1 * x.ne2);
+    const float * xr = (const float *) at(x, 0, i1, i2, i3);
+    float s = 0.0f;
+    for (int64_t i = threadIdx.x; i < x.ne0; i += 32) s += xr[i];
+    s = warp_sum(s);
+    if (threadIdx.x == 0) *(float *) at(y, 0, i1, i2, i3) = s;
+}
+int op_sum_rows(const TV & x, const TV & y, cudaStream_t st) {
+    const int64_t rows = nrows(x);
+    if (rows <= 0) return B200_OK;
+    sum_rows_kernel<<<(unsigned) rows, 32, 0, st>>>(dv(x), dv(y));
+    return (int) cudaGetLastError();
+}
+__global__ void repeat_kernel(const TVd s, const TVd d, int64_t n) {
+    pdl_wait();
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int64_t i0, i1, i2, i3;
+    unravel(i, d, i0, i1, i2, i3);
+    *(float *) at(d, i0, i1, i2, i3) = *(const float *) at(s, i0 % s.ne0, i1 % s.ne1, i2 % s.ne2, i3 % s.ne3);
+}
+int op_repeat(const TV & s, const TV & d, cudaStream_t st) {
+    const int64_t n = nelem(d);
+    if (n <= 0) return B200_OK;
+    repeat_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, st>>>(dv(s), dv(d), n);
+    return (int) cudaGetLastError();
+}
+
+// ---- TOP_K / ARGSORT on short rows (router logits: ne0 = number of experts <= 1024) ---------------------------------
+// one block per row; rank of element i = #{j : x[j] > x[i] or (x[j] == x[i] and j < i)} (stable, descending)
+__global__ void argsort_desc_kernel(const TVd x, const TVd y, int k_out, bool ascending) {
+    extern __shared__ float sx[];
+    pdl_wait();
+    const int64_t row = blockIdx.x;
+    const int64_t i1 = row % x.ne1, i2 = (row / x.ne1) % x.ne2, i3 = row / (x.ne1 * x.ne2);
+    const float * xr = (const float *) at(x, 0, i1, i2, i3);
+    int32_t * yr = (int32_t *) at(y, 0, i1, i2, i3);
+    const int n = (int) x.ne0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) sx[i] = xr[i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const float v = sx[i];
+        int rank = 0;
+        for (int j = 0; j < n; ++j) {
+            const float u = sx[j];
+            const bool before = ascending ? (u < v || (u == v && j < i)) : (u > v || (u == v && j < i));
+            rank += before ? 1 : 0;
+        }
+        if (rank < k_out) yr[rank] = i;
+    }
+}
+int op_argsort(const TV & x, const TV & y, int k_out, bool ascending, cudaStream_t st) {
+    const int64_t rows = nrows(x);
+    if (rows <= 0) return B200_OK;
+    if (x.ne[0] > 8192) return B200_ERR_UNSUPPORTED;
+    const int threads = x.ne[0] >= 256 ? 256 : 32;
+    argsort_desc_kernel<<<(unsigned) rows, threads, (size_t) x.ne[0] * 4, st>>>(dv(x), dv(y), k_out, ascending);
+    return (int) cudaGetLastError();
+}
+
+// ---- GET_ROWS for float tables with strides (quantized tables: get_rows_q in ops.cu) ---------------------------------
+template <typename T0>
+__global__ void get_rows_f_kernel(const TVd a, const TVd ids, const TVd d, int64_t n) {
+    pdl_wait();
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int64_t i0, i1, i2, i3;
+    unravel(i, d, i0, i1, i2, i3);
+    const int64_t r = *(const int32_t *) at(ids, i1, i2, i3, 0);
+    *(float *) at(d, i0, i1, i2, i3) = ldf<T0>(at(a, i0, r, i2 % a.ne2, i3 % a.ne3));
+}
+int op_get_rows_f(const TV & a, const TV & ids, const TV & d, cudaStream_t st) {
+    const int64_t n = nelem(d);
+    if (n <= 0) return B200_OK;
+    const unsigned grid = (unsigned) ((n + 255) / 256);
+    if (a.type == B200_TYPE_F32) get_rows_f_kernel<float><<<grid, 256, 0, st>>>(dv(a), dv(ids), dv(d), n);
+    else if (a.type == B200_TYPE_F16) get_rows_f_kernel<__half><<<grid, 256, 0, st>>>(dv(a), dv(ids), dv(d), n);
+    else return B200_ERR_UNSUPPORTED;
+    return (int) cudaGetLastError();
+}
+
+}  // namespace b200

@@ -1,0 +1,165 @@
+"""Drop-in boundary parity (-m gpu): the SAME ggml graph is executed by the reference's own CPU backend (the oracle,
+oracle/_ref/lib/libggml-cpu-*.so) and by our module libggml-cuda.so, both loaded through the reference's registry
+(ggml_backend_load_all_from_path) by oracle/ref_shim.cpp, in strict mode (every node must be supported by CUDA0 —
+no op may bounce to the CPU).  Graph shapes follow what chatllm emits."""
+import numpy as np
+import pytest
+
+import qformats as qf
+import refshim as rs
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not rs.available(), reason="oracle/_ref not built")]
+
+
+def both(build, tol=2e-5, atol=0.0):
+    outs = {}
+    for dev in ("CPU", "CUDA0"):
+        g = rs.Graph()
+        outputs = build(g)
+        outs[dev] = g.run(dev, outputs, n_threads=8, strict=True)
+    for a, b in zip(outs["CPU"], outs["CUDA0"]):
+        if a.dtype.kind in "iu":
+            assert np.array_equal(a, b)
+        else:
+            a32, b32 = a.astype(np.float32), b.astype(np.float32)
+            fin = np.isfinite(a32)
+            assert np.array_equal(fin, np.isfinite(b32))
+            scale = np.abs(a32[fin]).max() if fin.any() else 1.0
+            assert np.abs(a32[fin] - b32[fin]).max() <= tol * scale + atol, (np.abs(a32[fin] - b32[fin]).max(), scale)
+    return outs
+
+
+def acts(rng, *shape):
+    x = rng.standard_normal(shape).astype(np.float32)
+    x[rng.random(shape) < 1e-3] *= 20.0
+    return x
+
+
+def test_devices_registered_in_order():
+    devs = rs.devices()
+    assert devs[0] == "CUDA0" and devs[-1] == "CPU", devs   # CPU must be last (src/backend.cpp:727-733)
+
+
+@pytest.mark.parametrize("t", [qf.Q4_K, qf.Q4_0, qf.Q8_0])
+@pytest.mark.parametrize("n", [1, 2, 5, 8, 19])
+def test_mul_mat_quant_with_bias(t, n):
+    rng = np.random.default_rng(n + t)
+    k, m = 1024, 320
+    w = qf.random_blocks(t, m, k, rng=rng); x = acts(rng, n, k); b = rng.standard_normal(m).astype(np.float32)
+
+    def build(g):
+        y = g.add(g.mul_mat(g.input(w.reshape(-1), t, (k, m)), g.input(x)), g.input(b), inplace=True)
+        return [(y, np.float32, (n, m))]
+    both(build)
+
+
+@pytest.mark.parametrize("t,k,m", [(qf.Q4_K, 4096, 4096), (qf.Q4_K, 14336, 1024), (qf.Q4_0, 3584, 2048), (qf.Q8_0, 2048, 5632)])
+def test_mul_mat_quant_model_shapes(t, k, m):
+    rng = np.random.default_rng(k + m)
+    w = qf.random_blocks(t, m, k, rng=rng); x = acts(rng, 1, k)
+    both(lambda g: [(g.mul_mat(g.input(w.reshape(-1), t, (k, m)), g.input(x)), np.float32, (1, m))])
+
+
+def test_weights_round_trip_through_get_tensor():
+    """set_tensor converts Q4_0/Q8_0 to the device layout; get_tensor must give the native bytes back
+    (session save / map_tensor_element rely on it)."""
+    rng = np.random.default_rng(0)
+    for t in (qf.Q4_0, qf.Q8_0, qf.Q4_K):
+        w = qf.random_blocks(t, 9, 512, rng=rng)
+        g = rs.Graph()
+        inp = g.input(w.reshape(-1), t, (512, 9))
+        # a view of the weights is read back as raw bytes through ggml_backend_tensor_get
+        (back,) = g.run("CUDA0", [(g.view(inp, (512, 9), (qf.row_size(t, 512),)), np.uint8, (w.size,))])
+        assert np.array_equal(back, w.reshape(-1))
+
+
+def test_rms_norm_mul_and_residual():
+    rng = np.random.default_rng(1)
+    x = acts(rng, 3, 4096); w = (1 + 0.1 * rng.standard_normal(4096)).astype(np.float32); r = acts(rng, 3, 4096)
+    both(lambda g: [(g.add(g.mul(g.rms_norm(g.input(x), 1e-5), g.input(w)), g.input(r)), np.float32, x.shape)], tol=3e-6)
+
+
+@pytest.mark.parametrize("mode", [0, 2])
+@pytest.mark.parametrize("qlen", [1, 7])
+def test_rope_inplace_on_linear_output(mode, qlen):
+    rng = np.random.default_rng(mode + qlen)
+    heads, hd = 8, 128
+    x = acts(rng, qlen, heads * hd)
+    pos = (np.arange(qlen) + 4090).astype(np.int32)
+    ff = (1 + rng.random(hd // 2)).astype(np.float32)
+
+    def build(g):
+        q = g.reshape(g.input(x), (hd, heads, qlen))
+        r = g.rope(q, g.input(pos), hd, mode, 500000.0, ff=g.input(ff), inplace=True)
+        return [(r, np.float32, (qlen, heads, hd))]
+    both(build, tol=4e-6)
+
+
+@pytest.mark.parametrize("n_past,qlen", [(0, 5), (37, 1), (300, 3)])
+def test_kv_cache_write_and_attention(n_past, qlen):
+    """save_to_cache (src/layers.cpp:3044-3123): K via set_rows(F32->F16), V via transpose+cpy into the transposed cache;
+    then calc_attn_scores (:2541-2561): permuted K view, mul_mat(prec F32), scale, diag_mask_inf, soft_max, mul_mat(V,P),
+    permute, cont."""
+    rng = np.random.default_rng(n_past + qlen)
+    heads, kvh, hd, max_len = 8, 2, 64, 512
+    kv_hidden = kvh * hd
+    kc0 = (rng.standard_normal((max_len, kv_hidden))).astype(np.float16)
+    vc0 = (rng.standard_normal((kv_hidden, max_len))).astype(np.float16)
+    k_new = acts(rng, qlen, kv_hidden); v_new = acts(rng, qlen, kv_hidden); q = acts(rng, qlen, heads * hd)
+    pos = (np.arange(qlen) + n_past).astype(np.int32)
+    n_kv = n_past + qlen
+
+    def build(g):
+        kc = g.input(kc0); vc = g.input(vc0); P = g.input(pos)
+        # V: [kv_hidden, qlen] --transpose--> cpy into view [qlen, kv_hidden] of the transposed cache at column n_past
+        vcur = g.transpose(g.input(v_new))
+        vview = g.view(vc, (qlen, kv_hidden), (2 * max_len,), offset=n_past * 2)
+        vw = g.cpy(vcur, vview)
+        # K: set_rows into [kv_hidden, max_len]
+        kw = g.set_rows(kc, g.input(k_new), P)
+        # read back: K view [hd, kvh, n_kv] permuted -> [hd, n_kv, kvh]
+        K = g.permute(g.view(kw, (hd, kvh, n_kv), (2 * hd, 2 * kv_hidden)), (0, 2, 1, 3))
+        V = g.view(vw, (n_kv, hd, kvh), (2 * max_len, 2 * max_len * hd))   # note: view of the cpy result keeps the dependency
+        V = g.view(vc, (n_kv, hd, kvh), (2 * max_len, 2 * max_len * hd)) if False else V
+        Q = g.permute(g.reshape(g.input(q), (hd, heads, qlen)), (0, 2, 1, 3))      # [hd, qlen, heads]
+        s = g.mul_mat(K, Q, prec_f32=True)                                          # [n_kv, qlen, heads]
+        s = g.scale(s, 1.0 / np.sqrt(hd), inplace=True)
+        s = g.diag_mask_inf(s, n_past, inplace=True)
+        p = g.soft_max(s, inplace=True)
+        ctx = g.mul_mat(V, p)                                                       # [hd, qlen, heads]
+        ctx = g.cont(g.permute(ctx, (0, 2, 1, 3)))                                  # [hd, heads, qlen]
+        return [(ctx, np.float32, (qlen, heads, hd)), (kw, np.float16, (max_len, kv_hidden))]
+    # the V view above must alias the cache written by cpy: build it from the cache tensor through the cpy node
+    both(build, tol=3e-5)
+
+
+def test_swiglu_and_embedding():
+    rng = np.random.default_rng(3)
+    g_, u_ = acts(rng, 2, 1024) * 2, acts(rng, 2, 1024)
+    both(lambda g: [(g.mul(g.silu(g.input(g_)), g.input(u_), inplace=True), np.float32, g_.shape)], tol=3e-6)
+    for t in (qf.Q4_K, qf.Q4_0, qf.Q8_0):
+        tab = qf.random_blocks(t, 300, 512, rng=rng); ids = np.array([5, 299, 0, 5], dtype=np.int32)
+        both(lambda g: [(g.get_rows(g.input(tab.reshape(-1), t, (512, 300)), g.input(ids)), np.float32, (4, 512))], tol=1e-6)
+
+
+def test_soft_max_with_f16_mask_and_scale():
+    rng = np.random.default_rng(4)
+    x = acts(rng, 4, 6, 200) * 3
+    mask = np.where(rng.random((6, 200)) < 0.2, -np.inf, 0.0).astype(np.float16)
+    both(lambda g: [(g.soft_max(g.input(x), g.input(mask), scale=0.125), np.float32, x.shape)], atol=1e-6)
+
+
+def test_moe_router_ops():
+    """GenericSparseMLP router (src/layers.cpp:3755-3880): softmax -> top_k -> get_rows -> sum_rows -> div"""
+    rng = np.random.default_rng(5)
+    logits = acts(rng, 3, 8)
+
+    def build(g):
+        p = g.soft_max(g.input(logits))
+        ids = g.top_k(p, 2)                                            # I32 [2, n]
+        w = g.get_rows(g.reshape(p, (1, 8, 3)), ids)                   # [1, 2, n]
+        w = g.reshape(w, (2, 3))
+        w = g.div(w, g.sum_rows(w))
+        return [(w, np.float32, (3, 2))]
+    outs = both(build, tol=2e-6)
+    assert np.allclose(outs["CUDA0"][0].sum(-1), 1.0, atol=1e-6)
