@@ -119,8 +119,9 @@ def test_kv_cache_write_and_attention(n_past, qlen):
         kw = g.set_rows(kc, g.input(k_new), P)
         # read back: K view [hd, kvh, n_kv] permuted -> [hd, n_kv, kvh]
         K = g.permute(g.view(kw, (hd, kvh, n_kv), (2 * hd, 2 * kv_hidden)), (0, 2, 1, 3))
-        V = g.view(vw, (n_kv, hd, kvh), (2 * max_len, 2 * max_len * hd))   # note: view of the cpy result keeps the dependency
-        V = g.view(vc, (n_kv, hd, kvh), (2 * max_len, 2 * max_len * hd)) if False else V
+        # like chatllm, V is read through a fresh view of the cache tensor; the cpy node is ordered before it by listing
+        # `vw` first among the outputs (chatllm: build_forward_expand(cpy) before the attention nodes)
+        V = g.view(vc, (n_kv, hd, kvh), (2 * max_len, 2 * max_len * hd))
         Q = g.permute(g.reshape(g.input(q), (hd, heads, qlen)), (0, 2, 1, 3))      # [hd, qlen, heads]
         s = g.mul_mat(K, Q, prec_f32=True)                                          # [n_kv, qlen, heads]
         s = g.scale(s, 1.0 / np.sqrt(hd), inplace=True)
@@ -128,8 +129,7 @@ def test_kv_cache_write_and_attention(n_past, qlen):
         p = g.soft_max(s, inplace=True)
         ctx = g.mul_mat(V, p)                                                       # [hd, qlen, heads]
         ctx = g.cont(g.permute(ctx, (0, 2, 1, 3)))                                  # [hd, heads, qlen]
-        return [(ctx, np.float32, (qlen, heads, hd)), (kw, np.float16, (max_len, kv_hidden))]
-    # the V view above must alias the cache written by cpy: build it from the cache tensor through the cpy node
+        return [(g.cont(vw), np.float16, (kv_hidden, qlen)), (kw, np.float16, (max_len, kv_hidden)), (ctx, np.float32, (qlen, heads, hd))]
     both(build, tol=3e-5)
 
 
