@@ -1,0 +1,126 @@
+// host_harness.cpp — TEST / BENCH INFRASTRUCTURE (built into oracle/_ref/bin/host_harness).
+//
+// Drives the UNMODIFIED reference host (chatllm's ModelObject / AbstractModel API, src/chat.h:1371-1413, :1006-1056)
+// with raw token ids, so that the very same decode loop can be executed
+//   * on the reference's CPU backend  (-ngl 0)   -> the oracle / the CPU baseline, and
+//   * through the drop-in boundary    (-ngl all) -> our libggml-cuda.so,
+// and the logits compared bit-for-bit-ish (1e-3 relative, BASELINE.json) and the per-token wall time read.
+// It contains no arithmetic: it calls model->generate_next_token (src/models.cpp:1108-1123 -> run_model :1244-1312).
+//
+//   host_harness --model M.bin --ggml_dir DIR --ngl all|0 [--threads N] [--max_length L] [--prefill P] [--decode T]
+//                [--batch B] [--seed S] [--dump logits.bin] [--feed argmax|seeded]
+// Output: one JSON line on stdout.
+#include "chat.h"
+#include "backend.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace chatllm;
+
+// the host's log sink normally lives in main.cpp (src/main.cpp:984); the harness replaces main.cpp, so it provides one
+void log_internal(int level, const char * text) {
+    if (level >= 3) fprintf(stderr, "%s", text);  // GGML_LOG_LEVEL_WARN and above
+}
+
+static double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+int main(int argc, char ** argv) {
+    std::string model_path, ggml_dir, ngl = "0", dump, feed = "seeded";
+    int threads = 8, max_length = 4352, prefill = 16, decode = 8, batch = 4096, seed = 1, vocab_limit = 0;
+    for (int i = 1; i < argc; ++i) {
+        std::string a = argv[i];
+        auto next = [&]() -> const char * { return i + 1 < argc ? argv[++i] : ""; };
+        if (a == "--model") model_path = next();
+        else if (a == "--ggml_dir") ggml_dir = next();
+        else if (a == "--ngl") ngl = next();
+        else if (a == "--threads") threads = atoi(next());
+        else if (a == "--max_length") max_length = atoi(next());
+        else if (a == "--prefill") prefill = atoi(next());
+        else if (a == "--decode") decode = atoi(next());
+        else if (a == "--batch") batch = atoi(next());
+        else if (a == "--seed") seed = atoi(next());
+        else if (a == "--dump") dump = next();
+        else if (a == "--feed") feed = next();
+        else if (a == "--vocab_limit") vocab_limit = atoi(next());
+    }
+    if (model_path.empty()) { fprintf(stderr, "usage: host_harness --model M --ggml_dir D --ngl all|0 ...\n"); return 2; }
+
+    ComputeManager::init(ggml_dir);
+    std::vector<ComputeManager::DeviceInfo> devs;
+    ComputeManager::get_devices_info(devs);
+
+    ModelObject::extra_args args(max_length, "", false, threads, batch, "");
+    if (ngl != "0") args.model_n_gpu_layers["any"] = ngl;
+
+    const double t_load0 = now_ms();
+    ModelObject obj(model_path, args);
+    const double t_load = now_ms() - t_load0;
+    AbstractModel * model = obj.model.get();
+
+    GenerationConfig gen(max_length, max_length, false, false, 1, 1.0f, 1.0f, threads, "greedy", 1.0f, 1.0f);
+
+    // seeded token stream (LCG), ids in [0, vocab)
+    std::vector<float> logits;
+    uint64_t state = (uint64_t) seed * 6364136223846793005ULL + 1442695040888963407ULL;
+    auto next_id = [&](int vocab) {
+        state = state * 6364136223846793005ULL + 1442695040888963407ULL;
+        return (int) ((state >> 33) % (uint64_t) vocab);
+    };
+
+    // a first 1-token call to learn the vocabulary size (and warm the graph reserve), then rewind
+    std::vector<int> ids = {1};
+    model->set_n_past(0);
+    model->generate_next_token(ids, gen, logits);
+    int vocab = (int) logits.size();
+    if (vocab_limit > 0 && vocab_limit < vocab) vocab = vocab_limit;
+
+    // ---- prefill
+    ids.resize(prefill);
+    for (int i = 0; i < prefill; ++i) ids[i] = next_id(vocab);
+    model->set_n_past(0);
+    const double t_p0 = now_ms();
+    if (prefill > 0) model->generate_next_token(ids, gen, logits);
+    const double t_prefill = now_ms() - t_p0;
+    model->set_n_past(prefill);
+
+    FILE * fd = dump.empty() ? nullptr : fopen(dump.c_str(), "wb");
+    if (fd && prefill > 0) fwrite(logits.data(), sizeof(float), logits.size(), fd);
+
+    // ---- decode
+    std::vector<double> step_ms;
+    int n_past = prefill;
+    for (int s = 0; s < decode; ++s) {
+        int tok;
+        if (feed == "argmax" && !logits.empty()) tok = (int) (std::max_element(logits.begin(), logits.end()) - logits.begin());
+        else tok = next_id(vocab);
+        std::vector<int> one = {tok};
+        const double t0 = now_ms();
+        model->generate_next_token(one, gen, logits);
+        step_ms.push_back(now_ms() - t0);
+        n_past++;
+        model->set_n_past(n_past);
+        if (fd) fwrite(logits.data(), sizeof(float), logits.size(), fd);
+    }
+    if (fd) fclose(fd);
+
+    double sum = 0, best = 1e30;
+    for (double v : step_ms) { sum += v; best = std::min(best, v); }
+    std::vector<double> sorted = step_ms;
+    std::sort(sorted.begin(), sorted.end());
+    const double median = sorted.empty() ? 0 : sorted[sorted.size() / 2];
+
+    printf("{\"model\": \"%s\", \"ngl\": \"%s\", \"devices\": %d, \"device0\": \"%s\", \"threads\": %d, \"vocab\": %d, \"load_ms\": %.1f, "
+           "\"prefill_tokens\": %d, \"prefill_ms\": %.3f, \"decode_tokens\": %d, \"decode_ms_total\": %.3f, \"decode_ms_median\": %.4f, "
+           "\"decode_ms_min\": %.4f, \"n_past_end\": %d}\n",
+           model_path.c_str(), ngl.c_str(), (int) devs.size(), devs.empty() ? "" : devs[0].name.c_str(), threads, (int) logits.size(), t_load,
+           prefill, t_prefill, decode, sum, median, best == 1e30 ? 0 : best, n_past);
+    return 0;
+}

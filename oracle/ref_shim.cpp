@@ -54,13 +54,9 @@ enum rs_opcode {
     RS_MUL_MAT_PREC_F32 = 28, // mul_mat + ggml_mul_mat_set_prec(F32)
 };
 
-static bool g_loaded = false;
-
+// may be called once per directory; the order of the calls is the registration order of the devices
 int refshim_init(const char * backend_dir) {
-    if (!g_loaded) {
-        ggml_backend_load_all_from_path(backend_dir);
-        g_loaded = true;
-    }
+    ggml_backend_load_all_from_path(backend_dir);
     return (int) ggml_backend_dev_count();
 }
 
