@@ -55,9 +55,11 @@ enum rs_opcode {
 };
 
 // may be called once per directory; the order of the calls is the registration order of the devices
+// NOTE: this fork registers devices lazily on the first device query (ggml-backend-reg.cpp register_devices), so no
+// device query may happen before the last directory has been loaded.
 int refshim_init(const char * backend_dir) {
     ggml_backend_load_all_from_path(backend_dir);
-    return (int) ggml_backend_dev_count();
+    return 0;
 }
 
 int refshim_n_devices(void) { return (int) ggml_backend_dev_count(); }
