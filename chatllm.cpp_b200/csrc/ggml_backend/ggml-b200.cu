@@ -22,6 +22,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -249,7 +250,27 @@ static bool qtype_ok(const ggml_tensor * w) {
 }
 static bool f32c(const ggml_tensor * t) { return t && t->type == GGML_TYPE_F32 && ggml_is_contiguous(t); }
 
-static bool b200_supports_op(ggml_backend_dev_t, const ggml_tensor * op) {
+// debugging aid: B200_DISABLE_OPS="ROPE,SOFT_MAX" makes supports_op decline those ops so the host's scheduler runs them
+// on its CPU backend (used to bisect parity problems; never set in tests/bench)
+static bool op_disabled(const ggml_tensor * op) {
+    static const char * env = getenv("B200_DISABLE_OPS");
+    if (!env || !*env) return false;
+    const std::string list = std::string(",") + env + ",";
+    std::string name = std::string(",") + ggml_op_name(op->op) + ",";
+    if (list.find(name) != std::string::npos) return true;
+    if (op->op == GGML_OP_MUL_MAT && op->src[0]) {
+        const char * sub = ggml_is_quantized(op->src[0]->type) ? ",MUL_MAT_Q," : ",MUL_MAT_F,";
+        if (list.find(sub) != std::string::npos) return true;
+    }
+    return false;
+}
+
+static bool b200_supports_op_impl(ggml_backend_dev_t, const ggml_tensor * op);
+static bool b200_supports_op(ggml_backend_dev_t dev, const ggml_tensor * op) {
+    if (op_disabled(op)) return false;
+    return b200_supports_op_impl(dev, op);
+}
+static bool b200_supports_op_impl(ggml_backend_dev_t, const ggml_tensor * op) {
     const ggml_tensor * s0 = op->src[0];
     const ggml_tensor * s1 = op->src[1];
     switch (op->op) {
