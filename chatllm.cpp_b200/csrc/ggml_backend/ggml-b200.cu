@@ -430,8 +430,8 @@ static int compute_node(b200_backend_ctx * bc, ggml_tensor * node) {
         }
         case GGML_OP_SUM_ROWS: return op_sum_rows(tv(s0), tv(node), st);
         case GGML_OP_REPEAT: return op_repeat(tv(s0), tv(node), st);
-        case GGML_OP_ARGSORT: return op_argsort(tv(s0), tv(node), (int) s0->ne[0], node->op_params[0] == GGML_SORT_ORDER_ASC, st);
-        case GGML_OP_TOP_K: return op_argsort(tv(s0), tv(node), (int) node->ne[0], false, st);
+        case GGML_OP_ARGSORT: return op_argsort(tv(s0), tv(node), (int) s0->ne[0], node->op_params[0] == GGML_SORT_ORDER_ASC, false, st);
+        case GGML_OP_TOP_K: return op_argsort(tv(s0), tv(node), (int) node->ne[0], false, true, st);
         default: return B200_ERR_UNSUPPORTED;
     }
 }

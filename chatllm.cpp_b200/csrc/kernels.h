@@ -56,7 +56,7 @@ int op_rms_norm(const TV & x, const TV & y, float eps, cudaStream_t st);
 int op_mul_mat_f(const TV & a, const TV & b, const TV & d, cudaStream_t st);
 int op_sum_rows(const TV & x, const TV & y, cudaStream_t st);
 int op_repeat(const TV & s, const TV & d, cudaStream_t st);
-int op_argsort(const TV & x, const TV & y, int k_out, bool ascending, cudaStream_t st);
+int op_argsort(const TV & x, const TV & y, int k_out, bool ascending, bool swap01, cudaStream_t st);
 int op_get_rows_f(const TV & a, const TV & ids, const TV & d, cudaStream_t st);
 
 }  // namespace b200

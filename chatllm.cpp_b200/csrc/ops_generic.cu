@@ -322,7 +322,7 @@ int op_repeat(const TV & s, const TV & d, cudaStream_t st) {
 
 // ---- TOP_K / ARGSORT on short rows (router logits: ne0 = number of experts <= 1024) ---------------------------------
 // one block per row; rank of element i = #{j : x[j] > x[i] or (x[j] == x[i] and j < i)} (stable, descending)
-__global__ void argsort_desc_kernel(const TVd x, const TVd y, int k_out, bool ascending) {
+__global__ void argsort_desc_kernel(const TVd x, const TVd y, int k_out, bool ascending, bool swap01) {
     extern __shared__ float sx[];
     pdl_wait();
     const int64_t row = blockIdx.x;
@@ -340,15 +340,17 @@ __global__ void argsort_desc_kernel(const TVd x, const TVd y, int k_out, bool as
             const bool before = ascending ? (u < v || (u == v && j < i)) : (u > v || (u == v && j < i));
             rank += before ? 1 : 0;
         }
+        // ggml_compute_forward_top_k_f32 swaps the first two results ("order is not important", ops.cpp:8089-8092)
+        if (swap01 && rank < 2) rank ^= 1;
         if (rank < k_out) yr[rank] = i;
     }
 }
-int op_argsort(const TV & x, const TV & y, int k_out, bool ascending, cudaStream_t st) {
+int op_argsort(const TV & x, const TV & y, int k_out, bool ascending, bool swap01, cudaStream_t st) {
     const int64_t rows = nrows(x);
     if (rows <= 0) return B200_OK;
     if (x.ne[0] > 8192) return B200_ERR_UNSUPPORTED;
     const int threads = x.ne[0] >= 256 ? 256 : 32;
-    argsort_desc_kernel<<<(unsigned) rows, threads, (size_t) x.ne[0] * 4, st>>>(dv(x), dv(y), k_out, ascending);
+    argsort_desc_kernel<<<(unsigned) rows, threads, (size_t) x.ne[0] * 4, st>>>(dv(x), dv(y), k_out, ascending, swap01 && k_out > 1);
     return (int) cudaGetLastError();
 }
 
