@@ -163,3 +163,61 @@ def test_moe_router_ops():
         return [(w, np.float32, (3, 2))]
     outs = both(build, tol=2e-6)
     assert np.allclose(outs["CUDA0"][0].sum(-1), 1.0, atol=1e-6)
+
+
+def _layer_graph(g, rng_seed, t, hidden, heads, kvh, ffn, n_past, qlen, max_len, neox, bias, taps):
+    """One LMBlock1Forward layer exactly as chatllm emits it (src/layers.cpp:2719-2761, :3212-3227, :2475-2483)."""
+    rng = np.random.default_rng(rng_seed)
+    hd = hidden // heads
+    kv_hidden = kvh * hd
+    W = lambda m, k: g.input(qf.random_blocks(t, m, k, rng=rng).reshape(-1), t, (k, m))
+    vecn = lambda n: g.input((1 + 0.1 * rng.standard_normal(n)).astype(np.float32))
+    vecb = lambda n: g.input((0.02 * rng.standard_normal(n)).astype(np.float32))
+    x = g.input(acts(rng, qlen, hidden))
+    pos = g.input((np.arange(qlen) + n_past).astype(np.int32))
+    kc = g.input((rng.standard_normal((max_len, kv_hidden))).astype(np.float16))
+    vc = g.input((rng.standard_normal((kv_hidden, max_len))).astype(np.float16))
+    n_kv = n_past + qlen
+    mode = 2 if neox else 0
+
+    h = g.mul(g.rms_norm(x, 1e-5), vecn(hidden)); taps.append(("attn_norm", h, (qlen, hidden)))
+    q = g.mul_mat(W(hidden, hidden), h); k = g.mul_mat(W(kv_hidden, hidden), h); v = g.mul_mat(W(kv_hidden, hidden), h)
+    if bias:
+        q = g.add(q, vecb(hidden), inplace=True); k = g.add(k, vecb(kv_hidden), inplace=True); v = g.add(v, vecb(kv_hidden), inplace=True)
+    taps.append(("q", q, (qlen, hidden))); taps.append(("k", k, (qlen, kv_hidden)))
+    k4 = g.rope(g.reshape(k, (hd, kvh, qlen)), pos, hd, mode, 10000.0, inplace=True)
+    q4 = g.rope(g.reshape(q, (hd, heads, qlen)), pos, hd, mode, 10000.0, inplace=True)
+    taps.append(("q_rope", q4, (qlen, heads, hd)))
+    vw = g.cpy(g.transpose(v), g.view(vc, (qlen, kv_hidden), (2 * max_len,), offset=n_past * 2))
+    kw = g.set_rows(kc, g.reshape(k4, (kv_hidden, qlen)), pos)
+    K = g.permute(g.view(kw, (hd, kvh, n_kv), (2 * hd, 2 * kv_hidden)), (0, 2, 1, 3))
+    V = g.view(vc, (n_kv, hd, kvh), (2 * max_len, 2 * max_len * hd))
+    Q = g.permute(q4, (0, 2, 1, 3))
+    s = g.mul_mat(K, Q, prec_f32=True)
+    s = g.soft_max(g.diag_mask_inf(g.scale(s, 1.0 / np.sqrt(hd), inplace=True), n_past, inplace=True), inplace=True)
+    ctx = g.cont(g.permute(g.mul_mat(V, s), (0, 2, 1, 3)))
+    ctx = g.reshape(ctx, (hidden, qlen)); taps.append(("ctx", ctx, (qlen, hidden)))
+    o = g.mul_mat(W(hidden, hidden), ctx)
+    h1 = g.add(x, o); taps.append(("h1", h1, (qlen, hidden)))
+    hn = g.mul(g.rms_norm(h1, 1e-5), vecn(hidden))
+    gate = g.silu(g.mul_mat(W(ffn, hidden), hn), inplace=True); up = g.mul_mat(W(ffn, hidden), hn)
+    act = g.mul(gate, up, inplace=True); taps.append(("act", act, (qlen, ffn)))
+    down = g.mul_mat(W(hidden, ffn), act)
+    out = g.add(h1, down); taps.append(("out", out, (qlen, hidden)))
+    return vw
+
+
+@pytest.mark.parametrize("t", [qf.Q4_K, qf.Q4_0, qf.Q8_0])
+@pytest.mark.parametrize("neox,bias", [(False, False), (True, True)])
+@pytest.mark.parametrize("n_past,qlen", [(0, 37), (37, 1)])
+def test_full_decoder_layer_graph(t, neox, bias, n_past, qlen):
+    outs = {}
+    for dev in ("CPU", "CUDA0"):
+        g = rs.Graph(); taps = []
+        vw = _layer_graph(g, 7, t, 256, 4, 2, 512, n_past, qlen, 128, neox, bias, taps)
+        res = g.run(dev, [(g.cont(vw), np.float16, (128, qlen))] + [(tt, np.float32, shp) for (_, tt, shp) in taps], n_threads=8, strict=True)
+        outs[dev] = dict(zip(["v"] + [n for (n, _, _) in taps], res))
+    report = {n: float(np.abs(outs["CPU"][n].astype(np.float32) - outs["CUDA0"][n].astype(np.float32)).max() /
+                       (np.abs(outs["CPU"][n].astype(np.float32)).max() + 1e-30)) for n in outs["CPU"]}
+    print(qf.NAMES[t], "neox" if neox else "norm", n_past, qlen, {k: f"{v:.1e}" for k, v in report.items()})
+    assert max(report.values()) <= 1e-4, report
