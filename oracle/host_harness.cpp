@@ -10,16 +10,30 @@
 //   host_harness --model M.bin --ggml_dir DIR --ngl all|0 [--threads N] [--max_length L] [--prefill P] [--decode T]
 //                [--batch B] [--seed S] [--dump logits.bin] [--feed argmax|seeded]
 // Output: one JSON line on stdout.
-#include "chat.h"
-#include "backend.h"
-
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
+#include <map>
+#include <memory>
+#include <set>
+#include <sstream>
 #include <string>
+#include <unordered_map>
 #include <vector>
+
+// --trace needs the host's BackendContext (a protected member of the model classes); test infrastructure only.
+#define protected public
+#define private public
+#include "chat.h"
+#include "backend.h"
+#include "models.h"
+#include "models_priv.h"
+#undef protected
+#undef private
 
 using namespace chatllm;
 
@@ -28,12 +42,37 @@ void log_internal(int level, const char * text) {
     if (level >= 3) fprintf(stderr, "%s", text);  // GGML_LOG_LEVEL_WARN and above
 }
 
+// ---- --trace: per-node checksums through the host's eval-observe hook (src/backend.cpp:800-823, :845-851) ----------
+static FILE * g_trace = nullptr;
+static int g_trace_idx = 0;
+static bool trace_need(ggml::tensor * t, void *) { return true; }
+static bool trace_observe(ggml::tensor * t, void *) {
+    const size_t nb = ggml_nbytes(t);
+    std::vector<uint8_t> buf(nb);
+    ggml_backend_tensor_get(t, buf.data(), 0, nb);
+    double sum = 0, abs = 0;
+    const int64_t n = ggml_nelements(t);
+    if (ggml_is_contiguous(t)) {
+        if (t->type == GGML_TYPE_F32) { const float * p = (const float *) buf.data(); for (int64_t i = 0; i < n; ++i) { if (std::isfinite(p[i])) { sum += p[i]; abs += std::fabs(p[i]); } } }
+        else if (t->type == GGML_TYPE_F16) { const ggml_fp16_t * p = (const ggml_fp16_t *) buf.data(); for (int64_t i = 0; i < n; ++i) { float v = ggml_fp16_to_fp32(p[i]); sum += v; abs += std::fabs(v); } }
+        else if (t->type == GGML_TYPE_I32) { const int32_t * p = (const int32_t *) buf.data(); for (int64_t i = 0; i < n; ++i) { sum += p[i]; abs += std::abs(p[i]); } }
+    }
+    fprintf(g_trace, "%d %s %s [%lld,%lld,%lld,%lld] %s sum=%.9g abs=%.9g\n", g_trace_idx++, ggml_op_name(t->op), ggml_type_name(t->type),
+            (long long) t->ne[0], (long long) t->ne[1], (long long) t->ne[2], (long long) t->ne[3], ggml_is_contiguous(t) ? "c" : "nc", sum, abs);
+    return true;
+}
+static BackendContext * find_backend_context(AbstractModel * m) {
+    if (auto * p = dynamic_cast<ModelProxy *>(m)) m = p->model;
+    if (auto * b = dynamic_cast<BaseModelForConditionalGeneration *>(m)) return &b->backend_context;
+    return nullptr;
+}
+
 static double now_ms() {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
 int main(int argc, char ** argv) {
-    std::string model_path, ggml_dir, ngl = "0", dump, feed = "seeded";
+    std::string model_path, ggml_dir, ngl = "0", dump, feed = "seeded", trace;
     int threads = 8, max_length = 4352, prefill = 16, decode = 8, batch = 4096, seed = 1, vocab_limit = 0;
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];
@@ -50,6 +89,7 @@ int main(int argc, char ** argv) {
         else if (a == "--dump") dump = next();
         else if (a == "--feed") feed = next();
         else if (a == "--vocab_limit") vocab_limit = atoi(next());
+        else if (a == "--trace") trace = next();
     }
     if (model_path.empty()) { fprintf(stderr, "usage: host_harness --model M --ggml_dir D --ngl all|0 ...\n"); return 2; }
 
@@ -82,6 +122,13 @@ int main(int argc, char ** argv) {
     int vocab = (int) logits.size();
     if (vocab_limit > 0 && vocab_limit < vocab) vocab = vocab_limit;
 
+    if (!trace.empty()) {
+        g_trace = fopen(trace.c_str(), "w");
+        BackendContext * bc = find_backend_context(model);
+        if (bc && g_trace) bc->set_eval_observe_callback(trace_need, trace_observe, nullptr);
+        else fprintf(stderr, "trace: cannot reach the backend context\n");
+    }
+
     // ---- prefill
     ids.resize(prefill);
     for (int i = 0; i < prefill; ++i) ids[i] = next_id(vocab);
@@ -110,6 +157,7 @@ int main(int argc, char ** argv) {
         if (fd) fwrite(logits.data(), sizeof(float), logits.size(), fd);
     }
     if (fd) fclose(fd);
+    if (g_trace) fclose(g_trace);
 
     double sum = 0, best = 1e30;
     for (double v : step_ms) { sum += v; best = std::min(best, v); }
