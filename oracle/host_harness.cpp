@@ -45,8 +45,21 @@ void log_internal(int level, const char * text) {
 // ---- --trace: per-node checksums through the host's eval-observe hook (src/backend.cpp:800-823, :845-851) ----------
 static FILE * g_trace = nullptr;
 static int g_trace_idx = 0;
+static int g_dump_idx = -1;
+static std::string g_trace_path;
+static void dump_tensor_raw(ggml::tensor * t, const char * tag) {
+    if (!t) return;
+    std::vector<uint8_t> buf(ggml_nbytes(t));
+    ggml_backend_tensor_get(t, buf.data(), 0, buf.size());
+    char name[512];
+    snprintf(name, sizeof(name), "%s.node%d.%s", g_trace_path.c_str(), g_dump_idx, tag);
+    FILE * f = fopen(name, "wb");
+    if (f) { fwrite(buf.data(), 1, buf.size(), f); fclose(f); }
+    fprintf(g_trace, "# dump %s type=%s ne=[%lld,%lld,%lld,%lld] nb=[%zu,%zu,%zu,%zu]\n", tag, ggml_type_name(t->type), (long long) t->ne[0], (long long) t->ne[1], (long long) t->ne[2], (long long) t->ne[3], t->nb[0], t->nb[1], t->nb[2], t->nb[3]);
+}
 static bool trace_need(ggml::tensor * t, void *) { return true; }
 static bool trace_observe(ggml::tensor * t, void *) {
+    if (g_trace_idx == g_dump_idx) { dump_tensor_raw(t, "dst"); dump_tensor_raw(t->src[0], "src0"); dump_tensor_raw(t->src[1], "src1"); }
     const size_t nb = ggml_nbytes(t);
     std::vector<uint8_t> buf(nb);
     ggml_backend_tensor_get(t, buf.data(), 0, nb);
@@ -90,6 +103,7 @@ int main(int argc, char ** argv) {
         else if (a == "--feed") feed = next();
         else if (a == "--vocab_limit") vocab_limit = atoi(next());
         else if (a == "--trace") trace = next();
+        else if (a == "--trace_dump") g_dump_idx = atoi(next());
     }
     if (model_path.empty()) { fprintf(stderr, "usage: host_harness --model M --ggml_dir D --ngl all|0 ...\n"); return 2; }
 
@@ -124,6 +138,7 @@ int main(int argc, char ** argv) {
 
     if (!trace.empty()) {
         g_trace = fopen(trace.c_str(), "w");
+        g_trace_path = trace;
         BackendContext * bc = find_backend_context(model);
         if (bc && g_trace) bc->set_eval_observe_callback(trace_need, trace_observe, nullptr);
         else fprintf(stderr, "trace: cannot reach the backend context\n");
