@@ -46,6 +46,7 @@ void log_internal(int level, const char * text) {
 static FILE * g_trace = nullptr;
 static int g_trace_idx = 0;
 static int g_dump_idx = -1;
+static FILE * g_full = nullptr;  // --trace_full: raw bytes of every contiguous node output, in order
 static std::string g_trace_path;
 static void dump_tensor_raw(ggml::tensor * t, const char * tag) {
     if (!t) return;
@@ -63,6 +64,7 @@ static bool trace_observe(ggml::tensor * t, void *) {
     const size_t nb = ggml_nbytes(t);
     std::vector<uint8_t> buf(nb);
     ggml_backend_tensor_get(t, buf.data(), 0, nb);
+    if (g_full && ggml_is_contiguous(t)) fwrite(buf.data(), 1, nb, g_full);
     double sum = 0, abs = 0;
     const int64_t n = ggml_nelements(t);
     if (ggml_is_contiguous(t)) {
@@ -104,6 +106,7 @@ int main(int argc, char ** argv) {
         else if (a == "--vocab_limit") vocab_limit = atoi(next());
         else if (a == "--trace") trace = next();
         else if (a == "--trace_dump") g_dump_idx = atoi(next());
+        else if (a == "--trace_full") g_full = fopen(next(), "wb");
     }
     if (model_path.empty()) { fprintf(stderr, "usage: host_harness --model M --ggml_dir D --ngl all|0 ...\n"); return 2; }
 
@@ -173,6 +176,7 @@ int main(int argc, char ** argv) {
     }
     if (fd) fclose(fd);
     if (g_trace) fclose(g_trace);
+    if (g_full) fclose(g_full);
 
     double sum = 0, best = 1e30;
     for (double v : step_ms) { sum += v; best = std::min(best, v); }
