@@ -1,0 +1,290 @@
+#!/usr/bin/env python
+"""bench.py — decode tokens/s @4096 ctx, Q4_K Llama-3-8B (BASELINE.json metric), on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One JSON line on stdout (rank 0).  A "step" = one decode token of the whole model at n_past = 4096:
+  value    whole-job tokens/s with everything resident in HBM: the decode step (chatllm.cpp_b200/session.py, all kernels
+           through the C ABI) captured in one CUDA graph and replayed K times; timed with CUDA events on the replay
+           stream.  Inputs >> L2 (4.2 GB of weights + 0.5 GB of KV per token), so no L2 flush is needed.
+  e2e      the same metric through the reference-facing boundary with HOST buffers: the unmodified chatllm host
+           (oracle/_ref/bin/host_harness) drives libggml-cuda.so; every step uploads the token id / positions and reads
+           the 513 KB logits row back (h2d/d2h bytes counted from those tensors); wall clock of the host loop.
+  roofline the dominant kernel gemv_q_kernel<FmtQ4K,...>: algorithmic bytes of all quantized matmuls of a token
+           (m*(k/256)*144 + 4k + 4m each) / CUDA-event time of exactly those launches replayed alone,
+           vs MEASURED_PEAKS.json hbm_gbs.
+  cpu_baseline  the reference's own ggml CPU backend (oracle/_ref, `kind: reference`) on the same file, bounded sample.
+--impl reference: the reference CPU path is the arm being timed (rank 0 only).
+Multi-GPU (N>1, torchrun): the path is one sequential stream, sharded BY LAYER (KV cache sharded with it); the hidden
+state row is handed over with NCCL send/recv.  Total work is fixed as N grows -> scaling "strong".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+MODEL, QUANT, N_PAST = "llama3-8b", "q4_K", 4096
+HARNESS = os.path.join(ROOT, "oracle", "_ref", "bin", "host_harness")
+RUNDIR = os.path.join(ROOT, "oracle", "_ref", "run")
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line)."""
+    def __init__(self, idx=0):
+        super().__init__(daemon=True)
+        self.idx, self.rows, self._stop_evt = idx, [], threading.Event()
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.idx)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([v.strip() for v in out.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=3)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def ensure_model_file(layers=0):
+    path = f"/tmp/b200_{MODEL}_{QUANT}{'_L%d' % layers if layers else ''}.bin"
+    if not os.path.exists(path):
+        cmd = [sys.executable, os.path.join(ROOT, "tools", "make_model.py"), "--arch", MODEL, "--quant", QUANT, "--out", path + ".tmp",
+               "--max_length", str(N_PAST + 256)]
+        if layers:
+            cmd += ["--layers", str(layers)]
+        subprocess.run(cmd, check=True, capture_output=True)
+        os.replace(path + ".tmp", path)
+    return path
+
+
+def run_harness(model, ngl, decode, threads, extra=()):
+    cmd = [HARNESS, "--model", model, "--ggml_dir", RUNDIR, "--ngl", ngl, "--threads", str(threads), "--prefill", "0", "--fake_prefill", str(N_PAST),
+           "--decode", str(decode), "--max_length", str(N_PAST + 256)] + list(extra)
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=3000)
+    if p.returncode != 0:
+        raise RuntimeError("host_harness failed: " + p.stderr[-1500:])
+    return json.loads(p.stdout.strip().splitlines()[-1])
+
+
+def cpu_reference_arm(steps, warmup):
+    """the reference's own CPU implementation of the path (oracle/_ref = unmodified reference build), all host threads"""
+    cores = os.cpu_count() or 1
+    threads = min(cores, 64)
+    model = ensure_model_file()
+    r = run_harness(model, "0", warmup + steps, threads, ["--skip", str(warmup)])
+    ms = r["decode_ms_mean_after_skip"]
+    return {"value": 1000.0 / ms, "ms_per_step": ms, "cores": threads, "host_cores": cores,
+            "sample": f"{steps} decode tokens of the full {MODEL} {QUANT} model at n_past={N_PAST} (KV cache zero-filled, no prefill), {threads} threads"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=64)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--layers", type=int, default=0, help="debug: fewer layers (result is then NOT the BASELINE config)")
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    base = {"metric": "decode tokens/s @4096ctx (Q4_K Llama-3-8B)", "unit": "tokens/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int8 x int4 -> int32 dot, fp32 scales/accumulate",
+            "data": "synthetic (seeded random valid Q4_K blocks, random F16 KV cache; no checkpoints offline)",
+            "config": {"workload": "Llama-3-8B Q4_K single-token decode at n_past=4096 (BASELINE.json configs[1])", "n_past": N_PAST,
+                       "parallelism": "1 GPU" if a.gpus == 1 else f"layer-sharded x{a.gpus} (KV sharded by layer, NCCL send/recv of the hidden row)",
+                       "l2": "inputs (4.76 GB per token) exceed L2; no flush needed"}}
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        steps = min(a.steps, 8)  # bounded sample: the CPU path runs ~0.1-0.3 s per token
+        r = cpu_reference_arm(steps, min(a.warmup, 3))
+        out = dict(base)
+        out.update({"impl": "reference", "value": r["value"], "ms_per_step": r["ms_per_step"], "steps": steps,
+                    "cpu_baseline": {"value": r["value"], "unit": "tokens/s", "cores": r["cores"], "kind": "reference", "sample": r["sample"]},
+                    "e2e": {"value": r["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0})
+        print(json.dumps(out))
+        return
+
+    import torch
+    import __graft_entry__ as ge
+    pkg = ge.load_package()
+    pkg.lib()  # raises if the CUDA extension is missing: no fallback
+    from chatllm_cpp_b200 import session as S
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU (no CPU fallback)")
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl")
+
+    cfg = S.make_config(MODEL, pkg.Q4_K, layers=a.layers or None, max_len=N_PAST + 256)
+    per = cfg.layers // world
+    lo, hi = rank * per, (rank + 1) * per if rank < world - 1 else cfg.layers
+    sess = S.DecodeSession(cfg, seed=0, layer_lo=lo, layer_hi=hi, first=(rank == 0), last=(rank == world - 1))
+    sess.fill_kv_random(N_PAST, seed=rank)
+    sess.tok.fill_(12345 % cfg.vocab)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local) if rank == 0 else None
+    if world == 1:
+        graph = sess.capture(N_PAST)
+        for _ in range(a.warmup):
+            graph.replay()
+        sync_all()
+        if sampler: sampler.start()
+        e0.record()
+        for _ in range(a.steps):
+            graph.replay()
+        e1.record()
+        sync_all()
+    else:
+        def one_step():
+            if rank > 0:
+                dist.recv(sess.x, src=rank - 1)
+            sess.enqueue_step(N_PAST)
+            if rank < world - 1:
+                dist.send(sess.x, dst=rank + 1)
+        sess.pos.fill_(N_PAST)
+        for _ in range(a.warmup):
+            one_step()
+        sync_all()
+        if sampler: sampler.start()
+        e0.record()
+        for _ in range(a.steps):
+            one_step()
+        e1.record()
+        sync_all()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler else None
+    if dist:
+        t = torch.tensor([ms_total], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+        n_launch = torch.tensor([sess.launches_per_step], device="cuda")
+        dist.all_reduce(n_launch)
+        launches = int(n_launch.item()) * a.steps
+    else:
+        launches = sess.launches_per_step * a.steps
+    ms = ms_total / a.steps
+    value = 1000.0 / ms
+
+    # ---- roofline of the dominant kernel: exactly the token's quantized-matmul launches, replayed alone (rank 0's shard)
+    import ctypes
+    L = pkg.lib()
+    shapes = []
+    for W in sess.layers:
+        shapes += [(W.wq, cfg.hidden, cfg.hidden), (W.wk, cfg.hidden, cfg.kv_hidden), (W.wv, cfg.hidden, cfg.kv_hidden), (W.wo, cfg.hidden, cfg.hidden),
+                   (W.wgate, cfg.hidden, cfg.ffn), (W.wup, cfg.hidden, cfg.ffn), (W.wdown, cfg.ffn, cfg.hidden)]
+    if sess.last:
+        shapes.append((sess.lm_head, cfg.hidden, cfg.vocab))
+    xq = {k: None for k in (cfg.hidden, cfg.ffn)}
+    for k in xq:
+        x = torch.randn((1, k), device="cuda")
+        q = torch.empty(L.b200_qact_col_bytes(cfg.wtype, k), dtype=torch.uint8, device="cuda")
+        L.b200_quantize_act(cfg.wtype, x.data_ptr(), k, k, 1, q.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        xq[k] = q
+    ybuf = torch.empty(max(cfg.vocab, cfg.ffn), dtype=torch.float32, device="cuda")
+
+    def gemv_all():
+        st = torch.cuda.current_stream().cuda_stream
+        for (w, k, m) in shapes:
+            L.b200_mul_mat_q(cfg.wtype, w.data_ptr(), k, m, xq[k].data_ptr(), 1, ybuf.data_ptr(), m, 0, st)
+    gemv_all(); torch.cuda.synchronize()
+    gg = torch.cuda.CUDAGraph(); gs = torch.cuda.Stream()
+    with torch.cuda.stream(gs):
+        with torch.cuda.graph(gg, stream=gs):
+            gemv_all()
+    for _ in range(3):
+        gg.replay()
+    torch.cuda.synchronize()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = max(5, min(a.steps, 20))
+    g0.record()
+    for _ in range(reps):
+        gg.replay()
+    g1.record(); torch.cuda.synchronize()
+    gemv_ms = g0.elapsed_time(g1) / reps
+    b, s = S.BLK[cfg.wtype]
+    gemv_bytes = sum(m * (k // b) * s + 4 * k + 4 * m for (_, k, m) in shapes)
+    pk, pk_kind = peaks()
+    achieved = gemv_bytes / gemv_ms / 1e6
+    roofline = {"bound": "hbm", "kernel": "gemv_q_kernel<FmtQ4K>", "achieved": round(achieved, 1), "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": round(achieved / pk["hbm_gbs"], 4), "peak_kind": pk_kind + " (MEASURED_PEAKS.json hbm_gbs)" if pk_kind == "measured" else "fallback",
+                "frac_of_nominal_8TBps": round(achieved / 8000.0, 4), "launches": len(shapes), "avg_launch_us": round(gemv_ms * 1e3 / len(shapes), 2),
+                "algorithmic_MB_per_token_shard": round(gemv_bytes / 1e6, 1), "traffic": None,
+                "share_of_step": round(gemv_ms / ms, 3)}
+
+    if rank != 0:
+        return
+    out = dict(base)
+    tok_bytes = cfg.weight_bytes_per_token() + cfg.kv_bytes_per_token(N_PAST)
+    out.update({"value": round(value, 2), "ms_per_step": round(ms, 4), "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+                "frac_of_hbm_roofline_whole_token": round(value * tok_bytes / 1e9 / pk["hbm_gbs"], 4),
+                "bytes_per_token_MB": round(tok_bytes / 1e6, 1)})
+    if a.layers:
+        out["config"]["workload"] += f" [DEBUG: {cfg.layers} layers only]"
+
+    # ---- e2e through the drop-in boundary (N=1 only: the reference host is a single process)
+    if not a.no_e2e and world == 1 and os.path.exists(HARNESS):
+        try:
+            del sess, graph, gg
+            torch.cuda.empty_cache()
+            model = ensure_model_file(a.layers)
+            r = run_harness(model, "all", a.warmup + a.steps, 16, ["--skip", str(a.warmup)])
+            e_ms = r["decode_ms_mean_after_skip"]
+            out["e2e"] = {"value": round(1000.0 / e_ms, 2), "unit": "tokens/s", "ms_per_step": round(e_ms, 4),
+                          "h2d_bytes_per_step": 4 + 4 * cfg.layers, "d2h_bytes_per_step": 4 * cfg.vocab,
+                          "path": "unmodified chatllm host (graph rebuild + ggml sched per token) -> libggml-cuda.so; pageable host buffers of the host app",
+                          "plugin_launches_per_step": r.get("plugin_launches_per_step")}
+        except Exception as ex:  # noqa: BLE001
+            out["e2e"] = {"value": None, "error": str(ex)[-300:]}
+    if not a.no_cpu and world == 1 and os.path.exists(HARNESS):
+        try:
+            r = cpu_reference_arm(4, 1)
+            out["cpu_baseline"] = {"value": round(r["value"], 3), "unit": "tokens/s", "cores": r["cores"], "kind": "reference", "sample": r["sample"]}
+        except Exception as ex:  # noqa: BLE001
+            out["cpu_baseline"] = {"value": None, "error": str(ex)[-300:]}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -94,4 +94,14 @@ int b200_get_rows(int type, const void * table, int64_t k, const int32_t * ids, 
     return get_rows_q(type, table, k, ids, n, y, (cudaStream_t) stream);
 }
 
+size_t b200_attn_decode_scratch_bytes(int n_heads, int n_kv) { return attn_decode_scratch_bytes(n_heads, n_kv); }
+int b200_attn_decode(const float * q, const void * k_cache, const void * v_cache_t, float * out, float * scratch, int n_heads, int kv_heads, int head_dim,
+                     int n_kv, int64_t k_row_stride, int64_t v_row_stride, float scale, void * stream) {
+    return attn_decode(q, k_cache, v_cache_t, out, scratch, n_heads, kv_heads, head_dim, n_kv, k_row_stride, v_row_stride, scale, (cudaStream_t) stream);
+}
+int b200_kv_store(const float * k, const float * v, void * k_cache, void * v_cache_t, int kv_hidden, int64_t k_row_stride, int64_t v_row_stride, int pos,
+                  void * stream) {
+    return kv_store(k, v, k_cache, v_cache_t, kv_hidden, k_row_stride, v_row_stride, pos, (cudaStream_t) stream);
+}
+
 }  // extern "C"

@@ -191,6 +191,9 @@ static ggml_backend_buffer_t b200_buft_alloc(ggml_backend_buffer_type_t buft, si
         GGML_LOG_ERROR("b200: cudaMalloc(%zu) on device %d failed: %s\n", sz, dc->device, cudaGetErrorString(e));
         return nullptr;  // caller CHATLLM_CHECKs (src/backend.cpp:105-107)
     }
+    // deterministic contents (KV caches are read before every position has been written when a session is rewound)
+    cudaMemsetAsync(p, 0, sz, dc->xfer);
+    cudaStreamSynchronize(dc->xfer);
     b200_buffer_ctx * c = new b200_buffer_ctx{dc->device, p};
     return ggml_backend_buffer_init(buft, b200_buffer_iface, c, size);
 }

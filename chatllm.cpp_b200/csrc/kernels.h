@@ -35,6 +35,10 @@ int rope_f32(const float * x, float * y, const int32_t * pos, const float * freq
              float freq_base, float freq_scale, float ext_factor, float attn_factor, float beta_fast, float beta_slow, cudaStream_t st);
 int soft_max_f32(const float * x, const float * mask, float * y, int64_t ne0, int64_t nrows, float scale, cudaStream_t st);
 int get_rows_q(int type, const void * table, int64_t k, const int32_t * ids, int64_t n, float * y, cudaStream_t st);
+size_t attn_decode_scratch_bytes(int n_heads, int n_kv);
+int attn_decode(const float * q, const void * kc, const void * vc, float * out, float * scratch, int n_heads, int kv_heads, int head_dim, int n_kv,
+                int64_t k_row_stride, int64_t v_row_stride, float scale, cudaStream_t st);
+int kv_store(const float * k, const float * v, void * kc, void * vc, int kv_hidden, int64_t k_row_stride, int64_t v_row_stride, int pos, cudaStream_t st);
 
 
 // ---- ops_generic.cu: strided / broadcasting ops as ggml graphs present them (ne[0] fastest, nb in bytes)

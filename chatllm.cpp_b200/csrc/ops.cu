@@ -249,3 +249,142 @@ int get_rows_q(int type, const void * table, int64_t k, const int32_t * ids, int
 }
 
 }  // namespace b200
+
+// ======================================================================================================
+// Decode attention over the reference's F16 KV-cache layouts (one new token, GQA).
+//   K cache: [max_len][kv_heads*head_dim] f16, one row per position          (src/layers.cpp:2933)
+//   V cache: [kv_heads*head_dim][max_len] f16, TRANSPOSED: one row per channel (src/layers.cpp:2937)
+// Semantics = the reference's unfused graph (src/layers.cpp:2541-2561): scores = K.Q with both operands in f16 and
+// fp32 accumulation (ggml-cpu.c:213-219, vec.cpp:264), * scale, causal mask (all n_kv positions visible for the last
+// token), softmax (ops.cpp:5225-5335), then V.P with P rounded to f16.  Three kernels instead of the graph's seven,
+// each K / V element is read from HBM once for all query heads of its KV group.
+// ======================================================================================================
+namespace b200 {
+
+// scores[h][t] = scale * sum_d K[t][g][d] * f16(q[h][d])      grid (ceil(n_kv/TPB), kv_heads), block 256 (8 warps)
+template <int HD, int GQA>
+__global__ void __launch_bounds__(256) attn_scores_kernel(const float * __restrict__ q, const __half * __restrict__ kc, float * __restrict__ scores,
+                                                          int n_kv, int kv_heads, int64_t k_row_stride, float scale, int64_t s_stride) {
+    __shared__ float qs[GQA][HD];
+    pdl_wait();
+    const int g = blockIdx.y;
+    for (int i = threadIdx.x; i < GQA * HD; i += blockDim.x) {
+        const int h = i / HD, d = i % HD;
+        qs[h][d] = __half2float(__float2half_rn(q[(int64_t) (g * GQA + h) * HD + d]));
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int EPL = HD / 32;  // elements per lane (HD = 64 -> 2, 128 -> 4)
+    for (int t = blockIdx.x * 64 + warp; t < min(n_kv, (int) (blockIdx.x + 1) * 64); t += 8) {
+        const __half * kr = kc + (int64_t) t * k_row_stride + (int64_t) g * HD + lane * EPL;
+        float kv[EPL];
+        if (EPL == 4) {
+            const uint2 raw = *reinterpret_cast<const uint2 *>(kr);
+            const __half2 a = *reinterpret_cast<const __half2 *>(&raw.x), b = *reinterpret_cast<const __half2 *>(&raw.y);
+            kv[0] = __low2float(a); kv[1] = __high2float(a); kv[2] = __low2float(b); kv[3] = __high2float(b);
+        } else {
+#pragma unroll
+            for (int e = 0; e < EPL; ++e) kv[e] = __half2float(kr[e]);
+        }
+#pragma unroll
+        for (int h = 0; h < GQA; ++h) {
+            float s = 0.0f;
+#pragma unroll
+            for (int e = 0; e < EPL; ++e) s = fmaf(kv[e], qs[h][lane * EPL + e], s);
+            s = warp_sum(s);
+            if (lane == 0) scores[(int64_t) (g * GQA + h) * s_stride + t] = s * scale;
+        }
+    }
+}
+
+// in-place softmax over scores[h][0..n_kv), result rounded through f16 (it is the f16 operand of V.P)
+__global__ void __launch_bounds__(1024) attn_softmax_kernel(float * __restrict__ scores, int n_kv, int64_t s_stride) {
+    __shared__ float red[32];
+    pdl_wait();
+    float * s = scores + (int64_t) blockIdx.x * s_stride;
+    float mx = -INFINITY;
+    for (int i = threadIdx.x; i < n_kv; i += blockDim.x) mx = fmaxf(mx, s[i]);
+    mx = block_max(mx, red);
+    float sum = 0.0f;
+    for (int i = threadIdx.x; i < n_kv; i += blockDim.x) { const float e = expf(s[i] - mx); s[i] = e; sum += e; }
+    sum = block_sum(sum, red);
+    const float inv = 1.0f / sum;
+    for (int i = threadIdx.x; i < n_kv; i += blockDim.x) s[i] = __half2float(__float2half_rn(s[i] * inv));
+}
+
+// out[h][d] = sum_t Vt[g*HD+d][t] * P[h][t]          grid (HD*kv_heads/8), block 256: one warp per channel row
+template <int GQA>
+__global__ void __launch_bounds__(256) attn_pv_kernel(const float * __restrict__ P, const __half * __restrict__ vc, float * __restrict__ out, int n_kv,
+                                                      int head_dim, int64_t v_row_stride, int64_t s_stride) {
+    pdl_wait();
+    const int lane = threadIdx.x & 31;
+    const int ch = blockIdx.x * 8 + (threadIdx.x >> 5);  // channel = g*HD + d
+    const int g = ch / head_dim, d = ch % head_dim;
+    const __half * vr = vc + (int64_t) ch * v_row_stride;
+    float acc[GQA];
+#pragma unroll
+    for (int h = 0; h < GQA; ++h) acc[h] = 0.0f;
+    for (int t = lane * 2; t < n_kv; t += 64) {
+        float v0, v1 = 0.0f;
+        if (t + 1 < n_kv && ((v_row_stride & 1) == 0)) {
+            const __half2 hv = *reinterpret_cast<const __half2 *>(vr + t);
+            v0 = __low2float(hv); v1 = __high2float(hv);
+        } else {
+            v0 = __half2float(vr[t]);
+            if (t + 1 < n_kv) v1 = __half2float(vr[t + 1]);
+        }
+#pragma unroll
+        for (int h = 0; h < GQA; ++h) {
+            const float * p = P + (int64_t) (g * GQA + h) * s_stride + t;
+            acc[h] = fmaf(v0, p[0], acc[h]);
+            if (t + 1 < n_kv) acc[h] = fmaf(v1, p[1], acc[h]);
+        }
+    }
+#pragma unroll
+    for (int h = 0; h < GQA; ++h) {
+        const float s = warp_sum(acc[h]);
+        if (lane == 0) out[(int64_t) (g * GQA + h) * head_dim + d] = s;
+    }
+}
+
+template <int HD, int GQA>
+static int attn_decode_t(const float * q, const void * kc, const void * vc, float * out, float * scratch, int n_kv, int kv_heads, int64_t k_row_stride,
+                         int64_t v_row_stride, float scale, cudaStream_t st) {
+    const int64_t s_stride = (n_kv + 3) & ~3;
+    dim3 g1((unsigned) ((n_kv + 63) / 64), (unsigned) kv_heads);
+    attn_scores_kernel<HD, GQA><<<g1, 256, 0, st>>>(q, (const __half *) kc, scratch, n_kv, kv_heads, k_row_stride, scale, s_stride);
+    attn_softmax_kernel<<<(unsigned) (kv_heads * GQA), n_kv >= 2048 ? 1024 : 256, 0, st>>>(scratch, n_kv, s_stride);
+    attn_pv_kernel<GQA><<<(unsigned) (kv_heads * HD / 8), 256, 0, st>>>(scratch, (const __half *) vc, out, n_kv, HD, v_row_stride, s_stride);
+    return (int) cudaGetLastError();
+}
+
+size_t attn_decode_scratch_bytes(int n_heads, int n_kv) { return (size_t) n_heads * (size_t) ((n_kv + 3) & ~3) * 4; }
+
+int attn_decode(const float * q, const void * kc, const void * vc, float * out, float * scratch, int n_heads, int kv_heads, int head_dim, int n_kv,
+                int64_t k_row_stride, int64_t v_row_stride, float scale, cudaStream_t st) {
+    if (n_kv <= 0) return B200_OK;
+    const int gqa = n_heads / kv_heads;
+    if (n_heads % kv_heads) return B200_ERR_ARG;
+#define B200_ATTN_CASE(HD_, G_) \
+    if (head_dim == HD_ && gqa == G_) return attn_decode_t<HD_, G_>(q, kc, vc, out, scratch, n_kv, kv_heads, k_row_stride, v_row_stride, scale, st);
+    B200_ATTN_CASE(128, 4) B200_ATTN_CASE(128, 7) B200_ATTN_CASE(128, 1) B200_ATTN_CASE(128, 8) B200_ATTN_CASE(128, 2)
+    B200_ATTN_CASE(64, 8) B200_ATTN_CASE(64, 4) B200_ATTN_CASE(64, 2) B200_ATTN_CASE(64, 1)
+#undef B200_ATTN_CASE
+    return B200_ERR_UNSUPPORTED;
+}
+
+// write one token's K (row) and V (column of the transposed cache) as f16 — KVCacheAttention::save_to_cache
+__global__ void kv_store_kernel(const float * __restrict__ k, const float * __restrict__ v, __half * __restrict__ kc, __half * __restrict__ vc, int kv_hidden,
+                                int64_t k_row_stride, int64_t v_row_stride, int pos) {
+    pdl_wait();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= kv_hidden) return;
+    kc[(int64_t) pos * k_row_stride + i] = __float2half_rn(k[i]);
+    vc[(int64_t) i * v_row_stride + pos] = __float2half_rn(v[i]);
+}
+int kv_store(const float * k, const float * v, void * kc, void * vc, int kv_hidden, int64_t k_row_stride, int64_t v_row_stride, int pos, cudaStream_t st) {
+    kv_store_kernel<<<(unsigned) ((kv_hidden + 255) / 256), 256, 0, st>>>(k, v, (__half *) kc, (__half *) vc, kv_hidden, k_row_stride, v_row_stride, pos);
+    return (int) cudaGetLastError();
+}
+
+}  // namespace b200

@@ -81,6 +81,18 @@ int b200_soft_max(const float * x, const float * mask, float * y, int64_t ne0, i
 /* y[i, :] = dequant(table[ids[i], :]).  ggml/src/ggml-cpu/ops.cpp:4820 */
 int b200_get_rows(int type, const void * table, int64_t k, const int32_t * ids, int64_t n, float * y, void * stream);
 
+/* ---- decode attention over the reference's F16 KV-cache layouts ---------------------------------------------- */
+/* K cache [max_len][kv_heads*head_dim] (row stride k_row_stride halves), V cache TRANSPOSED [kv_heads*head_dim][max_len]
+ * (row stride v_row_stride halves) — src/layers.cpp:2933-2941.  out[h*head_dim+d] for one query token attending to
+ * positions [0, n_kv).  Replaces the mul_mat / scale / diag_mask_inf / soft_max / mul_mat / permute / cont chain of
+ * CoreAttention::calc_attn_scores (src/layers.cpp:2541-2561) with the same f16-operand, fp32-accumulate arithmetic. */
+size_t b200_attn_decode_scratch_bytes(int n_heads, int n_kv);
+int b200_attn_decode(const float * q, const void * k_cache, const void * v_cache_t, float * out, float * scratch, int n_heads,
+                     int kv_heads, int head_dim, int n_kv, int64_t k_row_stride, int64_t v_row_stride, float scale, void * stream);
+/* append one token: K row `pos`, V column `pos` (F32 -> F16, RNE).  KVCacheAttention::save_to_cache src/layers.cpp:3044-3123 */
+int b200_kv_store(const float * k, const float * v, void * k_cache, void * v_cache_t, int kv_hidden, int64_t k_row_stride,
+                  int64_t v_row_stride, int pos, void * stream);
+
 #ifdef __cplusplus
 }
 #endif
