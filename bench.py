@@ -180,7 +180,7 @@ def main():
         def one_step():
             if rank > 0:
                 dist.recv(sess.x, src=rank - 1)
-            sess.enqueue_step(N_PAST)
+            sess.enqueue(N_PAST)
             if rank < world - 1:
                 dist.send(sess.x, dst=rank + 1)
         sess.pos.fill_(N_PAST)

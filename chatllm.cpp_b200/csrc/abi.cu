@@ -94,10 +94,31 @@ int b200_get_rows(int type, const void * table, int64_t k, const int32_t * ids, 
     return get_rows_q(type, table, k, ids, n, y, (cudaStream_t) stream);
 }
 
-size_t b200_attn_decode_scratch_bytes(int n_heads, int n_kv) { return attn_decode_scratch_bytes(n_heads, n_kv); }
+size_t b200_attn_decode_scratch_bytes(int n_heads, int n_kv) {
+    const size_t a = attn_decode_scratch_bytes(n_heads, n_kv), b = attn_decode2_scratch_bytes(n_heads, n_kv);
+    return a > b ? a : b;
+}
 int b200_attn_decode(const float * q, const void * k_cache, const void * v_cache_t, float * out, float * scratch, int n_heads, int kv_heads, int head_dim,
                      int n_kv, int64_t k_row_stride, int64_t v_row_stride, float scale, void * stream) {
+    // two-launch version (16-byte row loads) when the cache strides allow it, else the three-launch one
+    if (k_row_stride % 8 == 0 && v_row_stride % 8 == 0) {
+        const int rc = attn_decode2(q, k_cache, v_cache_t, out, scratch, n_heads, kv_heads, head_dim, n_kv, k_row_stride, v_row_stride, scale, (cudaStream_t) stream);
+        if (rc != B200_ERR_UNSUPPORTED) return rc;
+    }
     return attn_decode(q, k_cache, v_cache_t, out, scratch, n_heads, kv_heads, head_dim, n_kv, k_row_stride, v_row_stride, scale, (cudaStream_t) stream);
+}
+int b200_add_rmsnorm_quant(int wtype, const float * x, const float * r, const float * w, float * x_out, float * y_out, void * qact, int64_t ne0, int64_t nrows,
+                           float eps, void * stream) {
+    return add_rmsnorm_quant(wtype, x, r, w, x_out, y_out, qact, ne0, nrows, eps, (cudaStream_t) stream);
+}
+int b200_rope_kv_store(float * q, const float * k, const float * v, const int32_t * pos, const float * freq_factors, void * k_cache, void * v_cache_t,
+                       int n_heads, int kv_heads, int head_dim, int mode, float freq_base, int64_t k_row_stride, int64_t v_row_stride, void * stream) {
+    return rope_kv_store(q, k, v, pos, freq_factors, k_cache, v_cache_t, n_heads, kv_heads, head_dim, mode, freq_base, k_row_stride, v_row_stride,
+                         (cudaStream_t) stream);
+}
+int b200_mul_mat_q_multi(int wtype, int mode, int nmat, const void * const * W, const int64_t * m, float * const * y, const int64_t * ldy,
+                         const float * const * bias, int64_t k, const void * qact, int64_t n, void * stream) {
+    return mul_mat_q_multi(wtype, mode, nmat, W, m, y, ldy, bias, k, qact, n, &g_tune, (cudaStream_t) stream);
 }
 int b200_kv_store(const float * k, const float * v, void * k_cache, void * v_cache_t, int kv_hidden, int64_t k_row_stride, int64_t v_row_stride, int pos,
                   void * stream) {

@@ -1,0 +1,376 @@
+// fused.cu — fused decode-step kernels.  Same arithmetic as the unfused ops (ops.cu / quantize.cu), fewer launches:
+//   add_rmsnorm_quant : [x += r] ; y = rms_norm(x) * w ; qact = Q(y)                (ADD + RMS_NORM + MUL + quantize)
+//   rope_kv_store     : RoPE(q) in place ; RoPE(k) -> K cache row ; v -> V cache column  (2 x ROPE + SET_ROWS + CPY)
+//   attn_scores2 / attn_softmax_pv : decode attention in two launches                    (7 graph nodes)
+// Every kernel signals launch_dependents at its top (so the next GEMV can become resident and prefetch weights) and
+// executes griddepcontrol.wait before touching data produced by its predecessor.
+#include "actlayout.cuh"
+#include "common.cuh"
+#include "kernels.h"
+
+#include <math.h>
+
+namespace b200 {
+
+__device__ __forceinline__ float blk_sum(float v, float * red) {
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    float t = (threadIdx.x < nw) ? red[threadIdx.x] : 0.0f;
+    if (warp == 0) t = warp_sum(t);
+    if (threadIdx.x == 0) red[0] = t;
+    __syncthreads();
+    return red[0];
+}
+__device__ __forceinline__ float blk_max(float v, float * red) {
+    v = warp_max(v);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    float t = (threadIdx.x < nw) ? red[threadIdx.x] : -INFINITY;
+    if (warp == 0) t = warp_max(t);
+    if (threadIdx.x == 0) red[0] = t;
+    __syncthreads();
+    return red[0];
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// add + rms_norm + mul + activation quantization.  One CTA per row; blockDim multiple of 64; thread t owns elements
+// 4t + 4*blockDim*j (j < J).  Arithmetic: rms_norm as ops.cu (reference ops.cpp:3710-3758), quantizers as quantize.cu
+// (reference ggml-quants.c:2555-2592 / arch/x86/quants.c:290-384) — bit-identical codes.
+// ------------------------------------------------------------------------------------------------------------------
+template <bool Q8K, int J>
+__global__ void __launch_bounds__(1024) add_rmsnorm_quant_kernel(const float * __restrict__ x, const float * __restrict__ r, const float * __restrict__ w,
+                                                                 float * __restrict__ x_out, float * __restrict__ y_out, uint8_t * __restrict__ qact,
+                                                                 int64_t ne0, float eps, size_t col_bytes) {
+    __shared__ float red[32];
+    __shared__ unsigned long long keys[32];
+    __shared__ float bmax[16];
+    pdl_launch_dependents();
+    pdl_wait();
+    const int t = threadIdx.x, T = blockDim.x;
+    const int64_t row = blockIdx.x;
+    const float * xr = x + row * ne0;
+    float v[J][4];
+    float ss = 0.0f;
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+        const int64_t e = 4 * (int64_t) t + 4 * (int64_t) T * j;
+        if (e < ne0) {
+            float4 a = *reinterpret_cast<const float4 *>(xr + e);
+            if (r) {
+                const float4 b = *reinterpret_cast<const float4 *>(r + row * ne0 + e);
+                a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+            }
+            if (x_out) *reinterpret_cast<float4 *>(x_out + row * ne0 + e) = a;
+            v[j][0] = a.x; v[j][1] = a.y; v[j][2] = a.z; v[j][3] = a.w;
+            ss = fmaf(a.x, a.x, ss); ss = fmaf(a.y, a.y, ss); ss = fmaf(a.z, a.z, ss); ss = fmaf(a.w, a.w, ss);
+        } else {
+            v[j][0] = v[j][1] = v[j][2] = v[j][3] = 0.0f;
+        }
+    }
+    ss = blk_sum(ss, red);
+    const float mean = ss / (float) ne0;
+    const float scale = 1.0f / sqrtf(mean + eps);
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+        const int64_t e = 4 * (int64_t) t + 4 * (int64_t) T * j;
+        if (e < ne0) {
+            const float4 ww = *reinterpret_cast<const float4 *>(w + e);
+            v[j][0] = (v[j][0] * scale) * ww.x; v[j][1] = (v[j][1] * scale) * ww.y;
+            v[j][2] = (v[j][2] * scale) * ww.z; v[j][3] = (v[j][3] * scale) * ww.w;
+            if (y_out) *reinterpret_cast<float4 *>(y_out + row * ne0 + e) = make_float4(v[j][0], v[j][1], v[j][2], v[j][3]);
+        }
+    }
+    if (!qact) return;
+    const ActLayout L = act_layout(Q8K, ne0);
+    uint8_t * base = qact + (size_t) row * col_bytes;
+    const int lane = t & 31, warp = t >> 5;
+    if (Q8K) {
+        float * dd = (float *) (base + L.d_off);
+        int16_t * bs = (int16_t *) (base + L.bs_off);
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            const int64_t e = 4 * (int64_t) t + 4 * (int64_t) T * j;
+            const bool on = e < ne0;
+            // first-occurrence argmax |v| over the 256-element block (= 64 consecutive threads = 2 warps)
+            unsigned long long key = 0ull;
+            if (on) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const unsigned long long kk = ((unsigned long long) __float_as_uint(fabsf(v[j][i])) << 32) | (unsigned) (255 - (4 * (t & 63) + i));
+                    key = kk > key ? kk : key;
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+                key = other > key ? other : key;
+            }
+            __syncthreads();
+            if (lane == 0) keys[warp] = key;
+            __syncthreads();
+            const unsigned long long k2 = keys[warp ^ 1];
+            key = k2 > key ? k2 : key;
+            const int idx = 255 - (int) (key & 0xffffffffu);
+            if (on && (idx >> 2) == (t & 63)) bmax[t >> 6] = v[j][idx & 3];
+            __syncthreads();
+            if (on) {
+                const float mx = bmax[t >> 6];
+                int q[4] = {0, 0, 0, 0};
+                float dv = 0.0f;
+                if (mx != 0.0f) {
+                    const float iscale = __fdiv_rn(-127.f, mx);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) q[i] = min(127, __float2int_rn(__fmul_rn(iscale, v[j][i])));
+                    dv = __fdiv_rn(1.0f, iscale);
+                }
+                const uint32_t packed = (uint32_t) (q[0] & 0xff) | ((uint32_t) (q[1] & 0xff) << 8) | ((uint32_t) (q[2] & 0xff) << 16) | ((uint32_t) (q[3] & 0xff) << 24);
+                *reinterpret_cast<uint32_t *>(base + act_qs_off_q8k(e)) = packed;
+                int s = q[0] + q[1] + q[2] + q[3];
+                s += __shfl_xor_sync(0xffffffffu, s, 1);
+                s += __shfl_xor_sync(0xffffffffu, s, 2);
+                s += __shfl_xor_sync(0xffffffffu, s, 4);
+                if ((t & 7) == 0) bs[e >> 5] = (int16_t) s;
+                if ((t & 63) == 0) dd[e >> 8] = dv;
+            }
+        }
+        // zero the padding of the last (partial) 1024-element group
+        for (int64_t e = ne0 + 4 * (int64_t) t; e < L.qs_bytes; e += 4 * (int64_t) T) *reinterpret_cast<uint32_t *>(base + act_qs_off_q8k(e)) = 0u;
+    } else {
+        float * dd = (float *) (base + L.d_off);
+        int * bs = (int *) (base + L.bs_off);
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            const int64_t e = 4 * (int64_t) t + 4 * (int64_t) T * j;
+            const bool on = e < ne0;
+            float amax = on ? fmaxf(fmaxf(fabsf(v[j][0]), fabsf(v[j][1])), fmaxf(fabsf(v[j][2]), fabsf(v[j][3]))) : 0.0f;
+            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
+            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 4));
+            const float dv = __fdiv_rn(amax, 127.f);
+            const float id = (amax != 0.0f) ? __fdiv_rn(127.f, amax) : 0.0f;
+            int q[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) q[i] = __float2int_rn(__fmul_rn(v[j][i], id));
+            int s = q[0] + q[1] + q[2] + q[3];
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            s += __shfl_xor_sync(0xffffffffu, s, 4);
+            if (on) {
+                const uint32_t packed = (uint32_t) (q[0] & 0xff) | ((uint32_t) (q[1] & 0xff) << 8) | ((uint32_t) (q[2] & 0xff) << 16) | ((uint32_t) (q[3] & 0xff) << 24);
+                *reinterpret_cast<uint32_t *>(base + act_qs_off_q80(e)) = packed;
+                if ((t & 7) == 0) { dd[e >> 5] = __half2float(__float2half_rn(dv)); bs[e >> 5] = s; }
+            }
+        }
+    }
+}
+
+int add_rmsnorm_quant(int wtype, const float * x, const float * r, const float * w, float * x_out, float * y_out, void * qact, int64_t ne0, int64_t nrows,
+                      float eps, cudaStream_t st) {
+    if (nrows <= 0) return B200_OK;
+    if (ne0 % 256 || ne0 > 20480) return B200_ERR_UNSUPPORTED;
+    const bool q8k = wtype == B200_TYPE_Q4_K;
+    if (qact && !q8k && wtype != B200_TYPE_Q4_0 && wtype != B200_TYPE_Q8_0) return B200_ERR_UNSUPPORTED;
+    int threads = (int) (ne0 / 4);
+    if (threads > 1024) threads = 1024;
+    const int J = (int) ((ne0 / 4 + threads - 1) / threads);
+    const size_t cb = qact ? qact_col_bytes(wtype, ne0) : 0;
+#define B200_ARQ(J_)                                                                                                                          \
+    if (J == J_) {                                                                                                                            \
+        if (q8k) add_rmsnorm_quant_kernel<true, J_><<<(unsigned) nrows, threads, 0, st>>>(x, r, w, x_out, y_out, (uint8_t *) qact, ne0, eps, cb); \
+        else add_rmsnorm_quant_kernel<false, J_><<<(unsigned) nrows, threads, 0, st>>>(x, r, w, x_out, y_out, (uint8_t *) qact, ne0, eps, cb);     \
+        return (int) cudaGetLastError();                                                                                                      \
+    }
+    B200_ARQ(1) B200_ARQ(2) B200_ARQ(3) B200_ARQ(4) B200_ARQ(5)
+#undef B200_ARQ
+    return B200_ERR_UNSUPPORTED;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// RoPE(q), RoPE(k) + KV-cache append for ONE token.  grid = n_heads + kv_heads, block = head_dim/2 threads.
+// angle recurrence exactly as rope_kernel (ops.cu).  mode 0 = adjacent pairs, 2 = NEOX.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void rope_kv_store_kernel(float * __restrict__ q, const float * __restrict__ k, const float * __restrict__ v, const int32_t * __restrict__ pos,
+                                     const float * __restrict__ ff, __half * __restrict__ kc, __half * __restrict__ vc, int n_heads, int kv_heads, int hd,
+                                     int mode, float theta_scale, int64_t k_row_stride, int64_t v_row_stride) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int i = threadIdx.x, half = hd / 2;
+    const int p = pos[0];
+    float theta = (float) p;
+    for (int j = 0; j < i; ++j) theta *= theta_scale;
+    const float th = theta / (ff ? ff[i] : 1.0f);
+    const float c = cosf(th), s = sinf(th);
+    const int i0 = (mode == 0) ? 2 * i : i, i1 = (mode == 0) ? 2 * i + 1 : i + half;
+    const int b = blockIdx.x;
+    if (b < n_heads) {
+        float * h = q + (int64_t) b * hd;
+        const float x0 = h[i0], x1 = h[i1];
+        h[i0] = x0 * c - x1 * s;
+        h[i1] = x0 * s + x1 * c;
+    } else {
+        const int g = b - n_heads;
+        const float * h = k + (int64_t) g * hd;
+        const float x0 = h[i0], x1 = h[i1];
+        __half * krow = kc + (int64_t) p * k_row_stride + (int64_t) g * hd;
+        krow[i0] = __float2half_rn(x0 * c - x1 * s);
+        krow[i1] = __float2half_rn(x0 * s + x1 * c);
+        const float * vv = v + (int64_t) g * hd;
+        vc[((int64_t) g * hd + i0) * v_row_stride + p] = __float2half_rn(vv[i0]);
+        vc[((int64_t) g * hd + i1) * v_row_stride + p] = __float2half_rn(vv[i1]);
+    }
+}
+int rope_kv_store(float * q, const float * k, const float * v, const int32_t * pos, const float * ff, void * kc, void * vc, int n_heads, int kv_heads,
+                  int head_dim, int mode, float freq_base, int64_t k_row_stride, int64_t v_row_stride, cudaStream_t st) {
+    if (mode != 0 && mode != 2) return B200_ERR_UNSUPPORTED;
+    if (head_dim % 2 || head_dim > 2048) return B200_ERR_ARG;
+    const float theta_scale = powf(freq_base, -2.0f / head_dim);
+    rope_kv_store_kernel<<<(unsigned) (n_heads + kv_heads), head_dim / 2, 0, st>>>(q, k, v, pos, ff, (__half *) kc, (__half *) vc, n_heads, kv_heads, head_dim,
+                                                                                  mode, theta_scale, k_row_stride, v_row_stride);
+    return (int) cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// decode attention, 2 launches.  Layouts / semantics as ops.cu attn_* (reference src/layers.cpp:2541-2561).
+// ------------------------------------------------------------------------------------------------------------------
+// scores[h][t] = scale * sum_d K[t][g][d] * f16(q[h][d]);  a row (HD halves) is covered by HD/8 lanes with 16-byte loads
+template <int HD, int GQA>
+__global__ void __launch_bounds__(256) attn_scores2_kernel(const float * __restrict__ q, const __half * __restrict__ kc, float * __restrict__ scores, int n_kv,
+                                                           int64_t k_row_stride, float scale, int64_t s_stride) {
+    constexpr int LPR = HD / 8;    // lanes per row
+    constexpr int RPW = 32 / LPR;  // rows per warp iteration
+    pdl_launch_dependents();
+    pdl_wait();
+    const int g = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int part = lane % LPR, rsel = lane / LPR;
+    float qv[GQA][8];
+#pragma unroll
+    for (int h = 0; h < GQA; ++h)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) qv[h][e] = __half2float(__float2half_rn(q[(int64_t) (g * GQA + h) * HD + part * 8 + e]));
+    const int t_end = min(n_kv, (int) (blockIdx.x + 1) * 128);
+    for (int t0 = blockIdx.x * 128 + warp * RPW; t0 < t_end; t0 += 8 * RPW) {
+        const int t = t0 + rsel;
+        float kv[8];
+        if (t < t_end) {
+            const uint4 raw = *reinterpret_cast<const uint4 *>(kc + (int64_t) t * k_row_stride + (int64_t) g * HD + part * 8);
+            const __half2 * hp = reinterpret_cast<const __half2 *>(&raw);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { kv[2 * e] = __low2float(hp[e]); kv[2 * e + 1] = __high2float(hp[e]); }
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) kv[e] = 0.0f;
+        }
+#pragma unroll
+        for (int h = 0; h < GQA; ++h) {
+            float s = 0.0f;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) s = fmaf(kv[e], qv[h][e], s);
+#pragma unroll
+            for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (part == 0 && t < t_end) scores[(int64_t) (g * GQA + h) * s_stride + t] = s * scale;
+        }
+    }
+}
+
+// softmax (per head, recomputed by every CTA of the KV group: 16 K expf, trivial) fused with out = V . P
+// grid (HD/8, kv_heads), block 256 = 8 warps, one V^T channel row per warp; P of the group's GQA heads lives in smem.
+template <int GQA>
+__global__ void __launch_bounds__(256) attn_softmax_pv_kernel(const float * __restrict__ scores, const __half * __restrict__ vc, float * __restrict__ out,
+                                                              int n_kv, int head_dim, int64_t v_row_stride, int64_t s_stride) {
+    extern __shared__ float P[];  // [GQA][s_stride]
+    __shared__ float red[32];
+    pdl_launch_dependents();
+    pdl_wait();
+    const int g = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int h = 0; h < GQA; ++h) {
+        const float * s = scores + (int64_t) (g * GQA + h) * s_stride;
+        float * ph = P + (int64_t) h * s_stride;
+        float mx = -INFINITY;
+        for (int i = threadIdx.x; i < n_kv; i += blockDim.x) { const float v = s[i]; ph[i] = v; mx = fmaxf(mx, v); }
+        mx = blk_max(mx, red);
+        float sum = 0.0f;
+        for (int i = threadIdx.x; i < n_kv; i += blockDim.x) { const float e = expf(ph[i] - mx); ph[i] = e; sum += e; }
+        sum = blk_sum(sum, red);
+        const float inv = 1.0f / sum;
+        for (int i = threadIdx.x; i < n_kv; i += blockDim.x) ph[i] = __half2float(__float2half_rn(ph[i] * inv));
+        for (int i = n_kv + threadIdx.x; i < s_stride; i += blockDim.x) ph[i] = 0.0f;
+    }
+    __syncthreads();
+    const int d = blockIdx.x * 8 + warp;
+    const int ch = g * head_dim + d;
+    const __half * vr = vc + (int64_t) ch * v_row_stride;
+    float acc[GQA];
+#pragma unroll
+    for (int h = 0; h < GQA; ++h) acc[h] = 0.0f;
+    const int n8 = n_kv & ~7;
+    for (int t = lane * 8; t < n8; t += 256) {
+        const uint4 raw = *reinterpret_cast<const uint4 *>(vr + t);
+        const __half2 * hp = reinterpret_cast<const __half2 *>(&raw);
+        float vv[8];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { vv[2 * e] = __low2float(hp[e]); vv[2 * e + 1] = __high2float(hp[e]); }
+#pragma unroll
+        for (int h = 0; h < GQA; ++h) {
+            const float4 p0 = *reinterpret_cast<const float4 *>(P + (int64_t) h * s_stride + t);
+            const float4 p1 = *reinterpret_cast<const float4 *>(P + (int64_t) h * s_stride + t + 4);
+            acc[h] = fmaf(vv[0], p0.x, acc[h]); acc[h] = fmaf(vv[1], p0.y, acc[h]); acc[h] = fmaf(vv[2], p0.z, acc[h]); acc[h] = fmaf(vv[3], p0.w, acc[h]);
+            acc[h] = fmaf(vv[4], p1.x, acc[h]); acc[h] = fmaf(vv[5], p1.y, acc[h]); acc[h] = fmaf(vv[6], p1.z, acc[h]); acc[h] = fmaf(vv[7], p1.w, acc[h]);
+        }
+    }
+    if (lane < n_kv - n8) {
+        const int t = n8 + lane;
+        const float vx = __half2float(vr[t]);
+#pragma unroll
+        for (int h = 0; h < GQA; ++h) acc[h] = fmaf(vx, P[(int64_t) h * s_stride + t], acc[h]);
+    }
+#pragma unroll
+    for (int h = 0; h < GQA; ++h) {
+        const float s = warp_sum(acc[h]);
+        if (lane == 0) out[(int64_t) (g * GQA + h) * head_dim + d] = s;
+    }
+}
+
+template <int HD, int GQA>
+static int attn_decode2_t(const float * q, const void * kc, const void * vc, float * out, float * scratch, int n_kv, int kv_heads, int64_t k_row_stride,
+                          int64_t v_row_stride, float scale, cudaStream_t st) {
+    const int64_t s_stride = (n_kv + 7) & ~7;
+    dim3 g1((unsigned) ((n_kv + 127) / 128), (unsigned) kv_heads);
+    attn_scores2_kernel<HD, GQA><<<g1, 256, 0, st>>>(q, (const __half *) kc, scratch, n_kv, k_row_stride, scale, s_stride);
+    const size_t smem = (size_t) GQA * s_stride * 4;
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(attn_softmax_pv_kernel<GQA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (smem > 200 * 1024 ? smem : 200 * 1024));
+        if (e != cudaSuccess) return (int) e;
+        configured = smem > 200 * 1024 ? smem : 200 * 1024;
+    }
+    if (smem > 227 * 1024) return B200_ERR_UNSUPPORTED;
+    dim3 g2((unsigned) (HD / 8), (unsigned) kv_heads);
+    attn_softmax_pv_kernel<GQA><<<g2, 256, smem, st>>>(scratch, (const __half *) vc, out, n_kv, HD, v_row_stride, s_stride);
+    return (int) cudaGetLastError();
+}
+
+size_t attn_decode2_scratch_bytes(int n_heads, int n_kv) { return (size_t) n_heads * (size_t) ((n_kv + 7) & ~7) * 4; }
+
+int attn_decode2(const float * q, const void * kc, const void * vc, float * out, float * scratch, int n_heads, int kv_heads, int head_dim, int n_kv,
+                 int64_t k_row_stride, int64_t v_row_stride, float scale, cudaStream_t st) {
+    if (n_kv <= 0) return B200_OK;
+    if (n_heads % kv_heads) return B200_ERR_ARG;
+    if ((k_row_stride % 8) || (v_row_stride % 8)) return B200_ERR_UNSUPPORTED;  // 16-byte row loads
+    const int gqa = n_heads / kv_heads;
+#define B200_ATTN2(HD_, G_) \
+    if (head_dim == HD_ && gqa == G_) return attn_decode2_t<HD_, G_>(q, kc, vc, out, scratch, n_kv, kv_heads, k_row_stride, v_row_stride, scale, st);
+    B200_ATTN2(128, 4) B200_ATTN2(128, 7) B200_ATTN2(128, 1) B200_ATTN2(128, 8) B200_ATTN2(128, 2)
+    B200_ATTN2(64, 8) B200_ATTN2(64, 4) B200_ATTN2(64, 2) B200_ATTN2(64, 1)
+#undef B200_ATTN2
+    return B200_ERR_UNSUPPORTED;
+}
+
+}  // namespace b200

@@ -177,28 +177,42 @@ struct FmtQ80 {
 
 // ======================================================================================================
 // The kernel: every warp is an independent bulk-copy pipeline over its own contiguous row range.
+//   MODE 0 (concat): up to 3 matrices that share the activation vector are treated as one tall matrix (QKV in one launch);
+//                    every m_i is a multiple of RG so a row group never straddles two matrices.
+//   MODE 1 (paired): two matrices of equal shape (gate, up); a row group holds RG/2 gate rows and the SAME RG/2 up rows,
+//                    and the epilogue writes silu(gate.x) * (up.x)  (SwiGLU of BaseMLP::forward, src/layers.cpp:2475-2483).
 // ======================================================================================================
-struct GemvParams {
+struct GemvMat {
     const uint8_t * W;
-    const uint8_t * qact;  // global, NC columns back to back
     float * y;
     const float * bias;
-    int64_t k, m, ldy;
-    int n;       // valid columns (<= NC)
-    int nunits;  // k / 256
-    int ks;      // units per stage (== nunits -> whole rows per stage, one bulk copy)
+    int64_t m;    // rows
+    int64_t ldy;  // column stride of y
+};
+struct GemvParams {
+    GemvMat mat[3];
+    int nmat;
+    const uint8_t * qact;  // global, NC columns back to back
+    int64_t k, m_total;    // MODE 0: sum of m_i ; MODE 1: m of one matrix (number of pairs)
+    int n;                 // valid columns (<= NC)
+    int nunits;            // k / 256
+    int ks;                // units per stage (== nunits -> whole rows per stage)
     int stages;
     uint32_t act_col_bytes;
 };
 
-template <class F, int RG, int NC>
+template <class F, int RG, int NC, int MODE>
 __global__ void __launch_bounds__(512) gemv_q_kernel(const GemvParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
+    pdl_launch_dependents();  // let the next kernel in the stream become resident and prefetch its own weights
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int nwarps = blockDim.x >> 5;
 
     constexpr int UNIT = F::A_UNIT + F::B_UNIT;
+    constexpr int HALF = RG / 2;
+    constexpr int GROUP = (MODE == 1) ? HALF : RG;  // logical rows advanced per row group
+    static_assert(MODE == 0 || RG >= 2, "paired mode needs RG >= 2");
     const bool whole = (p.ks == p.nunits);
     const uint32_t act_bytes = (uint32_t) al16((int64_t) p.act_col_bytes * NC);
     const uint32_t stage_bytes = (uint32_t) RG * p.ks * UNIT;
@@ -211,14 +225,30 @@ __global__ void __launch_bounds__(512) gemv_q_kernel(const GemvParams p) {
     uint64_t * bars = reinterpret_cast<uint64_t *>(smem + act_bytes) + (size_t) warp * p.stages;
     uint8_t * ring = smem + act_bytes + al16((int64_t) nwarps * p.stages * 8) + (size_t) warp * p.stages * stage_bytes;
 
-    // ---- this warp's rows and work items (row-group x k-segment)
+    // ---- this warp's logical rows (aligned to GROUP so groups never straddle a matrix) and its work items
     const int64_t gw = (int64_t) blockIdx.x * nwarps + warp;
     const int64_t GW = (int64_t) gridDim.x * nwarps;
-    const int64_t r0 = p.m * gw / GW, r1 = p.m * (gw + 1) / GW;
+    const int64_t ngrp_total = (p.m_total + GROUP - 1) / GROUP;
+    const int64_t r0 = (ngrp_total * gw / GW) * GROUP, r1 = min(p.m_total, (ngrp_total * (gw + 1) / GW) * GROUP);
     const int nseg = (p.nunits + p.ks - 1) / p.ks;
-    const int ngroups = (int) ((r1 - r0 + RG - 1) / RG);
+    const int ngroups = (int) ((r1 - r0 + GROUP - 1) / GROUP);
     const int nitems = ngroups * nseg;
     const int64_t row_bytes = (int64_t) p.nunits * UNIT;
+
+    // stage row i of the group starting at logical row `row0` -> global pointer of that weight row
+    auto row_src = [&](int64_t row0, int i) -> const uint8_t * {
+        if (MODE == 1) {
+            return (i < HALF) ? p.mat[0].W + (row0 + i) * row_bytes : p.mat[1].W + (row0 + i - HALF) * row_bytes;
+        } else {
+            int64_t r = row0 + i;
+            if (p.nmat > 1 && r >= p.mat[0].m) {
+                r -= p.mat[0].m;
+                if (p.nmat > 2 && r >= p.mat[1].m) return p.mat[2].W + (r - p.mat[1].m) * row_bytes;
+                return p.mat[1].W + r * row_bytes;
+            }
+            return p.mat[0].W + r * row_bytes;
+        }
+    };
 
     if (lane == 0) {
         for (int s = 0; s < p.stages; ++s) mbar_init(&bars[s], 1);
@@ -232,19 +262,29 @@ __global__ void __launch_bounds__(512) gemv_q_kernel(const GemvParams p) {
     auto issue = [&](int it) {  // lane 0 only
         const int s = it % p.stages;
         const int grp = it / nseg, seg = it - grp * nseg;
-        const int64_t row0 = r0 + (int64_t) grp * RG;
-        const int nr = (int) min((int64_t) RG, r1 - row0);
+        const int64_t row0 = r0 + (int64_t) grp * GROUP;
+        const int nlog = (int) min((int64_t) GROUP, r1 - row0);  // valid logical rows (pairs in MODE 1)
         uint8_t * st = ring + (size_t) s * stage_bytes;
         if (whole) {
-            const uint32_t bytes = (uint32_t) (nr * row_bytes);
-            mbar_arrive_expect_tx(&bars[s], bytes);
-            bulk_g2s_hint(st, p.W + row0 * row_bytes, bytes, &bars[s], pol);
+            if (MODE == 1) {
+                const uint32_t bytes = (uint32_t) (nlog * row_bytes);
+                mbar_arrive_expect_tx(&bars[s], 2 * bytes);
+                bulk_g2s_hint(st, row_src(row0, 0), bytes, &bars[s], pol);
+                bulk_g2s_hint(st + (size_t) HALF * rsA, row_src(row0, HALF), bytes, &bars[s], pol);
+            } else {
+                const uint32_t bytes = (uint32_t) (nlog * row_bytes);
+                mbar_arrive_expect_tx(&bars[s], bytes);
+                bulk_g2s_hint(st, row_src(row0, 0), bytes, &bars[s], pol);
+            }
         } else {
             const int u0 = seg * p.ks;
             const int nu = min(p.ks, p.nunits - u0);
-            mbar_arrive_expect_tx(&bars[s], (uint32_t) nr * nu * UNIT);
-            for (int r = 0; r < nr; ++r) {
-                const uint8_t * grow = p.W + (row0 + r) * row_bytes;
+            const int nrows = (MODE == 1) ? 2 * nlog : nlog;
+            mbar_arrive_expect_tx(&bars[s], (uint32_t) nrows * nu * UNIT);
+            for (int r = 0; r < RG; ++r) {
+                const bool valid = (MODE == 1) ? ((r < HALF ? r : r - HALF) < nlog) : (r < nlog);
+                if (!valid) continue;
+                const uint8_t * grow = row_src(row0, r);
                 bulk_g2s_hint(st + (size_t) r * rsA, grow + (size_t) u0 * F::A_UNIT, (uint32_t) nu * F::A_UNIT, &bars[s], pol);
                 if (F::B_UNIT)
                     bulk_g2s_hint(st + offB + (size_t) r * rsB, grow + (size_t) p.nunits * F::A_UNIT + (size_t) u0 * F::B_UNIT,
@@ -268,7 +308,6 @@ __global__ void __launch_bounds__(512) gemv_q_kernel(const GemvParams p) {
         for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = src[i];
     }
     __syncthreads();
-    pdl_launch_dependents();
 
     const ActLayout L = act_layout(F::Q8K, p.k);
     constexpr int LPU = F::LPU;
@@ -281,8 +320,8 @@ __global__ void __launch_bounds__(512) gemv_q_kernel(const GemvParams p) {
         const int s = it % p.stages;
         const uint32_t parity = (uint32_t) (it / p.stages) & 1u;
         const int grp = it / nseg, seg = it - grp * nseg;
-        const int64_t row0 = r0 + (int64_t) grp * RG;
-        const int nr = (int) min((int64_t) RG, r1 - row0);
+        const int64_t row0 = r0 + (int64_t) grp * GROUP;
+        const int nlog = (int) min((int64_t) GROUP, r1 - row0);
         const int u0 = seg * p.ks;
         const int nu = min(p.ks, p.nunits - u0);
         if (seg == 0) {
@@ -299,7 +338,8 @@ __global__ void __launch_bounds__(512) gemv_q_kernel(const GemvParams p) {
                 F::load_act(act_s, L, u0 + u, g, A);
 #pragma unroll
                 for (int r = 0; r < RG; ++r) {
-                    if (r < nr) {
+                    const bool valid = (MODE == 1) ? ((r < HALF ? r : r - HALF) < nlog) : (r < nlog);
+                    if (valid) {
                         typename F::Wt Wr;
                         F::load_w(st + (size_t) r * rsA, st + offB + (size_t) r * rsB, u, g, Wr);
                         acc[r][0] = F::dot(Wr, A, acc[r][0]);
@@ -308,7 +348,8 @@ __global__ void __launch_bounds__(512) gemv_q_kernel(const GemvParams p) {
             } else {
 #pragma unroll
                 for (int r = 0; r < RG; ++r) {
-                    if (r < nr) {
+                    const bool valid = (MODE == 1) ? ((r < HALF ? r : r - HALF) < nlog) : (r < nlog);
+                    if (valid) {
                         typename F::Wt Wr;
                         F::load_w(st + (size_t) r * rsA, st + offB + (size_t) r * rsB, u, g, Wr);
 #pragma unroll
@@ -325,15 +366,43 @@ __global__ void __launch_bounds__(512) gemv_q_kernel(const GemvParams p) {
         if (lane == 0 && it + p.stages < nitems) issue(it + p.stages);
 
         if (seg == nseg - 1) {
+            // full butterfly: every lane ends up with every sum
 #pragma unroll
-            for (int r = 0; r < RG; ++r) {
+            for (int r = 0; r < RG; ++r)
 #pragma unroll
-                for (int c = 0; c < NC; ++c) {
-                    const float v = warp_sum(acc[r][c]);
-                    if (lane == 0 && r < nr && c < p.n) {
-                        float o = v;
-                        if (p.bias) o += p.bias[row0 + r];
-                        p.y[(int64_t) c * p.ldy + row0 + r] = o;
+                for (int c = 0; c < NC; ++c) acc[r][c] = warp_sum(acc[r][c]);
+            if (lane == 0) {
+                if (MODE == 1) {
+#pragma unroll
+                    for (int q = 0; q < HALF; ++q) {
+                        if (q < nlog) {
+#pragma unroll
+                            for (int c = 0; c < NC; ++c) {
+                                if (c < p.n) {
+                                    const float gv = acc[q][c], uv = acc[HALF + q][c];
+                                    p.mat[0].y[(int64_t) c * p.mat[0].ldy + row0 + q] = (gv / (1.0f + expf(-gv))) * uv;
+                                }
+                            }
+                        }
+                    }
+                } else {
+                    // the whole group lies in one matrix
+                    int mi = 0;
+                    int64_t lrow = row0;
+                    if (p.nmat > 1 && lrow >= p.mat[0].m) { lrow -= p.mat[0].m; mi = 1; if (p.nmat > 2 && lrow >= p.mat[1].m) { lrow -= p.mat[1].m; mi = 2; } }
+                    const GemvMat & M = p.mat[mi];
+#pragma unroll
+                    for (int r = 0; r < RG; ++r) {
+                        if (r < nlog) {
+#pragma unroll
+                            for (int c = 0; c < NC; ++c) {
+                                if (c < p.n) {
+                                    float o = acc[r][c];
+                                    if (M.bias) o += M.bias[lrow + r];
+                                    M.y[(int64_t) c * M.ldy + lrow + r] = o;
+                                }
+                            }
+                        }
                     }
                 }
             }
@@ -360,9 +429,9 @@ static int env_int(const char * name, int dflt) {
     return v ? atoi(v) : dflt;
 }
 
-template <class F, int RG, int NC>
+template <class F, int RG, int NC, int MODE>
 static int launch(const GemvParams & p, int warps, int grid, size_t smem_bytes, cudaStream_t st) {
-    auto kern = gemv_q_kernel<F, RG, NC>;
+    auto kern = gemv_q_kernel<F, RG, NC, MODE>;
     static size_t configured = 0;  // per template instantiation
     if (smem_bytes > configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_bytes);
@@ -383,40 +452,31 @@ static int launch(const GemvParams & p, int warps, int grid, size_t smem_bytes, 
     return (int) cudaLaunchKernelEx(&cfg, kern, p);
 }
 
-template <class F, int RG>
-static int launch_nc(const GemvParams & p, int nc, int warps, int grid, size_t smem, cudaStream_t st) {
-    switch (nc) {
-        case 1: return launch<F, RG, 1>(p, warps, grid, smem, st);
-        case 2: return launch<F, RG, 2>(p, warps, grid, smem, st);
-        case 4: return launch<F, RG, 4>(p, warps, grid, smem, st);
-        default: return B200_ERR_ARG;
-    }
+template <class F, int MODE>
+static int launch_rg_nc(const GemvParams & p, int rg, int nc, int warps, int grid, size_t smem, cudaStream_t st) {
+#define B200_CASE(RG_, NC_) if (rg == RG_ && nc == NC_) return launch<F, RG_, NC_, MODE>(p, warps, grid, smem, st);
+    if constexpr (MODE == 0) { B200_CASE(1, 1) B200_CASE(1, 2) B200_CASE(1, 4) }
+    B200_CASE(2, 1) B200_CASE(2, 2) B200_CASE(2, 4) B200_CASE(4, 1) B200_CASE(4, 2) B200_CASE(4, 4)
+#undef B200_CASE
+    return B200_ERR_ARG;
 }
 
-template <class F>
-static int launch_rg(const GemvParams & p, int rg, int nc, int warps, int grid, size_t smem, cudaStream_t st) {
-    switch (rg) {
-        case 1: return launch_nc<F, 1>(p, nc, warps, grid, smem, st);
-        case 2: return launch_nc<F, 2>(p, nc, warps, grid, smem, st);
-        case 4: return launch_nc<F, 4>(p, nc, warps, grid, smem, st);
-        default: return B200_ERR_ARG;
-    }
-}
-
-static int launch_fmt(int wtype, const GemvParams & p, int rg, int nc, int warps, int grid, size_t smem, cudaStream_t st) {
+static int launch_fmt(int wtype, int mode, const GemvParams & p, int rg, int nc, int warps, int grid, size_t smem, cudaStream_t st) {
     switch (wtype) {
-        case B200_TYPE_Q4_K: return launch_rg<FmtQ4K>(p, rg, nc, warps, grid, smem, st);
-        case B200_TYPE_Q4_0: return launch_rg<FmtQ40>(p, rg, nc, warps, grid, smem, st);
-        case B200_TYPE_Q8_0: return launch_rg<FmtQ80>(p, rg, nc, warps, grid, smem, st);
+        case B200_TYPE_Q4_K: return mode ? launch_rg_nc<FmtQ4K, 1>(p, rg, nc, warps, grid, smem, st) : launch_rg_nc<FmtQ4K, 0>(p, rg, nc, warps, grid, smem, st);
+        case B200_TYPE_Q4_0: return mode ? launch_rg_nc<FmtQ40, 1>(p, rg, nc, warps, grid, smem, st) : launch_rg_nc<FmtQ40, 0>(p, rg, nc, warps, grid, smem, st);
+        case B200_TYPE_Q8_0: return mode ? launch_rg_nc<FmtQ80, 1>(p, rg, nc, warps, grid, smem, st) : launch_rg_nc<FmtQ80, 0>(p, rg, nc, warps, grid, smem, st);
         default: return B200_ERR_UNSUPPORTED;
     }
 }
 
-// y[c*ldy + i] = sum_k W[i,k] * x_c[k]   for c < n (processed in column groups of 4 / 2 / 1)
-int mul_mat_q(int wtype, const void * W, int64_t k, int64_t m, const void * qact, int64_t n, float * y, int64_t ldy, const float * bias,
-              const GemvTuning * tune, cudaStream_t st) {
-    if (k <= 0 || m <= 0 || n <= 0) return B200_OK;
-    if (k % 256) return B200_ERR_UNSUPPORTED;
+// mode 0: y_i[c*ldy_i + r] = sum_k W_i[r,k] x_c[k] (+ bias_i[r]) for up to 3 matrices sharing x  (QKV)
+// mode 1: y_0[c*ldy_0 + r] = silu(W_0[r,:].x_c) * (W_1[r,:].x_c)                                   (gate/up)
+int mul_mat_q_multi(int wtype, int mode, int nmat, const void * const * W, const int64_t * m, float * const * y, const int64_t * ldy,
+                    const float * const * bias, int64_t k, const void * qact, int64_t n, const GemvTuning * tune, cudaStream_t st) {
+    if (k <= 0 || n <= 0 || nmat <= 0) return B200_OK;
+    if (k % 256 || nmat > 3) return B200_ERR_UNSUPPORTED;
+    if (mode == 1 && (nmat != 2 || m[0] != m[1])) return B200_ERR_ARG;
     int unit;
     switch (wtype) {
         case B200_TYPE_Q4_K: unit = FmtQ4K::A_UNIT + FmtQ4K::B_UNIT; break;
@@ -427,6 +487,10 @@ int mul_mat_q(int wtype, const void * W, int64_t k, int64_t m, const void * qact
     const size_t acb = qact_col_bytes(wtype, k);
     const int nunits = (int) (k / 256);
     const int sms = sm_count();
+    int64_t m_total = 0, m_phys = 0;
+    for (int i = 0; i < nmat; ++i) m_phys += m[i];
+    m_total = mode == 1 ? m[0] : m_phys;
+    if (m_total <= 0) return B200_OK;
 
     int64_t c0 = 0;
     while (c0 < n) {
@@ -434,17 +498,23 @@ int mul_mat_q(int wtype, const void * W, int64_t k, int64_t m, const void * qact
         const int nc = left >= 4 ? 4 : (left >= 2 ? 2 : 1);
 
         GemvTuning t;
-        t.rg = tune && tune->rg ? tune->rg : env_int("B200_GEMV_RG", 2);
+        t.rg = tune && tune->rg ? tune->rg : env_int("B200_GEMV_RG", 4);
         t.warps = tune && tune->warps ? tune->warps : env_int("B200_GEMV_WARPS", 8);
-        t.stages = tune && tune->stages ? tune->stages : env_int("B200_GEMV_STAGES", 4);
+        t.stages = tune && tune->stages ? tune->stages : env_int("B200_GEMV_STAGES", 3);
         t.ks = tune && tune->ks ? tune->ks : env_int("B200_GEMV_KS", 16);
         t.grid = tune && tune->grid ? tune->grid : env_int("B200_GEMV_GRID", 0);
         if (t.ks > nunits) t.ks = nunits;
         // few rows: keep at least one row-group per warp
-        while (t.rg > 1 && m < (int64_t) sms * t.warps * t.rg / 2) t.rg >>= 1;
+        while (t.rg > 1 && m_phys < (int64_t) sms * t.warps * t.rg / 2) t.rg >>= 1;
+        if (mode == 1 && t.rg < 2) t.rg = 2;
+        if (mode == 0) {  // groups must not straddle matrices
+            for (int i = 0; i + 1 < nmat; ++i) while (t.rg > 1 && m[i] % t.rg) t.rg >>= 1;
+        }
+        if (nc > 1 && t.rg > 2) t.rg = 2;  // register budget of the multi-column variants
+        const int group = mode == 1 ? t.rg / 2 : t.rg;
         int grid = t.grid > 0 ? t.grid : sms;
         {
-            const int64_t max_warps = (m + t.rg - 1) / t.rg;
+            const int64_t max_warps = (m_total + group - 1) / group;
             const int64_t max_grid = (max_warps + t.warps - 1) / t.warps;
             if (grid > max_grid) grid = (int) max_grid;
         }
@@ -461,21 +531,38 @@ int mul_mat_q(int wtype, const void * W, int64_t k, int64_t m, const void * qact
         if (smem_for(t) > limit) return B200_ERR_UNSUPPORTED;
 
         GemvParams p;
-        p.W = (const uint8_t *) W;
+        p.nmat = nmat;
+        for (int i = 0; i < 3; ++i) {
+            if (i < nmat) {
+                p.mat[i].W = (const uint8_t *) W[i];
+                p.mat[i].y = y[i] ? y[i] + c0 * ldy[i] : nullptr;
+                p.mat[i].bias = bias ? bias[i] : nullptr;
+                p.mat[i].m = m[i];
+                p.mat[i].ldy = ldy[i];
+            } else {
+                p.mat[i] = GemvMat{nullptr, nullptr, nullptr, 0, 0};
+            }
+        }
         p.qact = (const uint8_t *) qact + (size_t) c0 * acb;
-        p.y = y + c0 * ldy;
-        p.bias = bias;
-        p.k = k; p.m = m; p.ldy = ldy;
+        p.k = k; p.m_total = m_total;
         p.n = nc;
         p.nunits = nunits;
         p.ks = t.ks;
         p.stages = t.stages;
         p.act_col_bytes = (uint32_t) acb;
-        const int rc = launch_fmt(wtype, p, t.rg, nc, t.warps, grid, smem_for(t), st);
+        const int rc = launch_fmt(wtype, mode, p, t.rg, nc, t.warps, grid, smem_for(t), st);
         if (rc) return rc;
         c0 += nc;
     }
     return B200_OK;
+}
+
+int mul_mat_q(int wtype, const void * W, int64_t k, int64_t m, const void * qact, int64_t n, float * y, int64_t ldy, const float * bias,
+              const GemvTuning * tune, cudaStream_t st) {
+    const void * Ws[1] = {W};
+    float * ys[1] = {y};
+    const float * bs[1] = {bias};
+    return mul_mat_q_multi(wtype, 0, 1, Ws, &m, ys, &ldy, bs, k, qact, n, tune, st);
 }
 
 }  // namespace b200

@@ -24,6 +24,8 @@ struct GemvTuning {
 enum : int { EPI_NONE = 0, EPI_BIAS = 1 };
 int mul_mat_q(int wtype, const void * W, int64_t k, int64_t m, const void * qact, int64_t n, float * y, int64_t ldy, const float * bias,
               const GemvTuning * tune, cudaStream_t st);
+int mul_mat_q_multi(int wtype, int mode, int nmat, const void * const * W, const int64_t * m, float * const * y, const int64_t * ldy,
+                    const float * const * bias, int64_t k, const void * qact, int64_t n, const GemvTuning * tune, cudaStream_t st);
 int sm_count();
 
 // ---- ops.cu
@@ -40,6 +42,15 @@ int attn_decode(const float * q, const void * kc, const void * vc, float * out, 
                 int64_t k_row_stride, int64_t v_row_stride, float scale, cudaStream_t st);
 int kv_store(const float * k, const float * v, void * kc, void * vc, int kv_hidden, int64_t k_row_stride, int64_t v_row_stride, int pos, cudaStream_t st);
 
+
+// ---- fused.cu
+int add_rmsnorm_quant(int wtype, const float * x, const float * r, const float * w, float * x_out, float * y_out, void * qact, int64_t ne0, int64_t nrows,
+                      float eps, cudaStream_t st);
+int rope_kv_store(float * q, const float * k, const float * v, const int32_t * pos, const float * ff, void * kc, void * vc, int n_heads, int kv_heads,
+                  int head_dim, int mode, float freq_base, int64_t k_row_stride, int64_t v_row_stride, cudaStream_t st);
+size_t attn_decode2_scratch_bytes(int n_heads, int n_kv);
+int attn_decode2(const float * q, const void * kc, const void * vc, float * out, float * scratch, int n_heads, int kv_heads, int head_dim, int n_kv,
+                 int64_t k_row_stride, int64_t v_row_stride, float scale, cudaStream_t st);
 
 // ---- ops_generic.cu: strided / broadcasting ops as ggml graphs present them (ne[0] fastest, nb in bytes)
 struct TV {

@@ -85,8 +85,9 @@ class LayerWeights:
 class DecodeSession:
     """Owns layers [layer_lo, layer_hi) of the model (all of them on one GPU), their KV-cache shard and the scratch."""
 
-    def __init__(self, cfg, weights=None, seed=0, layer_lo=0, layer_hi=None, first=True, last=True):
+    def __init__(self, cfg, weights=None, seed=0, layer_lo=0, layer_hi=None, first=True, last=True, fused=True):
         self.cfg = cfg
+        self.fused = fused
         self.lo, self.hi = layer_lo, cfg.layers if layer_hi is None else layer_hi
         self.first, self.last = first, last
         c = cfg
@@ -174,22 +175,84 @@ class DecodeSession:
             self._mm(self.lm_head, c.hidden, c.vocab, self.xn, self.logits)
         self.launches_per_step = self._n
 
+    # ---- fused step: 11 launches per layer ------------------------------------------------------------------------
+    def _ptr_arrays(self):
+        """host-side pointer tables for b200_mul_mat_q_multi (kept alive for the lifetime of the session / graph)"""
+        import ctypes as C
+        c = self.cfg
+        self._tables = []
+        for W in self.layers:
+            def arr(ctype, vals):
+                a = (ctype * len(vals))(*vals)
+                return a
+            W.qkv = dict(W=arr(C.c_void_p, [W.wq.data_ptr(), W.wk.data_ptr(), W.wv.data_ptr()]), m=arr(C.c_int64, [c.hidden, c.kv_hidden, c.kv_hidden]),
+                         y=arr(C.c_void_p, [self.q.data_ptr(), self.k.data_ptr(), self.v.data_ptr()]), ld=arr(C.c_int64, [c.hidden, c.kv_hidden, c.kv_hidden]),
+                         b=arr(C.c_void_p, [0 if W.bq is None else W.bq.data_ptr(), 0 if W.bk is None else W.bk.data_ptr(), 0 if W.bv is None else W.bv.data_ptr()]))
+            W.gu = dict(W=arr(C.c_void_p, [W.wgate.data_ptr(), W.wup.data_ptr()]), m=arr(C.c_int64, [c.ffn, c.ffn]),
+                        y=arr(C.c_void_p, [self.gate.data_ptr(), 0]), ld=arr(C.c_int64, [c.ffn, c.ffn]), b=arr(C.c_void_p, [0, 0]))
+
+    def enqueue_step_fused(self, n_past):
+        c = self.cfg
+        L = lib()
+        st = torch.cuda.current_stream().cuda_stream
+        if not hasattr(self, "_tables"):
+            self._ptr_arrays()
+        n = 0
+        hd, n_kv = c.head_dim, n_past + 1
+        q = self.qact.data_ptr()
+        rc = 0
+        if self.first:
+            rc |= L.b200_get_rows(c.wtype, self.embed.data_ptr(), c.hidden, self.tok.data_ptr(), 1, self.x.data_ptr(), st); n += 1
+        pending = 0  # residual branch output not yet added into x
+        for W in self.layers:
+            rc |= L.b200_add_rmsnorm_quant(c.wtype, self.x.data_ptr(), pending, W.attn_norm.data_ptr(), self.x.data_ptr() if pending else 0, 0, q,
+                                           c.hidden, 1, c.eps, st); n += 1
+            t = W.qkv
+            rc |= L.b200_mul_mat_q_multi(c.wtype, 0, 3, t["W"], t["m"], t["y"], t["ld"], t["b"], c.hidden, q, 1, st); n += 1
+            rc |= L.b200_rope_kv_store(self.q.data_ptr(), self.k.data_ptr(), self.v.data_ptr(), self.pos.data_ptr(), 0, W.kc.data_ptr(), W.vc.data_ptr(),
+                                       c.heads, c.kv_heads, hd, c.rope_mode, c.rope_theta, c.kv_hidden, c.max_len, st); n += 1
+            rc |= L.b200_attn_decode(self.q.data_ptr(), W.kc.data_ptr(), W.vc.data_ptr(), self.att.data_ptr(), self.scratch.data_ptr(), c.heads, c.kv_heads,
+                                     hd, n_kv, c.kv_hidden, c.max_len, 1.0 / math.sqrt(hd), st); n += 2
+            rc |= L.b200_quantize_act(c.wtype, self.att.data_ptr(), c.hidden, c.hidden, 1, q, st); n += 1
+            rc |= L.b200_mul_mat_q(c.wtype, W.wo.data_ptr(), c.hidden, c.hidden, q, 1, self.o.data_ptr(), c.hidden, 0, st); n += 1
+            rc |= L.b200_add_rmsnorm_quant(c.wtype, self.x.data_ptr(), self.o.data_ptr(), W.ffn_norm.data_ptr(), self.x.data_ptr(), 0, q, c.hidden, 1, c.eps, st); n += 1
+            t = W.gu
+            rc |= L.b200_mul_mat_q_multi(c.wtype, 1, 2, t["W"], t["m"], t["y"], t["ld"], t["b"], c.hidden, q, 1, st); n += 1
+            rc |= L.b200_quantize_act(c.wtype, self.gate.data_ptr(), c.ffn, c.ffn, 1, q, st); n += 1
+            rc |= L.b200_mul_mat_q(c.wtype, W.wdown.data_ptr(), c.ffn, c.hidden, q, 1, self.o.data_ptr(), c.hidden, 0, st); n += 1
+            pending = self.o.data_ptr()
+        if self.last:
+            rc |= L.b200_add_rmsnorm_quant(c.wtype, self.x.data_ptr(), pending, self.final_norm.data_ptr(), self.x.data_ptr() if pending else 0, 0, q,
+                                           c.hidden, 1, c.eps, st); n += 1
+            rc |= L.b200_mul_mat_q(c.wtype, self.lm_head.data_ptr(), c.hidden, c.vocab, q, 1, self.logits.data_ptr(), c.vocab, 0, st); n += 1
+        elif pending:
+            rc |= L.b200_add(self.x.data_ptr(), pending, self.x.data_ptr(), c.hidden, st); n += 1
+        if rc:
+            raise RuntimeError(f"fused step failed rc={rc}")
+        self.launches_per_step = n
+
+    def enqueue(self, n_past):
+        if self.fused:
+            self.enqueue_step_fused(n_past)
+        else:
+            self.enqueue_step(n_past)
+
     def step(self, token, n_past):
         """eager step with host token / position (tests)"""
         self.tok.fill_(int(token)); self.pos.fill_(int(n_past))
-        self.enqueue_step(n_past)
+        self.enqueue(n_past)
         return self.logits if self.last else self.x
 
     def capture(self, n_past):
         """capture the whole step at a fixed n_past into one CUDA graph (bench: `value`)"""
         self.pos.fill_(int(n_past))
-        self.enqueue_step(n_past)  # warm-up outside capture (first-use cudaFuncSetAttribute etc.)
+        self.enqueue(n_past)  # warm-up outside capture (first-use cudaFuncSetAttribute etc.)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         s = torch.cuda.Stream()
         with torch.cuda.stream(s):
             with torch.cuda.graph(g, stream=s):
-                self.enqueue_step(n_past)
+                self.enqueue(n_past)
         self._graph = g
         return g
 

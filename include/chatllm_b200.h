@@ -60,6 +60,12 @@ int b200_mul_mat_q(int wtype, const void * W, int64_t k, int64_t m, const void *
 /* convenience: quantize x into an internal per-device scratch, then b200_mul_mat_q */
 int b200_mul_mat(int wtype, const void * W, int64_t k, int64_t m, const float * x, int64_t x_col_stride, int64_t n, float * y,
                  int64_t ldy, const float * bias, void * stream);
+/* Several matrices that share the activation vector in ONE launch.
+ *   mode 0 (concat, nmat <= 3): y_i[c*ldy_i + r] = W_i[r,:].x_c (+ bias_i[r])       — q/k/v projections of a layer
+ *   mode 1 (paired, nmat == 2, m_0 == m_1): y_0[c*ldy_0 + r] = silu(W_0[r,:].x_c) * (W_1[r,:].x_c)
+ *                                            — gate/up projections + SwiGLU of BaseMLP::forward (src/layers.cpp:2475-2483) */
+int b200_mul_mat_q_multi(int wtype, int mode, int nmat, const void * const * W, const int64_t * m, float * const * y, const int64_t * ldy,
+                         const float * const * bias, int64_t k, const void * qact, int64_t n, void * stream);
 /* override the pipeline shape of the GEMV kernel (0 = keep default): units(256 elts)/stage, stages, warps/CTA,
  * rows/group, grid */
 int b200_gemv_set_tuning(int ks, int stages, int warps, int rg, int grid);
@@ -80,6 +86,18 @@ int b200_rope(const float * x, float * y, const int32_t * pos, const float * fre
 int b200_soft_max(const float * x, const float * mask, float * y, int64_t ne0, int64_t nrows, float scale, void * stream);
 /* y[i, :] = dequant(table[ids[i], :]).  ggml/src/ggml-cpu/ops.cpp:4820 */
 int b200_get_rows(int type, const void * table, int64_t k, const int32_t * ids, int64_t n, float * y, void * stream);
+
+/* ---- fused decode-step kernels --------------------------------------------------------------------------------- */
+/* [x_out = x + r] ; y = rms_norm(x_out) * w ; qact = quantized y for weight type `wtype` (r, x_out, y_out, qact may be NULL).
+ * Replaces ADD + RMS_NORM + MUL (src/layers.cpp:2719-2761, :2216-2225) + the src1 conversion of the following matmuls
+ * (ggml-cpu.c:1291-1326).  ne0 % 256 == 0, ne0 <= 20480. */
+int b200_add_rmsnorm_quant(int wtype, const float * x, const float * r, const float * w, float * x_out, float * y_out, void * qact,
+                           int64_t ne0, int64_t nrows, float eps, void * stream);
+/* one token: RoPE(q) in place, RoPE(k) -> K cache row pos[0], v -> V cache column pos[0] (F16, RNE).  Replaces the two
+ * rope_ext_inplace nodes + SET_ROWS + TRANSPOSE/CPY of src/layers.h:2103-2114, src/layers.cpp:3044-3123. */
+int b200_rope_kv_store(float * q, const float * k, const float * v, const int32_t * pos, const float * freq_factors, void * k_cache,
+                       void * v_cache_t, int n_heads, int kv_heads, int head_dim, int mode, float freq_base, int64_t k_row_stride,
+                       int64_t v_row_stride, void * stream);
 
 /* ---- decode attention over the reference's F16 KV-cache layouts ---------------------------------------------- */
 /* K cache [max_len][kv_heads*head_dim] (row stride k_row_stride halves), V cache TRANSPOSED [kv_heads*head_dim][max_len]

@@ -237,3 +237,77 @@ def test_get_rows(K, wtype):
     y = K.get_rows(wtype, K.upload_weights(wtype, w, k, rows), k, _t(ids)).cpu().numpy()
     ref = qf.dequant_np(wtype, w[ids], k)
     assert np.abs(y - ref).max() <= 1e-6 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("wtype", [qf.Q4_K, qf.Q4_0, qf.Q8_0])
+@pytest.mark.parametrize("ne0", [256, 2048, 4096, 5632, 14336, 18944])
+def test_add_rmsnorm_quant_matches_unfused(K, wtype, ne0):
+    """fused ADD+RMS_NORM+MUL+quantize == the separate kernels (codes bit-exact, floats exact)"""
+    import torch
+    import chatllm_cpp_b200 as pkg
+    rng = np.random.default_rng(ne0 + wtype)
+    x, r = _acts(rng, 3, ne0), _acts(rng, 3, ne0)
+    r[1, :256] = -x[1, :256]            # an all-zero block after the add
+    w = (1 + 0.1 * rng.standard_normal(ne0)).astype(np.float32)
+    xd, rd, wd = _t(x), _t(r), _t(w)
+    xs = K.add(xd, rd)
+    y_ref = K.rms_norm(xs, wd, 1e-5)
+    q_ref = K.quantize_act(wtype, y_ref)
+    x_out = torch.empty_like(xd); y_out = torch.empty_like(xd); q = torch.zeros_like(q_ref)
+    rc = pkg.lib().b200_add_rmsnorm_quant(wtype, xd.data_ptr(), rd.data_ptr(), wd.data_ptr(), x_out.data_ptr(), y_out.data_ptr(), q.data_ptr(), ne0, 3, 1e-5, 0)
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert torch.equal(x_out, xs)
+    # the block-sum association differs between the two norm kernels: y may differ by 1 ulp, codes by <= 1 on a tie
+    assert (y_out - y_ref).abs().max().item() <= 2e-6 * y_ref.abs().max().item()
+    a, b = _decode_qact(q.cpu().numpy(), wtype, ne0), _decode_qact(q_ref.cpu().numpy(), wtype, ne0)
+    assert np.abs(a[0].astype(int) - b[0].astype(int)).max() <= 1
+    assert (a[0] == b[0]).mean() > 0.999
+    assert np.allclose(a[1], b[1], rtol=1e-6)
+    # and bit-exact against the oracle quantizer applied to the fused kernel's own float output
+    yo = y_out.cpu().numpy()
+    if wtype == qf.Q4_K:
+        ref = np.zeros((3, ne0 // 256 * 292), dtype=np.uint8)
+        for i in range(3):
+            qf.port().oq_quantize_row_q8_K_ref(yo[i].ctypes.data, ref[i].ctypes.data, ne0)
+        assert np.array_equal(a[0], ref.reshape(3, -1, 292)[:, :, 4:260].view(np.int8).reshape(3, ne0))
+    else:
+        ref = np.zeros((3, ne0 // 32 * 34), dtype=np.uint8)
+        for i in range(3):
+            qf.port().oq_quantize_row_q8_0_x86(yo[i].ctypes.data, ref[i].ctypes.data, ne0)
+        assert np.array_equal(a[0], ref.reshape(3, -1, 34)[:, :, 2:].view(np.int8).reshape(3, ne0))
+
+
+@pytest.mark.parametrize("wtype", [qf.Q4_K, qf.Q4_0, qf.Q8_0])
+def test_mul_mat_multi_concat_and_paired(K, wtype):
+    import ctypes as C
+    import torch
+    import chatllm_cpp_b200 as pkg
+    rng = np.random.default_rng(5 + wtype)
+    k = 1024
+    ms = [512, 128, 128]
+    ws = [qf.random_blocks(wtype, m, k, rng=rng) for m in ms]
+    x = _acts(rng, 1, k)
+    biases = [rng.standard_normal(m).astype(np.float32) for m in ms]
+    wd = [K.upload_weights(wtype, w, k, m) for w, m in zip(ws, ms)]
+    bd = [_t(b) for b in biases]
+    q = K.quantize_act(wtype, _t(x))
+    ys = [torch.zeros((1, m), device="cuda") for m in ms]
+    arr = lambda ct, v: (ct * len(v))(*v)
+    rc = pkg.lib().b200_mul_mat_q_multi(wtype, 0, 3, arr(C.c_void_p, [w.data_ptr() for w in wd]), arr(C.c_int64, ms), arr(C.c_void_p, [y.data_ptr() for y in ys]),
+                                        arr(C.c_int64, ms), arr(C.c_void_p, [b.data_ptr() for b in bd]), k, q.data_ptr(), 1, 0)
+    assert rc == 0
+    for w, m, b, y in zip(ws, ms, biases, ys):
+        ref = qf.port_mul_mat(wtype, w, k, m, x)[0] + b
+        assert np.abs(y.cpu().numpy()[0] - ref).max() <= 2e-5 * np.abs(ref).max()
+    # paired SwiGLU: silu(Wg x) * (Wu x)
+    m = 768
+    wg, wu = qf.random_blocks(wtype, m, k, rng=rng), qf.random_blocks(wtype, m, k, rng=rng)
+    dg, du = K.upload_weights(wtype, wg, k, m), K.upload_weights(wtype, wu, k, m)
+    y = torch.zeros((1, m), device="cuda")
+    rc = pkg.lib().b200_mul_mat_q_multi(wtype, 1, 2, arr(C.c_void_p, [dg.data_ptr(), du.data_ptr()]), arr(C.c_int64, [m, m]), arr(C.c_void_p, [y.data_ptr(), 0]),
+                                        arr(C.c_int64, [m, m]), arr(C.c_void_p, [0, 0]), k, q.data_ptr(), 1, 0)
+    assert rc == 0
+    g = qf.port_mul_mat(wtype, wg, k, m, x); u = qf.port_mul_mat(wtype, wu, k, m, x)
+    ref = np.zeros_like(g); qf.port().oq_silu_mul(g.ctypes.data, u.ctypes.data, ref.ctypes.data, m)
+    assert np.abs(y.cpu().numpy() - ref).max() <= 3e-5 * np.abs(ref).max()

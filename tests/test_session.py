@@ -20,7 +20,8 @@ class OqLayer(C.Structure):
 
 @pytest.mark.parametrize("wtype", [qf.Q4_K, qf.Q4_0, qf.Q8_0])
 @pytest.mark.parametrize("rope_mode,bias", [(0, False), (2, True)])
-def test_decode_steps_match_oracle(wtype, rope_mode, bias):
+@pytest.mark.parametrize("fused", [False, True])
+def test_decode_steps_match_oracle(wtype, rope_mode, bias, fused):
     import torch
     import __graft_entry__ as ge
     pkg = ge.load_package()
@@ -40,7 +41,7 @@ def test_decode_steps_match_oracle(wtype, rope_mode, bias):
         host[(i, name)] = w
         return K.upload_weights(wtype, w, k, m)
 
-    sess = S.DecodeSession(cfg, weights=weights)
+    sess = S.DecodeSession(cfg, weights=weights, fused=fused)
     port = qf.port()
     port.oq_layer_step.argtypes = [C.POINTER(OqLayer), C.c_void_p, C.c_int, C.c_int]
     kcs = [np.zeros((max_len, kv_hidden), dtype=np.uint16) for _ in range(nl)]
@@ -67,13 +68,13 @@ def test_decode_steps_match_oracle(wtype, rope_mode, bias):
         port.oq_rms_norm(h.ctypes.data, host[(-1, "final_norm")].ctypes.data, hn.ctypes.data, hidden, 1, 1e-5)
         ref = qf.port_mul_mat(wtype, host[(-1, "lm_head")], hidden, vocab, hn, variant=1)[0]
         rel = np.abs(got - ref).max() / np.abs(ref).max()
-        assert rel <= 1e-3, (pos, rel)     # north-star tolerance; flip-free here (observed ~1e-6)
+        assert rel <= 1e-3, (pos, rel, fused)     # north-star tolerance; flip-free here (observed ~1e-6)
     # KV cache contents are bit-identical f16
     # KV cache contents agree to 1 f16 ulp (fp32 summation order of the k projection may move a value across an f16 tie)
     kg = sess.layers[0].kc.cpu().numpy()[:len(toks)].astype(np.float32)
     kr = kcs[0][:len(toks)].view(np.float16).astype(np.float32)
     assert np.abs(kg - kr).max() <= 2e-3 * np.abs(kr).max()
-    assert (kg == kr).mean() > 0.99
+    assert (kg == kr).mean() > 0.99, (kg == kr).mean()
 
 
 def test_graph_replay_equals_eager():
@@ -90,4 +91,4 @@ def test_graph_replay_equals_eager():
     sess.logits.zero_()
     g.replay(); torch.cuda.synchronize()
     assert torch.equal(eager, sess.logits)
-    assert sess.launches_per_step == 1 + 3 * (2 + 6 + 2 + 5 + 2 + 1 + 1 + 4 + 1 + 2 + 1) - 0 + 3 or sess.launches_per_step > 50
+    assert sess.launches_per_step == 1 + 3 * 11 + 2   # get_rows + 11 per layer + final norm + lm_head
