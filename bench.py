@@ -112,6 +112,8 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--tune", default="", help="ks,stages,warps,rg,grid for the GEMV pipeline (0 = default)")
+    ap.add_argument("--unfused", action="store_true")
     ap.add_argument("--layers", type=int, default=0, help="debug: fewer layers (result is then NOT the BASELINE config)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3)
@@ -150,10 +152,12 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl")
 
+    if a.tune:
+        pkg.lib().b200_gemv_set_tuning(*[int(v) for v in a.tune.split(",")])
     cfg = S.make_config(MODEL, pkg.Q4_K, layers=a.layers or None, max_len=N_PAST + 256)
     per = cfg.layers // world
     lo, hi = rank * per, (rank + 1) * per if rank < world - 1 else cfg.layers
-    sess = S.DecodeSession(cfg, seed=0, layer_lo=lo, layer_hi=hi, first=(rank == 0), last=(rank == world - 1))
+    sess = S.DecodeSession(cfg, seed=0, layer_lo=lo, layer_hi=hi, first=(rank == 0), last=(rank == world - 1), fused=not a.unfused)
     sess.fill_kv_random(N_PAST, seed=rank)
     sess.tok.fill_(12345 % cfg.vocab)
 

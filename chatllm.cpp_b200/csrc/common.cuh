@@ -78,6 +78,32 @@ __device__ __forceinline__ void bulk_g2s_hint(void * smem_dst, const void * gmem
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// Host-side launch helper: every kernel of the decode step is launched with programmatic stream serialization so that
+// its launch latency (and, for the GEMV, its weight prefetch) overlaps the predecessor's execution.  Contract for the
+// kernels: call pdl_launch_dependents() at the top, and pdl_wait() before the first access to anything a predecessor
+// may still be reading or writing.
+#ifdef __CUDACC__
+#include <cstdlib>
+inline bool pdl_enabled() {
+    static const bool on = !(getenv("B200_NO_PDL") && atoi(getenv("B200_NO_PDL")) != 0);
+    return on;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#endif
+
 // ---- misc -------------------------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

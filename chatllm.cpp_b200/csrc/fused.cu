@@ -181,8 +181,8 @@ int add_rmsnorm_quant(int wtype, const float * x, const float * r, const float *
     const size_t cb = qact ? qact_col_bytes(wtype, ne0) : 0;
 #define B200_ARQ(J_)                                                                                                                          \
     if (J == J_) {                                                                                                                            \
-        if (q8k) add_rmsnorm_quant_kernel<true, J_><<<(unsigned) nrows, threads, 0, st>>>(x, r, w, x_out, y_out, (uint8_t *) qact, ne0, eps, cb); \
-        else add_rmsnorm_quant_kernel<false, J_><<<(unsigned) nrows, threads, 0, st>>>(x, r, w, x_out, y_out, (uint8_t *) qact, ne0, eps, cb);     \
+        if (q8k) launch_pdl(add_rmsnorm_quant_kernel<true, J_>, dim3((unsigned) nrows), dim3(threads), 0, st, x, r, w, x_out, y_out, (uint8_t *) qact, ne0, eps, cb); \
+        else launch_pdl(add_rmsnorm_quant_kernel<false, J_>, dim3((unsigned) nrows), dim3(threads), 0, st, x, r, w, x_out, y_out, (uint8_t *) qact, ne0, eps, cb);     \
         return (int) cudaGetLastError();                                                                                                      \
     }
     B200_ARQ(1) B200_ARQ(2) B200_ARQ(3) B200_ARQ(4) B200_ARQ(5)
@@ -229,7 +229,7 @@ int rope_kv_store(float * q, const float * k, const float * v, const int32_t * p
     if (mode != 0 && mode != 2) return B200_ERR_UNSUPPORTED;
     if (head_dim % 2 || head_dim > 2048) return B200_ERR_ARG;
     const float theta_scale = powf(freq_base, -2.0f / head_dim);
-    rope_kv_store_kernel<<<(unsigned) (n_heads + kv_heads), head_dim / 2, 0, st>>>(q, k, v, pos, ff, (__half *) kc, (__half *) vc, n_heads, kv_heads, head_dim,
+    launch_pdl(rope_kv_store_kernel, dim3((unsigned) (n_heads + kv_heads)), dim3(head_dim / 2), 0, st, q, k, v, pos, ff, (__half *) kc, (__half *) vc, n_heads, kv_heads, head_dim,
                                                                                   mode, theta_scale, k_row_stride, v_row_stride);
     return (int) cudaGetLastError();
 }
@@ -343,7 +343,7 @@ static int attn_decode2_t(const float * q, const void * kc, const void * vc, flo
                           int64_t v_row_stride, float scale, cudaStream_t st) {
     const int64_t s_stride = (n_kv + 7) & ~7;
     dim3 g1((unsigned) ((n_kv + 127) / 128), (unsigned) kv_heads);
-    attn_scores2_kernel<HD, GQA><<<g1, 256, 0, st>>>(q, (const __half *) kc, scratch, n_kv, k_row_stride, scale, s_stride);
+    launch_pdl(attn_scores2_kernel<HD, GQA>, dim3(g1), dim3(256), 0, st, q, (const __half *) kc, scratch, n_kv, k_row_stride, scale, s_stride);
     const size_t smem = (size_t) GQA * s_stride * 4;
     static size_t configured = 0;
     if (smem > configured) {
@@ -353,7 +353,7 @@ static int attn_decode2_t(const float * q, const void * kc, const void * vc, flo
     }
     if (smem > 227 * 1024) return B200_ERR_UNSUPPORTED;
     dim3 g2((unsigned) (HD / 8), (unsigned) kv_heads);
-    attn_softmax_pv_kernel<GQA><<<g2, 256, smem, st>>>(scratch, (const __half *) vc, out, n_kv, HD, v_row_stride, s_stride);
+    launch_pdl(attn_softmax_pv_kernel<GQA>, dim3(g2), dim3(256), smem, st, scratch, (const __half *) vc, out, n_kv, HD, v_row_stride, s_stride);
     return (int) cudaGetLastError();
 }
 

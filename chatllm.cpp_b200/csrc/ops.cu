@@ -39,6 +39,7 @@ __device__ __forceinline__ float block_max(float v, float * red) {
 __global__ void __launch_bounds__(1024) rms_norm_mul_kernel(const float * __restrict__ x, const float * __restrict__ w, float * __restrict__ y,
                                                             int64_t ne0, float eps) {
     __shared__ float red[32];
+    pdl_launch_dependents();
     pdl_wait();
     const float * xr = x + (int64_t) blockIdx.x * ne0;
     float * yr = y + (int64_t) blockIdx.x * ne0;
@@ -55,30 +56,32 @@ __global__ void __launch_bounds__(1024) rms_norm_mul_kernel(const float * __rest
 int rms_norm_mul(const float * x, const float * w, float * y, int64_t ne0, int64_t nrows, float eps, cudaStream_t st) {
     if (nrows <= 0) return B200_OK;
     const int threads = ne0 >= 4096 ? 1024 : (ne0 >= 1024 ? 512 : 256);
-    rms_norm_mul_kernel<<<(unsigned) nrows, threads, 0, st>>>(x, w, y, ne0, eps);
+    launch_pdl(rms_norm_mul_kernel, dim3((unsigned) nrows), dim3(threads), 0, st, x, w, y, ne0, eps);
     return (int) cudaGetLastError();
 }
 
 // ---- elementwise ----------------------------------------------------------------------------------------
 __global__ void add_kernel(const float * __restrict__ a, const float * __restrict__ b, float * __restrict__ y, int64_t n) {
+    pdl_launch_dependents();
     pdl_wait();
     const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) y[i] = a[i] + b[i];
 }
 int add_f32(const float * a, const float * b, float * y, int64_t n, cudaStream_t st) {
     if (n <= 0) return B200_OK;
-    add_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, st>>>(a, b, y, n);
+    launch_pdl(add_kernel, dim3((unsigned) ((n + 255) / 256)), dim3(256), 0, st, a, b, y, n);
     return (int) cudaGetLastError();
 }
 // SwiGLU of BaseMLP::forward (src/layers.cpp:2475-2483): silu(gate) * up, silu = x/(1+exp(-x)) (vec.h:1061)
 __global__ void silu_mul_kernel(const float * __restrict__ g, const float * __restrict__ u, float * __restrict__ y, int64_t n) {
+    pdl_launch_dependents();
     pdl_wait();
     const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { const float v = g[i]; y[i] = (v / (1.0f + expf(-v))) * u[i]; }
 }
 int silu_mul(const float * gate, const float * up, float * y, int64_t n, cudaStream_t st) {
     if (n <= 0) return B200_OK;
-    silu_mul_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, st>>>(gate, up, y, n);
+    launch_pdl(silu_mul_kernel, dim3((unsigned) ((n + 255) / 256)), dim3(256), 0, st, gate, up, y, n);
     return (int) cudaGetLastError();
 }
 
@@ -93,6 +96,7 @@ struct RopeParams {
 };
 __global__ void rope_kernel(const float * __restrict__ x, float * __restrict__ y, const int32_t * __restrict__ pos,
                             const float * __restrict__ ff, const RopeParams p) {
+    pdl_launch_dependents();
     pdl_wait();
     const int64_t t = blockIdx.x;
     const int half = p.n_dims / 2;
@@ -146,7 +150,7 @@ int rope_f32(const float * x, float * y, const int32_t * pos, const float * freq
     p.corr0 = fmaxf(0.0f, start);
     p.corr1 = fminf((float) (n_dims - 1), end);
     const int threads = n_dims / 2 >= 64 ? 64 : 32;
-    rope_kernel<<<(unsigned) n_tokens, threads, 0, st>>>(x, y, pos, freq_factors, p);
+    launch_pdl(rope_kernel, dim3((unsigned) n_tokens), dim3(threads), 0, st, x, y, pos, freq_factors, p);
     return (int) cudaGetLastError();
 }
 
@@ -156,6 +160,7 @@ int rope_f32(const float * x, float * y, const int32_t * pos, const float * freq
 __global__ void __launch_bounds__(1024) soft_max_kernel(const float * __restrict__ x, const float * __restrict__ mask, float * __restrict__ y,
                                                         int64_t ne0, float scale) {
     __shared__ float red[32];
+    pdl_launch_dependents();
     pdl_wait();
     const float * xr = x + (int64_t) blockIdx.x * ne0;
     const float * mr = mask ? mask + (int64_t) blockIdx.x * ne0 : nullptr;
@@ -182,7 +187,7 @@ __global__ void __launch_bounds__(1024) soft_max_kernel(const float * __restrict
 int soft_max_f32(const float * x, const float * mask, float * y, int64_t ne0, int64_t nrows, float scale, cudaStream_t st) {
     if (nrows <= 0) return B200_OK;
     const int threads = ne0 >= 2048 ? 1024 : (ne0 >= 512 ? 256 : 128);
-    soft_max_kernel<<<(unsigned) nrows, threads, 0, st>>>(x, mask, y, ne0, scale);
+    launch_pdl(soft_max_kernel, dim3((unsigned) nrows), dim3(threads), 0, st, x, mask, y, ne0, scale);
     return (int) cudaGetLastError();
 }
 
@@ -191,6 +196,7 @@ int soft_max_f32(const float * x, const float * mask, float * y, int64_t ne0, in
 // Q4_0 / Q8_0 tables are in the repacked SoA row layout (quantize.cu).
 __global__ void get_rows_kernel(int type, const uint8_t * __restrict__ table, int64_t k, const int32_t * __restrict__ ids,
                                 float * __restrict__ y) {
+    pdl_launch_dependents();
     pdl_wait();
     const int64_t r = blockIdx.x;
     const int64_t row = ids[r];
@@ -244,7 +250,7 @@ int get_rows_q(int type, const void * table, int64_t k, const int32_t * ids, int
     if (n <= 0) return B200_OK;
     if (type != B200_TYPE_Q4_K && type != B200_TYPE_Q4_0 && type != B200_TYPE_Q8_0 && type != B200_TYPE_F32 && type != B200_TYPE_F16)
         return B200_ERR_UNSUPPORTED;
-    get_rows_kernel<<<(unsigned) n, 256, 0, st>>>(type, (const uint8_t *) table, k, ids, y);
+    launch_pdl(get_rows_kernel, dim3((unsigned) n), dim3(256), 0, st, type, (const uint8_t *) table, k, ids, y);
     return (int) cudaGetLastError();
 }
 
@@ -266,6 +272,7 @@ template <int HD, int GQA>
 __global__ void __launch_bounds__(256) attn_scores_kernel(const float * __restrict__ q, const __half * __restrict__ kc, float * __restrict__ scores,
                                                           int n_kv, int kv_heads, int64_t k_row_stride, float scale, int64_t s_stride) {
     __shared__ float qs[GQA][HD];
+    pdl_launch_dependents();
     pdl_wait();
     const int g = blockIdx.y;
     for (int i = threadIdx.x; i < GQA * HD; i += blockDim.x) {
@@ -300,6 +307,7 @@ __global__ void __launch_bounds__(256) attn_scores_kernel(const float * __restri
 // in-place softmax over scores[h][0..n_kv), result rounded through f16 (it is the f16 operand of V.P)
 __global__ void __launch_bounds__(1024) attn_softmax_kernel(float * __restrict__ scores, int n_kv, int64_t s_stride) {
     __shared__ float red[32];
+    pdl_launch_dependents();
     pdl_wait();
     float * s = scores + (int64_t) blockIdx.x * s_stride;
     float mx = -INFINITY;
@@ -316,6 +324,7 @@ __global__ void __launch_bounds__(1024) attn_softmax_kernel(float * __restrict__
 template <int GQA>
 __global__ void __launch_bounds__(256) attn_pv_kernel(const float * __restrict__ P, const __half * __restrict__ vc, float * __restrict__ out, int n_kv,
                                                       int head_dim, int64_t v_row_stride, int64_t s_stride) {
+    pdl_launch_dependents();
     pdl_wait();
     const int lane = threadIdx.x & 31;
     const int ch = blockIdx.x * 8 + (threadIdx.x >> 5);  // channel = g*HD + d
@@ -352,9 +361,9 @@ static int attn_decode_t(const float * q, const void * kc, const void * vc, floa
                          int64_t v_row_stride, float scale, cudaStream_t st) {
     const int64_t s_stride = (n_kv + 3) & ~3;
     dim3 g1((unsigned) ((n_kv + 63) / 64), (unsigned) kv_heads);
-    attn_scores_kernel<HD, GQA><<<g1, 256, 0, st>>>(q, (const __half *) kc, scratch, n_kv, kv_heads, k_row_stride, scale, s_stride);
-    attn_softmax_kernel<<<(unsigned) (kv_heads * GQA), n_kv >= 2048 ? 1024 : 256, 0, st>>>(scratch, n_kv, s_stride);
-    attn_pv_kernel<GQA><<<(unsigned) (kv_heads * HD / 8), 256, 0, st>>>(scratch, (const __half *) vc, out, n_kv, HD, v_row_stride, s_stride);
+    launch_pdl(attn_scores_kernel<HD, GQA>, dim3(g1), dim3(256), 0, st, q, (const __half *) kc, scratch, n_kv, kv_heads, k_row_stride, scale, s_stride);
+    launch_pdl(attn_softmax_kernel, dim3((unsigned) (kv_heads * GQA)), dim3(n_kv >= 2048 ? 1024 : 256), 0, st, scratch, n_kv, s_stride);
+    launch_pdl(attn_pv_kernel<GQA>, dim3((unsigned) (kv_heads * HD / 8)), dim3(256), 0, st, scratch, (const __half *) vc, out, n_kv, HD, v_row_stride, s_stride);
     return (int) cudaGetLastError();
 }
 
@@ -376,6 +385,7 @@ int attn_decode(const float * q, const void * kc, const void * vc, float * out, 
 // write one token's K (row) and V (column of the transposed cache) as f16 — KVCacheAttention::save_to_cache
 __global__ void kv_store_kernel(const float * __restrict__ k, const float * __restrict__ v, __half * __restrict__ kc, __half * __restrict__ vc, int kv_hidden,
                                 int64_t k_row_stride, int64_t v_row_stride, int pos) {
+    pdl_launch_dependents();
     pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= kv_hidden) return;
@@ -383,7 +393,7 @@ __global__ void kv_store_kernel(const float * __restrict__ k, const float * __re
     vc[(int64_t) i * v_row_stride + pos] = __float2half_rn(v[i]);
 }
 int kv_store(const float * k, const float * v, void * kc, void * vc, int kv_hidden, int64_t k_row_stride, int64_t v_row_stride, int pos, cudaStream_t st) {
-    kv_store_kernel<<<(unsigned) ((kv_hidden + 255) / 256), 256, 0, st>>>(k, v, (__half *) kc, (__half *) vc, kv_hidden, k_row_stride, v_row_stride, pos);
+    launch_pdl(kv_store_kernel, dim3((unsigned) ((kv_hidden + 255) / 256)), dim3(256), 0, st, k, v, (__half *) kc, (__half *) vc, kv_hidden, k_row_stride, v_row_stride, pos);
     return (int) cudaGetLastError();
 }
 

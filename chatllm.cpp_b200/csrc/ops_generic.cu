@@ -41,6 +41,7 @@ template <> __device__ __forceinline__ void stf<__half>(char * p, float v) { *(_
 // ---- ADD / MUL / DIV with ggml broadcasting of src1 (binary-ops.cpp apply_binary_op) --------------------------
 template <int OP>
 __global__ void bin_bcast_kernel(const TVd a, const TVd b, const TVd d, int64_t n) {
+    pdl_launch_dependents();
     pdl_wait();
     const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -59,9 +60,9 @@ int op_bin(int op, const TV & a, const TV & b, const TV & d, cudaStream_t st) {
     if (n <= 0) return B200_OK;
     const unsigned grid = (unsigned) ((n + 255) / 256);
     switch (op) {
-        case 0: bin_bcast_kernel<0><<<grid, 256, 0, st>>>(dv(a), dv(b), dv(d), n); break;
-        case 1: bin_bcast_kernel<1><<<grid, 256, 0, st>>>(dv(a), dv(b), dv(d), n); break;
-        case 2: bin_bcast_kernel<2><<<grid, 256, 0, st>>>(dv(a), dv(b), dv(d), n); break;
+        case 0: launch_pdl(bin_bcast_kernel<0>, dim3(grid), dim3(256), 0, st, dv(a), dv(b), dv(d), n); break;
+        case 1: launch_pdl(bin_bcast_kernel<1>, dim3(grid), dim3(256), 0, st, dv(a), dv(b), dv(d), n); break;
+        case 2: launch_pdl(bin_bcast_kernel<2>, dim3(grid), dim3(256), 0, st, dv(a), dv(b), dv(d), n); break;
         default: return B200_ERR_ARG;
     }
     return (int) cudaGetLastError();
@@ -71,6 +72,7 @@ int op_bin(int op, const TV & a, const TV & b, const TV & d, cudaStream_t st) {
 //      (ggml_compute_forward_dup, ops.cpp:4637: elements are matched by logical (row-major-in-ne) index)
 template <typename TS, typename TD>
 __global__ void cpy_kernel(const TVd s, const TVd d, int64_t n) {
+    pdl_launch_dependents();
     pdl_wait();
     const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -80,6 +82,7 @@ __global__ void cpy_kernel(const TVd s, const TVd d, int64_t n) {
     stf<TD>(at(d, b0, b1, b2, b3), ldf<TS>(at(s, a0, a1, a2, a3)));
 }
 __global__ void cpy_i32_kernel(const TVd s, const TVd d, int64_t n) {
+    pdl_launch_dependents();
     pdl_wait();
     const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -93,11 +96,11 @@ int op_cpy(const TV & s, const TV & d, cudaStream_t st) {
     if (n != nelem(d)) return B200_ERR_ARG;
     if (n <= 0) return B200_OK;
     const unsigned grid = (unsigned) ((n + 255) / 256);
-    if (s.type == B200_TYPE_F32 && d.type == B200_TYPE_F32) cpy_kernel<float, float><<<grid, 256, 0, st>>>(dv(s), dv(d), n);
-    else if (s.type == B200_TYPE_F32 && d.type == B200_TYPE_F16) cpy_kernel<float, __half><<<grid, 256, 0, st>>>(dv(s), dv(d), n);
-    else if (s.type == B200_TYPE_F16 && d.type == B200_TYPE_F16) cpy_kernel<__half, __half><<<grid, 256, 0, st>>>(dv(s), dv(d), n);
-    else if (s.type == B200_TYPE_F16 && d.type == B200_TYPE_F32) cpy_kernel<__half, float><<<grid, 256, 0, st>>>(dv(s), dv(d), n);
-    else if (s.type == 26 && d.type == 26) cpy_i32_kernel<<<grid, 256, 0, st>>>(dv(s), dv(d), n);
+    if (s.type == B200_TYPE_F32 && d.type == B200_TYPE_F32) launch_pdl(cpy_kernel<float, float>, dim3(grid), dim3(256), 0, st, dv(s), dv(d), n);
+    else if (s.type == B200_TYPE_F32 && d.type == B200_TYPE_F16) launch_pdl(cpy_kernel<float, __half>, dim3(grid), dim3(256), 0, st, dv(s), dv(d), n);
+    else if (s.type == B200_TYPE_F16 && d.type == B200_TYPE_F16) launch_pdl(cpy_kernel<__half, __half>, dim3(grid), dim3(256), 0, st, dv(s), dv(d), n);
+    else if (s.type == B200_TYPE_F16 && d.type == B200_TYPE_F32) launch_pdl(cpy_kernel<__half, float>, dim3(grid), dim3(256), 0, st, dv(s), dv(d), n);
+    else if (s.type == 26 && d.type == 26) launch_pdl(cpy_i32_kernel, dim3(grid), dim3(256), 0, st, dv(s), dv(d), n);
     else return B200_ERR_UNSUPPORTED;
     return (int) cudaGetLastError();
 }
@@ -105,6 +108,7 @@ int op_cpy(const TV & s, const TV & d, cudaStream_t st) {
 // ---- SET_ROWS: dst[:, ids[i1, i2 % ne11, i3 % ne12], i2, i3] = convert(src[:, i1, i2, i3])  (ops.cpp:4942)
 template <typename TD, typename TI>
 __global__ void set_rows_kernel(const TVd s, const TVd ids, const TVd d, int64_t n) {
+    pdl_launch_dependents();
     pdl_wait();
     const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -119,48 +123,52 @@ int op_set_rows(const TV & s, const TV & ids, const TV & d, cudaStream_t st) {
     const unsigned grid = (unsigned) ((n + 255) / 256);
     const bool i64 = ids.type == 27;
     if (d.type == B200_TYPE_F16) {
-        if (i64) set_rows_kernel<__half, int64_t><<<grid, 256, 0, st>>>(dv(s), dv(ids), dv(d), n);
-        else set_rows_kernel<__half, int32_t><<<grid, 256, 0, st>>>(dv(s), dv(ids), dv(d), n);
+        if (i64) launch_pdl(set_rows_kernel<__half, int64_t>, dim3(grid), dim3(256), 0, st, dv(s), dv(ids), dv(d), n);
+        else launch_pdl(set_rows_kernel<__half, int32_t>, dim3(grid), dim3(256), 0, st, dv(s), dv(ids), dv(d), n);
     } else if (d.type == B200_TYPE_F32) {
-        if (i64) set_rows_kernel<float, int64_t><<<grid, 256, 0, st>>>(dv(s), dv(ids), dv(d), n);
-        else set_rows_kernel<float, int32_t><<<grid, 256, 0, st>>>(dv(s), dv(ids), dv(d), n);
+        if (i64) launch_pdl(set_rows_kernel<float, int64_t>, dim3(grid), dim3(256), 0, st, dv(s), dv(ids), dv(d), n);
+        else launch_pdl(set_rows_kernel<float, int32_t>, dim3(grid), dim3(256), 0, st, dv(s), dv(ids), dv(d), n);
     } else return B200_ERR_UNSUPPORTED;
     return (int) cudaGetLastError();
 }
 
 // ---- SCALE (y = x*s + b, ops.cpp:4374), CLAMP, SILU, DIAG_MASK_INF on contiguous tensors -----------------------
 __global__ void scale_kernel(const float * __restrict__ x, float * __restrict__ y, int64_t n, float s, float b) {
+    pdl_launch_dependents();
     pdl_wait();
     const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) y[i] = (b == 0.0f) ? x[i] * s : fmaf(x[i], s, b);  // ggml_vec_scale_f32 / ggml_vec_mad1_f32
 }
 int op_scale(const float * x, float * y, int64_t n, float s, float b, cudaStream_t st) {
     if (n <= 0) return B200_OK;
-    scale_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, st>>>(x, y, n, s, b);
+    launch_pdl(scale_kernel, dim3((unsigned) ((n + 255) / 256)), dim3(256), 0, st, x, y, n, s, b);
     return (int) cudaGetLastError();
 }
 __global__ void clamp_kernel(const float * __restrict__ x, float * __restrict__ y, int64_t n, float lo, float hi) {
+    pdl_launch_dependents();
     pdl_wait();
     const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) y[i] = fminf(fmaxf(x[i], lo), hi);
 }
 int op_clamp(const float * x, float * y, int64_t n, float lo, float hi, cudaStream_t st) {
     if (n <= 0) return B200_OK;
-    clamp_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, st>>>(x, y, n, lo, hi);
+    launch_pdl(clamp_kernel, dim3((unsigned) ((n + 255) / 256)), dim3(256), 0, st, x, y, n, lo, hi);
     return (int) cudaGetLastError();
 }
 __global__ void silu_kernel(const float * __restrict__ x, float * __restrict__ y, int64_t n) {
+    pdl_launch_dependents();
     pdl_wait();
     const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { const float v = x[i]; y[i] = v / (1.0f + expf(-v)); }
 }
 int op_silu(const float * x, float * y, int64_t n, cudaStream_t st) {
     if (n <= 0) return B200_OK;
-    silu_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, st>>>(x, y, n);
+    launch_pdl(silu_kernel, dim3((unsigned) ((n + 255) / 256)), dim3(256), 0, st, x, y, n);
     return (int) cudaGetLastError();
 }
 // ggml_compute_forward_diag_mask_f32: for k in z, j in rows, i >= n_past: if (i > n_past + j) -inf
 __global__ void diag_mask_inf_kernel(const float * __restrict__ x, float * __restrict__ y, int64_t ne0, int64_t ne1, int64_t n, int n_past) {
+    pdl_launch_dependents();
     pdl_wait();
     const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -169,7 +177,7 @@ __global__ void diag_mask_inf_kernel(const float * __restrict__ x, float * __res
 }
 int op_diag_mask_inf(const float * x, float * y, int64_t ne0, int64_t ne1, int64_t n, int n_past, cudaStream_t st) {
     if (n <= 0) return B200_OK;
-    diag_mask_inf_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, st>>>(x, y, ne0, ne1, n, n_past);
+    launch_pdl(diag_mask_inf_kernel, dim3((unsigned) ((n + 255) / 256)), dim3(256), 0, st, x, y, ne0, ne1, n, n_past);
     return (int) cudaGetLastError();
 }
 
@@ -177,6 +185,7 @@ int op_diag_mask_inf(const float * x, float * y, int64_t ne0, int64_t ne1, int64
 template <typename TM>
 __global__ void __launch_bounds__(1024) soft_max_ext_kernel(const TVd x, const TVd m, const TVd y, float scale, bool has_mask) {
     __shared__ float red[32];
+    pdl_launch_dependents();
     pdl_wait();
     const int64_t row = blockIdx.x;
     const int64_t i1 = row % x.ne1, i2 = (row / x.ne1) % x.ne2, i3 = row / (x.ne1 * x.ne2);
@@ -221,14 +230,15 @@ int op_soft_max(const TV & x, const TV * mask, const TV & y, float scale, cudaSt
     if (rows <= 0) return B200_OK;
     const int threads = x.ne[0] >= 2048 ? 1024 : (x.ne[0] >= 512 ? 256 : 128);
     TVd m = mask ? dv(*mask) : dv(x);
-    if (mask && mask->type == B200_TYPE_F16) soft_max_ext_kernel<__half><<<(unsigned) rows, threads, 0, st>>>(dv(x), m, dv(y), scale, true);
-    else soft_max_ext_kernel<float><<<(unsigned) rows, threads, 0, st>>>(dv(x), m, dv(y), scale, mask != nullptr);
+    if (mask && mask->type == B200_TYPE_F16) launch_pdl(soft_max_ext_kernel<__half>, dim3((unsigned) rows), dim3(threads), 0, st, dv(x), m, dv(y), scale, true);
+    else launch_pdl(soft_max_ext_kernel<float>, dim3((unsigned) rows), dim3(threads), 0, st, dv(x), m, dv(y), scale, mask != nullptr);
     return (int) cudaGetLastError();
 }
 
 // ---- RMS_NORM on strided rows (ops.cpp:3710-3758) ----------------------------------------------------------------
 __global__ void __launch_bounds__(1024) rms_norm_strided_kernel(const TVd x, const TVd y, float eps) {
     __shared__ float red[32];
+    pdl_launch_dependents();
     pdl_wait();
     const int64_t row = blockIdx.x;
     const int64_t i1 = row % x.ne1, i2 = (row / x.ne1) % x.ne2, i3 = row / (x.ne1 * x.ne2);
@@ -251,7 +261,7 @@ int op_rms_norm(const TV & x, const TV & y, float eps, cudaStream_t st) {
     const int64_t rows = nrows(x);
     if (rows <= 0) return B200_OK;
     const int threads = x.ne[0] >= 4096 ? 1024 : (x.ne[0] >= 1024 ? 512 : 256);
-    rms_norm_strided_kernel<<<(unsigned) rows, threads, 0, st>>>(dv(x), dv(y), eps);
+    launch_pdl(rms_norm_strided_kernel, dim3((unsigned) rows), dim3(threads), 0, st, dv(x), dv(y), eps);
     return (int) cudaGetLastError();
 }
 
@@ -260,6 +270,7 @@ int op_rms_norm(const TV & x, const TV & y, float eps, cudaStream_t st) {
 // rounds src1 to F16 (ggml-cpu.c:213-219, :1291-1326) and accumulates in fp32 (vec.cpp:264).  One warp per output.
 template <typename T0>
 __global__ void mul_mat_f_kernel(const TVd a, const TVd b, const TVd d, int64_t nout) {
+    pdl_launch_dependents();
     pdl_wait();
     const int64_t o = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -282,14 +293,15 @@ int op_mul_mat_f(const TV & a, const TV & b, const TV & d, cudaStream_t st) {
     const int64_t nout = nelem(d);
     if (nout <= 0) return B200_OK;
     const unsigned grid = (unsigned) ((nout * 32 + 255) / 256);
-    if (a.type == B200_TYPE_F16) mul_mat_f_kernel<__half><<<grid, 256, 0, st>>>(dv(a), dv(b), dv(d), nout);
-    else if (a.type == B200_TYPE_F32) mul_mat_f_kernel<float><<<grid, 256, 0, st>>>(dv(a), dv(b), dv(d), nout);
+    if (a.type == B200_TYPE_F16) launch_pdl(mul_mat_f_kernel<__half>, dim3(grid), dim3(256), 0, st, dv(a), dv(b), dv(d), nout);
+    else if (a.type == B200_TYPE_F32) launch_pdl(mul_mat_f_kernel<float>, dim3(grid), dim3(256), 0, st, dv(a), dv(b), dv(d), nout);
     else return B200_ERR_UNSUPPORTED;
     return (int) cudaGetLastError();
 }
 
 // ---- SUM_ROWS, REPEAT -----------------------------------------------------------------------------------------------
 __global__ void sum_rows_kernel(const TVd x, const TVd y) {
+    pdl_launch_dependents();
     pdl_wait();
     const int64_t row = blockIdx.x;
     const int64_t i1 = row % x.ne1, i2 = (row / x.ne1) % x.ne2, i3 = row / (x.ne1 * x.ne2);
@@ -302,10 +314,11 @@ __global__ void sum_rows_kernel(const TVd x, const TVd y) {
 int op_sum_rows(const TV & x, const TV & y, cudaStream_t st) {
     const int64_t rows = nrows(x);
     if (rows <= 0) return B200_OK;
-    sum_rows_kernel<<<(unsigned) rows, 32, 0, st>>>(dv(x), dv(y));
+    launch_pdl(sum_rows_kernel, dim3((unsigned) rows), dim3(32), 0, st, dv(x), dv(y));
     return (int) cudaGetLastError();
 }
 __global__ void repeat_kernel(const TVd s, const TVd d, int64_t n) {
+    pdl_launch_dependents();
     pdl_wait();
     const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -316,7 +329,7 @@ __global__ void repeat_kernel(const TVd s, const TVd d, int64_t n) {
 int op_repeat(const TV & s, const TV & d, cudaStream_t st) {
     const int64_t n = nelem(d);
     if (n <= 0) return B200_OK;
-    repeat_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, st>>>(dv(s), dv(d), n);
+    launch_pdl(repeat_kernel, dim3((unsigned) ((n + 255) / 256)), dim3(256), 0, st, dv(s), dv(d), n);
     return (int) cudaGetLastError();
 }
 
@@ -324,6 +337,7 @@ int op_repeat(const TV & s, const TV & d, cudaStream_t st) {
 // one block per row; rank of element i = #{j : x[j] > x[i] or (x[j] == x[i] and j < i)} (stable, descending)
 __global__ void argsort_desc_kernel(const TVd x, const TVd y, int k_out, bool ascending, bool swap01) {
     extern __shared__ float sx[];
+    pdl_launch_dependents();
     pdl_wait();
     const int64_t row = blockIdx.x;
     const int64_t i1 = row % x.ne1, i2 = (row / x.ne1) % x.ne2, i3 = row / (x.ne1 * x.ne2);
@@ -350,13 +364,14 @@ int op_argsort(const TV & x, const TV & y, int k_out, bool ascending, bool swap0
     if (rows <= 0) return B200_OK;
     if (x.ne[0] > 8192) return B200_ERR_UNSUPPORTED;
     const int threads = x.ne[0] >= 256 ? 256 : 32;
-    argsort_desc_kernel<<<(unsigned) rows, threads, (size_t) x.ne[0] * 4, st>>>(dv(x), dv(y), k_out, ascending, swap01 && k_out > 1);
+    launch_pdl(argsort_desc_kernel, dim3((unsigned) rows), dim3(threads), (size_t) x.ne[0] * 4, st, dv(x), dv(y), k_out, ascending, swap01 && k_out > 1);
     return (int) cudaGetLastError();
 }
 
 // ---- GET_ROWS for float tables with strides (quantized tables: get_rows_q in ops.cu) ---------------------------------
 template <typename T0>
 __global__ void get_rows_f_kernel(const TVd a, const TVd ids, const TVd d, int64_t n) {
+    pdl_launch_dependents();
     pdl_wait();
     const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -369,8 +384,8 @@ int op_get_rows_f(const TV & a, const TV & ids, const TV & d, cudaStream_t st) {
     const int64_t n = nelem(d);
     if (n <= 0) return B200_OK;
     const unsigned grid = (unsigned) ((n + 255) / 256);
-    if (a.type == B200_TYPE_F32) get_rows_f_kernel<float><<<grid, 256, 0, st>>>(dv(a), dv(ids), dv(d), n);
-    else if (a.type == B200_TYPE_F16) get_rows_f_kernel<__half><<<grid, 256, 0, st>>>(dv(a), dv(ids), dv(d), n);
+    if (a.type == B200_TYPE_F32) launch_pdl(get_rows_f_kernel<float>, dim3(grid), dim3(256), 0, st, dv(a), dv(ids), dv(d), n);
+    else if (a.type == B200_TYPE_F16) launch_pdl(get_rows_f_kernel<__half>, dim3(grid), dim3(256), 0, st, dv(a), dv(ids), dv(d), n);
     else return B200_ERR_UNSUPPORTED;
     return (int) cudaGetLastError();
 }

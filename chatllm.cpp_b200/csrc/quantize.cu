@@ -21,6 +21,7 @@ size_t qact_col_bytes(int wtype, int64_t k) { return (size_t) act_layout(wtype =
 // q = nearest_int(iscale * x) clamped to 127 (RNE, :444-449), d = 1/iscale.
 __global__ void __launch_bounds__(256) quantize_q8_K_kernel(const float * __restrict__ x, int64_t x_col_stride, int64_t k,
                                                             uint8_t * __restrict__ qact, size_t col_bytes) {
+    pdl_launch_dependents();
     pdl_wait();
     const int blk = blockIdx.x;
     const int col = blockIdx.y;
@@ -83,6 +84,7 @@ __global__ void __launch_bounds__(256) quantize_q8_K_kernel(const float * __rest
 // amax = max|x|, d = amax/127 stored as fp16, id = 127/amax (0 if amax == 0), q = RNE(x*id).
 __global__ void __launch_bounds__(256) quantize_q8_0_kernel(const float * __restrict__ x, int64_t x_col_stride, int64_t k,
                                                             uint8_t * __restrict__ qact, size_t col_bytes) {
+    pdl_launch_dependents();
     pdl_wait();
     const int col = blockIdx.y;
     const int64_t blk = (int64_t) blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -115,11 +117,11 @@ int quantize_act(int wtype, const float * x, int64_t x_col_stride, int64_t k, in
     if (wtype == B200_TYPE_Q4_K) {
         if (k % 256) return B200_ERR_ARG;
         dim3 grid((unsigned) (k / 256), (unsigned) n);
-        quantize_q8_K_kernel<<<grid, 256, 0, st>>>(x, x_col_stride, k, (uint8_t *) qact, cb);
+        launch_pdl(quantize_q8_K_kernel, dim3(grid), dim3(256), 0, st, x, x_col_stride, k, (uint8_t *) qact, cb);
     } else if (wtype == B200_TYPE_Q4_0 || wtype == B200_TYPE_Q8_0) {
         if (k % 32) return B200_ERR_ARG;
         dim3 grid((unsigned) ((k / 32 + 7) / 8), (unsigned) n);
-        quantize_q8_0_kernel<<<grid, 256, 0, st>>>(x, x_col_stride, k, (uint8_t *) qact, cb);
+        launch_pdl(quantize_q8_0_kernel, dim3(grid), dim3(256), 0, st, x, x_col_stride, k, (uint8_t *) qact, cb);
     } else {
         return B200_ERR_UNSUPPORTED;
     }
@@ -155,9 +157,9 @@ int repack_window(int wtype, const void * host_layout_window, void * dev_tensor,
     const int threads = 256;
     const int blocks = (int) ((nbytes + threads - 1) / threads > 4096 ? 4096 : (nbytes + threads - 1) / threads);
     if (wtype == B200_TYPE_Q4_0)
-        repack_bytes_kernel<16><<<blocks, threads, 0, st>>>((const uint8_t *) host_layout_window, (uint8_t *) dev_tensor, tensor_off, nbytes, nb_row, inverse);
+        launch_pdl(repack_bytes_kernel<16>, dim3(blocks), dim3(threads), 0, st, (const uint8_t *) host_layout_window, (uint8_t *) dev_tensor, tensor_off, nbytes, nb_row, inverse);
     else if (wtype == B200_TYPE_Q8_0)
-        repack_bytes_kernel<32><<<blocks, threads, 0, st>>>((const uint8_t *) host_layout_window, (uint8_t *) dev_tensor, tensor_off, nbytes, nb_row, inverse);
+        launch_pdl(repack_bytes_kernel<32>, dim3(blocks), dim3(threads), 0, st, (const uint8_t *) host_layout_window, (uint8_t *) dev_tensor, tensor_off, nbytes, nb_row, inverse);
     else
         return B200_ERR_UNSUPPORTED;
     return (int) cudaGetLastError();
