@@ -196,7 +196,7 @@ def _layer_graph(g, rng_seed, t, hidden, heads, kvh, ffn, n_past, qlen, max_len,
     s = g.mul_mat(K, Q, prec_f32=True)
     s = g.soft_max(g.diag_mask_inf(g.scale(s, 1.0 / np.sqrt(hd), inplace=True), n_past, inplace=True), inplace=True)
     ctx = g.cont(g.permute(g.mul_mat(V, s), (0, 2, 1, 3)))
-    ctx = g.reshape(ctx, (hidden, qlen)); taps.append(("ctx", ctx, (qlen, hidden)))
+    ctx = g.reshape(ctx, (hidden, qlen))   # (not tapped: a view of the cont result, whose memory the allocator may reuse)
     o = g.mul_mat(W(hidden, hidden), ctx)
     h1 = g.add(x, o); taps.append(("h1", h1, (qlen, hidden)))
     hn = g.mul(g.rms_norm(h1, 1e-5), vecn(hidden))
