@@ -237,35 +237,44 @@ int rope_kv_store(float * q, const float * k, const float * v, const int32_t * p
 // ------------------------------------------------------------------------------------------------------------------
 // decode attention, 2 launches.  Layouts / semantics as ops.cu attn_* (reference src/layers.cpp:2541-2561).
 // ------------------------------------------------------------------------------------------------------------------
-// scores[h][t] = scale * sum_d K[t][g][d] * f16(q[h][d]);  a row (HD halves) is covered by HD/8 lanes with 16-byte loads
+// scores[h][t] = scale * sum_d K[t][g][d] * f16(q[h][d]);  a row (HD halves) is covered by HD/8 lanes with 16-byte loads.
+// Each CTA covers CH = 128 positions of one KV group and also emits, per query head, the chunk's max and
+// sum(exp(s - max)) so that the consumer can normalise without a pass over the whole row.
+#define B200_ATTN_CH 128
 template <int HD, int GQA>
-__global__ void __launch_bounds__(256) attn_scores2_kernel(const float * __restrict__ q, const __half * __restrict__ kc, float * __restrict__ scores, int n_kv,
-                                                           int64_t k_row_stride, float scale, int64_t s_stride) {
-    constexpr int LPR = HD / 8;    // lanes per row
-    constexpr int RPW = 32 / LPR;  // rows per warp iteration
+__global__ void __launch_bounds__(256) attn_scores2_kernel(const float * __restrict__ q, const __half * __restrict__ kc, float * __restrict__ scores,
+                                                           float2 * __restrict__ part, int n_kv, int64_t k_row_stride, float scale, int64_t s_stride,
+                                                           int nchunks) {
+    constexpr int LPR = HD / 8;               // lanes per row
+    constexpr int RPW = 32 / LPR;             // rows per warp load
+    constexpr int NLD = B200_ATTN_CH / 8 / RPW;  // loads per lane: each warp owns CH/8 = 16 consecutive positions
+    __shared__ float sc[GQA][B200_ATTN_CH];
     pdl_launch_dependents();
     pdl_wait();
     const int g = blockIdx.y;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int part = lane % LPR, rsel = lane / LPR;
+    const int part_i = lane % LPR, rsel = lane / LPR;
     float qv[GQA][8];
 #pragma unroll
     for (int h = 0; h < GQA; ++h)
 #pragma unroll
-        for (int e = 0; e < 8; ++e) qv[h][e] = __half2float(__float2half_rn(q[(int64_t) (g * GQA + h) * HD + part * 8 + e]));
-    const int t_end = min(n_kv, (int) (blockIdx.x + 1) * 128);
-    for (int t0 = blockIdx.x * 128 + warp * RPW; t0 < t_end; t0 += 8 * RPW) {
-        const int t = t0 + rsel;
+        for (int e = 0; e < 8; ++e) qv[h][e] = __half2float(__float2half_rn(q[(int64_t) (g * GQA + h) * HD + part_i * 8 + e]));
+    const int t_base = blockIdx.x * B200_ATTN_CH;
+    const int t_end = min(n_kv, t_base + B200_ATTN_CH);
+    // issue every load of this warp first (memory-level parallelism), then do the math
+    uint4 raw[NLD];
+#pragma unroll
+    for (int i = 0; i < NLD; ++i) {
+        const int t = t_base + warp * (B200_ATTN_CH / 8) + i * RPW + rsel;
+        raw[i] = (t < t_end) ? *reinterpret_cast<const uint4 *>(kc + (int64_t) t * k_row_stride + (int64_t) g * HD + part_i * 8) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int i = 0; i < NLD; ++i) {
+        const int tl = warp * (B200_ATTN_CH / 8) + i * RPW + rsel;
+        const __half2 * hp = reinterpret_cast<const __half2 *>(&raw[i]);
         float kv[8];
-        if (t < t_end) {
-            const uint4 raw = *reinterpret_cast<const uint4 *>(kc + (int64_t) t * k_row_stride + (int64_t) g * HD + part * 8);
-            const __half2 * hp = reinterpret_cast<const __half2 *>(&raw);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) { kv[2 * e] = __low2float(hp[e]); kv[2 * e + 1] = __high2float(hp[e]); }
-        } else {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) kv[e] = 0.0f;
-        }
+        for (int e = 0; e < 4; ++e) { kv[2 * e] = __low2float(hp[e]); kv[2 * e + 1] = __high2float(hp[e]); }
 #pragma unroll
         for (int h = 0; h < GQA; ++h) {
             float s = 0.0f;
@@ -273,56 +282,101 @@ __global__ void __launch_bounds__(256) attn_scores2_kernel(const float * __restr
             for (int e = 0; e < 8; ++e) s = fmaf(kv[e], qv[h][e], s);
 #pragma unroll
             for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (part == 0 && t < t_end) scores[(int64_t) (g * GQA + h) * s_stride + t] = s * scale;
+            if (part_i == 0) {
+                const float v = (t_base + tl < t_end) ? s * scale : -INFINITY;
+                sc[h][tl] = v;
+                if (t_base + tl < t_end) scores[(int64_t) (g * GQA + h) * s_stride + t_base + tl] = v;
+            }
         }
+    }
+    __syncthreads();
+    // per-head chunk statistics: warp h handles head h (GQA <= 8 warps)
+    if (warp < GQA) {
+        float mx = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < B200_ATTN_CH / 32; ++i) mx = fmaxf(mx, sc[warp][lane + 32 * i]);
+        mx = warp_max(mx);
+        float sum = 0.0f;
+#pragma unroll
+        for (int i = 0; i < B200_ATTN_CH / 32; ++i) sum += expf(sc[warp][lane + 32 * i] - mx);   // exp(-inf) = 0 for the padded tail
+        sum = warp_sum(sum);
+        if (lane == 0) part[(int64_t) (g * GQA + warp) * nchunks + blockIdx.x] = make_float2(mx, sum);
     }
 }
 
-// softmax (per head, recomputed by every CTA of the KV group: 16 K expf, trivial) fused with out = V . P
+// softmax normalisation (from the chunk statistics) fused with out = V . P
 // grid (HD/8, kv_heads), block 256 = 8 warps, one V^T channel row per warp; P of the group's GQA heads lives in smem.
 template <int GQA>
-__global__ void __launch_bounds__(256) attn_softmax_pv_kernel(const float * __restrict__ scores, const __half * __restrict__ vc, float * __restrict__ out,
-                                                              int n_kv, int head_dim, int64_t v_row_stride, int64_t s_stride) {
+__global__ void __launch_bounds__(256) attn_softmax_pv_kernel(const float * __restrict__ scores, const float2 * __restrict__ part, const __half * __restrict__ vc,
+                                                              float * __restrict__ out, int n_kv, int head_dim, int64_t v_row_stride, int64_t s_stride,
+                                                              int nchunks) {
     extern __shared__ float P[];  // [GQA][s_stride]
-    __shared__ float red[32];
+    __shared__ float hmax[GQA], hinv[GQA];
     pdl_launch_dependents();
-    pdl_wait();
     const int g = blockIdx.y;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int d = blockIdx.x * 8 + warp;
+    const int ch = g * head_dim + d;
+    const __half * vr = vc + (int64_t) ch * v_row_stride;
+    // V does not depend on the scores kernel (the KV cache was written two kernels earlier... but by THIS token's
+    // rope_kv_store, which the scores kernel already waited for): safe to prefetch only after the dependency resolves
+    pdl_wait();
+    if (warp < GQA) {
+        const float2 * pp = part + (int64_t) (g * GQA + warp) * nchunks;
+        float mx = -INFINITY;
+        for (int i = lane; i < nchunks; i += 32) mx = fmaxf(mx, pp[i].x);
+        mx = warp_max(mx);
+        float sum = 0.0f;
+        for (int i = lane; i < nchunks; i += 32) { const float2 v = pp[i]; sum += v.y * expf(v.x - mx); }
+        sum = warp_sum(sum);
+        if (lane == 0) { hmax[warp] = mx; hinv[warp] = 1.0f / sum; }
+    }
+    // first V loads in flight while P is being built
+    const int n8 = n_kv & ~7;
+    uint4 pre[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int t = lane * 8 + u * 256;
+        pre[u] = (t < n8) ? *reinterpret_cast<const uint4 *>(vr + t) : make_uint4(0, 0, 0, 0);
+    }
+    __syncthreads();
 #pragma unroll
     for (int h = 0; h < GQA; ++h) {
         const float * s = scores + (int64_t) (g * GQA + h) * s_stride;
         float * ph = P + (int64_t) h * s_stride;
-        float mx = -INFINITY;
-        for (int i = threadIdx.x; i < n_kv; i += blockDim.x) { const float v = s[i]; ph[i] = v; mx = fmaxf(mx, v); }
-        mx = blk_max(mx, red);
-        float sum = 0.0f;
-        for (int i = threadIdx.x; i < n_kv; i += blockDim.x) { const float e = expf(ph[i] - mx); ph[i] = e; sum += e; }
-        sum = blk_sum(sum, red);
-        const float inv = 1.0f / sum;
-        for (int i = threadIdx.x; i < n_kv; i += blockDim.x) ph[i] = __half2float(__float2half_rn(ph[i] * inv));
+        const float mx = hmax[h], inv = hinv[h];
+        for (int i = threadIdx.x; i < n_kv; i += blockDim.x) ph[i] = __half2float(__float2half_rn(expf(s[i] - mx) * inv));
         for (int i = n_kv + threadIdx.x; i < s_stride; i += blockDim.x) ph[i] = 0.0f;
     }
     __syncthreads();
-    const int d = blockIdx.x * 8 + warp;
-    const int ch = g * head_dim + d;
-    const __half * vr = vc + (int64_t) ch * v_row_stride;
     float acc[GQA];
 #pragma unroll
     for (int h = 0; h < GQA; ++h) acc[h] = 0.0f;
-    const int n8 = n_kv & ~7;
-    for (int t = lane * 8; t < n8; t += 256) {
-        const uint4 raw = *reinterpret_cast<const uint4 *>(vr + t);
-        const __half2 * hp = reinterpret_cast<const __half2 *>(&raw);
-        float vv[8];
+    for (int t0 = 0; t0 < n8; t0 += 1024) {
+        uint4 cur[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) { vv[2 * e] = __low2float(hp[e]); vv[2 * e + 1] = __high2float(hp[e]); }
+        for (int u = 0; u < 4; ++u) cur[u] = pre[u];
 #pragma unroll
-        for (int h = 0; h < GQA; ++h) {
-            const float4 p0 = *reinterpret_cast<const float4 *>(P + (int64_t) h * s_stride + t);
-            const float4 p1 = *reinterpret_cast<const float4 *>(P + (int64_t) h * s_stride + t + 4);
-            acc[h] = fmaf(vv[0], p0.x, acc[h]); acc[h] = fmaf(vv[1], p0.y, acc[h]); acc[h] = fmaf(vv[2], p0.z, acc[h]); acc[h] = fmaf(vv[3], p0.w, acc[h]);
-            acc[h] = fmaf(vv[4], p1.x, acc[h]); acc[h] = fmaf(vv[5], p1.y, acc[h]); acc[h] = fmaf(vv[6], p1.z, acc[h]); acc[h] = fmaf(vv[7], p1.w, acc[h]);
+        for (int u = 0; u < 4; ++u) {   // prefetch the next trip
+            const int t = t0 + 1024 + lane * 8 + u * 256;
+            pre[u] = (t < n8) ? *reinterpret_cast<const uint4 *>(vr + t) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int t = t0 + lane * 8 + u * 256;
+            if (t < n8) {
+                const __half2 * hp = reinterpret_cast<const __half2 *>(&cur[u]);
+                float vv[8];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { vv[2 * e] = __low2float(hp[e]); vv[2 * e + 1] = __high2float(hp[e]); }
+#pragma unroll
+                for (int h = 0; h < GQA; ++h) {
+                    const float4 p0 = *reinterpret_cast<const float4 *>(P + (int64_t) h * s_stride + t);
+                    const float4 p1 = *reinterpret_cast<const float4 *>(P + (int64_t) h * s_stride + t + 4);
+                    acc[h] = fmaf(vv[0], p0.x, acc[h]); acc[h] = fmaf(vv[1], p0.y, acc[h]); acc[h] = fmaf(vv[2], p0.z, acc[h]); acc[h] = fmaf(vv[3], p0.w, acc[h]);
+                    acc[h] = fmaf(vv[4], p1.x, acc[h]); acc[h] = fmaf(vv[5], p1.y, acc[h]); acc[h] = fmaf(vv[6], p1.z, acc[h]); acc[h] = fmaf(vv[7], p1.w, acc[h]);
+                }
+            }
         }
     }
     if (lane < n_kv - n8) {
@@ -342,8 +396,10 @@ template <int HD, int GQA>
 static int attn_decode2_t(const float * q, const void * kc, const void * vc, float * out, float * scratch, int n_kv, int kv_heads, int64_t k_row_stride,
                           int64_t v_row_stride, float scale, cudaStream_t st) {
     const int64_t s_stride = (n_kv + 7) & ~7;
-    dim3 g1((unsigned) ((n_kv + 127) / 128), (unsigned) kv_heads);
-    launch_pdl(attn_scores2_kernel<HD, GQA>, dim3(g1), dim3(256), 0, st, q, (const __half *) kc, scratch, n_kv, k_row_stride, scale, s_stride);
+    const int nchunks = (n_kv + B200_ATTN_CH - 1) / B200_ATTN_CH;
+    float2 * part = reinterpret_cast<float2 *>(scratch + (int64_t) kv_heads * GQA * s_stride);
+    dim3 g1((unsigned) nchunks, (unsigned) kv_heads);
+    launch_pdl(attn_scores2_kernel<HD, GQA>, g1, dim3(256), 0, st, q, (const __half *) kc, scratch, part, n_kv, k_row_stride, scale, s_stride, nchunks);
     const size_t smem = (size_t) GQA * s_stride * 4;
     static size_t configured = 0;
     if (smem > configured) {
@@ -353,11 +409,13 @@ static int attn_decode2_t(const float * q, const void * kc, const void * vc, flo
     }
     if (smem > 227 * 1024) return B200_ERR_UNSUPPORTED;
     dim3 g2((unsigned) (HD / 8), (unsigned) kv_heads);
-    launch_pdl(attn_softmax_pv_kernel<GQA>, dim3(g2), dim3(256), smem, st, scratch, (const __half *) vc, out, n_kv, HD, v_row_stride, s_stride);
+    launch_pdl(attn_softmax_pv_kernel<GQA>, g2, dim3(256), smem, st, scratch, (const float2 *) part, (const __half *) vc, out, n_kv, HD, v_row_stride, s_stride, nchunks);
     return (int) cudaGetLastError();
 }
 
-size_t attn_decode2_scratch_bytes(int n_heads, int n_kv) { return (size_t) n_heads * (size_t) ((n_kv + 7) & ~7) * 4; }
+size_t attn_decode2_scratch_bytes(int n_heads, int n_kv) {
+    return (size_t) n_heads * (size_t) ((n_kv + 7) & ~7) * 4 + (size_t) n_heads * (size_t) ((n_kv + B200_ATTN_CH - 1) / B200_ATTN_CH) * 8 + 64;
+}
 
 int attn_decode2(const float * q, const void * kc, const void * vc, float * out, float * scratch, int n_heads, int kv_heads, int head_dim, int n_kv,
                  int64_t k_row_stride, int64_t v_row_stride, float scale, cudaStream_t st) {

@@ -311,3 +311,39 @@ def test_mul_mat_multi_concat_and_paired(K, wtype):
     g = qf.port_mul_mat(wtype, wg, k, m, x); u = qf.port_mul_mat(wtype, wu, k, m, x)
     ref = np.zeros_like(g); qf.port().oq_silu_mul(g.ctypes.data, u.ctypes.data, ref.ctypes.data, m)
     assert np.abs(y.cpu().numpy() - ref).max() <= 3e-5 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("heads,kvh,hd", [(32, 8, 128), (32, 4, 64), (28, 4, 128), (4, 2, 64)])
+@pytest.mark.parametrize("n_kv", [1, 7, 128, 129, 1000, 4097])
+def test_attn_decode_vs_reference_semantics(K, heads, kvh, hd, n_kv):
+    """scores = K.f16(q) (fp32 acc) * scale -> softmax -> f16(P) -> V.P, on the reference's cache layouts
+    (src/layers.cpp:2541-2561, ggml-cpu.c:213-219), evaluated in float64 with explicit f16 roundings."""
+    import torch
+    import chatllm_cpp_b200 as pkg
+    rng = np.random.default_rng(n_kv + heads)
+    max_len = 4352
+    kv_hidden = kvh * hd
+    kc = rng.standard_normal((max_len, kv_hidden)).astype(np.float16)
+    vc = rng.standard_normal((kv_hidden, max_len)).astype(np.float16)
+    q = rng.standard_normal((heads, hd)).astype(np.float32) * 2
+    scale = 1.0 / np.sqrt(hd)
+    L = pkg.lib()
+    out = torch.zeros((heads, hd), device="cuda")
+    scratch = torch.empty(L.b200_attn_decode_scratch_bytes(heads, max_len) // 4 + 16, dtype=torch.float32, device="cuda")
+    qd, kd, vd = _t(q), _t(kc), _t(vc)
+    rc = L.b200_attn_decode(qd.data_ptr(), kd.data_ptr(), vd.data_ptr(), out.data_ptr(), scratch.data_ptr(), heads, kvh, hd, n_kv,
+                            kv_hidden, max_len, scale, 0)
+    assert rc == 0
+    torch.cuda.synchronize()
+    g = heads // kvh
+    q16 = q.astype(np.float16).astype(np.float64)
+    ref = np.zeros((heads, hd))
+    for h in range(heads):
+        kk = kc[:n_kv, (h // g) * hd:(h // g + 1) * hd].astype(np.float64)
+        s = (kk @ q16[h]).astype(np.float32) * np.float32(scale)
+        e = np.exp((s - s.max()).astype(np.float32)).astype(np.float32)
+        p = (e / np.float32(e.astype(np.float64).sum())).astype(np.float16).astype(np.float64)
+        vv = vc[(h // g) * hd:(h // g + 1) * hd, :n_kv].astype(np.float64)
+        ref[h] = vv @ p
+    got = out.cpu().numpy()
+    assert np.abs(got - ref).max() <= 2e-3 * np.abs(ref).max() + 1e-6   # f16 rounding of P can flip on an ulp: ~1e-3 of one term
