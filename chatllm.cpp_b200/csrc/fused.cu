@@ -340,13 +340,35 @@ __global__ void __launch_bounds__(256) attn_softmax_pv_kernel(const float * __re
         pre[u] = (t < n8) ? *reinterpret_cast<const uint4 *>(vr + t) : make_uint4(0, 0, 0, 0);
     }
     __syncthreads();
+    {
+        // P[h][t] = f16(exp(s - max_h) / sum_h): the group's GQA score rows are contiguous -> one flat float4 stream,
+        // loads batched 8 deep so the L2 round trips overlap (a one-load-at-a-time loop costs ~25 us here)
+        const float4 * src = reinterpret_cast<const float4 *>(scores + (int64_t) g * GQA * s_stride);
+        float4 * dst = reinterpret_cast<float4 *>(P);
+        const int total4 = (int) (GQA * s_stride / 4);
+        const int row4 = (int) (s_stride / 4);
+        for (int j0 = threadIdx.x; j0 < total4; j0 += 8 * 256) {
+            float4 v[8];
 #pragma unroll
-    for (int h = 0; h < GQA; ++h) {
-        const float * s = scores + (int64_t) (g * GQA + h) * s_stride;
-        float * ph = P + (int64_t) h * s_stride;
-        const float mx = hmax[h], inv = hinv[h];
-        for (int i = threadIdx.x; i < n_kv; i += blockDim.x) ph[i] = __half2float(__float2half_rn(expf(s[i] - mx) * inv));
-        for (int i = n_kv + threadIdx.x; i < s_stride; i += blockDim.x) ph[i] = 0.0f;
+            for (int u = 0; u < 8; ++u) {
+                const int j = j0 + u * 256;
+                v[u] = (j < total4) ? src[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int j = j0 + u * 256;
+                if (j < total4) {
+                    const int h = j / row4, t = (j - h * row4) * 4;
+                    const float mx = hmax[h], inv = hinv[h];
+                    float4 o;
+                    o.x = (t + 0 < n_kv) ? __half2float(__float2half_rn(expf(v[u].x - mx) * inv)) : 0.0f;
+                    o.y = (t + 1 < n_kv) ? __half2float(__float2half_rn(expf(v[u].y - mx) * inv)) : 0.0f;
+                    o.z = (t + 2 < n_kv) ? __half2float(__float2half_rn(expf(v[u].z - mx) * inv)) : 0.0f;
+                    o.w = (t + 3 < n_kv) ? __half2float(__float2half_rn(expf(v[u].w - mx) * inv)) : 0.0f;
+                    dst[j] = o;
+                }
+            }
+        }
     }
     __syncthreads();
     float acc[GQA];
