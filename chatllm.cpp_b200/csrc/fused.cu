@@ -243,8 +243,8 @@ int rope_kv_store(float * q, const float * k, const float * v, const int32_t * p
 #define B200_ATTN_CH 128
 template <int HD, int GQA>
 __global__ void __launch_bounds__(256) attn_scores2_kernel(const float * __restrict__ q, const __half * __restrict__ kc, float * __restrict__ scores,
-                                                           float2 * __restrict__ part, int * __restrict__ counters, int n_kv, int64_t k_row_stride,
-                                                           float scale, int64_t s_stride, int nchunks) {
+                                                           float2 * __restrict__ part, int n_kv, int64_t k_row_stride, float scale, int64_t s_stride,
+                                                           int nchunks) {
     constexpr int LPR = HD / 8;               // lanes per row
     constexpr int RPW = 32 / LPR;             // rows per warp load
     constexpr int NLD = B200_ATTN_CH / 8 / RPW;  // loads per lane: each warp owns CH/8 = 16 consecutive positions
@@ -302,33 +302,49 @@ __global__ void __launch_bounds__(256) attn_scores2_kernel(const float * __restr
         sum = warp_sum(sum);
         if (lane == 0) part[(int64_t) (g * GQA + warp) * nchunks + blockIdx.x] = make_float2(mx, sum);
     }
-    // ---- the LAST CTA of this KV group to finish turns the group's raw scores into P = f16(softmax) in place, so the
-    //      V.P kernel does not have to recompute 4 x n_kv exponentials in each of its CTAs
-    __shared__ int is_last;
+}
+
+// softmax normalisation (from the chunk statistics) fused with out = V . P
+// grid (HD/8, kv_heads), block 256 = 8 warps, one V^T channel row per warp; P of the group's GQA heads lives in smem.
+template <int GQA>
+__global__ void __launch_bounds__(256) attn_softmax_pv_kernel(const float * __restrict__ scores, const float2 * __restrict__ part, const __half * __restrict__ vc,
+                                                              float * __restrict__ out, int n_kv, int head_dim, int64_t v_row_stride, int64_t s_stride,
+                                                              int nchunks) {
+    extern __shared__ float P[];  // [GQA][s_stride]
     __shared__ float hmax[GQA], hinv[GQA];
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const int done = atomicAdd(&counters[g], 1);
-        is_last = (done == nchunks - 1);
-        if (is_last) counters[g] = 0;  // re-arm for the next launch (stream order protects it)
-    }
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
+    pdl_launch_dependents();
+    const int g = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int d = blockIdx.x * 8 + warp;
+    const int ch = g * head_dim + d;
+    const __half * vr = vc + (int64_t) ch * v_row_stride;
+    // V does not depend on the scores kernel (the KV cache was written two kernels earlier... but by THIS token's
+    // rope_kv_store, which the scores kernel already waited for): safe to prefetch only after the dependency resolves
+    pdl_wait();
     if (warp < GQA) {
-        const volatile float2 * pp = part + (int64_t) (g * GQA + warp) * nchunks;
+        const float2 * pp = part + (int64_t) (g * GQA + warp) * nchunks;
         float mx = -INFINITY;
         for (int i = lane; i < nchunks; i += 32) mx = fmaxf(mx, pp[i].x);
         mx = warp_max(mx);
         float sum = 0.0f;
-        for (int i = lane; i < nchunks; i += 32) sum += pp[i].y * expf(pp[i].x - mx);
+        for (int i = lane; i < nchunks; i += 32) { const float2 v = pp[i]; sum += v.y * expf(v.x - mx); }
         sum = warp_sum(sum);
         if (lane == 0) { hmax[warp] = mx; hinv[warp] = 1.0f / sum; }
     }
+    // first V loads in flight while P is being built
+    const int n8 = n_kv & ~7;
+    uint4 pre[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int t = lane * 8 + u * 256;
+        pre[u] = (t < n8) ? *reinterpret_cast<const uint4 *>(vr + t) : make_uint4(0, 0, 0, 0);
+    }
     __syncthreads();
     {
-        float4 * rows = reinterpret_cast<float4 *>(scores + (int64_t) g * GQA * s_stride);
+        // P[h][t] = f16(exp(s - max_h) / sum_h): the group's GQA score rows are contiguous -> one flat float4 stream,
+        // loads batched 8 deep so the L2 round trips overlap (a one-load-at-a-time loop costs ~25 us here)
+        const float4 * src = reinterpret_cast<const float4 *>(scores + (int64_t) g * GQA * s_stride);
+        float4 * dst = reinterpret_cast<float4 *>(P);
         const int total4 = (int) (GQA * s_stride / 4);
         const int row4 = (int) (s_stride / 4);
         for (int j0 = threadIdx.x; j0 < total4; j0 += 8 * 256) {
@@ -336,7 +352,7 @@ __global__ void __launch_bounds__(256) attn_scores2_kernel(const float * __restr
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const int j = j0 + u * 256;
-                v[u] = (j < total4) ? __ldcg(rows + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                v[u] = (j < total4) ? src[j] : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
@@ -349,44 +365,9 @@ __global__ void __launch_bounds__(256) attn_scores2_kernel(const float * __restr
                     o.y = (t + 1 < n_kv) ? __half2float(__float2half_rn(expf(v[u].y - mx) * inv)) : 0.0f;
                     o.z = (t + 2 < n_kv) ? __half2float(__float2half_rn(expf(v[u].z - mx) * inv)) : 0.0f;
                     o.w = (t + 3 < n_kv) ? __half2float(__float2half_rn(expf(v[u].w - mx) * inv)) : 0.0f;
-                    rows[j] = o;
+                    dst[j] = o;
                 }
             }
-        }
-    }
-}
-
-// out = V . P  with P (already normalised and rounded through f16 by the scores kernel) staged in shared memory.
-// grid (HD/8, kv_heads), block 256 = 8 warps, one V^T channel row per warp.
-template <int GQA>
-__global__ void __launch_bounds__(256) attn_softmax_pv_kernel(const float * __restrict__ scores, const __half * __restrict__ vc, float * __restrict__ out,
-                                                              int n_kv, int head_dim, int64_t v_row_stride, int64_t s_stride) {
-    extern __shared__ float P[];  // [GQA][s_stride]
-    pdl_launch_dependents();
-    const int g = blockIdx.y;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int d = blockIdx.x * 8 + warp;
-    const int ch = g * head_dim + d;
-    const __half * vr = vc + (int64_t) ch * v_row_stride;
-    pdl_wait();
-    // first V loads in flight while P is being staged
-    const int n8 = n_kv & ~7;
-    uint4 pre[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-        const int t = lane * 8 + u * 256;
-        pre[u] = (t < n8) ? *reinterpret_cast<const uint4 *>(vr + t) : make_uint4(0, 0, 0, 0);
-    }
-    {
-        const float4 * src = reinterpret_cast<const float4 *>(scores + (int64_t) g * GQA * s_stride);
-        float4 * dst = reinterpret_cast<float4 *>(P);
-        const int total4 = (int) (GQA * s_stride / 4);
-        for (int j0 = threadIdx.x; j0 < total4; j0 += 8 * 256) {
-            float4 v[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) { const int j = j0 + u * 256; v[u] = (j < total4) ? src[j] : make_float4(0.f, 0.f, 0.f, 0.f); }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) { const int j = j0 + u * 256; if (j < total4) dst[j] = v[u]; }
         }
     }
     __syncthreads();
@@ -433,28 +414,14 @@ __global__ void __launch_bounds__(256) attn_softmax_pv_kernel(const float * __re
     }
 }
 
-// per-device completion counters of the scores kernel (zero-initialised once; each launch leaves them at zero again)
-static int * attn_counters(int n) {
-    static int * ptr[16] = {nullptr};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (!ptr[dev]) {
-        if (cudaMalloc(&ptr[dev], 1024 * sizeof(int)) != cudaSuccess) return nullptr;
-        cudaMemset(ptr[dev], 0, 1024 * sizeof(int));
-    }
-    return n <= 1024 ? ptr[dev] : nullptr;
-}
-
 template <int HD, int GQA>
 static int attn_decode2_t(const float * q, const void * kc, const void * vc, float * out, float * scratch, int n_kv, int kv_heads, int64_t k_row_stride,
                           int64_t v_row_stride, float scale, cudaStream_t st) {
     const int64_t s_stride = (n_kv + 7) & ~7;
     const int nchunks = (n_kv + B200_ATTN_CH - 1) / B200_ATTN_CH;
     float2 * part = reinterpret_cast<float2 *>(scratch + (int64_t) kv_heads * GQA * s_stride);
-    int * counters = attn_counters(kv_heads);
-    if (!counters) return (int) cudaErrorMemoryAllocation;
     dim3 g1((unsigned) nchunks, (unsigned) kv_heads);
-    launch_pdl(attn_scores2_kernel<HD, GQA>, g1, dim3(256), 0, st, q, (const __half *) kc, scratch, part, counters, n_kv, k_row_stride, scale, s_stride, nchunks);
+    launch_pdl(attn_scores2_kernel<HD, GQA>, g1, dim3(256), 0, st, q, (const __half *) kc, scratch, part, n_kv, k_row_stride, scale, s_stride, nchunks);
     const size_t smem = (size_t) GQA * s_stride * 4;
     static size_t configured = 0;
     if (smem > configured) {
@@ -464,7 +431,7 @@ static int attn_decode2_t(const float * q, const void * kc, const void * vc, flo
     }
     if (smem > 227 * 1024) return B200_ERR_UNSUPPORTED;
     dim3 g2((unsigned) (HD / 8), (unsigned) kv_heads);
-    launch_pdl(attn_softmax_pv_kernel<GQA>, g2, dim3(256), smem, st, scratch, (const __half *) vc, out, n_kv, HD, v_row_stride, s_stride);
+    launch_pdl(attn_softmax_pv_kernel<GQA>, g2, dim3(256), smem, st, scratch, (const float2 *) part, (const __half *) vc, out, n_kv, HD, v_row_stride, s_stride, nchunks);
     return (int) cudaGetLastError();
 }
 
