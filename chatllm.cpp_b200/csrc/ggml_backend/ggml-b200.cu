@@ -67,7 +67,15 @@ struct b200_backend_ctx {
     cudaStream_t stream;
     void * qact = nullptr;
     size_t qact_bytes = 0;
+    float * attn_scratch = nullptr;
+    size_t attn_scratch_bytes = 0;
     long long launches = 0;
+    long long fused = 0;
+    // which tensor currently sits quantized in `qact` (valid inside one graph_compute call)
+    const ggml_tensor * q_src = nullptr;
+    const void * q_data = nullptr;
+    int q_kind = -1;  // 0 = Q8_K codes (Q4_K weights), 1 = Q8_0 codes (Q4_0 / Q8_0 weights)
+    int64_t q_k = 0, q_n = 0;
 };
 
 static ggml_backend_device g_devices[B200_MAX_DEVICES];
@@ -356,6 +364,161 @@ static void * ensure_qact(b200_backend_ctx * bc, size_t bytes) {
     return bc->qact;
 }
 
+static int kind_of(ggml_type t) { return t == GGML_TYPE_Q4_K ? 0 : 1; }
+
+// make sure `x` (F32, k x n, row stride nb1) is present in bc->qact quantized for weight type wtype
+static int ensure_quantized(b200_backend_ctx * bc, int wtype, const ggml_tensor * x) {
+    const int64_t k = x->ne[0], n = x->ne[1];
+    const int kind = kind_of((ggml_type) wtype);
+    if (bc->q_src == x && bc->q_data == x->data && bc->q_kind == kind && bc->q_k == k && bc->q_n == n) return 0;
+    const size_t cb = qact_col_bytes(wtype, k);
+    void * q = ensure_qact(bc, cb * (size_t) n);
+    const int rc = quantize_act(wtype, (const float *) x->data, (int64_t) (x->nb[1] / 4), k, n, q, bc->stream);
+    bc->launches++;
+    bc->q_src = x; bc->q_data = x->data; bc->q_kind = kind; bc->q_k = k; bc->q_n = n;
+    return rc;
+}
+
+static int mul_mat_quant(b200_backend_ctx * bc, const ggml_tensor * w, const ggml_tensor * x, float * y, int64_t ldy, const float * bias) {
+    int rc = ensure_quantized(bc, (int) w->type, x);
+    if (rc) return rc;
+    return mul_mat_q((int) w->type, w->data, w->ne[0], w->ne[1], bc->qact, x->ne[1], y, ldy, bias, nullptr, bc->stream);
+}
+
+static bool is_quant_mm(const ggml_tensor * t) {
+    return t->op == GGML_OP_MUL_MAT && ggml_is_quantized(t->src[0]->type) && qtype_ok(t->src[0]) && ggml_is_contiguous(t->src[0]) &&
+           t->src[0]->ne[2] == 1 && t->src[0]->ne[3] == 1 && t->src[1]->type == GGML_TYPE_F32 && t->src[1]->ne[2] == 1 && t->src[1]->ne[3] == 1 &&
+           t->src[1]->nb[0] == 4 && ggml_is_contiguous(t);
+}
+
+// ---- graph-level fusion (the reference's CUDA backend fuses too: ggml-cuda.cu:3629-3960).  Each try_* returns the number
+//      of consecutive nodes it consumed (0 = pattern not matched).  B200_NO_FUSION=1 disables all of them.
+static bool fusion_enabled() {
+    static const bool on = !(getenv("B200_NO_FUSION") && atoi(getenv("B200_NO_FUSION")) != 0);
+    return on;
+}
+
+// [ADD] -> RMS_NORM -> MUL(weight)  (+ quantization for the quantized matmuls that consume it)
+static int try_fuse_norm(b200_backend_ctx * bc, ggml_cgraph * g, int i, int * rc) {
+    int j = i;
+    ggml_tensor * add = nullptr;
+    if (g->nodes[j]->op == GGML_OP_ADD && j + 2 < g->n_nodes && g->nodes[j + 1]->op == GGML_OP_RMS_NORM && g->nodes[j + 1]->src[0] == g->nodes[j]) {
+        add = g->nodes[j];
+        if (!(f32c(add->src[0]) && f32c(add->src[1]) && f32c(add) && ggml_are_same_shape(add->src[0], add->src[1]))) return 0;
+        j++;
+    }
+    if (j + 1 >= g->n_nodes) return 0;
+    ggml_tensor * rms = g->nodes[j];
+    ggml_tensor * mul = g->nodes[j + 1];
+    if (rms->op != GGML_OP_RMS_NORM || mul->op != GGML_OP_MUL) return 0;
+    const ggml_tensor * w = nullptr;
+    if (mul->src[0] == rms) w = mul->src[1];
+    else if (mul->src[1] == rms) w = mul->src[0];
+    if (!w || !f32c(w) || ggml_nelements(w) != rms->ne[0] || !f32c(rms->src[0]) || !f32c(mul)) return 0;
+    if (rms->ne[0] % 256 || rms->ne[0] > 20480) return 0;
+    if (!add && !ggml_node_has_n_uses(g, j, 1)) return 0;
+    // which weight type will consume the normalised activations?
+    int wtype = -1;
+    for (int t = j + 2; t < g->n_nodes && t < j + 12; ++t) {
+        const ggml_tensor * c = g->nodes[t];
+        if (c->op == GGML_OP_MUL_MAT && c->src[1] == mul && is_quant_mm(c)) { wtype = (int) c->src[0]->type; break; }
+    }
+    float eps;
+    memcpy(&eps, rms->op_params, sizeof(float));
+    const int64_t ne0 = rms->ne[0], nrows = ggml_nrows(rms);
+    void * q = nullptr;
+    if (wtype >= 0 && mul->ne[2] == 1 && mul->ne[3] == 1) q = ensure_qact(bc, qact_col_bytes(wtype, ne0) * (size_t) nrows);
+    const float * x = (const float *) (add ? add->src[0]->data : rms->src[0]->data);
+    *rc = add_rmsnorm_quant(wtype >= 0 ? wtype : GGML_TYPE_Q4_K, x, add ? (const float *) add->src[1]->data : nullptr, (const float *) w->data,
+                            add ? (float *) add->data : nullptr, (float *) mul->data, q, ne0, nrows, eps, bc->stream);
+    if (q) { bc->q_src = mul; bc->q_data = mul->data; bc->q_kind = kind_of((ggml_type) wtype); bc->q_k = ne0; bc->q_n = nrows; }
+    return (add ? 3 : 2);
+}
+
+// MUL_MAT(gate) -> SILU -> MUL_MAT(up) -> MUL : one paired GEMV launch with the SwiGLU epilogue
+static int try_fuse_swiglu(b200_backend_ctx * bc, ggml_cgraph * g, int i, int * rc) {
+    if (i + 3 >= g->n_nodes) return 0;
+    ggml_tensor * gate = g->nodes[i], * act = g->nodes[i + 1], * up = g->nodes[i + 2], * mul = g->nodes[i + 3];
+    if (!is_quant_mm(gate) || !is_quant_mm(up) || act->op != GGML_OP_UNARY || ggml_get_unary_op(act) != GGML_UNARY_OP_SILU || mul->op != GGML_OP_MUL) return 0;
+    if (act->src[0] != gate || gate->src[1] != up->src[1] || gate->src[0]->type != up->src[0]->type || !ggml_are_same_shape(gate->src[0], up->src[0])) return 0;
+    if (!((mul->src[0] == act && mul->src[1] == up) || (mul->src[1] == act && mul->src[0] == up))) return 0;
+    if (!f32c(mul) || !ggml_node_has_n_uses(g, i, 1) || !ggml_node_has_n_uses(g, i + 2, 1)) return 0;
+    if (gate->src[0]->ne[1] % 2) return 0;
+    const ggml_tensor * x = gate->src[1];
+    *rc = ensure_quantized(bc, (int) gate->src[0]->type, x);
+    if (*rc) return 4;
+    const void * Ws[2] = {gate->src[0]->data, up->src[0]->data};
+    const int64_t ms[2] = {gate->src[0]->ne[1], up->src[0]->ne[1]};
+    float * ys[2] = {(float *) mul->data, nullptr};
+    const int64_t lds[2] = {(int64_t) (mul->nb[1] / 4), (int64_t) (mul->nb[1] / 4)};
+    *rc = mul_mat_q_multi((int) gate->src[0]->type, 1, 2, Ws, ms, ys, lds, nullptr, x->ne[0], bc->qact, x->ne[1], nullptr, bc->stream);
+    return 4;
+}
+
+// MUL_MAT -> ADD(bias): bias in the GEMV epilogue (Qwen2 q/k/v projections, src/layers.h:2950-2953)
+static int try_fuse_bias(b200_backend_ctx * bc, ggml_cgraph * g, int i, int * rc) {
+    if (i + 1 >= g->n_nodes) return 0;
+    ggml_tensor * mm = g->nodes[i], * add = g->nodes[i + 1];
+    if (!is_quant_mm(mm) || add->op != GGML_OP_ADD || add->src[0] != mm) return 0;
+    const ggml_tensor * b = add->src[1];
+    if (!f32c(b) || ggml_nelements(b) != mm->ne[0] || !f32c(add) || !ggml_are_same_shape(add, mm)) return 0;
+    *rc = mul_mat_quant(bc, mm->src[0], mm->src[1], (float *) add->data, (int64_t) (add->nb[1] / 4), (const float *) b->data);
+    return 2;
+}
+
+// decode attention: MUL_MAT(K,Q) -> SCALE -> DIAG_MASK_INF -> SOFT_MAX -> MUL_MAT(V,P) -> PERMUTE -> CONT, one query token
+static int try_fuse_attention(b200_backend_ctx * bc, ggml_cgraph * g, int i, int * rc) {
+    if (i + 6 >= g->n_nodes) return 0;
+    ggml_tensor * kq = g->nodes[i], * sc = g->nodes[i + 1], * dm = g->nodes[i + 2], * sm = g->nodes[i + 3], * pv = g->nodes[i + 4], * pm = g->nodes[i + 5],
+                * ct = g->nodes[i + 6];
+    if (kq->op != GGML_OP_MUL_MAT || sc->op != GGML_OP_SCALE || dm->op != GGML_OP_DIAG_MASK_INF || sm->op != GGML_OP_SOFT_MAX || pv->op != GGML_OP_MUL_MAT ||
+        pm->op != GGML_OP_PERMUTE || ct->op != GGML_OP_CONT)
+        return 0;
+    if (sc->src[0] != kq || dm->src[0] != sc || sm->src[0] != dm || sm->src[1] || sm->src[2] || pv->src[1] != sm || pm->src[0] != pv || ct->src[0] != pm) return 0;
+    const ggml_tensor * K = kq->src[0], * Q = kq->src[1], * V = pv->src[0];
+    if (K->type != GGML_TYPE_F16 || V->type != GGML_TYPE_F16 || Q->type != GGML_TYPE_F32) return 0;
+    const int64_t hd = K->ne[0], n_kv = K->ne[1], kvh = K->ne[2], heads = Q->ne[2];
+    if (Q->ne[0] != hd || Q->ne[1] != 1 || Q->ne[3] != 1 || K->ne[3] != 1 || V->ne[3] != 1 || heads % kvh) return 0;
+    if (V->ne[0] != n_kv || V->ne[1] != hd || V->ne[2] != kvh) return 0;
+    if (K->nb[0] != 2 || K->nb[2] != (size_t) hd * 2 || V->nb[0] != 2 || V->nb[2] != (size_t) hd * V->nb[1] || Q->nb[0] != 4 || Q->nb[2] != (size_t) hd * 4) return 0;
+    if ((K->nb[1] % 16) || (V->nb[1] % 16) || ((uintptr_t) K->data % 16) || ((uintptr_t) V->data % 16)) return 0;
+    float scale, sbias, smscale, smbias;
+    memcpy(&scale, (const float *) sc->op_params + 0, 4);
+    memcpy(&sbias, (const float *) sc->op_params + 1, 4);
+    memcpy(&smscale, (const float *) sm->op_params + 0, 4);
+    memcpy(&smbias, (const float *) sm->op_params + 1, 4);
+    if (sbias != 0.0f || smscale != 1.0f || smbias != 0.0f) return 0;
+    if (dm->op_params[0] != (int32_t) (n_kv - 1)) return 0;  // the single query row sees every cached position
+    if (!f32c(ct) || ct->ne[0] != hd || ct->ne[1] != heads || ggml_nelements(ct) != hd * heads) return 0;
+    const size_t need = attn_decode2_scratch_bytes((int) heads, (int) n_kv) + attn_decode_scratch_bytes((int) heads, (int) n_kv);
+    if (bc->attn_scratch_bytes < need) {
+        CUDA_OK(cudaStreamSynchronize(bc->stream));
+        if (bc->attn_scratch) CUDA_OK(cudaFree(bc->attn_scratch));
+        const size_t nb = need < (4u << 20) ? (4u << 20) : need * 2;
+        CUDA_OK(cudaMalloc((void **) &bc->attn_scratch, nb));
+        bc->attn_scratch_bytes = nb;
+    }
+    int r = attn_decode2((const float *) Q->data, K->data, V->data, (float *) ct->data, bc->attn_scratch, (int) heads, (int) kvh, (int) hd, (int) n_kv,
+                         (int64_t) (K->nb[1] / 2), (int64_t) (V->nb[1] / 2), scale, bc->stream);
+    if (r == B200_ERR_UNSUPPORTED) return 0;
+    *rc = r;
+    bc->launches++;
+    return 7;
+}
+
+static int try_fuse(b200_backend_ctx * bc, ggml_cgraph * g, int i, int * rc) {
+    if (!fusion_enabled()) return 0;
+    int n;
+    const ggml_tensor * node = g->nodes[i];
+    if (node->op == GGML_OP_ADD || node->op == GGML_OP_RMS_NORM) { if ((n = try_fuse_norm(bc, g, i, rc))) return n; }
+    if (node->op == GGML_OP_MUL_MAT) {
+        if ((n = try_fuse_attention(bc, g, i, rc))) return n;
+        if ((n = try_fuse_swiglu(bc, g, i, rc))) return n;
+        if ((n = try_fuse_bias(bc, g, i, rc))) return n;
+    }
+    return 0;
+}
+
 static int compute_node(b200_backend_ctx * bc, ggml_tensor * node) {
     cudaStream_t st = bc->stream;
     const ggml_tensor * s0 = node->src[0];
@@ -376,19 +539,7 @@ static int compute_node(b200_backend_ctx * bc, ggml_tensor * node) {
         case GGML_OP_DIV: return op_bin(2, tv(s0), tv(s1), tv(node), st);
         case GGML_OP_MUL_MAT: {
             if (ggml_is_quantized(s0->type)) {
-                const int64_t k = s0->ne[0], m = s0->ne[1], n = s1->ne[1];
-                const size_t cb = qact_col_bytes((int) s0->type, k);
-                const int64_t batch = 64;
-                void * q = ensure_qact(bc, cb * (size_t) (n < batch ? n : batch));
-                const int64_t ldx = (int64_t) (s1->nb[1] / 4), ldy = (int64_t) (node->nb[1] / 4);
-                for (int64_t c0 = 0; c0 < n; c0 += batch) {
-                    const int64_t nc = (n - c0) < batch ? (n - c0) : batch;
-                    int rc = quantize_act((int) s0->type, (const float *) s1->data + c0 * ldx, ldx, k, nc, q, st);
-                    if (rc) return rc;
-                    rc = mul_mat_q((int) s0->type, s0->data, k, m, q, nc, (float *) node->data + c0 * ldy, ldy, nullptr, nullptr, st);
-                    if (rc) return rc;
-                }
-                return 0;
+                return mul_mat_quant(bc, s0, s1, (float *) node->data, (int64_t) (node->nb[1] / 4), nullptr);
             }
             return op_mul_mat_f(tv(s0), tv(s1), tv(node), st);
         }
@@ -448,6 +599,7 @@ static void b200_backend_free(ggml_backend_t backend) {
     cudaSetDevice(bc->device);
     cudaStreamSynchronize(bc->stream);
     if (bc->qact) cudaFree(bc->qact);
+    if (bc->attn_scratch) cudaFree(bc->attn_scratch);
     cudaStreamDestroy(bc->stream);
     delete bc;
     delete backend;
@@ -460,16 +612,25 @@ static void b200_backend_synchronize(ggml_backend_t backend) {
 static enum ggml_status b200_graph_compute(ggml_backend_t backend, ggml_cgraph * cgraph) {
     b200_backend_ctx * bc = (b200_backend_ctx *) backend->context;
     CUDA_OK(cudaSetDevice(bc->device));
+    bc->q_src = nullptr;  // nothing is known to be quantized at the start of a graph
     for (int i = 0; i < cgraph->n_nodes; ++i) {
         ggml_tensor * node = cgraph->nodes[i];
         if (is_view_op(node->op) || ggml_is_empty(node)) continue;
-        const int rc = compute_node(bc, node);
+        int rc = 0;
+        const int consumed = try_fuse(bc, cgraph, i, &rc);
+        if (consumed > 0) {
+            bc->fused += consumed;
+            bc->launches++;
+            i += consumed - 1;
+        } else {
+            rc = compute_node(bc, node);
+            bc->launches++;
+        }
         if (rc != 0) {
             GGML_LOG_ERROR("b200: op %s (%s) failed rc=%d%s\n", ggml_op_name(node->op), node->name, rc,
                            rc > 0 ? cudaGetErrorString((cudaError_t) rc) : "");
             return GGML_STATUS_FAILED;
         }
-        bc->launches++;
     }
     return GGML_STATUS_SUCCESS;
 }

@@ -116,7 +116,8 @@ __global__ void rope_kernel(const float * __restrict__ x, float * __restrict__ y
         const float c = cosf(th) * mscale, s = sinf(th) * mscale;
         const int64_t i0 = (p.mode == 0) ? 2 * (int64_t) i : i;
         const int64_t i1 = (p.mode == 0) ? i0 + 1 : i + half;
-        for (int64_t h = 0; h < p.n_heads; ++h) {
+        {
+            const int64_t h = blockIdx.y;
             const float * src = x + t * p.xs_t + h * p.xs_h;
             float * dst = y + t * p.ys_t + h * p.ys_h;
             const float x0 = src[i0], x1 = src[i1];
@@ -126,9 +127,9 @@ __global__ void rope_kernel(const float * __restrict__ x, float * __restrict__ y
     }
     // pass-through of the un-rotated tail (n_dims < ne0), ops.cpp:5849-5858
     if (p.n_dims < p.ne0 && x != y) {
-        for (int64_t h = 0; h < p.n_heads; ++h)
-            for (int64_t i = p.n_dims + threadIdx.x; i < p.ne0; i += blockDim.x)
-                y[t * p.ys_t + h * p.ys_h + i] = x[t * p.xs_t + h * p.xs_h + i];
+        const int64_t h = blockIdx.y;
+        for (int64_t i = p.n_dims + threadIdx.x; i < p.ne0; i += blockDim.x)
+            y[t * p.ys_t + h * p.ys_h + i] = x[t * p.xs_t + h * p.xs_h + i];
     }
 }
 static float yarn_corr_dim(int n_dims, int n_ctx_orig, float n_rot, float base) {
@@ -150,7 +151,7 @@ int rope_f32(const float * x, float * y, const int32_t * pos, const float * freq
     p.corr0 = fmaxf(0.0f, start);
     p.corr1 = fminf((float) (n_dims - 1), end);
     const int threads = n_dims / 2 >= 64 ? 64 : 32;
-    launch_pdl(rope_kernel, dim3((unsigned) n_tokens), dim3(threads), 0, st, x, y, pos, freq_factors, p);
+    launch_pdl(rope_kernel, dim3((unsigned) n_tokens, (unsigned) n_heads), dim3(threads), 0, st, x, y, pos, freq_factors, p);
     return (int) cudaGetLastError();
 }
 
