@@ -9,6 +9,7 @@
 #include "kernels.h"
 
 #include <math.h>
+#include <stdlib.h>
 
 namespace b200 {
 
@@ -414,6 +415,236 @@ __global__ void __launch_bounds__(256) attn_softmax_pv_kernel(const float * __re
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Tensor-core decode attention (mma.sync m16n8k16 f16 x f16 -> f32; HBM-bound op, the legacy warp MMA is plenty).
+// Same arithmetic as the reference: f16 operands, fp32 accumulation, P rounded through f16 before V.P.
+// The k index of each MMA is permuted (identically for A and B) so that every lane feeds its fragments from
+// contiguous 16-byte global loads: lane t of a quad owns elements [8t + 32u, 8t + 32u + 8) of a 128-element k group.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+    const __half2 h = __halves2half2(__float2half_rn(lo), __float2half_rn(hi));
+    return *reinterpret_cast<const uint32_t *>(&h);
+}
+
+// scores[h][t] = scale * K[t][grp] . f16(q[h]) for the GQA heads of KV group `grp`; CTA = 128 positions, warp = 16.
+// Also emits per (head, chunk) max and sum(exp(s - max)).
+template <int HD, int GQA>
+__global__ void __launch_bounds__(256) attn_scores_mma_kernel(const float * __restrict__ q, const __half * __restrict__ kc, float * __restrict__ scores,
+                                                              float2 * __restrict__ part, int n_kv, int64_t k_row_stride, float scale, int64_t s_stride,
+                                                              int nchunks) {
+    constexpr int NU = HD / 32;  // 16-byte chunks per lane per row
+    __shared__ float wmax[8][8], wsum[8][8];
+    pdl_launch_dependents();
+    pdl_wait();
+    const int grp = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    // B fragments: q of head n = g (zero for the padding heads)
+    uint32_t bq[NU][4];
+#pragma unroll
+    for (int u = 0; u < NU; ++u) {
+        if (g < GQA) {
+            const float * qp = q + (int64_t) (grp * GQA + g) * HD + 8 * t + 32 * u;
+            const float4 x0 = *reinterpret_cast<const float4 *>(qp), x1 = *reinterpret_cast<const float4 *>(qp + 4);
+            bq[u][0] = pack_h2(x0.x, x0.y); bq[u][1] = pack_h2(x0.z, x0.w); bq[u][2] = pack_h2(x1.x, x1.y); bq[u][3] = pack_h2(x1.z, x1.w);
+        } else {
+            bq[u][0] = bq[u][1] = bq[u][2] = bq[u][3] = 0u;
+        }
+    }
+    const int t_base = blockIdx.x * 128 + warp * 16;
+    const int rowA = t_base + g, rowB = rowA + 8;
+    uint4 alo[NU], ahi[NU];
+#pragma unroll
+    for (int u = 0; u < NU; ++u) {
+        alo[u] = (rowA < n_kv) ? *reinterpret_cast<const uint4 *>(kc + (int64_t) rowA * k_row_stride + (int64_t) grp * HD + 8 * t + 32 * u) : make_uint4(0, 0, 0, 0);
+        ahi[u] = (rowB < n_kv) ? *reinterpret_cast<const uint4 *>(kc + (int64_t) rowB * k_row_stride + (int64_t) grp * HD + 8 * t + 32 * u) : make_uint4(0, 0, 0, 0);
+    }
+    float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int u = 0; u < NU; ++u) {
+        mma16816(c, alo[u].x, ahi[u].x, alo[u].y, ahi[u].y, bq[u][0], bq[u][1]);
+        mma16816(c, alo[u].z, ahi[u].z, alo[u].w, ahi[u].w, bq[u][2], bq[u][3]);
+    }
+    // c0 = (rowA, head 2t), c1 = (rowA, head 2t+1), c2 = (rowB, head 2t), c3 = (rowB, head 2t+1)
+    const int h0 = 2 * t, h1 = 2 * t + 1;
+    float v[4];
+    v[0] = (rowA < n_kv) ? c[0] * scale : -INFINITY; v[1] = (rowA < n_kv) ? c[1] * scale : -INFINITY;
+    v[2] = (rowB < n_kv) ? c[2] * scale : -INFINITY; v[3] = (rowB < n_kv) ? c[3] * scale : -INFINITY;
+    if (h0 < GQA) {
+        if (rowA < n_kv) scores[(int64_t) (grp * GQA + h0) * s_stride + rowA] = v[0];
+        if (rowB < n_kv) scores[(int64_t) (grp * GQA + h0) * s_stride + rowB] = v[2];
+    }
+    if (h1 < GQA) {
+        if (rowA < n_kv) scores[(int64_t) (grp * GQA + h1) * s_stride + rowA] = v[1];
+        if (rowB < n_kv) scores[(int64_t) (grp * GQA + h1) * s_stride + rowB] = v[3];
+    }
+    // chunk statistics per head: max over the CTA's 128 positions, then sum exp(s - max)
+    float m0 = fmaxf(v[0], v[2]), m1 = fmaxf(v[1], v[3]);
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) { m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, o)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, o)); }
+    if (g == 0) { wmax[warp][h0] = m0; wmax[warp][h1] = m1; }
+    __syncthreads();
+    float M0 = -INFINITY, M1 = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { M0 = fmaxf(M0, wmax[w][h0]); M1 = fmaxf(M1, wmax[w][h1]); }
+    float s0 = (M0 == -INFINITY) ? 0.0f : expf(v[0] - M0) + expf(v[2] - M0);
+    float s1 = (M1 == -INFINITY) ? 0.0f : expf(v[1] - M1) + expf(v[3] - M1);
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
+    if (g == 0) { wsum[warp][h0] = s0; wsum[warp][h1] = s1; }
+    __syncthreads();
+    if (threadIdx.x < GQA) {
+        const int h = threadIdx.x;
+        float M = -INFINITY, S = 0.0f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) M = fmaxf(M, wmax[w][h]);
+#pragma unroll
+        for (int w = 0; w < 8; ++w) S += wsum[w][h];
+        part[(int64_t) (grp * GQA + h) * nchunks + blockIdx.x] = make_float2(M, S);
+    }
+}
+
+// out[h][d] = sum_t Vt[grp*HD + d][t] * P[h][t];  CTA = 16 channels of one KV group, 8 warps split the positions.
+template <int GQA>
+__global__ void __launch_bounds__(256) attn_pv_mma_kernel(const float * __restrict__ scores, const float2 * __restrict__ part, const __half * __restrict__ vc,
+                                                          float * __restrict__ out, int n_kv, int head_dim, int64_t v_row_stride, int64_t s_stride,
+                                                          int nchunks, int sp) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    __half * Ph = reinterpret_cast<__half *>(smraw);                    // [8][sp]  (rows >= GQA are zero)
+    float * red = reinterpret_cast<float *>(smraw + (size_t) 8 * sp * 2);  // [8 warps][128]
+    __shared__ float hmax[8], hinv[8];
+    pdl_launch_dependents();
+    pdl_wait();
+    const int grp = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    if (warp < GQA) {
+        const float2 * pp = part + (int64_t) (grp * GQA + warp) * nchunks;
+        float mx = -INFINITY;
+        for (int i = lane; i < nchunks; i += 32) mx = fmaxf(mx, pp[i].x);
+        mx = warp_max(mx);
+        float sum = 0.0f;
+        for (int i = lane; i < nchunks; i += 32) { const float2 pv = pp[i]; sum += pv.y * expf(pv.x - mx); }
+        sum = warp_sum(sum);
+        if (lane == 0) { hmax[warp] = mx; hinv[warp] = 1.0f / sum; }
+    }
+    __syncthreads();
+    // P build: Ph[h][t] = f16(exp(s - max_h) * inv_h), zero beyond n_kv and for the padding heads
+    const int npos = ((n_kv + 127) / 128) * 128;
+    {
+        const int per_row4 = npos / 4;
+        for (int j0 = threadIdx.x; j0 < 8 * per_row4; j0 += 4 * 256) {
+            float4 sv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = j0 + u * 256;
+                const int h = j / per_row4, p4 = (j - h * per_row4) * 4;
+                sv[u] = (j < 8 * per_row4 && h < GQA && p4 < n_kv) ? *reinterpret_cast<const float4 *>(scores + (int64_t) (grp * GQA + h) * s_stride + p4)
+                                                                   : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = j0 + u * 256;
+                if (j < 8 * per_row4) {
+                    const int h = j / per_row4, p4 = (j - h * per_row4) * 4;
+                    float e[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (h < GQA) {
+                        const float mx = hmax[h], inv = hinv[h];
+                        e[0] = (p4 + 0 < n_kv) ? expf(sv[u].x - mx) * inv : 0.0f;
+                        e[1] = (p4 + 1 < n_kv) ? expf(sv[u].y - mx) * inv : 0.0f;
+                        e[2] = (p4 + 2 < n_kv) ? expf(sv[u].z - mx) * inv : 0.0f;
+                        e[3] = (p4 + 3 < n_kv) ? expf(sv[u].w - mx) * inv : 0.0f;
+                    }
+                    uint2 pk;
+                    pk.x = pack_h2(e[0], e[1]); pk.y = pack_h2(e[2], e[3]);
+                    *reinterpret_cast<uint2 *>(Ph + (size_t) h * sp + p4) = pk;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const int c0 = blockIdx.x * 16;
+    const __half * rowA = vc + (int64_t) (grp * head_dim + c0 + g) * v_row_stride;
+    const __half * rowB = rowA + 8 * v_row_stride;
+    float c[4] = {0.f, 0.f, 0.f, 0.f};
+    const int ngroups = npos / 128;
+    auto ldv = [&](const __half * row, int p0) -> uint4 {
+        if (p0 >= n_kv) return make_uint4(0, 0, 0, 0);
+        uint4 v = *reinterpret_cast<const uint4 *>(row + p0);
+        const int r = n_kv - p0;  // valid halves in this chunk
+        if (r < 8) {              // tail: zero what lies beyond n_kv (P is zero there, but the cache may hold anything)
+            uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) w[j] = (2 * j + 1 < r) ? w[j] : ((2 * j < r) ? (w[j] & 0xffffu) : 0u);
+            v = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        return v;
+    };
+    uint4 alo[4], ahi[4];
+    int gi = warp;
+    if (gi < ngroups) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { alo[u] = ldv(rowA, gi * 128 + 8 * t + 32 * u); ahi[u] = ldv(rowB, gi * 128 + 8 * t + 32 * u); }
+    }
+    for (; gi < ngroups; gi += 8) {
+        uint4 clo[4], chi[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { clo[u] = alo[u]; chi[u] = ahi[u]; }
+        if (gi + 8 < ngroups) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { alo[u] = ldv(rowA, (gi + 8) * 128 + 8 * t + 32 * u); ahi[u] = ldv(rowB, (gi + 8) * 128 + 8 * t + 32 * u); }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint4 b = *reinterpret_cast<const uint4 *>(Ph + (size_t) g * sp + gi * 128 + 8 * t + 32 * u);
+            mma16816(c, clo[u].x, chi[u].x, clo[u].y, chi[u].y, b.x, b.y);
+            mma16816(c, clo[u].z, chi[u].z, clo[u].w, chi[u].w, b.z, b.w);
+        }
+    }
+    // c0 = (ch g, head 2t), c1 = (ch g, head 2t+1), c2 = (ch g+8, head 2t), c3 = (ch g+8, head 2t+1)
+    float * rw = red + warp * 128;
+    rw[g * 8 + 2 * t] = c[0]; rw[g * 8 + 2 * t + 1] = c[1]; rw[(g + 8) * 8 + 2 * t] = c[2]; rw[(g + 8) * 8 + 2 * t + 1] = c[3];
+    __syncthreads();
+    if (threadIdx.x < 128) {
+        const int m = threadIdx.x >> 3, n = threadIdx.x & 7;
+        if (n < GQA) {
+            float s = 0.0f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) s += red[w * 128 + threadIdx.x];
+            out[(int64_t) (grp * GQA + n) * head_dim + c0 + m] = s;
+        }
+    }
+}
+
+template <int HD, int GQA>
+static int attn_decode_mma_t(const float * q, const void * kc, const void * vc, float * out, float * scratch, int n_kv, int kv_heads, int64_t k_row_stride,
+                             int64_t v_row_stride, float scale, cudaStream_t st) {
+    const int64_t s_stride = (n_kv + 7) & ~7;
+    const int nchunks = (n_kv + 127) / 128;
+    float2 * part = reinterpret_cast<float2 *>(scratch + (int64_t) kv_heads * GQA * s_stride);
+    launch_pdl(attn_scores_mma_kernel<HD, GQA>, dim3((unsigned) nchunks, (unsigned) kv_heads), dim3(256), 0, st, q, (const __half *) kc, scratch, part, n_kv,
+               k_row_stride, scale, s_stride, nchunks);
+    const int npos = nchunks * 128;
+    const int sp = npos + 32;  // +64 bytes: the 8 head rows land in different bank groups (conflict-free 16-byte B loads)
+    const size_t smem = (size_t) 8 * sp * 2 + 8 * 128 * 4;
+    static size_t configured = 0;
+    if (smem > configured) {
+        const size_t want = smem > 160 * 1024 ? smem : 160 * 1024;
+        cudaError_t e = cudaFuncSetAttribute(attn_pv_mma_kernel<GQA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) want);
+        if (e != cudaSuccess) return (int) e;
+        configured = want;
+    }
+    if (smem > 227 * 1024) return B200_ERR_UNSUPPORTED;
+    launch_pdl(attn_pv_mma_kernel<GQA>, dim3((unsigned) (HD / 16), (unsigned) kv_heads), dim3(256), smem, st, (const float *) scratch, (const float2 *) part,
+               (const __half *) vc, out, n_kv, HD, v_row_stride, s_stride, nchunks, sp);
+    return (int) cudaGetLastError();
+}
+
 template <int HD, int GQA>
 static int attn_decode2_t(const float * q, const void * kc, const void * vc, float * out, float * scratch, int n_kv, int kv_heads, int64_t k_row_stride,
                           int64_t v_row_stride, float scale, cudaStream_t st) {
@@ -445,8 +676,12 @@ int attn_decode2(const float * q, const void * kc, const void * vc, float * out,
     if (n_heads % kv_heads) return B200_ERR_ARG;
     if ((k_row_stride % 8) || (v_row_stride % 8)) return B200_ERR_UNSUPPORTED;  // 16-byte row loads
     const int gqa = n_heads / kv_heads;
-#define B200_ATTN2(HD_, G_) \
-    if (head_dim == HD_ && gqa == G_) return attn_decode2_t<HD_, G_>(q, kc, vc, out, scratch, n_kv, kv_heads, k_row_stride, v_row_stride, scale, st);
+    static const int no_mma = getenv("B200_ATTN_NO_MMA") ? atoi(getenv("B200_ATTN_NO_MMA")) : 0;
+#define B200_ATTN2(HD_, G_)                                                                                                                       \
+    if (head_dim == HD_ && gqa == G_) {                                                                                                           \
+        if (!no_mma) return attn_decode_mma_t<HD_, G_>(q, kc, vc, out, scratch, n_kv, kv_heads, k_row_stride, v_row_stride, scale, st);           \
+        return attn_decode2_t<HD_, G_>(q, kc, vc, out, scratch, n_kv, kv_heads, k_row_stride, v_row_stride, scale, st);                           \
+    }
     B200_ATTN2(128, 4) B200_ATTN2(128, 7) B200_ATTN2(128, 1) B200_ATTN2(128, 8) B200_ATTN2(128, 2)
     B200_ATTN2(64, 8) B200_ATTN2(64, 4) B200_ATTN2(64, 2) B200_ATTN2(64, 1)
 #undef B200_ATTN2
