@@ -555,10 +555,11 @@ __global__ void __launch_bounds__(256) attn_pv_mma_kernel(const float * __restri
                     float e[4] = {0.f, 0.f, 0.f, 0.f};
                     if (h < GQA) {
                         const float mx = hmax[h], inv = hinv[h];
-                        e[0] = (p4 + 0 < n_kv) ? expf(sv[u].x - mx) * inv : 0.0f;
-                        e[1] = (p4 + 1 < n_kv) ? expf(sv[u].y - mx) * inv : 0.0f;
-                        e[2] = (p4 + 2 < n_kv) ? expf(sv[u].z - mx) * inv : 0.0f;
-                        e[3] = (p4 + 3 < n_kv) ? expf(sv[u].w - mx) * inv : 0.0f;
+                        // __expf (ex2.approx, ~2 ulp): the value is rounded to f16 (11 bits) on the next line
+                        e[0] = (p4 + 0 < n_kv) ? __expf(sv[u].x - mx) * inv : 0.0f;
+                        e[1] = (p4 + 1 < n_kv) ? __expf(sv[u].y - mx) * inv : 0.0f;
+                        e[2] = (p4 + 2 < n_kv) ? __expf(sv[u].z - mx) * inv : 0.0f;
+                        e[3] = (p4 + 3 < n_kv) ? __expf(sv[u].w - mx) * inv : 0.0f;
                     }
                     uint2 pk;
                     pk.x = pack_h2(e[0], e[1]); pk.y = pack_h2(e[2], e[3]);
