@@ -155,8 +155,8 @@ def main():
     if a.tune:
         pkg.lib().b200_gemv_set_tuning(*[int(v) for v in a.tune.split(",")])
     cfg = S.make_config(MODEL, pkg.Q4_K, layers=a.layers or None, max_len=N_PAST + 256)
-    per = cfg.layers // world
-    lo, hi = rank * per, (rank + 1) * per if rank < world - 1 else cfg.layers
+    from chatllm_cpp_b200 import sharding
+    lo, hi = sharding.plan_layers(cfg.layers, world)[rank]
     sess = S.DecodeSession(cfg, seed=0, layer_lo=lo, layer_hi=hi, first=(rank == 0), last=(rank == world - 1), fused=not a.unfused)
     sess.fill_kv_random(N_PAST, seed=rank)
     sess.tok.fill_(12345 % cfg.vocab)
@@ -181,12 +181,8 @@ def main():
         e1.record()
         sync_all()
     else:
-        def one_step():
-            if rank > 0:
-                dist.recv(sess.x, src=rank - 1)
-            sess.enqueue(N_PAST)
-            if rank < world - 1:
-                dist.send(sess.x, dst=rank + 1)
+        pipe = sharding.Pipeline(rank, world, sess.x, lambda _x: sess.enqueue(N_PAST))
+        one_step = pipe.step
         sess.pos.fill_(N_PAST)
         for _ in range(a.warmup):
             one_step()
