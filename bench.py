@@ -181,7 +181,7 @@ def main():
         e1.record()
         sync_all()
     else:
-        pipe = sharding.Pipeline(rank, world, sess.x, lambda _x: sess.enqueue(N_PAST))
+        pipe = sharding.Pipeline(rank, world, sess.x, lambda _x: sess.enqueue(N_PAST), tok_buf=sess.tok)
         one_step = pipe.step
         sess.pos.fill_(N_PAST)
         for _ in range(a.warmup):
@@ -191,6 +191,7 @@ def main():
         e0.record()
         for _ in range(a.steps):
             one_step()
+        pipe.drain()
         e1.record()
         sync_all()
     ms_total = e0.elapsed_time(e1)
@@ -254,6 +255,8 @@ def main():
                 "share_of_step": round(gemv_ms / ms, 3)}
 
     if rank != 0:
+        if dist:
+            dist.destroy_process_group()
         return
     out = dict(base)
     tok_bytes = cfg.weight_bytes_per_token() + cfg.kv_bytes_per_token(N_PAST)
@@ -284,6 +287,8 @@ def main():
         except Exception as ex:  # noqa: BLE001
             out["cpu_baseline"] = {"value": None, "error": str(ex)[-300:]}
     print(json.dumps(out))
+    if dist:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

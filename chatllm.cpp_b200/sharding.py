@@ -17,14 +17,29 @@ def plan_layers(n_layers, world):
 
 
 class Pipeline:
-    """run_shard(x) -> x for this rank's layers; step() moves one token through all ranks"""
+    """run_shard(x) -> x for this rank's layers; step() moves ONE token through all ranks.
 
-    def __init__(self, rank, world, hidden_buf, run_shard):
-        self.rank, self.world, self.x, self.run = rank, world, hidden_buf, run_shard
+    Single-stream decode is sequential: token i+1 is sampled from the logits of token i.  The last rank therefore returns
+    the next token id to rank 0 (`tok`, 1 x int32) and rank 0 waits for it before it starts the next step — without this
+    feedback edge the ranks would pipeline independent tokens and report a throughput no single stream can have."""
+
+    def __init__(self, rank, world, hidden_buf, run_shard, tok_buf=None):
+        self.rank, self.world, self.x, self.run, self.tok = rank, world, hidden_buf, run_shard, tok_buf
+        self.steps = 0
 
     def step(self):
+        if self.world > 1 and self.tok is not None and self.rank == 0 and self.steps > 0:
+            dist.recv(self.tok, src=self.world - 1)
         if self.rank > 0:
             dist.recv(self.x, src=self.rank - 1)
         self.run(self.x)
         if self.rank < self.world - 1:
             dist.send(self.x, dst=self.rank + 1)
+        elif self.world > 1 and self.tok is not None:
+            dist.send(self.tok, dst=0)
+        self.steps += 1
+
+    def drain(self):
+        """consume the token of the final step so no message is left in flight"""
+        if self.world > 1 and self.tok is not None and self.rank == 0 and self.steps > 0:
+            dist.recv(self.tok, src=self.world - 1)

@@ -18,15 +18,27 @@ def _worker(rank, world, port, n_layers, steps, out):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     lo, hi = sharding.plan_layers(n_layers, world)[rank]
     x = torch.zeros(8)
+    tok = torch.zeros(1, dtype=torch.int32)
 
     def run(buf):
         if rank == 0:
             buf.fill_(1.0)                      # "embedding"
         for layer in range(lo, hi):
             buf.mul_(1.5).add_(float(layer))    # stand-in for a decoder layer: order-sensitive
-    pipe = sharding.Pipeline(rank, world, x, run)
+    order = []
+
+    def run_logged(buf):
+        if rank == 0:
+            order.append(int(tok.item()))     # the token fed back by the last rank (0 on the first step)
+        run(buf)
+        if rank == world - 1:
+            tok.fill_(pipe.steps + 1)          # "sampled" token of this step
+    pipe = sharding.Pipeline(rank, world, x, run_logged, tok_buf=tok)
     for _ in range(steps):
         pipe.step()
+    pipe.drain()
+    if rank == 0:
+        assert order == list(range(steps)), order   # step i+1 started only after step i's token arrived
     if rank == world - 1:
         out.put(x.clone())
     dist.barrier()
