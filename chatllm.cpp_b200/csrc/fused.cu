@@ -444,6 +444,15 @@ __global__ void __launch_bounds__(256) attn_scores_mma_kernel(const float * __re
     const int grp = blockIdx.y;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
+    // K fragments first (DRAM latency), then the q fragments (L2) — all loads of the thread in flight together
+    const int t_base = blockIdx.x * 128 + warp * 16;
+    const int rowA = t_base + g, rowB = rowA + 8;
+    uint4 alo[NU], ahi[NU];
+#pragma unroll
+    for (int u = 0; u < NU; ++u) {
+        alo[u] = (rowA < n_kv) ? *reinterpret_cast<const uint4 *>(kc + (int64_t) rowA * k_row_stride + (int64_t) grp * HD + 8 * t + 32 * u) : make_uint4(0, 0, 0, 0);
+        ahi[u] = (rowB < n_kv) ? *reinterpret_cast<const uint4 *>(kc + (int64_t) rowB * k_row_stride + (int64_t) grp * HD + 8 * t + 32 * u) : make_uint4(0, 0, 0, 0);
+    }
     // B fragments: q of head n = g (zero for the padding heads)
     uint32_t bq[NU][4];
 #pragma unroll
@@ -455,14 +464,6 @@ __global__ void __launch_bounds__(256) attn_scores_mma_kernel(const float * __re
         } else {
             bq[u][0] = bq[u][1] = bq[u][2] = bq[u][3] = 0u;
         }
-    }
-    const int t_base = blockIdx.x * 128 + warp * 16;
-    const int rowA = t_base + g, rowB = rowA + 8;
-    uint4 alo[NU], ahi[NU];
-#pragma unroll
-    for (int u = 0; u < NU; ++u) {
-        alo[u] = (rowA < n_kv) ? *reinterpret_cast<const uint4 *>(kc + (int64_t) rowA * k_row_stride + (int64_t) grp * HD + 8 * t + 32 * u) : make_uint4(0, 0, 0, 0);
-        ahi[u] = (rowB < n_kv) ? *reinterpret_cast<const uint4 *>(kc + (int64_t) rowB * k_row_stride + (int64_t) grp * HD + 8 * t + 32 * u) : make_uint4(0, 0, 0, 0);
     }
     float c[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -509,20 +510,36 @@ __global__ void __launch_bounds__(256) attn_scores_mma_kernel(const float * __re
     }
 }
 
-// out[h][d] = sum_t Vt[grp*HD + d][t] * P[h][t];  CTA = 16 channels of one KV group, 8 warps split the positions.
+// out[h][d] = sum_t Vt[grp*HD + d][t] * P[h][t];  CTA = 16 channels of one KV group, 16 warps split the positions.
+// The kernel is latency-bound (few CTAs, short dependent chains), so every phase issues all of its loads up front.
+#define B200_PV_WARPS 16
 template <int GQA>
-__global__ void __launch_bounds__(256) attn_pv_mma_kernel(const float * __restrict__ scores, const float2 * __restrict__ part, const __half * __restrict__ vc,
-                                                          float * __restrict__ out, int n_kv, int head_dim, int64_t v_row_stride, int64_t s_stride,
-                                                          int nchunks, int sp) {
+__global__ void __launch_bounds__(B200_PV_WARPS * 32) attn_pv_mma_kernel(const float * __restrict__ scores, const float2 * __restrict__ part,
+                                                                         const __half * __restrict__ vc, float * __restrict__ out, int n_kv, int head_dim,
+                                                                         int64_t v_row_stride, int64_t s_stride, int nchunks, int sp) {
+    constexpr int NT = B200_PV_WARPS * 32;
     extern __shared__ __align__(16) unsigned char smraw[];
-    __half * Ph = reinterpret_cast<__half *>(smraw);                    // [8][sp]  (rows >= GQA are zero)
-    float * red = reinterpret_cast<float *>(smraw + (size_t) 8 * sp * 2);  // [8 warps][128]
+    __half * Ph = reinterpret_cast<__half *>(smraw);                       // [8][sp]  (rows >= GQA are zero)
+    float * red = reinterpret_cast<float *>(smraw + (size_t) 8 * sp * 2);  // [warps][128]
     __shared__ float hmax[8], hinv[8];
     pdl_launch_dependents();
     pdl_wait();
     const int grp = blockIdx.y;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
+    const int npos = ((n_kv + 127) / 128) * 128;
+    const int per_row4 = npos / 4;
+    // ---- raw scores of the group's heads: all loads of this thread in flight at once (<= 3 float4 per head at 4K context)
+    constexpr int MAXV = 3;
+    float4 sv[GQA][MAXV];
+#pragma unroll
+    for (int h = 0; h < GQA; ++h)
+#pragma unroll
+        for (int u = 0; u < MAXV; ++u) {
+            const int i = threadIdx.x + u * NT;
+            sv[h][u] = (i < per_row4 && 4 * i < n_kv) ? *reinterpret_cast<const float4 *>(scores + (int64_t) (grp * GQA + h) * s_stride + 4 * i)
+                                                      : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        }
     if (warp < GQA) {
         const float2 * pp = part + (int64_t) (grp * GQA + warp) * nchunks;
         float mx = -INFINITY;
@@ -533,46 +550,10 @@ __global__ void __launch_bounds__(256) attn_pv_mma_kernel(const float * __restri
         sum = warp_sum(sum);
         if (lane == 0) { hmax[warp] = mx; hinv[warp] = 1.0f / sum; }
     }
-    __syncthreads();
-    // P build: Ph[h][t] = f16(exp(s - max_h) * inv_h), zero beyond n_kv and for the padding heads
-    const int npos = ((n_kv + 127) / 128) * 128;
-    {
-        const int per_row4 = npos / 4;
-        for (int j0 = threadIdx.x; j0 < 8 * per_row4; j0 += 4 * 256) {
-            float4 sv[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int j = j0 + u * 256;
-                const int h = j / per_row4, p4 = (j - h * per_row4) * 4;
-                sv[u] = (j < 8 * per_row4 && h < GQA && p4 < n_kv) ? *reinterpret_cast<const float4 *>(scores + (int64_t) (grp * GQA + h) * s_stride + p4)
-                                                                   : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int j = j0 + u * 256;
-                if (j < 8 * per_row4) {
-                    const int h = j / per_row4, p4 = (j - h * per_row4) * 4;
-                    float e[4] = {0.f, 0.f, 0.f, 0.f};
-                    if (h < GQA) {
-                        const float mx = hmax[h], inv = hinv[h];
-                        // __expf (ex2.approx, ~2 ulp): the value is rounded to f16 (11 bits) on the next line
-                        e[0] = (p4 + 0 < n_kv) ? __expf(sv[u].x - mx) * inv : 0.0f;
-                        e[1] = (p4 + 1 < n_kv) ? __expf(sv[u].y - mx) * inv : 0.0f;
-                        e[2] = (p4 + 2 < n_kv) ? __expf(sv[u].z - mx) * inv : 0.0f;
-                        e[3] = (p4 + 3 < n_kv) ? __expf(sv[u].w - mx) * inv : 0.0f;
-                    }
-                    uint2 pk;
-                    pk.x = pack_h2(e[0], e[1]); pk.y = pack_h2(e[2], e[3]);
-                    *reinterpret_cast<uint2 *>(Ph + (size_t) h * sp + p4) = pk;
-                }
-            }
-        }
-    }
-    __syncthreads();
+    // ---- first V fragments (two position groups per warp) in flight while P is built
     const int c0 = blockIdx.x * 16;
     const __half * rowA = vc + (int64_t) (grp * head_dim + c0 + g) * v_row_stride;
     const __half * rowB = rowA + 8 * v_row_stride;
-    float c[4] = {0.f, 0.f, 0.f, 0.f};
     const int ngroups = npos / 128;
     auto ldv = [&](const __half * row, int p0) -> uint4 {
         if (p0 >= n_kv) return make_uint4(0, 0, 0, 0);
@@ -586,25 +567,72 @@ __global__ void __launch_bounds__(256) attn_pv_mma_kernel(const float * __restri
         }
         return v;
     };
-    uint4 alo[4], ahi[4];
-    int gi = warp;
-    if (gi < ngroups) {
+    uint4 alo[2][4], ahi[2][4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { alo[u] = ldv(rowA, gi * 128 + 8 * t + 32 * u); ahi[u] = ldv(rowB, gi * 128 + 8 * t + 32 * u); }
-    }
-    for (; gi < ngroups; gi += 8) {
-        uint4 clo[4], chi[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) { clo[u] = alo[u]; chi[u] = ahi[u]; }
-        if (gi + 8 < ngroups) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) { alo[u] = ldv(rowA, (gi + 8) * 128 + 8 * t + 32 * u); ahi[u] = ldv(rowB, (gi + 8) * 128 + 8 * t + 32 * u); }
-        }
+    for (int s2 = 0; s2 < 2; ++s2) {
+        const int gi = warp + s2 * B200_PV_WARPS;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
+            alo[s2][u] = (gi < ngroups) ? ldv(rowA, gi * 128 + 8 * t + 32 * u) : make_uint4(0, 0, 0, 0);
+            ahi[s2][u] = (gi < ngroups) ? ldv(rowB, gi * 128 + 8 * t + 32 * u) : make_uint4(0, 0, 0, 0);
+        }
+    }
+    __syncthreads();
+    // ---- P build: Ph[h][t] = f16(exp(s - max_h) * inv_h); zero beyond n_kv and for the padding heads
+#pragma unroll
+    for (int h = 0; h < GQA; ++h) {
+        const float mx = hmax[h], inv = hinv[h];
+#pragma unroll
+        for (int u = 0; u < MAXV; ++u) {
+            const int i = threadIdx.x + u * NT;
+            if (i < per_row4) {
+                const int p4 = 4 * i;
+                // __expf (ex2.approx, ~2 ulp): the value is rounded to f16 (11 bits) right away
+                const float e0 = (p4 + 0 < n_kv) ? __expf(sv[h][u].x - mx) * inv : 0.0f;
+                const float e1 = (p4 + 1 < n_kv) ? __expf(sv[h][u].y - mx) * inv : 0.0f;
+                const float e2 = (p4 + 2 < n_kv) ? __expf(sv[h][u].z - mx) * inv : 0.0f;
+                const float e3 = (p4 + 3 < n_kv) ? __expf(sv[h][u].w - mx) * inv : 0.0f;
+                uint2 pk;
+                pk.x = pack_h2(e0, e1); pk.y = pack_h2(e2, e3);
+                *reinterpret_cast<uint2 *>(Ph + (size_t) h * sp + p4) = pk;
+            }
+        }
+    }
+    for (int h = GQA; h < 8; ++h)
+        for (int i = threadIdx.x; i < per_row4; i += NT) *reinterpret_cast<uint2 *>(Ph + (size_t) h * sp + 4 * i) = make_uint2(0u, 0u);
+    // contexts longer than MAXV * NT * 4 positions: remaining score columns (rare; keeps the kernel general)
+    for (int h = 0; h < GQA; ++h)
+        for (int i = threadIdx.x + MAXV * NT; i < per_row4; i += NT) {
+            const int p4 = 4 * i;
+            const float mx = hmax[h], inv = hinv[h];
+            float e[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) e[j] = (p4 + j < n_kv) ? __expf(scores[(int64_t) (grp * GQA + h) * s_stride + p4 + j] - mx) * inv : 0.0f;
+            uint2 pk;
+            pk.x = pack_h2(e[0], e[1]); pk.y = pack_h2(e[2], e[3]);
+            *reinterpret_cast<uint2 *>(Ph + (size_t) h * sp + p4) = pk;
+        }
+    __syncthreads();
+    float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int s2 = 0; s2 < 2; ++s2) {
+        const int gi = warp + s2 * B200_PV_WARPS;
+        if (gi < ngroups) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint4 b = *reinterpret_cast<const uint4 *>(Ph + (size_t) g * sp + gi * 128 + 8 * t + 32 * u);
+                mma16816(c, alo[s2][u].x, ahi[s2][u].x, alo[s2][u].y, ahi[s2][u].y, b.x, b.y);
+                mma16816(c, alo[s2][u].z, ahi[s2][u].z, alo[s2][u].w, ahi[s2][u].w, b.z, b.w);
+            }
+        }
+    }
+    for (int gi = warp + 2 * B200_PV_WARPS; gi < ngroups; gi += B200_PV_WARPS) {   // contexts beyond 4096 positions
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint4 lo = ldv(rowA, gi * 128 + 8 * t + 32 * u), hi = ldv(rowB, gi * 128 + 8 * t + 32 * u);
             const uint4 b = *reinterpret_cast<const uint4 *>(Ph + (size_t) g * sp + gi * 128 + 8 * t + 32 * u);
-            mma16816(c, clo[u].x, chi[u].x, clo[u].y, chi[u].y, b.x, b.y);
-            mma16816(c, clo[u].z, chi[u].z, clo[u].w, chi[u].w, b.z, b.w);
+            mma16816(c, lo.x, hi.x, lo.y, hi.y, b.x, b.y);
+            mma16816(c, lo.z, hi.z, lo.w, hi.w, b.z, b.w);
         }
     }
     // c0 = (ch g, head 2t), c1 = (ch g, head 2t+1), c2 = (ch g+8, head 2t), c3 = (ch g+8, head 2t+1)
@@ -616,7 +644,7 @@ __global__ void __launch_bounds__(256) attn_pv_mma_kernel(const float * __restri
         if (n < GQA) {
             float s = 0.0f;
 #pragma unroll
-            for (int w = 0; w < 8; ++w) s += red[w * 128 + threadIdx.x];
+            for (int w = 0; w < B200_PV_WARPS; ++w) s += red[w * 128 + threadIdx.x];
             out[(int64_t) (grp * GQA + n) * head_dim + c0 + m] = s;
         }
     }
@@ -632,7 +660,7 @@ static int attn_decode_mma_t(const float * q, const void * kc, const void * vc, 
                k_row_stride, scale, s_stride, nchunks);
     const int npos = nchunks * 128;
     const int sp = npos + 32;  // +64 bytes: the 8 head rows land in different bank groups (conflict-free 16-byte B loads)
-    const size_t smem = (size_t) 8 * sp * 2 + 8 * 128 * 4;
+    const size_t smem = (size_t) 8 * sp * 2 + B200_PV_WARPS * 128 * 4;
     static size_t configured = 0;
     if (smem > configured) {
         const size_t want = smem > 160 * 1024 ? smem : 160 * 1024;
@@ -641,7 +669,7 @@ static int attn_decode_mma_t(const float * q, const void * kc, const void * vc, 
         configured = want;
     }
     if (smem > 227 * 1024) return B200_ERR_UNSUPPORTED;
-    launch_pdl(attn_pv_mma_kernel<GQA>, dim3((unsigned) (HD / 16), (unsigned) kv_heads), dim3(256), smem, st, (const float *) scratch, (const float2 *) part,
+    launch_pdl(attn_pv_mma_kernel<GQA>, dim3((unsigned) (HD / 16), (unsigned) kv_heads), dim3(B200_PV_WARPS * 32), smem, st, (const float *) scratch, (const float2 *) part,
                (const __half *) vc, out, n_kv, HD, v_row_stride, s_stride, nchunks, sp);
     return (int) cudaGetLastError();
 }
