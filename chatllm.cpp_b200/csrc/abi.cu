@@ -56,19 +56,27 @@ int b200_mul_mat_q(int wtype, const void * W, int64_t k, int64_t m, const void *
 int b200_mul_mat(int wtype, const void * W, int64_t k, int64_t m, const float * x, int64_t x_col_stride, int64_t n, float * y, int64_t ldy,
                  const float * bias, void * stream) {
     if (n <= 0) return B200_OK;
-    const size_t cb = qact_col_bytes(wtype, k);
-    // process in column batches so the scratch stays small for prefill-sized n
-    const int64_t batch = 64;
-    void * q = scratch(cb * (size_t) (n < batch ? n : batch));
-    if (!q) return (int) cudaErrorMemoryAllocation;
-    for (int64_t c0 = 0; c0 < n; c0 += batch) {
-        const int64_t nc = (n - c0) < batch ? (n - c0) : batch;
-        int rc = quantize_act(wtype, x + c0 * x_col_stride, x_col_stride, k, nc, q, (cudaStream_t) stream);
+    if (n > B200_GEMV_MAX_COLS) {  // prompt-sized batch: int8 tensor-core path (prefill.cu)
+        void * q = scratch(pact_col_bytes(wtype, k) * (size_t) n);
+        if (!q) return (int) cudaErrorMemoryAllocation;
+        int rc = quantize_plain(wtype, x, x_col_stride, k, n, q, (cudaStream_t) stream);
         if (rc) return rc;
-        rc = mul_mat_q(wtype, W, k, m, q, nc, y + c0 * ldy, ldy, bias, &g_tune, (cudaStream_t) stream);
-        if (rc) return rc;
+        return mul_mat_q_batched(wtype, W, k, m, q, n, y, ldy, bias, (cudaStream_t) stream);
     }
-    return B200_OK;
+    void * q = scratch(qact_col_bytes(wtype, k) * (size_t) n);
+    if (!q) return (int) cudaErrorMemoryAllocation;
+    int rc = quantize_act(wtype, x, x_col_stride, k, n, q, (cudaStream_t) stream);
+    if (rc) return rc;
+    return mul_mat_q(wtype, W, k, m, q, n, y, ldy, bias, &g_tune, (cudaStream_t) stream);
+}
+
+size_t b200_pact_col_bytes(int wtype, int64_t k) { return pact_col_bytes(wtype, k); }
+int b200_quantize_plain(int wtype, const float * x, int64_t x_col_stride, int64_t k, int64_t n, void * pact, void * stream) {
+    return quantize_plain(wtype, x, x_col_stride, k, n, pact, (cudaStream_t) stream);
+}
+int b200_mul_mat_q_batched(int wtype, const void * W, int64_t k, int64_t m, const void * pact, int64_t n, float * y, int64_t ldy, const float * bias,
+                           void * stream) {
+    return mul_mat_q_batched(wtype, W, k, m, pact, n, y, ldy, bias, (cudaStream_t) stream);
 }
 
 int b200_gemv_set_tuning(int ks, int stages, int warps, int rg, int grid) {

@@ -365,15 +365,18 @@ static void * ensure_qact(b200_backend_ctx * bc, size_t bytes) {
 }
 
 static int kind_of(ggml_type t) { return t == GGML_TYPE_Q4_K ? 0 : 1; }
+static const int64_t GEMV_MAX_COLS = 8;  // more src1 columns than this -> batched tensor-core path
 
 // make sure `x` (F32, k x n, row stride nb1) is present in bc->qact quantized for weight type wtype
 static int ensure_quantized(b200_backend_ctx * bc, int wtype, const ggml_tensor * x) {
     const int64_t k = x->ne[0], n = x->ne[1];
-    const int kind = kind_of((ggml_type) wtype);
+    const bool batched = n > GEMV_MAX_COLS;  // prompt-sized: plain layout for the tensor-core path (prefill.cu)
+    const int kind = kind_of((ggml_type) wtype) + (batched ? 2 : 0);
     if (bc->q_src == x && bc->q_data == x->data && bc->q_kind == kind && bc->q_k == k && bc->q_n == n) return 0;
-    const size_t cb = qact_col_bytes(wtype, k);
+    const size_t cb = batched ? pact_col_bytes(wtype, k) : qact_col_bytes(wtype, k);
     void * q = ensure_qact(bc, cb * (size_t) n);
-    const int rc = quantize_act(wtype, (const float *) x->data, (int64_t) (x->nb[1] / 4), k, n, q, bc->stream);
+    const int rc = batched ? quantize_plain(wtype, (const float *) x->data, (int64_t) (x->nb[1] / 4), k, n, q, bc->stream)
+                           : quantize_act(wtype, (const float *) x->data, (int64_t) (x->nb[1] / 4), k, n, q, bc->stream);
     bc->launches++;
     bc->q_src = x; bc->q_data = x->data; bc->q_kind = kind; bc->q_k = k; bc->q_n = n;
     return rc;
@@ -382,6 +385,7 @@ static int ensure_quantized(b200_backend_ctx * bc, int wtype, const ggml_tensor 
 static int mul_mat_quant(b200_backend_ctx * bc, const ggml_tensor * w, const ggml_tensor * x, float * y, int64_t ldy, const float * bias) {
     int rc = ensure_quantized(bc, (int) w->type, x);
     if (rc) return rc;
+    if (x->ne[1] > GEMV_MAX_COLS) return mul_mat_q_batched((int) w->type, w->data, w->ne[0], w->ne[1], bc->qact, x->ne[1], y, ldy, bias, bc->stream);
     return mul_mat_q((int) w->type, w->data, w->ne[0], w->ne[1], bc->qact, x->ne[1], y, ldy, bias, nullptr, bc->stream);
 }
 
@@ -427,7 +431,7 @@ static int try_fuse_norm(b200_backend_ctx * bc, ggml_cgraph * g, int i, int * rc
     memcpy(&eps, rms->op_params, sizeof(float));
     const int64_t ne0 = rms->ne[0], nrows = ggml_nrows(rms);
     void * q = nullptr;
-    if (wtype >= 0 && mul->ne[2] == 1 && mul->ne[3] == 1) q = ensure_qact(bc, qact_col_bytes(wtype, ne0) * (size_t) nrows);
+    if (wtype >= 0 && mul->ne[2] == 1 && mul->ne[3] == 1 && nrows <= GEMV_MAX_COLS) q = ensure_qact(bc, qact_col_bytes(wtype, ne0) * (size_t) nrows);
     const float * x = (const float *) (add ? add->src[0]->data : rms->src[0]->data);
     *rc = add_rmsnorm_quant(wtype >= 0 ? wtype : GGML_TYPE_Q4_K, x, add ? (const float *) add->src[1]->data : nullptr, (const float *) w->data,
                             add ? (float *) add->data : nullptr, (float *) mul->data, q, ne0, nrows, eps, bc->stream);
@@ -445,6 +449,7 @@ static int try_fuse_swiglu(b200_backend_ctx * bc, ggml_cgraph * g, int i, int * 
     if (!f32c(mul) || !ggml_node_has_n_uses(g, i, 1) || !ggml_node_has_n_uses(g, i + 2, 1)) return 0;
     if (gate->src[0]->ne[1] % 2) return 0;
     const ggml_tensor * x = gate->src[1];
+    if (x->ne[1] > GEMV_MAX_COLS) return 0;
     *rc = ensure_quantized(bc, (int) gate->src[0]->type, x);
     if (*rc) return 4;
     const void * Ws[2] = {gate->src[0]->data, up->src[0]->data};

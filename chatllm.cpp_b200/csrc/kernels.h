@@ -28,6 +28,12 @@ int mul_mat_q_multi(int wtype, int mode, int nmat, const void * const * W, const
                     const float * const * bias, int64_t k, const void * qact, int64_t n, const GemvTuning * tune, cudaStream_t st);
 int sm_count();
 
+// ---- prefill.cu: batched (n > 8) quantized matmul on the int8 tensor cores, plain activation layout
+size_t pact_col_bytes(int wtype, int64_t k);
+int quantize_plain(int wtype, const float * x, int64_t x_col_stride, int64_t k, int64_t n, void * pact, cudaStream_t st);
+int mul_mat_q_batched(int wtype, const void * W, int64_t k, int64_t m, const void * pact, int64_t n, float * y, int64_t ldy, const float * bias,
+                      cudaStream_t st);
+
 // ---- ops.cu
 int rms_norm_mul(const float * x, const float * w, float * y, int64_t ne0, int64_t nrows, float eps, cudaStream_t st);
 int add_f32(const float * a, const float * b, float * y, int64_t n, cudaStream_t st);

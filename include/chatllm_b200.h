@@ -60,6 +60,16 @@ int b200_mul_mat_q(int wtype, const void * W, int64_t k, int64_t m, const void *
 /* convenience: quantize x into an internal per-device scratch, then b200_mul_mat_q */
 int b200_mul_mat(int wtype, const void * W, int64_t k, int64_t m, const float * x, int64_t x_col_stride, int64_t n, float * y,
                  int64_t ldy, const float * bias, void * stream);
+/* ---- prompt-sized batches (n > B200_GEMV_MAX_COLS): exact int8 tensor-core GEMM -------------------------------------
+ * Same arithmetic as above (the CPU reference quantizes every src1 column to Q8_K / Q8_0, ggml-cpu.c:1291-1326, and
+ * sums exact int8 block dots); activations use a plain k-contiguous layout: qs[k] | d | block sums, 16-byte padded.
+ * Replaces the prompt branch of ggml_compute_forward_mul_mat (ggml/src/ggml-cpu/ggml-cpu.c:1229-1421; llamafile
+ * tinyBLAS ggml/src/ggml-cpu/llamafile/sgemm.cpp) and mul_mat_q (ggml/src/ggml-cuda/mmq.cuh). b200_mul_mat picks it. */
+#define B200_GEMV_MAX_COLS 8
+size_t b200_pact_col_bytes(int wtype, int64_t k);
+int b200_quantize_plain(int wtype, const float * x, int64_t x_col_stride, int64_t k, int64_t n, void * pact, void * stream);
+int b200_mul_mat_q_batched(int wtype, const void * W, int64_t k, int64_t m, const void * pact, int64_t n, float * y, int64_t ldy,
+                           const float * bias, void * stream);
 /* Several matrices that share the activation vector in ONE launch.
  *   mode 0 (concat, nmat <= 3): y_i[c*ldy_i + r] = W_i[r,:].x_c (+ bias_i[r])       — q/k/v projections of a layer
  *   mode 1 (paired, nmat == 2, m_0 == m_1): y_0[c*ldy_0 + r] = silu(W_0[r,:].x_c) * (W_1[r,:].x_c)

@@ -144,6 +144,35 @@ def test_mul_mat_vs_reference_golden(K, wtype, n):
     assert np.abs(y - ref).max() <= 2e-5 * np.abs(ref).max()
 
 
+@pytest.mark.parametrize("wtype", [qf.Q4_0, qf.Q8_0, qf.Q4_K])
+@pytest.mark.parametrize("k,m,n", [(256, 1, 9), (512, 33, 16), (1024, 48, 37), (2048, 257, 64), (4096, 300, 200), (5632, 130, 65)])
+def test_mul_mat_batched_vs_oracle(K, wtype, k, m, n):
+    """prompt-sized batches take the int8 tensor-core path (prefill.cu): same quantized arithmetic as the oracle"""
+    rng = np.random.default_rng(k * 3 + m + n)
+    w = qf.random_blocks(wtype, m, k, rng=rng)
+    x = _acts(rng, n, k)
+    bias = rng.standard_normal(m).astype(np.float32) if (m + n) % 2 else None
+    y = K.mul_mat(wtype, K.upload_weights(wtype, w, k, m), k, m, _t(x), bias=None if bias is None else _t(bias)).cpu().numpy()
+    ref = qf.port_mul_mat(wtype, w, k, m, x, variant=1)
+    if bias is not None:
+        ref = ref + bias[None, :]
+    assert np.abs(y - ref).max() <= 2e-5 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("wtype", [qf.Q4_0, qf.Q4_K])
+def test_mul_mat_batched_matches_gemv(K, wtype):
+    """the prompt path and the decode path must agree column by column (a token's logits may not depend on batch size
+    beyond fp32 summation order)"""
+    rng = np.random.default_rng(11)
+    k, m, n = 4096, 1024, 24
+    w = qf.random_blocks(wtype, m, k, rng=rng)
+    x = _acts(rng, n, k)
+    wd = K.upload_weights(wtype, w, k, m)
+    yb = K.mul_mat(wtype, wd, k, m, _t(x)).cpu().numpy()
+    yg = np.concatenate([K.mul_mat(wtype, wd, k, m, _t(x[c:c + 8])).cpu().numpy() for c in range(0, n, 8)])
+    assert np.abs(yb - yg).max() <= 2e-5 * np.abs(yg).max()
+
+
 @pytest.mark.parametrize("wtype,k,m", [(qf.Q4_K, 4096, 14336), (qf.Q4_K, 14336, 4096), (qf.Q4_0, 3584, 18944), (qf.Q8_0, 2048, 5632),
                                        (qf.Q4_K, 4096, 128256)])
 def test_mul_mat_full_size_semantics(K, wtype, k, m):

@@ -41,7 +41,7 @@ def test_devices_registered_in_order():
 
 
 @pytest.mark.parametrize("t", [qf.Q4_K, qf.Q4_0, qf.Q8_0])
-@pytest.mark.parametrize("n", [1, 2, 5, 8, 19])
+@pytest.mark.parametrize("n", [1, 2, 5, 8, 19, 64, 130])
 def test_mul_mat_quant_with_bias(t, n):
     rng = np.random.default_rng(n + t)
     k, m = 1024, 320
