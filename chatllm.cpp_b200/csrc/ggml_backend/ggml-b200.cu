@@ -365,7 +365,8 @@ static void * ensure_qact(b200_backend_ctx * bc, size_t bytes) {
 }
 
 static int kind_of(ggml_type t) { return t == GGML_TYPE_Q4_K ? 0 : 1; }
-static const int64_t GEMV_MAX_COLS = 8;  // more src1 columns than this -> batched tensor-core path
+// more src1 columns than this -> batched tensor-core path (B200_NO_MMQ=1: bisect aid, always the GEMV)
+static const int64_t GEMV_MAX_COLS = (getenv("B200_NO_MMQ") && atoi(getenv("B200_NO_MMQ"))) ? (int64_t) 1 << 40 : 8;
 
 // make sure `x` (F32, k x n, row stride nb1) is present in bc->qact quantized for weight type wtype
 static int ensure_quantized(b200_backend_ctx * bc, int wtype, const ggml_tensor * x) {
@@ -431,7 +432,8 @@ static int try_fuse_norm(b200_backend_ctx * bc, ggml_cgraph * g, int i, int * rc
     memcpy(&eps, rms->op_params, sizeof(float));
     const int64_t ne0 = rms->ne[0], nrows = ggml_nrows(rms);
     void * q = nullptr;
-    if (wtype >= 0 && mul->ne[2] == 1 && mul->ne[3] == 1 && nrows <= GEMV_MAX_COLS) q = ensure_qact(bc, qact_col_bytes(wtype, ne0) * (size_t) nrows);
+    static const bool noq = getenv("B200_NORM_NOQ") != nullptr;  // bisect aid: never quantize inside the fused norm
+    if (!noq && wtype >= 0 && mul->ne[2] == 1 && mul->ne[3] == 1 && nrows <= GEMV_MAX_COLS) q = ensure_qact(bc, qact_col_bytes(wtype, ne0) * (size_t) nrows);
     const float * x = (const float *) (add ? add->src[0]->data : rms->src[0]->data);
     *rc = add_rmsnorm_quant(wtype >= 0 ? wtype : GGML_TYPE_Q4_K, x, add ? (const float *) add->src[1]->data : nullptr, (const float *) w->data,
                             add ? (float *) add->data : nullptr, (float *) mul->data, q, ne0, nrows, eps, bc->stream);
@@ -513,13 +515,14 @@ static int try_fuse_attention(b200_backend_ctx * bc, ggml_cgraph * g, int i, int
 
 static int try_fuse(b200_backend_ctx * bc, ggml_cgraph * g, int i, int * rc) {
     if (!fusion_enabled()) return 0;
+    static const int off = getenv("B200_FUSE_OFF") ? atoi(getenv("B200_FUSE_OFF")) : 0;  // bisect aid: bit0 norm, 1 attention, 2 swiglu, 3 bias
     int n;
     const ggml_tensor * node = g->nodes[i];
-    if (node->op == GGML_OP_ADD || node->op == GGML_OP_RMS_NORM) { if ((n = try_fuse_norm(bc, g, i, rc))) return n; }
+    if (!(off & 1) && (node->op == GGML_OP_ADD || node->op == GGML_OP_RMS_NORM)) { if ((n = try_fuse_norm(bc, g, i, rc))) return n; }
     if (node->op == GGML_OP_MUL_MAT) {
-        if ((n = try_fuse_attention(bc, g, i, rc))) return n;
-        if ((n = try_fuse_swiglu(bc, g, i, rc))) return n;
-        if ((n = try_fuse_bias(bc, g, i, rc))) return n;
+        if (!(off & 2) && (n = try_fuse_attention(bc, g, i, rc))) return n;
+        if (!(off & 4) && (n = try_fuse_swiglu(bc, g, i, rc))) return n;
+        if (!(off & 8) && (n = try_fuse_bias(bc, g, i, rc))) return n;
     }
     return 0;
 }
@@ -614,10 +617,28 @@ static void b200_backend_synchronize(ggml_backend_t backend) {
     CUDA_OK(cudaSetDevice(bc->device));
     CUDA_OK(cudaStreamSynchronize(bc->stream));
 }
+// B200_TRACE=1: after every executed node / fused group print a checksum of each output it produced (debug aid; syncs)
+static void trace_node(b200_backend_ctx * bc, int idx, const ggml_tensor * t) {
+    if (!t->data || !ggml_is_contiguous(t) || (t->type != GGML_TYPE_F32 && t->type != GGML_TYPE_F16)) return;
+    cudaStreamSynchronize(bc->stream);
+    const size_t nb = ggml_nbytes(t);
+    std::vector<uint8_t> h(nb);
+    cudaMemcpy(h.data(), t->data, nb, cudaMemcpyDeviceToHost);
+    double s = 0, a = 0;
+    const int64_t n = ggml_nelements(t);
+    for (int64_t i = 0; i < n; ++i) {
+        const double v = t->type == GGML_TYPE_F32 ? ((const float *) h.data())[i] : (double) ggml_fp16_to_fp32(((const ggml_fp16_t *) h.data())[i]);
+        if (v == v && v - v == 0) { s += v; a += v < 0 ? -v : v; }
+    }
+    fprintf(stderr, "B200TRACE %d %s %s [%lld,%lld,%lld,%lld] sum=%.9g abs=%.9g\n", idx, ggml_op_name(t->op), t->name, (long long) t->ne[0], (long long) t->ne[1],
+            (long long) t->ne[2], (long long) t->ne[3], s, a);
+}
+
 static enum ggml_status b200_graph_compute(ggml_backend_t backend, ggml_cgraph * cgraph) {
     b200_backend_ctx * bc = (b200_backend_ctx *) backend->context;
     CUDA_OK(cudaSetDevice(bc->device));
     bc->q_src = nullptr;  // nothing is known to be quantized at the start of a graph
+    static const bool trace = getenv("B200_TRACE") != nullptr;
     for (int i = 0; i < cgraph->n_nodes; ++i) {
         ggml_tensor * node = cgraph->nodes[i];
         if (is_view_op(node->op) || ggml_is_empty(node)) continue;
@@ -626,10 +647,12 @@ static enum ggml_status b200_graph_compute(ggml_backend_t backend, ggml_cgraph *
         if (consumed > 0) {
             bc->fused += consumed;
             bc->launches++;
+            if (trace) for (int t = i; t < i + consumed; ++t) if (t == i + consumed - 1 || cgraph->nodes[t]->op == GGML_OP_ADD) trace_node(bc, t, cgraph->nodes[t]);
             i += consumed - 1;
         } else {
             rc = compute_node(bc, node);
             bc->launches++;
+            if (trace) trace_node(bc, i, node);
         }
         if (rc != 0) {
             GGML_LOG_ERROR("b200: op %s (%s) failed rc=%d%s\n", ggml_op_name(node->op), node->name, rc,

