@@ -195,9 +195,9 @@ int add_rmsnorm_quant(int wtype, const float * x, const float * r, const float *
 // RoPE(q), RoPE(k) + KV-cache append for ONE token.  grid = n_heads + kv_heads, block = head_dim/2 threads.
 // angle recurrence exactly as rope_kernel (ops.cu).  mode 0 = adjacent pairs, 2 = NEOX.
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void rope_kv_store_kernel(float * __restrict__ q, const float * __restrict__ k, const float * __restrict__ v, const int32_t * __restrict__ pos,
-                                     const float * __restrict__ ff, __half * __restrict__ kc, __half * __restrict__ vc, int n_heads, int kv_heads, int hd,
-                                     int mode, float theta_scale, int64_t k_row_stride, int64_t v_row_stride) {
+__global__ void rope_kv_store_kernel(const float * q, float * q_out, const float * __restrict__ k, const float * __restrict__ v,
+                                     const int32_t * __restrict__ pos, const float * __restrict__ ff, __half * __restrict__ kc, __half * __restrict__ vc,
+                                     int n_heads, int kv_heads, int hd, int mode, float theta_scale, int64_t k_row_stride, int64_t v_row_stride, int v_col) {
     pdl_launch_dependents();
     pdl_wait();
     const int i = threadIdx.x, half = hd / 2;
@@ -209,10 +209,11 @@ __global__ void rope_kv_store_kernel(float * __restrict__ q, const float * __res
     const int i0 = (mode == 0) ? 2 * i : i, i1 = (mode == 0) ? 2 * i + 1 : i + half;
     const int b = blockIdx.x;
     if (b < n_heads) {
-        float * h = q + (int64_t) b * hd;
+        const float * h = q + (int64_t) b * hd;
+        float * o = q_out + (int64_t) b * hd;
         const float x0 = h[i0], x1 = h[i1];
-        h[i0] = x0 * c - x1 * s;
-        h[i1] = x0 * s + x1 * c;
+        o[i0] = x0 * c - x1 * s;
+        o[i1] = x0 * s + x1 * c;
     } else {
         const int g = b - n_heads;
         const float * h = k + (int64_t) g * hd;
@@ -221,18 +222,23 @@ __global__ void rope_kv_store_kernel(float * __restrict__ q, const float * __res
         krow[i0] = __float2half_rn(x0 * c - x1 * s);
         krow[i1] = __float2half_rn(x0 * s + x1 * c);
         const float * vv = v + (int64_t) g * hd;
-        vc[((int64_t) g * hd + i0) * v_row_stride + p] = __float2half_rn(vv[i0]);
-        vc[((int64_t) g * hd + i1) * v_row_stride + p] = __float2half_rn(vv[i1]);
+        const int col = v_col >= 0 ? v_col : p;  // v_col >= 0: vc already points at this token's column
+        vc[((int64_t) g * hd + i0) * v_row_stride + col] = __float2half_rn(vv[i0]);
+        vc[((int64_t) g * hd + i1) * v_row_stride + col] = __float2half_rn(vv[i1]);
     }
 }
-int rope_kv_store(float * q, const float * k, const float * v, const int32_t * pos, const float * ff, void * kc, void * vc, int n_heads, int kv_heads,
-                  int head_dim, int mode, float freq_base, int64_t k_row_stride, int64_t v_row_stride, cudaStream_t st) {
+int rope_kv_store2(const float * q, float * q_out, const float * k, const float * v, const int32_t * pos, const float * ff, void * kc, void * vc, int n_heads,
+                   int kv_heads, int head_dim, int mode, float freq_base, int64_t k_row_stride, int64_t v_row_stride, int v_col, cudaStream_t st) {
     if (mode != 0 && mode != 2) return B200_ERR_UNSUPPORTED;
     if (head_dim % 2 || head_dim > 2048) return B200_ERR_ARG;
     const float theta_scale = powf(freq_base, -2.0f / head_dim);
-    launch_pdl(rope_kv_store_kernel, dim3((unsigned) (n_heads + kv_heads)), dim3(head_dim / 2), 0, st, q, k, v, pos, ff, (__half *) kc, (__half *) vc, n_heads, kv_heads, head_dim,
-                                                                                  mode, theta_scale, k_row_stride, v_row_stride);
+    launch_pdl(rope_kv_store_kernel, dim3((unsigned) (n_heads + kv_heads)), dim3(head_dim / 2), 0, st, q, q_out, k, v, pos, ff, (__half *) kc, (__half *) vc, n_heads,
+               kv_heads, head_dim, mode, theta_scale, k_row_stride, v_row_stride, v_col);
     return (int) cudaGetLastError();
+}
+int rope_kv_store(float * q, const float * k, const float * v, const int32_t * pos, const float * ff, void * kc, void * vc, int n_heads, int kv_heads,
+                  int head_dim, int mode, float freq_base, int64_t k_row_stride, int64_t v_row_stride, cudaStream_t st) {
+    return rope_kv_store2(q, q, k, v, pos, ff, kc, vc, n_heads, kv_heads, head_dim, mode, freq_base, k_row_stride, v_row_stride, -1, st);
 }
 
 // ------------------------------------------------------------------------------------------------------------------

@@ -500,7 +500,7 @@ int mul_mat_q_multi(int wtype, int mode, int nmat, const void * const * W, const
         GemvTuning t;
         t.rg = tune && tune->rg ? tune->rg : env_int("B200_GEMV_RG", 4);
         t.warps = tune && tune->warps ? tune->warps : env_int("B200_GEMV_WARPS", 8);
-        t.stages = tune && tune->stages ? tune->stages : env_int("B200_GEMV_STAGES", 3);
+        t.stages = tune && tune->stages ? tune->stages : env_int("B200_GEMV_STAGES", 2);
         t.ks = tune && tune->ks ? tune->ks : env_int("B200_GEMV_KS", 16);
         t.grid = tune && tune->grid ? tune->grid : env_int("B200_GEMV_GRID", 0);
         if (t.ks > nunits) t.ks = nunits;

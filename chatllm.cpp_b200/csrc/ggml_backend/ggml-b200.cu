@@ -21,6 +21,7 @@
 
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -69,6 +70,8 @@ struct b200_backend_ctx {
     size_t qact_bytes = 0;
     float * attn_scratch = nullptr;
     size_t attn_scratch_bytes = 0;
+    float * kv_scratch = nullptr;  // k / v projections of the fused q/k/v group (try_fuse_qkv)
+    size_t kv_scratch_bytes = 0;
     long long launches = 0;
     long long fused = 0;
     // which tensor currently sits quantized in `qact` (valid inside one graph_compute call)
@@ -76,6 +79,10 @@ struct b200_backend_ctx {
     const void * q_data = nullptr;
     int q_kind = -1;  // 0 = Q8_K codes (Q4_K weights), 1 = Q8_0 codes (Q4_0 / Q8_0 weights)
     int64_t q_k = 0, q_n = 0;
+    // B200_PROFILE=1: per-graph host time inside graph_compute and GPU time between its first and last kernel
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double prof_host_ms = 0, prof_gpu_ms = 0, prof_sync_ms = 0;
+    long long prof_graphs = 0, prof_launches0 = 0;
 };
 
 static ggml_backend_device g_devices[B200_MAX_DEVICES];
@@ -513,14 +520,122 @@ static int try_fuse_attention(b200_backend_ctx * bc, ggml_cgraph * g, int i, int
     return 7;
 }
 
+// ---- decode q/k/v group of BaseAttention::forward + KVCacheAttention::save_to_cache (src/layers.cpp:3212-3224, :3044-3122) as the host's
+// graph orders it for ONE token:  MUL_MAT(v) [ADD bias] .. CPY(-> v_cache view) .. MUL_MAT(k) [ADD] .. ROPE(k) .. SET_ROWS(k_cache, pos) ..
+// MUL_MAT(q) [ADD] .. ROPE(q)   (".." = view ops).  Executed as ONE concatenated GEMV launch + ONE rope/KV-append launch.
+static const ggml_tensor * view_root(const ggml_tensor * t) {
+    while (t && is_view_op(t->op) && t->src[0]) t = t->src[0];
+    return t;
+}
+static bool plain_rope(const ggml_tensor * r, int64_t hd) {
+    float fp[6];
+    memcpy(fp, (const int32_t *) r->op_params + 5, sizeof(fp));
+    const int n_dims = r->op_params[1], mode = r->op_params[2];
+    return n_dims == hd && (mode == 0 || mode == GGML_ROPE_TYPE_NEOX) && fp[1] == 1.0f && fp[2] == 0.0f && fp[3] == 1.0f &&
+           (!r->src[2] || (r->src[2]->type == GGML_TYPE_F32 && ggml_is_contiguous(r->src[2])));
+}
+static int try_fuse_qkv(b200_backend_ctx * bc, ggml_cgraph * g, int i, int * rc) {
+    int j = i;
+    auto next_real = [&](int from) { while (from < g->n_nodes && is_view_op(g->nodes[from]->op)) ++from; return from; };
+    // one projection: MUL_MAT [+ ADD bias]; returns the tensor holding the projection's result
+    const ggml_tensor * mm[3] = {nullptr, nullptr, nullptr}, * out[3], * bias[3] = {nullptr, nullptr, nullptr};
+    int idx_out[3];
+    auto take_proj = [&](int s) -> bool {
+        j = next_real(j);
+        if (j >= g->n_nodes || !is_quant_mm(g->nodes[j]) || g->nodes[j]->src[1]->ne[1] != 1) return false;
+        mm[s] = out[s] = g->nodes[j]; idx_out[s] = j;
+        int n = next_real(j + 1);
+        if (n < g->n_nodes && g->nodes[n]->op == GGML_OP_ADD && g->nodes[n]->src[0] == mm[s]) {
+            const ggml_tensor * b = g->nodes[n]->src[1];
+            if (!f32c(b) || ggml_nelements(b) != mm[s]->ne[0] || !f32c(g->nodes[n]) || !ggml_are_same_shape(g->nodes[n], mm[s])) return false;
+            if (!ggml_node_has_n_uses(g, j, 1)) return false;
+            bias[s] = b; out[s] = g->nodes[n]; idx_out[s] = n;
+        }
+        j = idx_out[s] + 1;
+        return true;
+    };
+    // v -> CPY
+    if (!take_proj(0)) return 0;
+    j = next_real(j);
+    if (j >= g->n_nodes || g->nodes[j]->op != GGML_OP_CPY) return 0;
+    const ggml_tensor * cpy = g->nodes[j];
+    if (view_root(cpy->src[0]) != out[0] || cpy->type != GGML_TYPE_F16 || !ggml_node_has_n_uses(g, idx_out[0], 1)) return 0;
+    const int64_t kvh_dim = out[0]->ne[0];
+    if (cpy->ne[0] != 1 || cpy->ne[1] != kvh_dim || ggml_nelements(cpy) != kvh_dim || cpy->nb[1] % 2) return 0;  // one column of the transposed V cache
+    ++j;
+    // k -> ROPE -> SET_ROWS
+    if (!take_proj(1)) return 0;
+    j = next_real(j);
+    if (j >= g->n_nodes || g->nodes[j]->op != GGML_OP_ROPE) return 0;
+    const ggml_tensor * rk = g->nodes[j];
+    const int idx_rk = j;
+    // the host ropes in place (the ROPE node is a view of its input), so only the use COUNT can be checked for it
+    if (view_root(rk->src[0]) != out[1] || !ggml_node_has_n_uses(g, idx_out[1], 1) || ggml_node_get_use_count(g, idx_rk) != 1 ||
+        (rk->flags & GGML_TENSOR_FLAG_OUTPUT))
+        return 0;
+    j = next_real(j + 1);
+    if (j >= g->n_nodes || g->nodes[j]->op != GGML_OP_SET_ROWS) return 0;
+    const ggml_tensor * sr = g->nodes[j];
+    if (view_root(sr->src[0]) != rk || sr->src[1] != rk->src[1] || sr->type != GGML_TYPE_F16 || sr->ne[0] != out[1]->ne[0] || sr->nb[0] != 2 || sr->ne[2] != 1 ||
+        sr->ne[3] != 1)
+        return 0;
+    ++j;
+    // q -> ROPE
+    if (!take_proj(2)) return 0;
+    j = next_real(j);
+    if (j >= g->n_nodes || g->nodes[j]->op != GGML_OP_ROPE) return 0;
+    const ggml_tensor * rq = g->nodes[j];
+    const int idx_rq = j;
+    if (view_root(rq->src[0]) != out[2] || rq->src[1] != rk->src[1] || rq->src[2] != rk->src[2]) return 0;
+    // shapes: rope inputs are [head_dim, heads, 1]
+    const int64_t hd = rk->ne[0], kvh = rk->ne[1], heads = rq->ne[1];
+    if (rq->ne[0] != hd || rk->ne[2] != 1 || rq->ne[2] != 1 || hd * kvh != kvh_dim || hd * kvh != out[1]->ne[0] || hd * heads != out[2]->ne[0]) return 0;
+    if (!plain_rope(rk, hd) || !plain_rope(rq, hd) || memcmp(rk->op_params, rq->op_params, sizeof(int32_t) * 11) != 0) return 0;
+    if (!f32c(rq) || rk->src[1]->type != GGML_TYPE_I32) return 0;
+    if (mm[0]->src[1] != mm[1]->src[1] || mm[0]->src[1] != mm[2]->src[1] || mm[0]->src[0]->type != mm[1]->src[0]->type ||
+        mm[0]->src[0]->type != mm[2]->src[0]->type)
+        return 0;
+    for (int s = 0; s < 3; ++s) if (mm[s]->src[0]->ne[1] % 2) return 0;
+
+    const ggml_tensor * x = mm[0]->src[1];
+    *rc = ensure_quantized(bc, (int) mm[0]->src[0]->type, x);
+    if (*rc) return idx_rq - i + 1;
+    const void * Ws[3] = {mm[2]->src[0]->data, mm[1]->src[0]->data, mm[0]->src[0]->data};  // q, k, v
+    const int64_t ms[3] = {mm[2]->src[0]->ne[1], mm[1]->src[0]->ne[1], mm[0]->src[0]->ne[1]};
+    // The host's graph allocator recycles the v projection's buffer for k and then for q (each dies before the next is born), so the
+    // three results cannot land in their node buffers in one launch: k and v (which only feed the cache) go to backend scratch.
+    const size_t kv_need = (size_t) (ms[1] + ms[2]) * sizeof(float);
+    if (bc->kv_scratch_bytes < kv_need) {
+        CUDA_OK(cudaStreamSynchronize(bc->stream));
+        if (bc->kv_scratch) CUDA_OK(cudaFree(bc->kv_scratch));
+        CUDA_OK(cudaMalloc((void **) &bc->kv_scratch, kv_need));
+        bc->kv_scratch_bytes = kv_need;
+    }
+    float * k_tmp = bc->kv_scratch, * v_tmp = bc->kv_scratch + ms[1];
+    float * ys[3] = {(float *) out[2]->data, k_tmp, v_tmp};
+    const int64_t lds[3] = {ms[0], ms[1], ms[2]};
+    const float * bs[3] = {bias[2] ? (const float *) bias[2]->data : nullptr, bias[1] ? (const float *) bias[1]->data : nullptr,
+                           bias[0] ? (const float *) bias[0]->data : nullptr};
+    *rc = mul_mat_q_multi((int) mm[0]->src[0]->type, 0, 3, Ws, ms, ys, lds, bs, x->ne[0], bc->qact, 1, nullptr, bc->stream);
+    if (*rc) return idx_rq - i + 1;
+    bc->launches++;
+    float fp[6];
+    memcpy(fp, (const int32_t *) rq->op_params + 5, sizeof(fp));
+    *rc = rope_kv_store2((const float *) out[2]->data, (float *) rq->data, k_tmp, v_tmp,
+                         (const int32_t *) rk->src[1]->data, rk->src[2] ? (const float *) rk->src[2]->data : nullptr, sr->data, cpy->data, (int) heads, (int) kvh,
+                         (int) hd, rq->op_params[2], fp[0], (int64_t) (sr->nb[1] / 2), (int64_t) (cpy->nb[1] / 2), 0, bc->stream);
+    return idx_rq - i + 1;
+}
+
 static int try_fuse(b200_backend_ctx * bc, ggml_cgraph * g, int i, int * rc) {
     if (!fusion_enabled()) return 0;
-    static const int off = getenv("B200_FUSE_OFF") ? atoi(getenv("B200_FUSE_OFF")) : 0;  // bisect aid: bit0 norm, 1 attention, 2 swiglu, 3 bias
+    static const int off = getenv("B200_FUSE_OFF") ? atoi(getenv("B200_FUSE_OFF")) : 0;  // bisect aid: bit0 norm, 1 attention, 2 swiglu, 3 bias, 4 qkv
     int n;
     const ggml_tensor * node = g->nodes[i];
     if (!(off & 1) && (node->op == GGML_OP_ADD || node->op == GGML_OP_RMS_NORM)) { if ((n = try_fuse_norm(bc, g, i, rc))) return n; }
     if (node->op == GGML_OP_MUL_MAT) {
         if (!(off & 2) && (n = try_fuse_attention(bc, g, i, rc))) return n;
+        if (!(off & 16) && (n = try_fuse_qkv(bc, g, i, rc))) return n;
         if (!(off & 4) && (n = try_fuse_swiglu(bc, g, i, rc))) return n;
         if (!(off & 8) && (n = try_fuse_bias(bc, g, i, rc))) return n;
     }
@@ -608,6 +723,7 @@ static void b200_backend_free(ggml_backend_t backend) {
     cudaStreamSynchronize(bc->stream);
     if (bc->qact) cudaFree(bc->qact);
     if (bc->attn_scratch) cudaFree(bc->attn_scratch);
+    if (bc->kv_scratch) cudaFree(bc->kv_scratch);
     cudaStreamDestroy(bc->stream);
     delete bc;
     delete backend;
@@ -639,6 +755,13 @@ static enum ggml_status b200_graph_compute(ggml_backend_t backend, ggml_cgraph *
     CUDA_OK(cudaSetDevice(bc->device));
     bc->q_src = nullptr;  // nothing is known to be quantized at the start of a graph
     static const bool trace = getenv("B200_TRACE") != nullptr;
+    static const bool prof = getenv("B200_PROFILE") != nullptr;
+    std::chrono::steady_clock::time_point t0;
+    if (prof) {
+        if (!bc->ev0) { cudaEventCreate(&bc->ev0); cudaEventCreate(&bc->ev1); }
+        t0 = std::chrono::steady_clock::now();
+        cudaEventRecord(bc->ev0, bc->stream);
+    }
     for (int i = 0; i < cgraph->n_nodes; ++i) {
         ggml_tensor * node = cgraph->nodes[i];
         if (is_view_op(node->op) || ggml_is_empty(node)) continue;
@@ -658,6 +781,24 @@ static enum ggml_status b200_graph_compute(ggml_backend_t backend, ggml_cgraph *
             GGML_LOG_ERROR("b200: op %s (%s) failed rc=%d%s\n", ggml_op_name(node->op), node->name, rc,
                            rc > 0 ? cudaGetErrorString((cudaError_t) rc) : "");
             return GGML_STATUS_FAILED;
+        }
+    }
+    if (prof) {
+        cudaEventRecord(bc->ev1, bc->stream);
+        const auto t1 = std::chrono::steady_clock::now();
+        cudaEventSynchronize(bc->ev1);
+        const auto t2 = std::chrono::steady_clock::now();
+        float ms = 0;
+        cudaEventElapsedTime(&ms, bc->ev0, bc->ev1);
+        if (cgraph->n_nodes > 100) {  // whole-model graphs only
+            bc->prof_host_ms += std::chrono::duration<double, std::milli>(t1 - t0).count();
+            bc->prof_sync_ms += std::chrono::duration<double, std::milli>(t2 - t1).count();
+            bc->prof_gpu_ms += ms;
+            bc->prof_graphs++;
+            if (bc->prof_graphs % 16 == 0)
+                fprintf(stderr, "B200PROF graphs=%lld nodes=%d host_ms/graph=%.3f gpu_ms/graph=%.3f wait_after_enqueue_ms=%.3f launches/graph=%.1f\n", bc->prof_graphs,
+                        cgraph->n_nodes, bc->prof_host_ms / 16, bc->prof_gpu_ms / 16, bc->prof_sync_ms / 16, (bc->launches - bc->prof_launches0) / 16.0);
+            if (bc->prof_graphs % 16 == 0) { bc->prof_host_ms = bc->prof_gpu_ms = bc->prof_sync_ms = 0; bc->prof_launches0 = bc->launches; }
         }
     }
     return GGML_STATUS_SUCCESS;

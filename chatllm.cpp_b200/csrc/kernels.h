@@ -54,6 +54,9 @@ int add_rmsnorm_quant(int wtype, const float * x, const float * r, const float *
                       float eps, cudaStream_t st);
 int rope_kv_store(float * q, const float * k, const float * v, const int32_t * pos, const float * ff, void * kc, void * vc, int n_heads, int kv_heads,
                   int head_dim, int mode, float freq_base, int64_t k_row_stride, int64_t v_row_stride, cudaStream_t st);
+// q_out may differ from q; v_col >= 0: vc already points at the token's column (the host's V-cache view), else column = pos[0]
+int rope_kv_store2(const float * q, float * q_out, const float * k, const float * v, const int32_t * pos, const float * ff, void * kc, void * vc, int n_heads,
+                   int kv_heads, int head_dim, int mode, float freq_base, int64_t k_row_stride, int64_t v_row_stride, int v_col, cudaStream_t st);
 size_t attn_decode2_scratch_bytes(int n_heads, int n_kv);
 int attn_decode2(const float * q, const void * kc, const void * vc, float * out, float * scratch, int n_heads, int kv_heads, int head_dim, int n_kv,
                  int64_t k_row_stride, int64_t v_row_stride, float scale, cudaStream_t st);

@@ -149,6 +149,24 @@ def test_soft_max_with_f16_mask_and_scale():
     both(lambda g: [(g.soft_max(g.input(x), g.input(mask), scale=0.125), np.float32, x.shape)], atol=1e-6)
 
 
+@pytest.mark.parametrize("t", [qf.Q4_K, qf.Q4_0])
+@pytest.mark.parametrize("neox,bias", [(False, False), (True, True)])
+def test_decode_layer_graph_untapped_fused_groups(t, neox, bias):
+    """same layer, one token, NO intermediate outputs: the plugin's fused groups (norm+quantize, q/k/v + rope + cache append,
+    attention, SwiGLU) all fire; K/V cache contents and the layer output must match the CPU backend"""
+    outs = {}
+    for dev in ("CPU", "CUDA0"):
+        g = rs.Graph(); taps = []
+        vw = _layer_graph(g, 11, t, 256, 4, 2, 512, 37, 1, 128, neox, bias, taps, want_kw=True)
+        named = dict((n, (tt, shp)) for (n, tt, shp) in taps)
+        res = g.run(dev, [(g.cont(vw), np.float16, (128, 1)), (named["kw"][0], np.float16, named["kw"][1]), (named["out"][0], np.float32, named["out"][1])],
+                    n_threads=8, strict=True)
+        outs[dev] = res
+    for a, b, tol in zip(outs["CPU"], outs["CUDA0"], (1e-3, 1e-3, 2e-3)):
+        a = a.astype(np.float32); b = b.astype(np.float32)
+        assert np.abs(a - b).max() <= tol * np.abs(a).max()
+
+
 def test_moe_router_ops():
     """GenericSparseMLP router (src/layers.cpp:3755-3880): softmax -> top_k -> get_rows -> sum_rows -> div"""
     rng = np.random.default_rng(5)
@@ -165,7 +183,7 @@ def test_moe_router_ops():
     assert np.allclose(outs["CUDA0"][0].sum(-1), 1.0, atol=1e-6)
 
 
-def _layer_graph(g, rng_seed, t, hidden, heads, kvh, ffn, n_past, qlen, max_len, neox, bias, taps):
+def _layer_graph(g, rng_seed, t, hidden, heads, kvh, ffn, n_past, qlen, max_len, neox, bias, taps, want_kw=False):
     """One LMBlock1Forward layer exactly as chatllm emits it (src/layers.cpp:2719-2761, :3212-3227, :2475-2483)."""
     rng = np.random.default_rng(rng_seed)
     hd = hidden // heads
@@ -190,6 +208,8 @@ def _layer_graph(g, rng_seed, t, hidden, heads, kvh, ffn, n_past, qlen, max_len,
     taps.append(("q_rope", q4, (qlen, heads, hd)))
     vw = g.cpy(g.transpose(v), g.view(vc, (qlen, kv_hidden), (2 * max_len,), offset=n_past * 2))
     kw = g.set_rows(kc, g.reshape(k4, (kv_hidden, qlen)), pos)
+    if want_kw:
+        taps.clear(); taps.append(("kw", kw, (max_len, kv_hidden)))
     K = g.permute(g.view(kw, (hd, kvh, n_kv), (2 * hd, 2 * kv_hidden)), (0, 2, 1, 3))
     V = g.view(vc, (n_kv, hd, kvh), (2 * max_len, 2 * max_len * hd))
     Q = g.permute(q4, (0, 2, 1, 3))
