@@ -115,6 +115,18 @@ int b200_attn_decode(const float * q, const void * k_cache, const void * v_cache
     }
     return attn_decode(q, k_cache, v_cache_t, out, scratch, n_heads, kv_heads, head_dim, n_kv, k_row_stride, v_row_stride, scale, (cudaStream_t) stream);
 }
+int b200_attn_decode_quant(const float * q, const void * k_cache, const void * v_cache_t, float * out, float * scratch, int n_heads, int kv_heads,
+                           int head_dim, int n_kv, int64_t k_row_stride, int64_t v_row_stride, float scale, int wtype, void * qact, void * stream) {
+    if (qact && ((int64_t) n_heads * head_dim) % 256) return B200_ERR_UNSUPPORTED;
+    if (k_row_stride % 8 == 0 && v_row_stride % 8 == 0) {
+        const int rc = attn_decode3(q, k_cache, v_cache_t, out, scratch, n_heads, kv_heads, head_dim, n_kv, k_row_stride, v_row_stride, scale, wtype, qact,
+                                    (cudaStream_t) stream);
+        if (rc != B200_ERR_UNSUPPORTED) return rc;
+    }
+    const int rc = attn_decode(q, k_cache, v_cache_t, out, scratch, n_heads, kv_heads, head_dim, n_kv, k_row_stride, v_row_stride, scale, (cudaStream_t) stream);
+    if (rc || !qact) return rc;
+    return quantize_act(wtype, out, (int64_t) n_heads * head_dim, (int64_t) n_heads * head_dim, 1, qact, (cudaStream_t) stream);
+}
 int b200_add_rmsnorm_quant(int wtype, const float * x, const float * r, const float * w, float * x_out, float * y_out, void * qact, int64_t ne0, int64_t nrows,
                            float eps, void * stream) {
     return add_rmsnorm_quant(wtype, x, r, w, x_out, y_out, qact, ne0, nrows, eps, (cudaStream_t) stream);
@@ -127,6 +139,10 @@ int b200_rope_kv_store(float * q, const float * k, const float * v, const int32_
 int b200_mul_mat_q_multi(int wtype, int mode, int nmat, const void * const * W, const int64_t * m, float * const * y, const int64_t * ldy,
                          const float * const * bias, int64_t k, const void * qact, int64_t n, void * stream) {
     return mul_mat_q_multi(wtype, mode, nmat, W, m, y, ldy, bias, k, qact, n, &g_tune, (cudaStream_t) stream);
+}
+int b200_mul_mat_q_id(int wtype, int paired, const void * W0, const void * W1, int64_t k, int64_t m, int n_expert, const int32_t * ids, int n_ids,
+                      const void * qact, int act_cols, float * y, int64_t ldy, void * stream) {
+    return mul_mat_q_id(wtype, paired, W0, W1, k, m, n_expert, ids, n_ids, qact, act_cols, y, ldy, &g_tune, (cudaStream_t) stream);
 }
 int b200_kv_store(const float * k, const float * v, void * k_cache, void * v_cache_t, int kv_hidden, int64_t k_row_stride, int64_t v_row_stride, int pos,
                   void * stream) {

@@ -46,7 +46,7 @@ __device__ __forceinline__ float blk_max(float v, float * red) {
 template <bool Q8K, int J>
 __global__ void __launch_bounds__(1024) add_rmsnorm_quant_kernel(const float * __restrict__ x, const float * __restrict__ r, const float * __restrict__ w,
                                                                  float * __restrict__ x_out, float * __restrict__ y_out, uint8_t * __restrict__ qact,
-                                                                 int64_t ne0, float eps, size_t col_bytes) {
+                                                                 int64_t ne0, float eps, size_t col_bytes, int nsplit) {
     __shared__ float red[32];
     __shared__ unsigned long long keys[32];
     __shared__ float bmax[16];
@@ -57,6 +57,23 @@ __global__ void __launch_bounds__(1024) add_rmsnorm_quant_kernel(const float * _
     const float * xr = x + row * ne0;
     float v[J][4];
     float ss = 0.0f;
+    if (nsplit > 0) {
+        // reduction tail of the split decode attention (attn_pv_split_kernel): x = nsplit partial rows of ne0 floats, summed in
+        // split order; no normalisation.  x_out receives the sum, qact its quantization (the o-projection's activations).
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            const int64_t e = 4 * (int64_t) t + 4 * (int64_t) T * j;
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (e < ne0) {
+                for (int c = 0; c < nsplit; ++c) {
+                    const float4 b = *reinterpret_cast<const float4 *>(x + (int64_t) c * ne0 + e);
+                    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+                }
+                if (x_out) *reinterpret_cast<float4 *>(x_out + e) = a;
+            }
+            v[j][0] = a.x; v[j][1] = a.y; v[j][2] = a.z; v[j][3] = a.w;
+        }
+    } else {
 #pragma unroll
     for (int j = 0; j < J; ++j) {
         const int64_t e = 4 * (int64_t) t + 4 * (int64_t) T * j;
@@ -86,6 +103,7 @@ __global__ void __launch_bounds__(1024) add_rmsnorm_quant_kernel(const float * _
             if (y_out) *reinterpret_cast<float4 *>(y_out + row * ne0 + e) = make_float4(v[j][0], v[j][1], v[j][2], v[j][3]);
         }
     }
+    }  // nsplit == 0
     if (!qact) return;
     const ActLayout L = act_layout(Q8K, ne0);
     uint8_t * base = qact + (size_t) row * col_bytes;
@@ -182,12 +200,34 @@ int add_rmsnorm_quant(int wtype, const float * x, const float * r, const float *
     const size_t cb = qact ? qact_col_bytes(wtype, ne0) : 0;
 #define B200_ARQ(J_)                                                                                                                          \
     if (J == J_) {                                                                                                                            \
-        if (q8k) launch_pdl(add_rmsnorm_quant_kernel<true, J_>, dim3((unsigned) nrows), dim3(threads), 0, st, x, r, w, x_out, y_out, (uint8_t *) qact, ne0, eps, cb); \
-        else launch_pdl(add_rmsnorm_quant_kernel<false, J_>, dim3((unsigned) nrows), dim3(threads), 0, st, x, r, w, x_out, y_out, (uint8_t *) qact, ne0, eps, cb);     \
+        if (q8k) launch_pdl(add_rmsnorm_quant_kernel<true, J_>, dim3((unsigned) nrows), dim3(threads), 0, st, x, r, w, x_out, y_out, (uint8_t *) qact, ne0, eps, cb, 0); \
+        else launch_pdl(add_rmsnorm_quant_kernel<false, J_>, dim3((unsigned) nrows), dim3(threads), 0, st, x, r, w, x_out, y_out, (uint8_t *) qact, ne0, eps, cb, 0);     \
         return (int) cudaGetLastError();                                                                                                      \
     }
     B200_ARQ(1) B200_ARQ(2) B200_ARQ(3) B200_ARQ(4) B200_ARQ(5)
 #undef B200_ARQ
+    return B200_ERR_UNSUPPORTED;
+}
+
+// out[e] = sum_c partial[c][e] (c < nsplit, in order) ; qact = quantized out for weight type wtype (NULL: no quantization)
+static int sum_partials_quant(int wtype, const float * partial, int nsplit, float * out, void * qact, int64_t ne0, cudaStream_t st) {
+    if (ne0 % 256 || ne0 > 20480 || nsplit <= 0) return B200_ERR_UNSUPPORTED;
+    const bool q8k = wtype == B200_TYPE_Q4_K;
+    if (qact && !q8k && wtype != B200_TYPE_Q4_0 && wtype != B200_TYPE_Q8_0) return B200_ERR_UNSUPPORTED;
+    int threads = (int) (ne0 / 4);
+    if (threads > 1024) threads = 1024;
+    const int J = (int) ((ne0 / 4 + threads - 1) / threads);
+    const size_t cb = qact ? qact_col_bytes(wtype, ne0) : 0;
+    const float * nul = nullptr;
+    float * nulo = nullptr;
+#define B200_SPQ(J_)                                                                                                                          \
+    if (J == J_) {                                                                                                                            \
+        if (q8k) launch_pdl(add_rmsnorm_quant_kernel<true, J_>, dim3(1), dim3(threads), 0, st, partial, nul, nul, out, nulo, (uint8_t *) qact, ne0, 0.0f, cb, nsplit); \
+        else launch_pdl(add_rmsnorm_quant_kernel<false, J_>, dim3(1), dim3(threads), 0, st, partial, nul, nul, out, nulo, (uint8_t *) qact, ne0, 0.0f, cb, nsplit);     \
+        return (int) cudaGetLastError();                                                                                                      \
+    }
+    B200_SPQ(1) B200_SPQ(2) B200_SPQ(3) B200_SPQ(4) B200_SPQ(5)
+#undef B200_SPQ
     return B200_ERR_UNSUPPORTED;
 }
 
@@ -656,14 +696,135 @@ __global__ void __launch_bounds__(B200_PV_WARPS * 32) attn_pv_mma_kernel(const f
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Position-split V.P (third design; replaces attn_pv_mma_kernel on the default path).  The channel-split kernel above uses
+// only HD/16 x kv_heads = 64 CTAs and every one of them rebuilds P for ALL positions of its group from the raw scores.
+// Here a CTA owns `span` consecutive positions of one KV group: it builds P only for those (nothing is recomputed anywhere),
+// multiplies the [HD x span] slab of the transposed V cache with it on the tensor cores (warp w = channels 16w .. 16w+15) and
+// writes an fp32 partial [GQA heads][HD].  nsplit x kv_heads CTAs (136 for Llama-3-8B at 4K context: one wave of the 148
+// SMs); the partials are summed in split order by the tail kernel (sum_partials_quant), which also emits the quantized
+// activations of the o-projection, so the launch count of the layer does not change.
+// Arithmetic is unchanged: P = f16(exp(s - max) / sum) with the GLOBAL max / sum (from the scores kernel's chunk statistics).
+// ------------------------------------------------------------------------------------------------------------------
+#define B200_PVS_ROUND 256  // positions per inner round (two 128-position k groups held in registers)
+template <int HD, int GQA>
+__global__ void __launch_bounds__(HD * 2) attn_pv_split_kernel(const float * __restrict__ scores, const float2 * __restrict__ part,
+                                                               const __half * __restrict__ vc, float * __restrict__ partial, int n_kv,
+                                                               int64_t v_row_stride, int64_t s_stride, int nchunks, int span, int n_heads) {
+    constexpr int NT = HD * 2;
+    constexpr int SP = B200_PVS_ROUND + 32;  // +64 bytes: the 8 head rows land in different bank groups (conflict-free 16-byte B loads)
+    __shared__ __align__(16) __half Ph[8 * SP];
+    __shared__ float hmax[8], hinv[8];
+    pdl_launch_dependents();
+    const int grp = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int p_begin = blockIdx.x * span;
+    const int p_end = min(n_kv, p_begin + span);
+    // padding head rows of P stay zero for the whole kernel
+    for (int i = threadIdx.x; i < (8 - GQA) * SP / 2; i += NT) reinterpret_cast<uint32_t *>(Ph + GQA * SP)[i] = 0u;
+
+    const int c0 = warp * 16;
+    const __half * rowA = vc + (int64_t) (grp * HD + c0 + g) * v_row_stride;
+    const __half * rowB = rowA + 8 * v_row_stride;
+    auto ldv = [&](const __half * row, int p0) -> uint4 {
+        if (p0 >= p_end) return make_uint4(0, 0, 0, 0);
+        uint4 v = *reinterpret_cast<const uint4 *>(row + p0);
+        const int r = p_end - p0;  // valid halves in this 16-byte chunk
+        if (r < 8) {               // tail: zero what lies beyond n_kv (P is zero there, but the cache may hold anything, NaN included)
+            uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) w[j] = (2 * j + 1 < r) ? w[j] : ((2 * j < r) ? (w[j] & 0xffffu) : 0u);
+            v = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        return v;
+    };
+    uint4 alo[2][4], ahi[2][4];
+    auto load_round = [&](int p0) {
+#pragma unroll
+        for (int s2 = 0; s2 < 2; ++s2)
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                alo[s2][u] = ldv(rowA, p0 + s2 * 128 + 8 * t + 32 * u);
+                ahi[s2][u] = ldv(rowB, p0 + s2 * 128 + 8 * t + 32 * u);
+            }
+    };
+
+    pdl_wait();  // the scores / statistics come from the predecessor; the newest V column from the kernel before it
+    load_round(p_begin);  // DRAM loads first, the (L2-resident) scores behind them
+    if (warp < GQA) {
+        const float2 * pp = part + (int64_t) (grp * GQA + warp) * nchunks;
+        float mx = -INFINITY;
+        for (int i = lane; i < nchunks; i += 32) mx = fmaxf(mx, pp[i].x);
+        mx = warp_max(mx);
+        float sum = 0.0f;
+        for (int i = lane; i < nchunks; i += 32) { const float2 pv = pp[i]; sum += pv.y * expf(pv.x - mx); }
+        sum = warp_sum(sum);
+        if (lane == 0) { hmax[warp] = mx; hinv[warp] = 1.0f / sum; }
+    }
+    __syncthreads();
+
+    float c[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int p0 = p_begin; p0 < p_end; p0 += B200_PVS_ROUND) {
+        if (p0 != p_begin) { __syncthreads(); load_round(p0); }  // every warp is done with the previous round's P
+        // ---- P of this round: Ph[h][i] = f16(exp(s - max_h) * inv_h), zero beyond n_kv
+        for (int i = threadIdx.x; i < B200_PVS_ROUND; i += NT) {
+            const int pp0 = p0 + i;
+#pragma unroll
+            for (int h = 0; h < GQA; ++h) {
+                // __expf (ex2.approx, ~2 ulp): the value is rounded to f16 (11 bits) right away
+                const float e = (pp0 < p_end) ? __expf(scores[(int64_t) (grp * GQA + h) * s_stride + pp0] - hmax[h]) * hinv[h] : 0.0f;
+                Ph[h * SP + i] = __float2half_rn(e);
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int s2 = 0; s2 < 2; ++s2) {
+            if (p0 + s2 * 128 < p_end) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint4 b = *reinterpret_cast<const uint4 *>(Ph + g * SP + s2 * 128 + 8 * t + 32 * u);
+                    mma16816(c, alo[s2][u].x, ahi[s2][u].x, alo[s2][u].y, ahi[s2][u].y, b.x, b.y);
+                    mma16816(c, alo[s2][u].z, ahi[s2][u].z, alo[s2][u].w, ahi[s2][u].w, b.z, b.w);
+                }
+            }
+        }
+    }
+    // c0 = (ch g, head 2t), c1 = (ch g, head 2t+1), c2 = (ch g+8, head 2t), c3 = (ch g+8, head 2t+1)
+    float * po = partial + ((int64_t) blockIdx.x * n_heads + (int64_t) grp * GQA) * HD + c0;
+    if (2 * t < GQA) { po[(int64_t) (2 * t) * HD + g] = c[0]; po[(int64_t) (2 * t) * HD + g + 8] = c[2]; }
+    if (2 * t + 1 < GQA) { po[(int64_t) (2 * t + 1) * HD + g] = c[1]; po[(int64_t) (2 * t + 1) * HD + g + 8] = c[3]; }
+}
+
+// positions per CTA of the split V.P kernel: 256 up to 8K context (<= 32 splits), then grown in steps of 256
+static int pv_span(int n_kv) {
+    int span = B200_PVS_ROUND;
+    while ((n_kv + span - 1) / span > 32) span += B200_PVS_ROUND;
+    return span;
+}
+
 template <int HD, int GQA>
 static int attn_decode_mma_t(const float * q, const void * kc, const void * vc, float * out, float * scratch, int n_kv, int kv_heads, int64_t k_row_stride,
-                             int64_t v_row_stride, float scale, cudaStream_t st) {
+                             int64_t v_row_stride, float scale, int wtype, void * qact, cudaStream_t st) {
     const int64_t s_stride = (n_kv + 7) & ~7;
     const int nchunks = (n_kv + 127) / 128;
     float2 * part = reinterpret_cast<float2 *>(scratch + (int64_t) kv_heads * GQA * s_stride);
     launch_pdl(attn_scores_mma_kernel<HD, GQA>, dim3((unsigned) nchunks, (unsigned) kv_heads), dim3(256), 0, st, q, (const __half *) kc, scratch, part, n_kv,
                k_row_stride, scale, s_stride, nchunks);
+    static const int old_pv = getenv("B200_ATTN_OLD_PV") ? atoi(getenv("B200_ATTN_OLD_PV")) : 0;  // A/B aid: the channel-split kernel
+    const int n_heads = kv_heads * GQA;
+    if (!old_pv && ((int64_t) n_heads * HD) % 256 == 0 && (int64_t) n_heads * HD <= 20480) {
+        const int span = pv_span(n_kv);
+        const int nsplit = (n_kv + span - 1) / span;
+        // partial sums live behind the scores and the chunk statistics (attn_decode2_scratch_bytes)
+        float * partial = scratch + (((int64_t) n_heads * s_stride + 2 * (int64_t) n_heads * nchunks + 15) & ~(int64_t) 15);
+        launch_pdl(attn_pv_split_kernel<HD, GQA>, dim3((unsigned) nsplit, (unsigned) kv_heads), dim3(HD * 2), 0, st, (const float *) scratch, (const float2 *) part,
+                   (const __half *) vc, partial, n_kv, v_row_stride, s_stride, nchunks, span, n_heads);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return (int) e;
+        return sum_partials_quant(wtype, partial, nsplit, out, qact, (int64_t) n_heads * HD, st);
+    }
     const int npos = nchunks * 128;
     const int sp = npos + 32;  // +64 bytes: the 8 head rows land in different bank groups (conflict-free 16-byte B loads)
     const size_t smem = (size_t) 8 * sp * 2 + B200_PV_WARPS * 128 * 4;
@@ -677,7 +838,10 @@ static int attn_decode_mma_t(const float * q, const void * kc, const void * vc, 
     if (smem > 227 * 1024) return B200_ERR_UNSUPPORTED;
     launch_pdl(attn_pv_mma_kernel<GQA>, dim3((unsigned) (HD / 16), (unsigned) kv_heads), dim3(B200_PV_WARPS * 32), smem, st, (const float *) scratch, (const float2 *) part,
                (const __half *) vc, out, n_kv, HD, v_row_stride, s_stride, nchunks, sp);
-    return (int) cudaGetLastError();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return (int) e;
+    if (qact) return quantize_act(wtype, out, (int64_t) n_heads * HD, (int64_t) n_heads * HD, 1, qact, st);
+    return B200_OK;
 }
 
 template <int HD, int GQA>
@@ -702,11 +866,19 @@ static int attn_decode2_t(const float * q, const void * kc, const void * vc, flo
 }
 
 size_t attn_decode2_scratch_bytes(int n_heads, int n_kv) {
-    return (size_t) n_heads * (size_t) ((n_kv + 7) & ~7) * 4 + (size_t) n_heads * (size_t) ((n_kv + B200_ATTN_CH - 1) / B200_ATTN_CH) * 8 + 64;
+    // raw scores [n_heads][n_kv] + chunk statistics + (split V.P) up to 32 partial outputs of at most 20480 floats
+    return (size_t) n_heads * (size_t) ((n_kv + 7) & ~7) * 4 + (size_t) n_heads * (size_t) ((n_kv + B200_ATTN_CH - 1) / B200_ATTN_CH) * 8 + 128 +
+           (size_t) 32 * 20480 * 4;
 }
 
 int attn_decode2(const float * q, const void * kc, const void * vc, float * out, float * scratch, int n_heads, int kv_heads, int head_dim, int n_kv,
                  int64_t k_row_stride, int64_t v_row_stride, float scale, cudaStream_t st) {
+    return attn_decode3(q, kc, vc, out, scratch, n_heads, kv_heads, head_dim, n_kv, k_row_stride, v_row_stride, scale, 0, nullptr, st);
+}
+
+// as attn_decode2, and additionally qact = the output quantized as the activations of a following matmul with weight type wtype
+int attn_decode3(const float * q, const void * kc, const void * vc, float * out, float * scratch, int n_heads, int kv_heads, int head_dim, int n_kv,
+                 int64_t k_row_stride, int64_t v_row_stride, float scale, int wtype, void * qact, cudaStream_t st) {
     if (n_kv <= 0) return B200_OK;
     if (n_heads % kv_heads) return B200_ERR_ARG;
     if ((k_row_stride % 8) || (v_row_stride % 8)) return B200_ERR_UNSUPPORTED;  // 16-byte row loads
@@ -714,8 +886,10 @@ int attn_decode2(const float * q, const void * kc, const void * vc, float * out,
     static const int no_mma = getenv("B200_ATTN_NO_MMA") ? atoi(getenv("B200_ATTN_NO_MMA")) : 0;
 #define B200_ATTN2(HD_, G_)                                                                                                                       \
     if (head_dim == HD_ && gqa == G_) {                                                                                                           \
-        if (!no_mma) return attn_decode_mma_t<HD_, G_>(q, kc, vc, out, scratch, n_kv, kv_heads, k_row_stride, v_row_stride, scale, st);           \
-        return attn_decode2_t<HD_, G_>(q, kc, vc, out, scratch, n_kv, kv_heads, k_row_stride, v_row_stride, scale, st);                           \
+        if (!no_mma) return attn_decode_mma_t<HD_, G_>(q, kc, vc, out, scratch, n_kv, kv_heads, k_row_stride, v_row_stride, scale, wtype, qact, st); \
+        const int rc_ = attn_decode2_t<HD_, G_>(q, kc, vc, out, scratch, n_kv, kv_heads, k_row_stride, v_row_stride, scale, st);                  \
+        if (rc_ || !qact) return rc_;                                                                                                             \
+        return quantize_act(wtype, out, (int64_t) n_heads * head_dim, (int64_t) n_heads * head_dim, 1, qact, st);                                 \
     }
     B200_ATTN2(128, 4) B200_ATTN2(128, 7) B200_ATTN2(128, 1) B200_ATTN2(128, 8) B200_ATTN2(128, 2)
     B200_ATTN2(64, 8) B200_ATTN2(64, 4) B200_ATTN2(64, 2) B200_ATTN2(64, 1)

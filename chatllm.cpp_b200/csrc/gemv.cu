@@ -181,6 +181,12 @@ struct FmtQ80 {
 //                    every m_i is a multiple of RG so a row group never straddles two matrices.
 //   MODE 1 (paired): two matrices of equal shape (gate, up); a row group holds RG/2 gate rows and the SAME RG/2 up rows,
 //                    and the epilogue writes silu(gate.x) * (up.x)  (SwiGLU of BaseMLP::forward, src/layers.cpp:2475-2483).
+//   MODE 2 / 3 (expert-indexed concat / paired): ggml_mul_mat_id for ONE token (ggml/src/ggml.c:3225-3240, CPU
+//                    ggml-cpu.c:1503-1700; caller MultiLinear::forward src/layers.cpp:2145-2151).  mat[0] (and mat[1] in the
+//                    paired mode) is a stack of n_expert matrices of m rows; logical row = slot * m + row, slot < n_ids, and slot
+//                    s streams the rows of expert ids[s] (read from DEVICE memory: the router's top_k runs on the GPU just before).
+//                    Every slot either shares activation column 0 (gate/up: src1 is broadcast over the slots) or owns column s
+//                    (down: src1 has one column per slot).  y[slot * ldy + row].
 // ======================================================================================================
 struct GemvMat {
     const uint8_t * W;
@@ -199,6 +205,11 @@ struct GemvParams {
     int ks;                // units per stage (== nunits -> whole rows per stage)
     int stages;
     uint32_t act_col_bytes;
+    // expert-indexed modes only
+    const int32_t * ids;    // device, n_ids expert indices of this token
+    int n_ids, n_expert;
+    int act_cols;           // 1 = every slot reads activation column 0, n_ids = slot s reads column s
+    int64_t expert_bytes;   // bytes between consecutive experts of a stack
 };
 
 template <class F, int RG, int NC, int MODE>
@@ -211,10 +222,14 @@ __global__ void __launch_bounds__(512) gemv_q_kernel(const GemvParams p) {
 
     constexpr int UNIT = F::A_UNIT + F::B_UNIT;
     constexpr int HALF = RG / 2;
-    constexpr int GROUP = (MODE == 1) ? HALF : RG;  // logical rows advanced per row group
-    static_assert(MODE == 0 || RG >= 2, "paired mode needs RG >= 2");
+    constexpr bool PAIRED = (MODE & 1) != 0;
+    constexpr bool IDX = MODE >= 2;
+    constexpr int GROUP = PAIRED ? HALF : RG;  // logical rows advanced per row group
+    static_assert(!PAIRED || RG >= 2, "paired mode needs RG >= 2");
+    static_assert(!IDX || NC == 1, "expert-indexed modes process one token");
     const bool whole = (p.ks == p.nunits);
-    const uint32_t act_bytes = (uint32_t) al16((int64_t) p.act_col_bytes * NC);
+    const int stage_cols = IDX ? p.act_cols : NC;  // activation columns kept in shared memory
+    const uint32_t act_bytes = (uint32_t) al16((int64_t) p.act_col_bytes * stage_cols);
     const uint32_t stage_bytes = (uint32_t) RG * p.ks * UNIT;
     // row r of a stage: A part at st + r*rsA, B part at st + offB + r*rsB
     const uint32_t rsA = whole ? p.ks * UNIT : p.ks * F::A_UNIT;
@@ -237,7 +252,15 @@ __global__ void __launch_bounds__(512) gemv_q_kernel(const GemvParams p) {
 
     // stage row i of the group starting at logical row `row0` -> global pointer of that weight row
     auto row_src = [&](int64_t row0, int i) -> const uint8_t * {
-        if (MODE == 1) {
+        if constexpr (IDX) {
+            // a group never straddles two slots (m % GROUP == 0, checked on the host)
+            const int64_t slot = row0 / p.mat[0].m;
+            const int64_t lr = row0 - slot * p.mat[0].m;
+            const int e = min(max(__ldg(p.ids + slot), 0), p.n_expert - 1);
+            const int64_t eoff = (int64_t) e * p.expert_bytes;
+            if (PAIRED) return (i < HALF) ? p.mat[0].W + eoff + (lr + i) * row_bytes : p.mat[1].W + eoff + (lr + i - HALF) * row_bytes;
+            return p.mat[0].W + eoff + (lr + i) * row_bytes;
+        } else if (PAIRED) {
             return (i < HALF) ? p.mat[0].W + (row0 + i) * row_bytes : p.mat[1].W + (row0 + i - HALF) * row_bytes;
         } else {
             int64_t r = row0 + i;
@@ -266,7 +289,7 @@ __global__ void __launch_bounds__(512) gemv_q_kernel(const GemvParams p) {
         const int nlog = (int) min((int64_t) GROUP, r1 - row0);  // valid logical rows (pairs in MODE 1)
         uint8_t * st = ring + (size_t) s * stage_bytes;
         if (whole) {
-            if (MODE == 1) {
+            if (PAIRED) {
                 const uint32_t bytes = (uint32_t) (nlog * row_bytes);
                 mbar_arrive_expect_tx(&bars[s], 2 * bytes);
                 bulk_g2s_hint(st, row_src(row0, 0), bytes, &bars[s], pol);
@@ -279,10 +302,10 @@ __global__ void __launch_bounds__(512) gemv_q_kernel(const GemvParams p) {
         } else {
             const int u0 = seg * p.ks;
             const int nu = min(p.ks, p.nunits - u0);
-            const int nrows = (MODE == 1) ? 2 * nlog : nlog;
+            const int nrows = PAIRED ? 2 * nlog : nlog;
             mbar_arrive_expect_tx(&bars[s], (uint32_t) nrows * nu * UNIT);
             for (int r = 0; r < RG; ++r) {
-                const bool valid = (MODE == 1) ? ((r < HALF ? r : r - HALF) < nlog) : (r < nlog);
+                const bool valid = PAIRED ? ((r < HALF ? r : r - HALF) < nlog) : (r < nlog);
                 if (!valid) continue;
                 const uint8_t * grow = row_src(row0, r);
                 bulk_g2s_hint(st + (size_t) r * rsA, grow + (size_t) u0 * F::A_UNIT, (uint32_t) nu * F::A_UNIT, &bars[s], pol);
@@ -294,17 +317,19 @@ __global__ void __launch_bounds__(512) gemv_q_kernel(const GemvParams p) {
     };
 
     // weights do not depend on the producer kernel: start streaming them before the PDL dependency resolves
+    // (expert-indexed modes: WHICH weights are streamed is the producer's output, so they wait first)
+    if constexpr (IDX) pdl_wait();
     if (lane == 0) {
         const int pre = min(p.stages, nitems);
         for (int it = 0; it < pre; ++it) issue(it);
     }
 
     // ---- activations: wait for the producer kernel (PDL), then stage the quantized columns in smem
-    pdl_wait();
+    if constexpr (!IDX) pdl_wait();
     {
         const uint4 * src = reinterpret_cast<const uint4 *>(p.qact);
         uint4 * dst = reinterpret_cast<uint4 *>(act_s);
-        const int n16 = (int) (((size_t) p.act_col_bytes * NC) >> 4);
+        const int n16 = (int) (((size_t) p.act_col_bytes * stage_cols) >> 4);
         for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = src[i];
     }
     __syncthreads();
@@ -335,10 +360,12 @@ __global__ void __launch_bounds__(512) gemv_q_kernel(const GemvParams p) {
         for (int u = ul; u < nu; u += UPS) {
             if constexpr (NC == 1) {
                 typename F::Act A;
-                F::load_act(act_s, L, u0 + u, g, A);
+                const uint8_t * acol = act_s;
+                if constexpr (IDX) { if (p.act_cols > 1) acol += (size_t) (row0 / p.mat[0].m) * p.act_col_bytes; }
+                F::load_act(acol, L, u0 + u, g, A);
 #pragma unroll
                 for (int r = 0; r < RG; ++r) {
-                    const bool valid = (MODE == 1) ? ((r < HALF ? r : r - HALF) < nlog) : (r < nlog);
+                    const bool valid = PAIRED ? ((r < HALF ? r : r - HALF) < nlog) : (r < nlog);
                     if (valid) {
                         typename F::Wt Wr;
                         F::load_w(st + (size_t) r * rsA, st + offB + (size_t) r * rsB, u, g, Wr);
@@ -348,7 +375,7 @@ __global__ void __launch_bounds__(512) gemv_q_kernel(const GemvParams p) {
             } else {
 #pragma unroll
                 for (int r = 0; r < RG; ++r) {
-                    const bool valid = (MODE == 1) ? ((r < HALF ? r : r - HALF) < nlog) : (r < nlog);
+                    const bool valid = PAIRED ? ((r < HALF ? r : r - HALF) < nlog) : (r < nlog);
                     if (valid) {
                         typename F::Wt Wr;
                         F::load_w(st + (size_t) r * rsA, st + offB + (size_t) r * rsB, u, g, Wr);
@@ -372,7 +399,22 @@ __global__ void __launch_bounds__(512) gemv_q_kernel(const GemvParams p) {
 #pragma unroll
                 for (int c = 0; c < NC; ++c) acc[r][c] = warp_sum(acc[r][c]);
             if (lane == 0) {
-                if (MODE == 1) {
+                if constexpr (IDX) {
+                    const int64_t slot = row0 / p.mat[0].m;
+                    float * yo = p.mat[0].y + slot * p.mat[0].ldy + (row0 - slot * p.mat[0].m);
+                    if (PAIRED) {
+#pragma unroll
+                        for (int q = 0; q < HALF; ++q) {
+                            if (q < nlog) {
+                                const float gv = acc[q][0], uv = acc[HALF + q][0];
+                                yo[q] = (gv / (1.0f + expf(-gv))) * uv;
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < RG; ++r) if (r < nlog) yo[r] = acc[r][0];
+                    }
+                } else if (PAIRED) {
 #pragma unroll
                     for (int q = 0; q < HALF; ++q) {
                         if (q < nlog) {
@@ -455,18 +497,42 @@ static int launch(const GemvParams & p, int warps, int grid, size_t smem_bytes, 
 template <class F, int MODE>
 static int launch_rg_nc(const GemvParams & p, int rg, int nc, int warps, int grid, size_t smem, cudaStream_t st) {
 #define B200_CASE(RG_, NC_) if (rg == RG_ && nc == NC_) return launch<F, RG_, NC_, MODE>(p, warps, grid, smem, st);
-    if constexpr (MODE == 0) { B200_CASE(1, 1) B200_CASE(1, 2) B200_CASE(1, 4) }
-    B200_CASE(2, 1) B200_CASE(2, 2) B200_CASE(2, 4) B200_CASE(4, 1) B200_CASE(4, 2) B200_CASE(4, 4)
+    if constexpr (MODE >= 2) {  // expert-indexed: one token
+        if constexpr (MODE == 2) { B200_CASE(1, 1) }
+        B200_CASE(2, 1) B200_CASE(4, 1)
+    } else {
+        if constexpr (MODE == 0) { B200_CASE(1, 1) B200_CASE(1, 2) B200_CASE(1, 4) }
+        B200_CASE(2, 1) B200_CASE(2, 2) B200_CASE(2, 4) B200_CASE(4, 1) B200_CASE(4, 2) B200_CASE(4, 4)
+    }
 #undef B200_CASE
     return B200_ERR_ARG;
 }
 
+template <class F>
+static int launch_mode(int mode, const GemvParams & p, int rg, int nc, int warps, int grid, size_t smem, cudaStream_t st) {
+    switch (mode) {
+        case 0: return launch_rg_nc<F, 0>(p, rg, nc, warps, grid, smem, st);
+        case 1: return launch_rg_nc<F, 1>(p, rg, nc, warps, grid, smem, st);
+        case 2: return launch_rg_nc<F, 2>(p, rg, nc, warps, grid, smem, st);
+        case 3: return launch_rg_nc<F, 3>(p, rg, nc, warps, grid, smem, st);
+        default: return B200_ERR_ARG;
+    }
+}
 static int launch_fmt(int wtype, int mode, const GemvParams & p, int rg, int nc, int warps, int grid, size_t smem, cudaStream_t st) {
     switch (wtype) {
-        case B200_TYPE_Q4_K: return mode ? launch_rg_nc<FmtQ4K, 1>(p, rg, nc, warps, grid, smem, st) : launch_rg_nc<FmtQ4K, 0>(p, rg, nc, warps, grid, smem, st);
-        case B200_TYPE_Q4_0: return mode ? launch_rg_nc<FmtQ40, 1>(p, rg, nc, warps, grid, smem, st) : launch_rg_nc<FmtQ40, 0>(p, rg, nc, warps, grid, smem, st);
-        case B200_TYPE_Q8_0: return mode ? launch_rg_nc<FmtQ80, 1>(p, rg, nc, warps, grid, smem, st) : launch_rg_nc<FmtQ80, 0>(p, rg, nc, warps, grid, smem, st);
+        case B200_TYPE_Q4_K: return launch_mode<FmtQ4K>(mode, p, rg, nc, warps, grid, smem, st);
+        case B200_TYPE_Q4_0: return launch_mode<FmtQ40>(mode, p, rg, nc, warps, grid, smem, st);
+        case B200_TYPE_Q8_0: return launch_mode<FmtQ80>(mode, p, rg, nc, warps, grid, smem, st);
         default: return B200_ERR_UNSUPPORTED;
+    }
+}
+
+static int unit_bytes(int wtype) {
+    switch (wtype) {
+        case B200_TYPE_Q4_K: return FmtQ4K::A_UNIT + FmtQ4K::B_UNIT;
+        case B200_TYPE_Q4_0: return FmtQ40::A_UNIT + FmtQ40::B_UNIT;
+        case B200_TYPE_Q8_0: return FmtQ80::A_UNIT + FmtQ80::B_UNIT;
+        default: return 0;
     }
 }
 
@@ -550,11 +616,74 @@ int mul_mat_q_multi(int wtype, int mode, int nmat, const void * const * W, const
         p.ks = t.ks;
         p.stages = t.stages;
         p.act_col_bytes = (uint32_t) acb;
+        p.ids = nullptr; p.n_ids = 0; p.n_expert = 0; p.act_cols = 0; p.expert_bytes = 0;
         const int rc = launch_fmt(wtype, mode, p, t.rg, nc, t.warps, grid, smem_for(t), st);
         if (rc) return rc;
         c0 += nc;
     }
     return B200_OK;
+}
+
+// ggml_mul_mat_id for one token (see MODE 2 / 3 above):  paired = 0:  y[s*ldy + r] = W0[ids[s]][r,:] . x_{c(s)}
+//                                                         paired = 1:  y[s*ldy + r] = silu(W0[ids[s]][r,:] . x) * (W1[ids[s]][r,:] . x)
+// c(s) = s if act_cols == n_ids, 0 if act_cols == 1.  W0 / W1: stacks of n_expert matrices [m, k] in the device layout.
+int mul_mat_q_id(int wtype, int paired, const void * W0, const void * W1, int64_t k, int64_t m, int n_expert, const int32_t * ids, int n_ids,
+                 const void * qact, int act_cols, float * y, int64_t ldy, const GemvTuning * tune, cudaStream_t st) {
+    if (k <= 0 || m <= 0 || n_ids <= 0) return B200_OK;
+    const int unit = unit_bytes(wtype);
+    if (!unit || k % 256) return B200_ERR_UNSUPPORTED;
+    if (!ids || n_expert <= 0 || (act_cols != 1 && act_cols != n_ids) || (paired && !W1)) return B200_ERR_ARG;
+    const size_t acb = qact_col_bytes(wtype, k);
+    const int nunits = (int) (k / 256);
+    const int sms = sm_count();
+    const int64_t m_total = (int64_t) n_ids * m, m_phys = m_total * (paired ? 2 : 1);
+
+    GemvTuning t;
+    t.rg = tune && tune->rg ? tune->rg : env_int("B200_GEMV_RG", 4);
+    t.warps = tune && tune->warps ? tune->warps : env_int("B200_GEMV_WARPS", 8);
+    t.stages = tune && tune->stages ? tune->stages : env_int("B200_GEMV_STAGES", 2);
+    t.ks = tune && tune->ks ? tune->ks : env_int("B200_GEMV_KS", 16);
+    t.grid = tune && tune->grid ? tune->grid : env_int("B200_GEMV_GRID", 0);
+    if (t.ks > nunits) t.ks = nunits;
+    while (t.rg > 1 && m_phys < (int64_t) sms * t.warps * t.rg / 2) t.rg >>= 1;
+    if (paired && t.rg < 2) t.rg = 2;
+    // a row group must not straddle two slots
+    while (t.rg > (paired ? 2 : 1) && m % (paired ? t.rg / 2 : t.rg)) t.rg >>= 1;
+    const int group = paired ? t.rg / 2 : t.rg;
+    if (m % group) return B200_ERR_UNSUPPORTED;
+    int grid = t.grid > 0 ? t.grid : sms;
+    {
+        const int64_t max_warps = (m_total + group - 1) / group;
+        const int64_t max_grid = (max_warps + t.warps - 1) / t.warps;
+        if (grid > max_grid) grid = (int) max_grid;
+    }
+    const size_t act_bytes = (size_t) al16((int64_t) acb * act_cols);
+    auto smem_for = [&](const GemvTuning & q) {
+        return act_bytes + (size_t) al16((int64_t) q.warps * q.stages * 8) + (size_t) q.warps * q.stages * q.rg * q.ks * unit;
+    };
+    const size_t limit = 227 * 1024;
+    while (smem_for(t) > limit && t.stages > 3) t.stages--;
+    while (smem_for(t) > limit && t.ks > 4) t.ks = (t.ks + 1) / 2;
+    while (smem_for(t) > limit && t.stages > 2) t.stages--;
+    while (smem_for(t) > limit && t.warps > 1) t.warps >>= 1;
+    while (smem_for(t) > limit && t.ks > 1) t.ks = (t.ks + 1) / 2;
+    if (smem_for(t) > limit) return B200_ERR_UNSUPPORTED;
+
+    GemvParams p;
+    p.nmat = paired ? 2 : 1;
+    p.mat[0] = GemvMat{(const uint8_t *) W0, y, nullptr, m, ldy};
+    p.mat[1] = paired ? GemvMat{(const uint8_t *) W1, nullptr, nullptr, m, ldy} : GemvMat{nullptr, nullptr, nullptr, 0, 0};
+    p.mat[2] = GemvMat{nullptr, nullptr, nullptr, 0, 0};
+    p.qact = (const uint8_t *) qact;
+    p.k = k; p.m_total = m_total;
+    p.n = 1;
+    p.nunits = nunits;
+    p.ks = t.ks;
+    p.stages = t.stages;
+    p.act_col_bytes = (uint32_t) acb;
+    p.ids = ids; p.n_ids = n_ids; p.n_expert = n_expert; p.act_cols = act_cols;
+    p.expert_bytes = m * (int64_t) nunits * unit;
+    return launch_fmt(wtype, paired ? 3 : 2, p, t.rg, 1, t.warps, grid, smem_for(t), st);
 }
 
 int mul_mat_q(int wtype, const void * W, int64_t k, int64_t m, const void * qact, int64_t n, float * y, int64_t ldy, const float * bias,

@@ -318,6 +318,15 @@ static bool b200_supports_op_impl(ggml_backend_dev_t, const ggml_tensor * op) {
             if (s0->type == GGML_TYPE_F16 || s0->type == GGML_TYPE_F32)
                 return s0->nb[0] == ggml_type_size(s0->type) && op->nb[0] == 4 && s1->ne[2] % s0->ne[2] == 0 && s1->ne[3] % s0->ne[3] == 0;
             return false;
+        case GGML_OP_MUL_MAT_ID: {
+            // as [k, m, n_expert] quantized, b [k, 1 | n_used, n_tokens] F32, ids [n_used, n_tokens] I32 -> [m, n_used, n_tokens]
+            const ggml_tensor * ids = op->src[2];
+            if (!ids || op->type != GGML_TYPE_F32 || s1->type != GGML_TYPE_F32 || ids->type != GGML_TYPE_I32) return false;
+            if (!qtype_ok(s0) || s0->ne[0] % 256 || !ggml_is_contiguous(s0) || s0->ne[3] != 1 || !ggml_is_contiguous(op)) return false;
+            if (s1->nb[0] != 4 || s1->ne[3] != 1 || (s1->ne[1] != 1 && s1->ne[1] != ids->ne[0]) || s1->ne[2] != ids->ne[1]) return false;
+            if (s1->nb[1] % 4 || s1->nb[2] % 4 || (s1->ne[1] > 1 && s1->nb[2] != s1->nb[1] * (size_t) s1->ne[1])) return false;
+            return ids->nb[0] == 4 && ids->ne[2] == 1 && ids->ne[3] == 1 && ids->ne[0] <= 64;
+        }
         case GGML_OP_ROPE: {
             const int mode = op->op_params[2];
             return s0->type == GGML_TYPE_F32 && op->type == GGML_TYPE_F32 && s0->nb[0] == 4 && op->nb[0] == 4 && s1->type == GGML_TYPE_I32 &&
@@ -395,6 +404,72 @@ static int mul_mat_quant(b200_backend_ctx * bc, const ggml_tensor * w, const ggm
     if (rc) return rc;
     if (x->ne[1] > GEMV_MAX_COLS) return mul_mat_q_batched((int) w->type, w->data, w->ne[0], w->ne[1], bc->qact, x->ne[1], y, ldy, bias, bc->stream);
     return mul_mat_q((int) w->type, w->data, w->ne[0], w->ne[1], bc->qact, x->ne[1], y, ldy, bias, nullptr, bc->stream);
+}
+
+// ---- ggml_mul_mat_id (MultiLinear::forward, src/layers.cpp:2145-2151): per token, the selected experts' rows stream through the
+// expert-indexed GEMV (gemv.cu MODE 2/3) with the expert ids read on the device.
+static const int MOE_SLOT_CHUNK = 4;  // slots per launch when every slot has its own activation column (shared-memory budget)
+
+// all src1 columns of a MUL_MAT_ID quantized (GEMV layout) into bc->qact; column c = t * b->ne[1] + e
+static int ensure_quantized_id(b200_backend_ctx * bc, int wtype, const ggml_tensor * b) {
+    const int64_t k = b->ne[0], n = b->ne[1] * b->ne[2];
+    const int kind = kind_of((ggml_type) wtype) + 4;
+    if (bc->q_src == b && bc->q_data == b->data && bc->q_kind == kind && bc->q_k == k && bc->q_n == n) return 0;
+    void * q = ensure_qact(bc, qact_col_bytes(wtype, k) * (size_t) n);
+    const int64_t col_stride = (int64_t) ((b->ne[1] == 1 ? b->nb[2] : b->nb[1]) / 4);
+    const int rc = quantize_act(wtype, (const float *) b->data, b->ne[1] * b->ne[2] == 1 ? k : col_stride, k, n, q, bc->stream);
+    bc->launches++;
+    bc->q_src = b; bc->q_data = b->data; bc->q_kind = kind; bc->q_k = k; bc->q_n = n;
+    return rc;
+}
+
+// W1 != nullptr: the experts' SwiGLU silu(W0 x) * (W1 x) (only with a broadcast src1); y: [m, n_used, n_tokens] with strides ldy / tok_stride floats
+static int mul_mat_id_quant(b200_backend_ctx * bc, const ggml_tensor * as, const ggml_tensor * as1, const ggml_tensor * b, const ggml_tensor * ids, float * y,
+                            int64_t ldy, int64_t tok_stride) {
+    int rc = ensure_quantized_id(bc, (int) as->type, b);
+    if (rc) return rc;
+    const int64_t k = as->ne[0], m = as->ne[1], n_expert = as->ne[2], n_used = ids->ne[0], n_tok = ids->ne[1], nb1 = b->ne[1];
+    const size_t acb = qact_col_bytes((int) as->type, k);
+    const int chunk = nb1 == 1 ? (int) n_used : MOE_SLOT_CHUNK;
+    for (int64_t t = 0; t < n_tok; ++t) {
+        for (int64_t s0 = 0; s0 < n_used; s0 += chunk) {
+            const int ns = (int) (n_used - s0 < chunk ? n_used - s0 : chunk);
+            const int32_t * idp = (const int32_t *) ((const char *) ids->data + t * ids->nb[1]) + s0;
+            const uint8_t * q = (const uint8_t *) bc->qact + (size_t) (t * nb1 + (nb1 == 1 ? 0 : s0)) * acb;
+            rc = mul_mat_q_id((int) as->type, as1 ? 1 : 0, as->data, as1 ? as1->data : nullptr, k, m, (int) n_expert, idp, ns, q, nb1 == 1 ? 1 : ns,
+                              y + t * tok_stride + s0 * ldy, ldy, nullptr, bc->stream);
+            if (rc) return rc;
+            bc->launches++;
+        }
+    }
+    bc->launches--;  // the caller counts one
+    return 0;
+}
+
+static bool is_quant_mm_id(const ggml_tensor * t) {
+    return t->op == GGML_OP_MUL_MAT_ID && b200_supports_op_impl(nullptr, t);
+}
+
+// MultiMLP::forward (src/layers.cpp:3674-3688) for one token:  up = MUL_MAT_ID(up_w, x, ids); gate = MUL_MAT_ID(gate_w, x, ids); act = SILU(gate);
+// par = MUL(up, act) [in place on up]  — in either node order — as ONE paired expert-indexed launch.
+static int try_fuse_moe_swiglu(b200_backend_ctx * bc, ggml_cgraph * g, int i, int * rc) {
+    if (i + 3 >= g->n_nodes) return 0;
+    ggml_tensor * a = g->nodes[i];
+    if (!is_quant_mm_id(a)) return 0;
+    ggml_tensor * gate = nullptr, * up = nullptr, * act = nullptr, * mul = g->nodes[i + 3];
+    int i_gate, i_up;
+    if (g->nodes[i + 1]->op == GGML_OP_UNARY) { gate = a; act = g->nodes[i + 1]; up = g->nodes[i + 2]; i_gate = i; i_up = i + 2; }
+    else { up = a; gate = g->nodes[i + 1]; act = g->nodes[i + 2]; i_up = i; i_gate = i + 1; }
+    if (!is_quant_mm_id(gate) || !is_quant_mm_id(up) || act->op != GGML_OP_UNARY || ggml_get_unary_op(act) != GGML_UNARY_OP_SILU || mul->op != GGML_OP_MUL) return 0;
+    if (act->src[0] != gate || gate->src[1] != up->src[1] || gate->src[2] != up->src[2] || gate->src[0]->type != up->src[0]->type ||
+        !ggml_are_same_shape(gate->src[0], up->src[0]))
+        return 0;
+    if (!((mul->src[0] == act && mul->src[1] == up) || (mul->src[1] == act && mul->src[0] == up))) return 0;
+    if (!f32c(mul) || !ggml_are_same_shape(mul, up) || !ggml_node_has_n_uses(g, i_gate, 1) || !ggml_node_has_n_uses(g, i_up, 1)) return 0;
+    const ggml_tensor * b = gate->src[1], * ids = gate->src[2];
+    if (b->ne[1] != 1 || ids->ne[1] != 1) return 0;  // one token, activation shared by the slots
+    *rc = mul_mat_id_quant(bc, gate->src[0], up->src[0], b, ids, (float *) mul->data, (int64_t) (mul->nb[1] / 4), (int64_t) (mul->nb[2] / 4));
+    return 4;
 }
 
 static bool is_quant_mm(const ggml_tensor * t) {
@@ -480,6 +555,7 @@ static int try_fuse_bias(b200_backend_ctx * bc, ggml_cgraph * g, int i, int * rc
     return 2;
 }
 
+static const ggml_tensor * view_root(const ggml_tensor * t);
 // decode attention: MUL_MAT(K,Q) -> SCALE -> DIAG_MASK_INF -> SOFT_MAX -> MUL_MAT(V,P) -> PERMUTE -> CONT, one query token
 static int try_fuse_attention(b200_backend_ctx * bc, ggml_cgraph * g, int i, int * rc) {
     if (i + 6 >= g->n_nodes) return 0;
@@ -512,11 +588,29 @@ static int try_fuse_attention(b200_backend_ctx * bc, ggml_cgraph * g, int i, int
         CUDA_OK(cudaMalloc((void **) &bc->attn_scratch, nb));
         bc->attn_scratch_bytes = nb;
     }
-    int r = attn_decode2((const float *) Q->data, K->data, V->data, (float *) ct->data, bc->attn_scratch, (int) heads, (int) kvh, (int) hd, (int) n_kv,
-                         (int64_t) (K->nb[1] / 2), (int64_t) (V->nb[1] / 2), scale, bc->stream);
+    // the consumer is the o-projection: its activation quantization is emitted by the attention's tail kernel
+    int wtype = 0;
+    void * qo = nullptr;
+    const ggml_tensor * xo = nullptr;
+    const int64_t ne0 = hd * heads;
+    if (ne0 % 256 == 0 && ne0 <= 20480) {
+        for (int t = i + 7; t < g->n_nodes && t < i + 12; ++t) {
+            const ggml_tensor * c = g->nodes[t];
+            if (c->op == GGML_OP_MUL_MAT && is_quant_mm(c) && view_root(c->src[1]) == ct && c->src[1]->ne[0] == ne0 && c->src[1]->ne[1] == 1 &&
+                c->src[1]->data == ct->data) {
+                wtype = (int) c->src[0]->type;
+                xo = c->src[1];
+                qo = ensure_qact(bc, qact_col_bytes(wtype, ne0));
+                break;
+            }
+        }
+    }
+    int r = attn_decode3((const float *) Q->data, K->data, V->data, (float *) ct->data, bc->attn_scratch, (int) heads, (int) kvh, (int) hd, (int) n_kv,
+                         (int64_t) (K->nb[1] / 2), (int64_t) (V->nb[1] / 2), scale, wtype, qo, bc->stream);
     if (r == B200_ERR_UNSUPPORTED) return 0;
     *rc = r;
-    bc->launches++;
+    bc->launches += 2;
+    if (qo) { bc->q_src = xo; bc->q_data = xo->data; bc->q_kind = kind_of((ggml_type) wtype); bc->q_k = ne0; bc->q_n = 1; }
     return 7;
 }
 
@@ -629,7 +723,7 @@ static int try_fuse_qkv(b200_backend_ctx * bc, ggml_cgraph * g, int i, int * rc)
 
 static int try_fuse(b200_backend_ctx * bc, ggml_cgraph * g, int i, int * rc) {
     if (!fusion_enabled()) return 0;
-    static const int off = getenv("B200_FUSE_OFF") ? atoi(getenv("B200_FUSE_OFF")) : 0;  // bisect aid: bit0 norm, 1 attention, 2 swiglu, 3 bias, 4 qkv
+    static const int off = getenv("B200_FUSE_OFF") ? atoi(getenv("B200_FUSE_OFF")) : 0;  // bisect aid: bit0 norm, 1 attention, 2 swiglu, 3 bias, 4 qkv, 5 moe swiglu
     int n;
     const ggml_tensor * node = g->nodes[i];
     if (!(off & 1) && (node->op == GGML_OP_ADD || node->op == GGML_OP_RMS_NORM)) { if ((n = try_fuse_norm(bc, g, i, rc))) return n; }
@@ -639,6 +733,7 @@ static int try_fuse(b200_backend_ctx * bc, ggml_cgraph * g, int i, int * rc) {
         if (!(off & 4) && (n = try_fuse_swiglu(bc, g, i, rc))) return n;
         if (!(off & 8) && (n = try_fuse_bias(bc, g, i, rc))) return n;
     }
+    if (node->op == GGML_OP_MUL_MAT_ID && !(off & 32)) { if ((n = try_fuse_moe_swiglu(bc, g, i, rc))) return n; }
     return 0;
 }
 
@@ -666,6 +761,8 @@ static int compute_node(b200_backend_ctx * bc, ggml_tensor * node) {
             }
             return op_mul_mat_f(tv(s0), tv(s1), tv(node), st);
         }
+        case GGML_OP_MUL_MAT_ID:
+            return mul_mat_id_quant(bc, s0, nullptr, s1, node->src[2], (float *) node->data, (int64_t) (node->nb[1] / 4), (int64_t) (node->nb[2] / 4));
         case GGML_OP_ROPE: {
             const int n_dims = node->op_params[1], mode = node->op_params[2], n_ctx_orig = node->op_params[4];
             float fp[6];

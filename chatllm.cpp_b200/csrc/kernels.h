@@ -26,6 +26,9 @@ int mul_mat_q(int wtype, const void * W, int64_t k, int64_t m, const void * qact
               const GemvTuning * tune, cudaStream_t st);
 int mul_mat_q_multi(int wtype, int mode, int nmat, const void * const * W, const int64_t * m, float * const * y, const int64_t * ldy,
                     const float * const * bias, int64_t k, const void * qact, int64_t n, const GemvTuning * tune, cudaStream_t st);
+// expert-indexed GEMV (ggml_mul_mat_id, one token): ids on the device; act_cols = 1 (shared column) or n_ids (one per slot)
+int mul_mat_q_id(int wtype, int paired, const void * W0, const void * W1, int64_t k, int64_t m, int n_expert, const int32_t * ids, int n_ids,
+                 const void * qact, int act_cols, float * y, int64_t ldy, const GemvTuning * tune, cudaStream_t st);
 int sm_count();
 
 // ---- prefill.cu: batched (n > 8) quantized matmul on the int8 tensor cores, plain activation layout
@@ -60,6 +63,9 @@ int rope_kv_store2(const float * q, float * q_out, const float * k, const float 
 size_t attn_decode2_scratch_bytes(int n_heads, int n_kv);
 int attn_decode2(const float * q, const void * kc, const void * vc, float * out, float * scratch, int n_heads, int kv_heads, int head_dim, int n_kv,
                  int64_t k_row_stride, int64_t v_row_stride, float scale, cudaStream_t st);
+// + qact (may be NULL) = out quantized as the activations of a following matmul with weight type wtype (n_heads*head_dim % 256 == 0)
+int attn_decode3(const float * q, const void * kc, const void * vc, float * out, float * scratch, int n_heads, int kv_heads, int head_dim, int n_kv,
+                 int64_t k_row_stride, int64_t v_row_stride, float scale, int wtype, void * qact, cudaStream_t st);
 
 // ---- ops_generic.cu: strided / broadcasting ops as ggml graphs present them (ne[0] fastest, nb in bytes)
 struct TV {

@@ -57,6 +57,19 @@ def mul_mat_q(wtype, w_dev, k, m, qact, n, bias=None, out=None):
     return y
 
 
+def mul_mat_id(wtype, w0_dev, k, m, n_expert, ids, x, w1_dev=None):
+    """ggml_mul_mat_id for one token.  w0_dev (w1_dev): expert stacks [n_expert, m, k] in the device layout; ids: int32 cuda
+    [n_ids]; x: float32 cuda [1, k] (shared by every slot) or [n_ids, k] (one column per slot).  w1_dev given -> the experts'
+    SwiGLU silu(w0 x) * (w1 x).  Returns [n_ids, m]."""
+    n_ids = ids.numel()
+    assert x.shape[0] in (1, n_ids)
+    q = quantize_act(wtype, x)
+    y = torch.empty((n_ids, m), dtype=torch.float32, device=x.device)
+    _chk(lib().b200_mul_mat_q_id(wtype, 1 if w1_dev is not None else 0, w0_dev.data_ptr(), _p(w1_dev), k, m, n_expert, ids.data_ptr(), n_ids,
+                                 q.data_ptr(), x.shape[0], y.data_ptr(), y.stride(0), _stream()), "mul_mat_q_id")
+    return y
+
+
 def mul_mat(wtype, w_dev, k, m, x, bias=None, out=None):
     n = x.shape[0]
     y = out if out is not None else torch.empty((n, m), dtype=torch.float32, device=x.device)

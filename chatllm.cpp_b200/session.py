@@ -211,9 +211,9 @@ class DecodeSession:
             rc |= L.b200_mul_mat_q_multi(c.wtype, 0, 3, t["W"], t["m"], t["y"], t["ld"], t["b"], c.hidden, q, 1, st); n += 1
             rc |= L.b200_rope_kv_store(self.q.data_ptr(), self.k.data_ptr(), self.v.data_ptr(), self.pos.data_ptr(), 0, W.kc.data_ptr(), W.vc.data_ptr(),
                                        c.heads, c.kv_heads, hd, c.rope_mode, c.rope_theta, c.kv_hidden, c.max_len, st); n += 1
-            rc |= L.b200_attn_decode(self.q.data_ptr(), W.kc.data_ptr(), W.vc.data_ptr(), self.att.data_ptr(), self.scratch.data_ptr(), c.heads, c.kv_heads,
-                                     hd, n_kv, c.kv_hidden, c.max_len, 1.0 / math.sqrt(hd), st); n += 2
-            rc |= L.b200_quantize_act(c.wtype, self.att.data_ptr(), c.hidden, c.hidden, 1, q, st); n += 1
+            # scores, split V.P, and the tail that sums the partials AND quantizes the result for the o-projection
+            rc |= L.b200_attn_decode_quant(self.q.data_ptr(), W.kc.data_ptr(), W.vc.data_ptr(), self.att.data_ptr(), self.scratch.data_ptr(), c.heads,
+                                           c.kv_heads, hd, n_kv, c.kv_hidden, c.max_len, 1.0 / math.sqrt(hd), c.wtype, q, st); n += 3
             rc |= L.b200_mul_mat_q(c.wtype, W.wo.data_ptr(), c.hidden, c.hidden, q, 1, self.o.data_ptr(), c.hidden, 0, st); n += 1
             rc |= L.b200_add_rmsnorm_quant(c.wtype, self.x.data_ptr(), self.o.data_ptr(), W.ffn_norm.data_ptr(), self.x.data_ptr(), 0, q, c.hidden, 1, c.eps, st); n += 1
             t = W.gu

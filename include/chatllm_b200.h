@@ -76,6 +76,15 @@ int b200_mul_mat_q_batched(int wtype, const void * W, int64_t k, int64_t m, cons
  *                                            — gate/up projections + SwiGLU of BaseMLP::forward (src/layers.cpp:2475-2483) */
 int b200_mul_mat_q_multi(int wtype, int mode, int nmat, const void * const * W, const int64_t * m, float * const * y, const int64_t * ldy,
                          const float * const * bias, int64_t k, const void * qact, int64_t n, void * stream);
+/* Expert-indexed matmul for ONE token = ggml_mul_mat_id (ggml/src/ggml.c:3225-3240; CPU ggml_compute_forward_mul_mat_id
+ * ggml/src/ggml-cpu/ggml-cpu.c:1503-1700; caller MultiLinear::forward src/layers.cpp:2145-2151, MultiMLP::forward :3674-3688).
+ *   W0 (and W1): stacks of n_expert matrices [m, k] in the device layout, expert e at byte offset e * m * row_bytes.
+ *   ids: n_ids expert indices in DEVICE memory (the router's top_k output).  qact: act_cols quantized columns;
+ *   act_cols == 1: every slot uses column 0 (src1 broadcast: gate / up), act_cols == n_ids: slot s uses column s (down).
+ *   paired = 0:  y[s*ldy + r] = W0[ids[s]][r,:] . x_c(s)
+ *   paired = 1:  y[s*ldy + r] = silu(W0[ids[s]][r,:] . x) * (W1[ids[s]][r,:] . x)        (experts' SwiGLU in one launch) */
+int b200_mul_mat_q_id(int wtype, int paired, const void * W0, const void * W1, int64_t k, int64_t m, int n_expert, const int32_t * ids,
+                      int n_ids, const void * qact, int act_cols, float * y, int64_t ldy, void * stream);
 /* override the pipeline shape of the GEMV kernel (0 = keep default): units(256 elts)/stage, stages, warps/CTA,
  * rows/group, grid */
 int b200_gemv_set_tuning(int ks, int stages, int warps, int rg, int grid);
@@ -117,6 +126,12 @@ int b200_rope_kv_store(float * q, const float * k, const float * v, const int32_
 size_t b200_attn_decode_scratch_bytes(int n_heads, int n_kv);
 int b200_attn_decode(const float * q, const void * k_cache, const void * v_cache_t, float * out, float * scratch, int n_heads,
                      int kv_heads, int head_dim, int n_kv, int64_t k_row_stride, int64_t v_row_stride, float scale, void * stream);
+/* Same, and additionally qact (may be NULL) = `out` quantized as the activations of the following matmul with weight type
+ * wtype (the o-projection: src1 conversion of ggml-cpu.c:1291-1326), written by the kernel that sums the split V.P partials.
+ * Requires n_heads*head_dim % 256 == 0 when qact != NULL. */
+int b200_attn_decode_quant(const float * q, const void * k_cache, const void * v_cache_t, float * out, float * scratch, int n_heads,
+                           int kv_heads, int head_dim, int n_kv, int64_t k_row_stride, int64_t v_row_stride, float scale, int wtype,
+                           void * qact, void * stream);
 /* append one token: K row `pos`, V column `pos` (F32 -> F16, RNE).  KVCacheAttention::save_to_cache src/layers.cpp:3044-3123 */
 int b200_kv_store(const float * k, const float * v, void * k_cache, void * v_cache_t, int kv_hidden, int64_t k_row_stride,
                   int64_t v_row_stride, int pos, void * stream);

@@ -393,6 +393,29 @@ int oq_mul_mat(int type, const void *w, size_t w_row_stride, int64_t k, int64_t 
     return 0;
 }
 
+/* ggml/src/ggml.c:3225-3240 (semantics) + ggml/src/ggml-cpu/ggml-cpu.c:1503-1700 ggml_compute_forward_mul_mat_id:
+ *   as  [k, m, n_expert]  (expert stride = m rows), b [k, nb1, n_tokens] with nb1 == n_used or 1 (broadcast),
+ *   ids [n_used, n_tokens] i32,  dst [m, n_used, n_tokens]:
+ *   dst[:, e, t] = as[:, :, ids[e, t]] . b[:, e % nb1, t]
+ * The CPU converts every src1 row to the weight type's vec_dot_type first (:1547-1580) and each dst element is one
+ * vec_dot (one_chunk :1432-1501) — the same per-column arithmetic as oq_mul_mat, so this just routes columns to experts.
+ * Returns -3 for an expert index outside [0, n_expert) (the reference asserts, :1611). */
+int oq_mul_mat_id(int type, const void *as, size_t w_row_stride, int64_t k, int64_t m, int64_t n_expert,
+                  const float *b, int64_t nb1, const int32_t *ids, int64_t n_used, int64_t n_tokens,
+                  float *dst, int q8_0_variant) {
+    for (int64_t t = 0; t < n_tokens; ++t) {
+        for (int64_t e = 0; e < n_used; ++e) {
+            const int32_t ex = ids[t * n_used + e];
+            if (ex < 0 || ex >= n_expert) return -3;
+            const uint8_t *w = (const uint8_t *)as + (size_t)ex * (size_t)m * w_row_stride;
+            const float *x = b + (t * nb1 + (e % nb1)) * k;
+            int rc = oq_mul_mat(type, w, w_row_stride, k, m, x, 1, dst + (t * n_used + e) * m, q8_0_variant);
+            if (rc) return rc;
+        }
+    }
+    return 0;
+}
+
 /* ============================ glue ops ================================= */
 
 /* ggml/src/ggml-cpu/ops.cpp:3710-3758  rms_norm (double sum, float mean), then the `mul` by weight that

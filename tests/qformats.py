@@ -110,6 +110,7 @@ def port():
         for n in ("oq_vec_dot_q4_0_q8_0", "oq_vec_dot_q8_0_q8_0", "oq_vec_dot_q4_K_q8_K"):
             getattr(L, n).argtypes = [i32, vp, vp]; getattr(L, n).restype = C.c_float
         L.oq_mul_mat.argtypes = [i32, vp, C.c_size_t, i64, i64, vp, i64, vp, i32]
+        L.oq_mul_mat_id.argtypes = [i32, vp, C.c_size_t, i64, i64, i64, vp, i64, vp, i64, i64, vp, i32]
         L.oq_rms_norm.argtypes = [vp, vp, vp, i64, i64, C.c_float]
         L.oq_soft_max.argtypes = [vp, vp, vp, i64, i64, C.c_float]
         L.oq_rope.argtypes = [vp, vp, vp, vp, i64, i64, i64, i32, i32, i32] + [C.c_float] * 6
@@ -133,6 +134,19 @@ def port_mul_mat(t, w_bytes, k, m, x, variant=1):
     w = np.ascontiguousarray(w_bytes)
     rc = port().oq_mul_mat(t, p(w), row_size(t, k), k, m, p(x), n, p(y), variant)
     assert rc == 0
+    return y
+
+
+def port_mul_mat_id(t, as_bytes, k, m, n_expert, b, ids, variant=1):
+    """as_bytes: n_expert stacked [m, row_size] matrices; b: float32 [n_tokens, nb1, k]; ids: int32 [n_tokens, n_used]
+    -> float32 [n_tokens, n_used, m] via the oracle port."""
+    b = np.ascontiguousarray(b, dtype=np.float32); ids = np.ascontiguousarray(ids, dtype=np.int32)
+    n_tokens, nb1, _ = b.shape
+    n_used = ids.shape[1]
+    y = np.empty((n_tokens, n_used, m), dtype=np.float32)
+    w = np.ascontiguousarray(as_bytes)
+    rc = port().oq_mul_mat_id(t, p(w), row_size(t, k), k, m, n_expert, p(b), nb1, p(ids), n_used, n_tokens, p(y), variant)
+    assert rc == 0, rc
     return y
 
 

@@ -376,3 +376,69 @@ def test_attn_decode_vs_reference_semantics(K, heads, kvh, hd, n_kv):
         ref[h] = vv @ p
     got = out.cpu().numpy()
     assert np.abs(got - ref).max() <= 2e-3 * np.abs(ref).max() + 1e-6   # f16 rounding of P can flip on an ulp: ~1e-3 of one term
+
+
+@pytest.mark.parametrize("wtype", [qf.Q4_K, qf.Q4_0])
+@pytest.mark.parametrize("heads,kvh,hd,n_kv", [(32, 8, 128, 4097), (32, 8, 128, 300), (28, 4, 128, 1000), (32, 4, 64, 777), (4, 2, 64, 9000)])
+def test_attn_decode_quant_tail_emits_the_o_proj_activations(K, wtype, heads, kvh, hd, n_kv):
+    """b200_attn_decode_quant: `out` equals b200_attn_decode's, and qact is bit-identical to quantizing that `out` with the
+    stand-alone quantizer (which test_quantize_* pin to the reference bit for bit).  n_kv = 9000 exercises multi-round spans."""
+    import torch
+    import chatllm_cpp_b200 as pkg
+    rng = np.random.default_rng(n_kv + heads + wtype)
+    max_len = ((n_kv + 255) // 256) * 256 + 256
+    kv_hidden = kvh * hd
+    kd = _t(rng.standard_normal((max_len, kv_hidden)).astype(np.float16))
+    vd = _t(rng.standard_normal((kv_hidden, max_len)).astype(np.float16))
+    vd[:, n_kv:] = float("nan")   # beyond the context the cache may hold anything
+    qd = _t(rng.standard_normal((heads, hd)).astype(np.float32) * 2)
+    L = pkg.lib()
+    scratch = torch.empty(L.b200_attn_decode_scratch_bytes(heads, max_len) // 4 + 16, dtype=torch.float32, device="cuda")
+    out_a = torch.zeros((1, heads * hd), device="cuda"); out_b = torch.zeros_like(out_a)
+    scale = 1.0 / np.sqrt(hd)
+    assert L.b200_attn_decode(qd.data_ptr(), kd.data_ptr(), vd.data_ptr(), out_a.data_ptr(), scratch.data_ptr(), heads, kvh, hd, n_kv, kv_hidden, max_len,
+                              scale, 0) == 0
+    q = torch.zeros(L.b200_qact_col_bytes(wtype, heads * hd), dtype=torch.uint8, device="cuda")
+    assert L.b200_attn_decode_quant(qd.data_ptr(), kd.data_ptr(), vd.data_ptr(), out_b.data_ptr(), scratch.data_ptr(), heads, kvh, hd, n_kv, kv_hidden,
+                                    max_len, scale, wtype, q.data_ptr(), 0) == 0
+    torch.cuda.synchronize()
+    assert torch.isfinite(out_b).all()
+    assert torch.equal(out_a, out_b)
+    assert torch.equal(q, K.quantize_act(wtype, out_b).reshape(-1))
+
+
+@pytest.mark.parametrize("wtype", [qf.Q4_K, qf.Q4_0, qf.Q8_0])
+@pytest.mark.parametrize("k,m,n_expert,n_used", [(512, 48, 8, 2), (4096, 14336, 8, 2), (14336, 4096, 8, 2), (2048, 1408, 60, 4), (1024, 6, 8, 3)])
+def test_mul_mat_id_vs_oracle(K, wtype, k, m, n_expert, n_used):
+    """expert-indexed GEMV (ggml_mul_mat_id, one token) against the oracle port (pinned to the reference's CPU backend in
+    test_oracle_pin.py): shared activation column (gate / up) and one column per slot (down)."""
+    import torch
+    rng = np.random.default_rng(k + m + wtype)
+    pool = qf.random_blocks(wtype, min(m, 512) * 2, k, rng=rng)
+    as_ = pool[rng.integers(0, pool.shape[0], size=n_expert * m)]
+    wd = K.upload_weights(wtype, as_, k, n_expert * m)
+    ids = rng.choice(n_expert, size=n_used, replace=False).astype(np.int32)
+    for nb1 in (1, n_used):
+        x = _acts(rng, nb1, k)
+        y = K.mul_mat_id(wtype, wd, k, m, n_expert, _t(ids), _t(x)).cpu().numpy()
+        ref = qf.port_mul_mat_id(wtype, as_, k, m, n_expert, x[None], ids[None])[0]
+        assert np.abs(y - ref).max() <= 2e-5 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("wtype", [qf.Q4_K, qf.Q4_0])
+@pytest.mark.parametrize("k,m", [(4096, 14336), (512, 96)])
+def test_mul_mat_id_paired_swiglu_vs_oracle(K, wtype, k, m):
+    """MultiMLP::forward's gate/act/up/mul for the selected experts in one launch (src/layers.cpp:3674-3688)."""
+    import torch
+    rng = np.random.default_rng(k + m + wtype + 1)
+    n_expert, n_used = 8, 2
+    pool = qf.random_blocks(wtype, 1024, k, rng=rng)
+    wg = pool[rng.integers(0, 1024, size=n_expert * m)]; wu = pool[rng.integers(0, 1024, size=n_expert * m)]
+    dg, du = K.upload_weights(wtype, wg, k, n_expert * m), K.upload_weights(wtype, wu, k, n_expert * m)
+    ids = np.array([5, 2], dtype=np.int32)
+    x = _acts(rng, 1, k)
+    y = K.mul_mat_id(wtype, dg, k, m, n_expert, _t(ids), _t(x), w1_dev=du).cpu().numpy()
+    g = qf.port_mul_mat_id(wtype, wg, k, m, n_expert, x[None], ids[None])[0]
+    u = qf.port_mul_mat_id(wtype, wu, k, m, n_expert, x[None], ids[None])[0]
+    ref = np.zeros_like(g); qf.port().oq_silu_mul(g.ctypes.data, u.ctypes.data, ref.ctypes.data, g.size)
+    assert np.abs(y - ref).max() <= 3e-5 * np.abs(ref).max()

@@ -166,3 +166,31 @@ def test_vec_dot_live_vs_reference_simd_and_generic(t, wfn, cpu_fn, port_fn, qfn
         # -mfma reference objects vs -ffp-contract=off here) differs -> a few ulp of the largest partial sum
         tol = (2e-6 if variant.endswith("_generic") else 2e-5) * np.abs(ref).max()
         assert np.abs(ref - mine).max() <= tol
+
+
+import refshim as rs  # noqa: E402
+
+needs_shim = pytest.mark.skipif(not rs.available(), reason="oracle/_ref/lib/libref_shim.so not built")
+
+
+@needs_shim
+@pytest.mark.parametrize("t", [qf.Q4_K, qf.Q4_0, qf.Q8_0])
+@pytest.mark.parametrize("n_tokens,broadcast", [(1, True), (1, False), (5, True), (5, False)])
+def test_mul_mat_id_live_vs_reference_cpu_backend(t, n_tokens, broadcast):
+    """oq_mul_mat_id pinned against the reference executing ggml_mul_mat_id on its own CPU backend (ggml-cpu.c:1503-1700)
+    through the public ggml API (oracle/ref_shim.cpp): expert routing, the src1 broadcast rule and the per-row arithmetic."""
+    rng = np.random.default_rng(100 * t + n_tokens + broadcast)
+    k, m, n_expert, n_used = 512, 48, 8, 2
+    as_ = qf.random_blocks(t, n_expert * m, k, rng=rng)
+    nb1 = 1 if broadcast else n_used
+    b = rng.standard_normal((n_tokens, nb1, k)).astype(np.float32)
+    ids = np.stack([rng.choice(n_expert, size=n_used, replace=False) for _ in range(n_tokens)]).astype(np.int32)
+    g = rs.Graph()
+    y = g.mul_mat_id(g.input(as_.reshape(-1), t, (k, m, n_expert)), g.input(b), g.input(ids))
+    ref = g.run("CPU", [(y, np.float32, (n_tokens, n_used, m))], n_threads=4, strict=True)[0]
+    mine = qf.port_mul_mat_id(t, as_, k, m, n_expert, b, ids)
+    assert np.abs(ref - mine).max() <= 2e-5 * np.abs(ref).max()
+    # routing sanity: swapping the two selected experts swaps the two output slots (only when src1 is shared)
+    if broadcast:
+        mine_sw = qf.port_mul_mat_id(t, as_, k, m, n_expert, b, ids[:, ::-1])
+        assert np.array_equal(mine_sw, mine[:, ::-1])

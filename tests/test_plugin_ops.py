@@ -244,3 +244,57 @@ def test_full_decoder_layer_graph(t, neox, bias, n_past, qlen):
     # the tensor scale downstream — the q4_K/neox/prefill case of this seed has one
     assert max(report.values()) <= 2e-3, report
     assert np.median(list(report.values())) <= 1e-4, report
+
+
+@pytest.mark.parametrize("t", [qf.Q4_K, qf.Q4_0, qf.Q8_0])
+@pytest.mark.parametrize("qlen", [1, 5])
+def test_mul_mat_id_broadcast_and_per_slot(t, qlen):
+    """MultiLinear::forward (src/layers.cpp:2145-2151): src1 broadcast over the slots (gate/up) and one column per slot (down)."""
+    rng = np.random.default_rng(7 + t + qlen)
+    k, m, n_expert, n_used = 512, 64, 8, 2
+    as_ = qf.random_blocks(t, n_expert * m, k, rng=rng)
+    ids = np.stack([rng.choice(n_expert, size=n_used, replace=False) for _ in range(qlen)]).astype(np.int32)
+    for nb1 in (1, n_used):
+        b = acts(rng, qlen, nb1, k)
+
+        def build(g):
+            y = g.mul_mat_id(g.input(as_.reshape(-1), t, (k, m, n_expert)), g.input(b), g.input(ids))
+            return [(y, np.float32, (qlen, n_used, m))]
+        both(build)
+
+
+@pytest.mark.parametrize("t", [qf.Q4_K, qf.Q4_0])
+@pytest.mark.parametrize("qlen", [1, 3])
+def test_sparse_moe_block_graph(t, qlen):
+    """The whole GenericSparseMLP::forward + MultiMLP::forward graph as chatllm emits it for Mixtral (src/layers.cpp:3755-3880,
+    :3674-3688): router matmul -> softmax -> top_k -> get_rows -> normalise -> mul_mat_id(gate) / silu / mul_mat_id(up) / mul ->
+    mul_mat_id(down) -> weight -> sum over the slots.  qlen = 1 takes the fused paired launch."""
+    rng = np.random.default_rng(31 + t + qlen)
+    hidden, ffn, n_expert, n_used = 256, 512, 8, 2
+    wr = qf.random_blocks(t, n_expert, hidden, rng=rng)
+    wg = qf.random_blocks(t, n_expert * ffn, hidden, rng=rng); wu = qf.random_blocks(t, n_expert * ffn, hidden, rng=rng)
+    wd = qf.random_blocks(t, n_expert * hidden, ffn, rng=rng)
+    x = acts(rng, qlen, hidden)
+
+    def build(g):
+        h = g.input(x)
+        logits = g.scale(g.mul_mat(g.input(wr.reshape(-1), t, (hidden, n_expert)), h), 40.0)   # spread the router logits: no near-ties in top_k
+        probs = g.soft_max(logits)
+        sel = g.top_k(probs, n_used)                                                # I32 [n_used, qlen]
+        w = g.get_rows(g.reshape(probs, (1, n_expert, qlen)), sel)                  # [1, n_used, qlen]
+        w = g.reshape(w, (n_used, qlen))
+        w = g.div(w, g.sum_rows(w))
+        w = g.reshape(w, (1, n_used, qlen))
+        h3 = g.reshape(h, (hidden, 1, qlen))
+        gated = g.mul_mat_id(g.input(wg.reshape(-1), t, (hidden, ffn, n_expert)), h3, sel)
+        act = g.silu(gated)
+        upped = g.mul_mat_id(g.input(wu.reshape(-1), t, (hidden, ffn, n_expert)), h3, sel)
+        par = g.mul(upped, act, inplace=True)
+        experts = g.mul_mat_id(g.input(wd.reshape(-1), t, (ffn, hidden, n_expert)), par, sel)   # [hidden, n_used, qlen]
+        experts = g.mul(experts, w)
+        out = None
+        for i in range(n_used):
+            cur = g.view(experts, (hidden, qlen), nb=(hidden * n_used * 4,), offset=i * hidden * 4)
+            out = cur if out is None else g.add(out, cur)
+        return [(sel, np.int32, (qlen, n_used)), (out, np.float32, (qlen, hidden))]
+    both(build, tol=5e-5)

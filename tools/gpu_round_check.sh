@@ -16,6 +16,7 @@ echo "bench rc=$?"; tail -c 2500 $OUT/bench.json
 
 timeout 120 python tools/step_breakdown.py > $OUT/step_breakdown.txt 2>&1
 cat $OUT/step_breakdown.txt | tail -14
+B200_ATTN_OLD_PV=1 timeout 120 python tools/step_breakdown.py 2>&1 | grep attn > $OUT/step_breakdown_old_pv.txt; cat $OUT/step_breakdown_old_pv.txt
 
 timeout 240 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $OUT/launches.csv \
     python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu > $OUT/ncu_bench.log 2>&1

@@ -29,7 +29,11 @@ ARCHS = {
     "llama3-8b": ("llama3", 128256, 4096, 32, 8, 32, 14336, 500000.0),
     "qwen2.5-7b": ("qwen2", 152064, 3584, 28, 4, 28, 18944, 1000000.0),
     "qwen2-test": ("qwen2", 512, 256, 4, 2, 2, 512, 1000000.0),
+    # Mixtral: 8 experts, top-2 (the reference's model class hard-codes both, models/mistral.h:143-146), sliding window 4096
+    "mixtral-test": ("mixtral", 512, 256, 4, 2, 2, 512, 1000000.0),
+    "mixtral-8x7b": ("mixtral", 32000, 4096, 32, 8, 32, 14336, 1000000.0),
 }
+N_EXPERTS, EXPERTS_PER_TOK = 8, 2
 
 
 def bytes_to_unicode():
@@ -41,6 +45,15 @@ def bytes_to_unicode():
         if b not in bs:
             bs.append(b); cs.append(256 + n); n += 1
     return dict(zip(bs, [chr(c) for c in cs]))
+
+
+def write_vocab_sp(f, vocab_size):
+    """i32 len | bytes | f32 score ... -1   (sentencepiece-style list read by BPEProcessor1::Load -> load_vocab_list(has_score=true,
+    has_type=false), src/tokenizer.cpp:310-440; llama v2 / Mistral / Mixtral tokenizers, models/llama.cpp:30-33)"""
+    for i in range(vocab_size):
+        t = f"<t{i}>".encode()
+        f.write(struct.pack("i", len(t))); f.write(t); f.write(struct.pack("<f", -float(i)))
+    f.write(struct.pack("i", -1))
 
 
 def write_vocab_bpe2(f, vocab_size):
@@ -125,17 +138,29 @@ def main():
             f.write(struct.pack("i", kv_heads)); f.write(struct.pack("<f", theta))
         elif family == "qwen2":
             f.write(struct.pack("ii", kv_heads, a.max_length)); f.write(struct.pack("<f", theta))
+        elif family == "mixtral":  # mistral::Config + mixtral::Config (models/mistral.h:5-10, :45-49)
+            f.write(struct.pack("ii", kv_heads, 4096)); f.write(struct.pack("<f", theta)); f.write(struct.pack("ii", EXPERTS_PER_TOK, N_EXPERTS))
         mark(12)
-        write_vocab_bpe2(f, vocab)
+        if family == "mixtral":
+            write_vocab_sp(f, vocab)
+        else:
+            write_vocab_bpe2(f, vocab)
         mark(16)
 
         dump_tensor(f, "model.embed_tokens.weight", (vocab, hidden), t, qmat(vocab, hidden))
         for i in range(layers):
             p = f"model.layers.{i}."
             dump_tensor(f, p + "input_layernorm.weight", (hidden,), 0, vec(hidden, "norm"))
-            dump_tensor(f, p + "mlp.down_proj.weight", (hidden, ffn), t, qmat(hidden, ffn))
-            dump_tensor(f, p + "mlp.gate_proj.weight", (ffn, hidden), t, qmat(ffn, hidden))
-            dump_tensor(f, p + "mlp.up_proj.weight", (ffn, hidden), t, qmat(ffn, hidden))
+            if family == "mixtral":
+                # merged expert stacks [n_expert, rows, k] (loader: models/mistral.h:112-114 -> src/chat.cpp:1606-1613) + the router
+                dump_tensor(f, p + "mlp.experts_down.weight", (N_EXPERTS, hidden, ffn), t, qmat(N_EXPERTS * hidden, ffn))
+                dump_tensor(f, p + "mlp.experts_gate.weight", (N_EXPERTS, ffn, hidden), t, qmat(N_EXPERTS * ffn, hidden))
+                dump_tensor(f, p + "mlp.experts_up.weight", (N_EXPERTS, ffn, hidden), t, qmat(N_EXPERTS * ffn, hidden))
+                dump_tensor(f, p + "block_sparse_moe.gate.weight", (N_EXPERTS, hidden), t, qmat(N_EXPERTS, hidden))
+            else:
+                dump_tensor(f, p + "mlp.down_proj.weight", (hidden, ffn), t, qmat(hidden, ffn))
+                dump_tensor(f, p + "mlp.gate_proj.weight", (ffn, hidden), t, qmat(ffn, hidden))
+                dump_tensor(f, p + "mlp.up_proj.weight", (ffn, hidden), t, qmat(ffn, hidden))
             dump_tensor(f, p + "post_attention_layernorm.weight", (hidden,), 0, vec(hidden, "norm"))
             dump_tensor(f, p + "self_attn.k_proj.weight", (kv_heads * hd, hidden), t, qmat(kv_heads * hd, hidden))
             dump_tensor(f, p + "self_attn.o_proj.weight", (hidden, hidden), t, qmat(hidden, hidden))

@@ -17,8 +17,7 @@ kern = {
  "add_rmsnorm_quant": (2, lambda i: L.b200_add_rmsnorm_quant(c.wtype, s.x.data_ptr(), s.o.data_ptr(), W[i % NL].attn_norm.data_ptr(), s.x.data_ptr(), 0, q, c.hidden, 1, c.eps, st())),
  "gemv_qkv(multi)": (1, lambda i: L.b200_mul_mat_q_multi(c.wtype, 0, 3, W[i % NL].qkv["W"], W[i % NL].qkv["m"], W[i % NL].qkv["y"], W[i % NL].qkv["ld"], W[i % NL].qkv["b"], c.hidden, q, 1, st())),
  "rope_kv_store": (1, lambda i: L.b200_rope_kv_store(s.q.data_ptr(), s.k.data_ptr(), s.v.data_ptr(), s.pos.data_ptr(), 0, W[i % NL].kc.data_ptr(), W[i % NL].vc.data_ptr(), c.heads, c.kv_heads, hd, c.rope_mode, c.rope_theta, c.kv_hidden, c.max_len, st())),
- "attn_decode(2 launches)": (1, lambda i: L.b200_attn_decode(s.q.data_ptr(), W[i % NL].kc.data_ptr(), W[i % NL].vc.data_ptr(), s.att.data_ptr(), s.scratch.data_ptr(), c.heads, c.kv_heads, hd, 4097, c.kv_hidden, c.max_len, 1.0 / math.sqrt(hd), st())),
- "quantize(hidden)": (1, lambda i: L.b200_quantize_act(c.wtype, s.att.data_ptr(), c.hidden, c.hidden, 1, q, st())),
+ "attn_decode_quant(3 launches)": (1, lambda i: L.b200_attn_decode_quant(s.q.data_ptr(), W[i % NL].kc.data_ptr(), W[i % NL].vc.data_ptr(), s.att.data_ptr(), s.scratch.data_ptr(), c.heads, c.kv_heads, hd, 4097, c.kv_hidden, c.max_len, 1.0 / math.sqrt(hd), c.wtype, q, st())),
  "gemv_o": (1, lambda i: L.b200_mul_mat_q(c.wtype, W[i % NL].wo.data_ptr(), c.hidden, c.hidden, q, 1, s.o.data_ptr(), c.hidden, 0, st())),
  "gemv_gate_up(paired)": (1, lambda i: L.b200_mul_mat_q_multi(c.wtype, 1, 2, W[i % NL].gu["W"], W[i % NL].gu["m"], W[i % NL].gu["y"], W[i % NL].gu["ld"], W[i % NL].gu["b"], c.hidden, q, 1, st())),
  "quantize(ffn)": (1, lambda i: L.b200_quantize_act(c.wtype, s.gate.data_ptr(), c.ffn, c.ffn, 1, q, st())),
