@@ -178,11 +178,13 @@ def main():
             graph.replay()
         sync_all()
         if sampler: sampler.start()
+        torch.cuda.cudart().cudaProfilerStart()   # `ncu --profile-from-start off` then sees exactly the timed steps (profiles/)
         e0.record()
         for _ in range(a.steps):
             graph.replay()
         e1.record()
         sync_all()
+        torch.cuda.cudart().cudaProfilerStop()
     else:
         pipe = sharding.Pipeline(rank, world, sess.x, lambda _x: sess.enqueue(N_PAST), tok_buf=sess.tok)
         one_step = pipe.step

@@ -482,11 +482,15 @@ __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
 template <int HD, int GQA>
 __global__ void __launch_bounds__(256) attn_scores_mma_kernel(const float * __restrict__ q, const __half * __restrict__ kc, float * __restrict__ scores,
                                                               float2 * __restrict__ part, int n_kv, int64_t k_row_stride, float scale, int64_t s_stride,
-                                                              int nchunks) {
+                                                              int nchunks, int preload) {
     constexpr int NU = HD / 32;  // 16-byte chunks per lane per row
     __shared__ float wmax[8][8], wsum[8][8];
     pdl_launch_dependents();
-    pdl_wait();
+    // Only the newest position's K row (written by the kernel just before this one) depends on the predecessor: every older row was
+    // written by an earlier decode step, hundreds of launches ago.  So all chunks but the last start their K loads BEFORE
+    // griddepcontrol.wait and overlap the predecessor's tail; q (the predecessor's output) is read after the wait.
+    const bool early = preload && (int) blockIdx.x + 1 < nchunks;
+    if (!early) pdl_wait();
     const int grp = blockIdx.y;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
@@ -499,6 +503,7 @@ __global__ void __launch_bounds__(256) attn_scores_mma_kernel(const float * __re
         alo[u] = (rowA < n_kv) ? *reinterpret_cast<const uint4 *>(kc + (int64_t) rowA * k_row_stride + (int64_t) grp * HD + 8 * t + 32 * u) : make_uint4(0, 0, 0, 0);
         ahi[u] = (rowB < n_kv) ? *reinterpret_cast<const uint4 *>(kc + (int64_t) rowB * k_row_stride + (int64_t) grp * HD + 8 * t + 32 * u) : make_uint4(0, 0, 0, 0);
     }
+    if (early) pdl_wait();
     // B fragments: q of head n = g (zero for the padding heads)
     uint32_t bq[NU][4];
 #pragma unroll
@@ -711,7 +716,7 @@ __global__ void __launch_bounds__(B200_PV_WARPS * 32) attn_pv_mma_kernel(const f
 template <int HD, int GQA>
 __global__ void __launch_bounds__(HD * 2) attn_pv_split_kernel(const float * __restrict__ scores, const float2 * __restrict__ part,
                                                                const __half * __restrict__ vc, float * __restrict__ partial, int n_kv,
-                                                               int64_t v_row_stride, int64_t s_stride, int nchunks, int span, int n_heads) {
+                                                               int64_t v_row_stride, int64_t s_stride, int nchunks, int span, int n_heads, int preload) {
     constexpr int NT = HD * 2;
     constexpr int SP = B200_PVS_ROUND + 32;  // +64 bytes: the 8 head rows land in different bank groups (conflict-free 16-byte B loads)
     __shared__ __align__(16) __half Ph[8 * SP];
@@ -751,8 +756,12 @@ __global__ void __launch_bounds__(HD * 2) attn_pv_split_kernel(const float * __r
             }
     };
 
-    pdl_wait();  // the scores / statistics come from the predecessor; the newest V column from the kernel before it
-    load_round(p_begin);  // DRAM loads first, the (L2-resident) scores behind them
+    // the scores / statistics come from the predecessor and the newest V column from the kernel before it; every older column was
+    // written by an earlier decode step, so all splits but the last stream their V slab while the scores kernel is still running
+    const bool early = preload && p_end < n_kv;
+    if (early) load_round(p_begin);
+    pdl_wait();
+    if (!early) load_round(p_begin);  // DRAM loads first, the (L2-resident) scores behind them
     if (warp < GQA) {
         const float2 * pp = part + (int64_t) (grp * GQA + warp) * nchunks;
         float mx = -INFINITY;
@@ -810,8 +819,11 @@ static int attn_decode_mma_t(const float * q, const void * kc, const void * vc, 
     const int64_t s_stride = (n_kv + 7) & ~7;
     const int nchunks = (n_kv + 127) / 128;
     float2 * part = reinterpret_cast<float2 *>(scratch + (int64_t) kv_heads * GQA * s_stride);
+    // B200_ATTN_PRELOAD=0: every CTA waits for its predecessor before its first load (A/B aid).  Contract of the default: cache positions
+    // below n_kv - 1 were written by earlier decode steps, not by the launches immediately preceding this call (include/chatllm_b200.h).
+    static const int preload = getenv("B200_ATTN_PRELOAD") ? atoi(getenv("B200_ATTN_PRELOAD")) : 1;
     launch_pdl(attn_scores_mma_kernel<HD, GQA>, dim3((unsigned) nchunks, (unsigned) kv_heads), dim3(256), 0, st, q, (const __half *) kc, scratch, part, n_kv,
-               k_row_stride, scale, s_stride, nchunks);
+               k_row_stride, scale, s_stride, nchunks, preload);
     static const int old_pv = getenv("B200_ATTN_OLD_PV") ? atoi(getenv("B200_ATTN_OLD_PV")) : 0;  // A/B aid: the channel-split kernel
     const int n_heads = kv_heads * GQA;
     if (!old_pv && ((int64_t) n_heads * HD) % 256 == 0 && (int64_t) n_heads * HD <= 20480) {
@@ -820,7 +832,7 @@ static int attn_decode_mma_t(const float * q, const void * kc, const void * vc, 
         // partial sums live behind the scores and the chunk statistics (attn_decode2_scratch_bytes)
         float * partial = scratch + (((int64_t) n_heads * s_stride + 2 * (int64_t) n_heads * nchunks + 15) & ~(int64_t) 15);
         launch_pdl(attn_pv_split_kernel<HD, GQA>, dim3((unsigned) nsplit, (unsigned) kv_heads), dim3(HD * 2), 0, st, (const float *) scratch, (const float2 *) part,
-                   (const __half *) vc, partial, n_kv, v_row_stride, s_stride, nchunks, span, n_heads);
+                   (const __half *) vc, partial, n_kv, v_row_stride, s_stride, nchunks, span, n_heads, preload);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return (int) e;
         return sum_partials_quant(wtype, partial, nsplit, out, qact, (int64_t) n_heads * HD, st);

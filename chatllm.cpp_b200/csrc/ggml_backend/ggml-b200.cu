@@ -33,6 +33,8 @@ using namespace b200;
 
 #define B200_MAX_DEVICES 16
 #define B200_ALIGN 256
+#define B200_RING_SLOTS 64
+#define B200_RING_SLOT_BYTES 4096
 
 #define CUDA_OK(expr)                                                                                       \
     do {                                                                                                    \
@@ -56,6 +58,15 @@ struct b200_device_ctx {
     void * staging = nullptr;
     size_t staging_bytes = 0;
     cudaStream_t xfer = nullptr;
+    // small host -> device writes (token ids, per-layer positions: ~33 per decoded token, src/layers.cpp:2360-2366) are staged through
+    // a ring of pinned slots and NOT waited for: the payload is copied out of the caller's memory before set_tensor returns (so the
+    // call keeps its synchronous contract), the DMA runs on `xfer`, and the next graph_compute / synchronize orders itself behind it.
+    uint8_t * ring = nullptr;
+    cudaEvent_t ring_ev[B200_RING_SLOTS] = {};
+    bool ring_used[B200_RING_SLOTS] = {};
+    int ring_next = 0;
+    cudaEvent_t xfer_ev = nullptr;
+    bool xfer_dirty = false;  // an un-waited copy is in flight on `xfer`
 };
 
 struct b200_buffer_ctx {
@@ -80,6 +91,7 @@ struct b200_backend_ctx {
     int q_kind = -1;  // 0 = Q8_K codes (Q4_K weights), 1 = Q8_0 codes (Q4_0 / Q8_0 weights)
     int64_t q_k = 0, q_n = 0;
     // B200_PROFILE=1: per-graph host time inside graph_compute and GPU time between its first and last kernel
+    cudaEvent_t p2p_ev = nullptr;  // "my stream has produced the tensor another device is about to copy"
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double prof_host_ms = 0, prof_gpu_ms = 0, prof_sync_ms = 0;
     long long prof_graphs = 0, prof_launches0 = 0;
@@ -122,6 +134,36 @@ static void b200_buffer_memset_tensor(ggml_backend_buffer_t buffer, ggml_tensor 
     CUDA_OK(cudaStreamSynchronize(dc->xfer));
 }
 
+// stage a small payload through the pinned ring and enqueue its DMA on `xfer` without waiting for it; false = not eligible
+static bool small_h2d_async(b200_device_ctx * dc, void * dst, const void * data, size_t size) {
+    static const bool off = getenv("B200_SYNC_INPUTS") != nullptr;  // bisect aid: every write waits, as in the reference backend
+    if (off || size == 0 || size > B200_RING_SLOT_BYTES) return false;
+    std::lock_guard<std::mutex> lk(dc->mu);
+    if (!dc->ring) {
+        if (cudaMallocHost((void **) &dc->ring, (size_t) B200_RING_SLOTS * B200_RING_SLOT_BYTES) != cudaSuccess) { cudaGetLastError(); dc->ring = nullptr; return false; }
+        for (int i = 0; i < B200_RING_SLOTS; ++i) CUDA_OK(cudaEventCreateWithFlags(&dc->ring_ev[i], cudaEventDisableTiming));
+        CUDA_OK(cudaEventCreateWithFlags(&dc->xfer_ev, cudaEventDisableTiming));
+    }
+    const int slot = dc->ring_next;
+    dc->ring_next = (slot + 1) % B200_RING_SLOTS;
+    if (dc->ring_used[slot]) CUDA_OK(cudaEventSynchronize(dc->ring_ev[slot]));  // its previous DMA (64 writes ago) has long finished
+    uint8_t * stg = dc->ring + (size_t) slot * B200_RING_SLOT_BYTES;
+    memcpy(stg, data, size);
+    CUDA_OK(cudaMemcpyAsync(dst, stg, size, cudaMemcpyHostToDevice, dc->xfer));
+    CUDA_OK(cudaEventRecord(dc->ring_ev[slot], dc->xfer));
+    dc->ring_used[slot] = true;
+    dc->xfer_dirty = true;
+    return true;
+}
+// make `stream` (a compute stream of this device) wait for the staged writes issued so far
+static void order_after_inputs(b200_device_ctx * dc, cudaStream_t stream) {
+    if (!dc->xfer_dirty) return;
+    std::lock_guard<std::mutex> lk(dc->mu);
+    CUDA_OK(cudaEventRecord(dc->xfer_ev, dc->xfer));
+    CUDA_OK(cudaStreamWaitEvent(stream, dc->xfer_ev, 0));
+    dc->xfer_dirty = false;
+}
+
 // host (native ggml layout) -> device.  Q4_0 / Q8_0 tensors are converted to the per-row SoA device layout
 // window by window (the loader writes 1 MiB chunks at arbitrary offsets, src/chat.cpp:1322-1338).
 static void b200_buffer_set_tensor(ggml_backend_buffer_t buffer, ggml_tensor * tensor, const void * data, size_t offset, size_t size) {
@@ -136,6 +178,7 @@ static void b200_buffer_set_tensor(ggml_backend_buffer_t buffer, ggml_tensor * t
         GGML_ASSERT(rc == 0);
         CUDA_OK(cudaStreamSynchronize(dc->xfer));
     } else {
+        if (small_h2d_async(dc, (char *) tensor->data + offset, data, size)) return;
         CUDA_OK(cudaMemcpyAsync((char *) tensor->data + offset, data, size, cudaMemcpyHostToDevice, dc->xfer));
         CUDA_OK(cudaStreamSynchronize(dc->xfer));
     }
@@ -165,6 +208,11 @@ static bool b200_buffer_cpy_tensor(ggml_backend_buffer_t buffer, const ggml_tens
     b200_buffer_ctx * dc = (b200_buffer_ctx *) buffer->context;
     b200_buffer_ctx * sc = (b200_buffer_ctx *) (src->view_src ? src->view_src->buffer : src->buffer)->context;
     if (!ggml_is_contiguous(src) || !ggml_is_contiguous(dst) || ggml_nbytes(src) != ggml_nbytes(dst)) return false;
+    if (sc->device != dc->device && g_dev_ctx[sc->device].xfer_dirty) {  // staged writes to the source still in flight on the other device's stream
+        CUDA_OK(cudaSetDevice(sc->device));
+        CUDA_OK(cudaStreamSynchronize(g_dev_ctx[sc->device].xfer));
+        g_dev_ctx[sc->device].xfer_dirty = false;
+    }
     CUDA_OK(cudaSetDevice(dc->device));
     if (sc->device == dc->device) CUDA_OK(cudaMemcpyAsync(dst->data, src->data, ggml_nbytes(src), cudaMemcpyDeviceToDevice, g_dev_ctx[dc->device].xfer));
     else CUDA_OK(cudaMemcpyPeerAsync(dst->data, dc->device, src->data, sc->device, ggml_nbytes(src), g_dev_ctx[dc->device].xfer));
@@ -828,7 +876,43 @@ static void b200_backend_free(ggml_backend_t backend) {
 static void b200_backend_synchronize(ggml_backend_t backend) {
     b200_backend_ctx * bc = (b200_backend_ctx *) backend->context;
     CUDA_OK(cudaSetDevice(bc->device));
+    b200_device_ctx * dc = &g_dev_ctx[bc->device];
+    if (dc->xfer_dirty) { CUDA_OK(cudaStreamSynchronize(dc->xfer)); dc->xfer_dirty = false; }
     CUDA_OK(cudaStreamSynchronize(bc->stream));
+}
+
+// ggml_backend_i.cpy_tensor_async (ggml-backend-impl.h:99-100; caller ggml_backend_sched_compute_splits, ggml-backend.cpp:1468-1577).
+//   * host -> this device, small contiguous tensor (the token ids flagged GGML_TENSOR_FLAG_INPUT): staged write, no waiting.
+//   * another device of ours -> this device (the hidden-state row crossing a layer-split boundary): peer copy on this
+//     backend's stream, ordered behind the producer's stream with an event.  The scheduler synchronizes this backend after its input
+//     copies (parallel = false, ggml-backend.cpp:1581-1583), so the source cannot be overwritten before the copy has run.
+// Anything else returns false and the caller falls back to synchronize + blocking copy.
+static const char * b200_backend_name(ggml_backend_t backend);
+static bool b200_cpy_tensor_async(ggml_backend_t backend_src, ggml_backend_t backend_dst, const ggml_tensor * src, ggml_tensor * dst) {
+    b200_backend_ctx * bd = (b200_backend_ctx *) backend_dst->context;
+    if (!src->buffer || !dst->buffer || !b200_buffer_is_ours(dst->view_src ? dst->view_src->buffer : dst->buffer)) return false;
+    if (!ggml_is_contiguous(src) || !ggml_is_contiguous(dst) || ggml_nbytes(src) != ggml_nbytes(dst) || is_repacked(dst) || is_repacked(src)) return false;
+    ggml_backend_buffer_t sbuf = src->view_src ? src->view_src->buffer : src->buffer;
+    const size_t nb = ggml_nbytes(src);
+    if (ggml_backend_buffer_is_host(sbuf)) {
+        CUDA_OK(cudaSetDevice(bd->device));
+        return small_h2d_async(&g_dev_ctx[bd->device], dst->data, src->data, nb);
+    }
+    if (!b200_buffer_is_ours(sbuf) || backend_src->iface.get_name != b200_backend_name) return false;
+    b200_backend_ctx * bs = (b200_backend_ctx *) backend_src->context;
+    static const bool off = getenv("B200_SYNC_P2P") != nullptr;
+    if (off) return false;
+    if (!bs->p2p_ev) {
+        CUDA_OK(cudaSetDevice(bs->device));
+        CUDA_OK(cudaEventCreateWithFlags(&bs->p2p_ev, cudaEventDisableTiming));
+    }
+    CUDA_OK(cudaSetDevice(bs->device));
+    CUDA_OK(cudaEventRecord(bs->p2p_ev, bs->stream));
+    CUDA_OK(cudaSetDevice(bd->device));
+    CUDA_OK(cudaStreamWaitEvent(bd->stream, bs->p2p_ev, 0));
+    if (bs->device == bd->device) CUDA_OK(cudaMemcpyAsync(dst->data, src->data, nb, cudaMemcpyDeviceToDevice, bd->stream));
+    else CUDA_OK(cudaMemcpyPeerAsync(dst->data, bd->device, src->data, bs->device, nb, bd->stream));
+    return true;
 }
 // B200_TRACE=1: after every executed node / fused group print a checksum of each output it produced (debug aid; syncs)
 static void trace_node(b200_backend_ctx * bc, int idx, const ggml_tensor * t) {
@@ -850,6 +934,7 @@ static void trace_node(b200_backend_ctx * bc, int idx, const ggml_tensor * t) {
 static enum ggml_status b200_graph_compute(ggml_backend_t backend, ggml_cgraph * cgraph) {
     b200_backend_ctx * bc = (b200_backend_ctx *) backend->context;
     CUDA_OK(cudaSetDevice(bc->device));
+    order_after_inputs(&g_dev_ctx[bc->device], bc->stream);
     bc->q_src = nullptr;  // nothing is known to be quantized at the start of a graph
     static const bool trace = getenv("B200_TRACE") != nullptr;
     static const bool prof = getenv("B200_PROFILE") != nullptr;
@@ -906,7 +991,7 @@ static const ggml_backend_i b200_backend_iface = {
     /* .free               = */ b200_backend_free,
     /* .set_tensor_async   = */ nullptr,
     /* .get_tensor_async   = */ nullptr,
-    /* .cpy_tensor_async   = */ nullptr,
+    /* .cpy_tensor_async   = */ b200_cpy_tensor_async,
     /* .synchronize        = */ b200_backend_synchronize,
     /* .graph_plan_create  = */ nullptr,
     /* .graph_plan_free    = */ nullptr,

@@ -122,7 +122,10 @@ int b200_rope_kv_store(float * q, const float * k, const float * v, const int32_
 /* K cache [max_len][kv_heads*head_dim] (row stride k_row_stride halves), V cache TRANSPOSED [kv_heads*head_dim][max_len]
  * (row stride v_row_stride halves) — src/layers.cpp:2933-2941.  out[h*head_dim+d] for one query token attending to
  * positions [0, n_kv).  Replaces the mul_mat / scale / diag_mask_inf / soft_max / mul_mat / permute / cont chain of
- * CoreAttention::calc_attn_scores (src/layers.cpp:2541-2561) with the same f16-operand, fp32-accumulate arithmetic. */
+ * CoreAttention::calc_attn_scores (src/layers.cpp:2541-2561) with the same f16-operand, fp32-accumulate arithmetic.
+ * Ordering contract: only position n_kv-1 (the token just appended by b200_rope_kv_store / b200_kv_store on the same stream) may have
+ * been written by the launches immediately preceding this call; older positions must come from earlier decode steps (or from work the
+ * host has synchronized with) — the kernels start streaming them before their programmatic-dependent-launch wait. */
 size_t b200_attn_decode_scratch_bytes(int n_heads, int n_kv);
 int b200_attn_decode(const float * q, const void * k_cache, const void * v_cache_t, float * out, float * scratch, int n_heads,
                      int kv_heads, int head_dim, int n_kv, int64_t k_row_stride, int64_t v_row_stride, float scale, void * stream);

@@ -16,9 +16,14 @@ echo "bench rc=$?"; tail -c 2500 $OUT/bench.json
 
 timeout 120 python tools/step_breakdown.py > $OUT/step_breakdown.txt 2>&1
 cat $OUT/step_breakdown.txt | tail -14
-B200_ATTN_OLD_PV=1 timeout 120 python tools/step_breakdown.py 2>&1 | grep attn > $OUT/step_breakdown_old_pv.txt; cat $OUT/step_breakdown_old_pv.txt
+( echo "B200_ATTN_OLD_PV=1:"; B200_ATTN_OLD_PV=1 timeout 120 python tools/step_breakdown.py 2>&1 | grep attn
+  echo "B200_ATTN_PRELOAD=0:"; B200_ATTN_PRELOAD=0 timeout 120 python tools/step_breakdown.py 2>&1 | grep attn ) > $OUT/step_breakdown_ab.txt; cat $OUT/step_breakdown_ab.txt
 
-timeout 240 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $OUT/launches.csv \
+# host-side breakdown of the e2e arm (B200PROF lines: enqueue time / GPU time / launches per whole-model graph), staged vs synchronous inputs
+( timeout 200 python tools/plugin_profile.py; echo "--- B200_SYNC_INPUTS=1"; timeout 200 python tools/plugin_profile.py B200_SYNC_INPUTS=1 ) > $OUT/plugin_profile.txt 2>&1
+cat $OUT/plugin_profile.txt
+
+timeout 240 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 1500 --csv --log-file $OUT/launches.csv \
     python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu > $OUT/ncu_bench.log 2>&1
 echo "ncu list rc=$? rows=$(wc -l < $OUT/launches.csv)"
 
