@@ -762,15 +762,15 @@ __global__ void __launch_bounds__(HD * 2) attn_pv_split_kernel(const float * __r
     if (early) load_round(p_begin);
     pdl_wait();
     if (!early) load_round(p_begin);  // DRAM loads first, the (L2-resident) scores behind them
-    if (warp < GQA) {
-        const float2 * pp = part + (int64_t) (grp * GQA + warp) * nchunks;
+    for (int h = warp; h < GQA; h += NT / 32) {  // HD = 64 has 4 warps for up to 8 heads
+        const float2 * pp = part + (int64_t) (grp * GQA + h) * nchunks;
         float mx = -INFINITY;
         for (int i = lane; i < nchunks; i += 32) mx = fmaxf(mx, pp[i].x);
         mx = warp_max(mx);
         float sum = 0.0f;
         for (int i = lane; i < nchunks; i += 32) { const float2 pv = pp[i]; sum += pv.y * expf(pv.x - mx); }
         sum = warp_sum(sum);
-        if (lane == 0) { hmax[warp] = mx; hinv[warp] = 1.0f / sum; }
+        if (lane == 0) { hmax[h] = mx; hinv[h] = 1.0f / sum; }
     }
     __syncthreads();
 

@@ -4,6 +4,9 @@
 #include "common.cuh"
 #include "kernels.h"
 
+#include <cstdint>
+#include <cstdlib>
+
 namespace b200 {
 
 struct TVd {  // device-side copy of a TV
@@ -289,9 +292,134 @@ __global__ void mul_mat_f_kernel(const TVd a, const TVd b, const TVd d, int64_t 
     s = warp_sum(s);
     if (lane == 0) *(float *) at(d, i0, i1, i2, i3) = s;
 }
+
+// ---- the same MUL_MAT (F16 src0) for prompt-sized src1 (>= 16 columns): tiled tensor-core GEMM --------------------------------
+// The warp-per-output kernel above re-reads a whole src0 row for every output element; for the prefill attention matmuls
+// (scores = K^T.Q with [n_kv x qlen] outputs per head, ctx = V.P) that is tens of GB of L2 traffic per layer.  Here a CTA owns a
+// 64 x 64 output tile of one (i2, i3) slice: both operands are staged through shared memory as f16 (src1 is rounded to f16 exactly
+// as the reference does before its f16 dot, ggml-cpu.c:213-219, :1291-1326) and multiplied with mma.sync m16n8k16 f16 x f16 -> f32
+// (f16 products are exact in fp32; only the fp32 summation order differs from vec.cpp:264).  4 warps, each a 32 x 32 sub-tile.
+// Arbitrary strides / ragged edges: 16-byte vector loads where a chunk is aligned and in bounds, guarded scalar loads elsewhere.
+#define MMF_TM 64
+#define MMF_TN 64
+#define MMF_TK 32
+#define MMF_LD 40  // halves per smem row: 80-byte stride -> the 8 rows of a fragment load hit 8 distinct 4-bank groups
+__global__ void __launch_bounds__(128) mul_mat_f16_mma_kernel(const TVd a, const TVd b, const TVd d) {
+    __shared__ __align__(16) __half As[MMF_TM * MMF_LD];
+    __shared__ __align__(16) __half Bs[MMF_TN * MMF_LD];
+    pdl_launch_dependents();
+    pdl_wait();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = (warp & 1) * 32, wn = (warp >> 1) * 32;
+    const int64_t m0 = (int64_t) blockIdx.x * MMF_TM, n0 = (int64_t) blockIdx.y * MMF_TN;
+    const int64_t i2 = blockIdx.z % d.ne2, i3 = blockIdx.z / d.ne2;
+    const int64_t r2 = b.ne2 / a.ne2, r3 = b.ne3 / a.ne3;
+    const char * abase = a.data + (i2 / r2) * a.nb2 + (i3 / r3) * a.nb3;
+    const char * bbase = b.data + i2 * b.nb2 + i3 * b.nb3;
+    const int64_t K = a.ne0, M = a.ne1, N = b.ne1;
+    const bool a_vec = (a.nb1 % 16 == 0) && (((uintptr_t) abase) % 16 == 0);
+    const bool b_vec = (b.nb1 % 16 == 0) && (((uintptr_t) bbase) % 16 == 0);
+
+    float acc[2][4][4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = acc[i][j][2] = acc[i][j][3] = 0.0f;
+
+    for (int64_t k0 = 0; k0 < K; k0 += MMF_TK) {
+        // ---- A tile: 64 rows x 32 halves = 256 chunks of 8 halves
+        for (int c = threadIdx.x; c < MMF_TM * 4; c += 128) {
+            const int r = c >> 2, ch = c & 3;
+            const int64_t row = m0 + r, kk = k0 + ch * 8;
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (row < M) {
+                const char * src = abase + row * a.nb1 + kk * 2;
+                if (a_vec && kk + 8 <= K) {
+                    v = *reinterpret_cast<const uint4 *>(src);
+                } else {
+                    __align__(16) __half h[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) h[e] = (kk + e < K) ? *reinterpret_cast<const __half *>(src + 2 * e) : __float2half_rn(0.0f);
+                    v = *reinterpret_cast<const uint4 *>(h);
+                }
+            }
+            *reinterpret_cast<uint4 *>(As + r * MMF_LD + ch * 8) = v;
+        }
+        // ---- B tile: 64 columns x 32 floats -> f16 (RNE, as GGML_FP32_TO_FP16)
+        for (int c = threadIdx.x; c < MMF_TN * 8; c += 128) {
+            const int r = c >> 3, ch = c & 7;
+            const int64_t col = n0 + r, kk = k0 + ch * 4;
+            float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (col < N) {
+                const char * src = bbase + col * b.nb1 + kk * 4;
+                if (b_vec && kk + 4 <= K) {
+                    f = *reinterpret_cast<const float4 *>(src);
+                } else {
+                    if (kk + 0 < K) f.x = *reinterpret_cast<const float *>(src + 0);
+                    if (kk + 1 < K) f.y = *reinterpret_cast<const float *>(src + 4);
+                    if (kk + 2 < K) f.z = *reinterpret_cast<const float *>(src + 8);
+                    if (kk + 3 < K) f.w = *reinterpret_cast<const float *>(src + 12);
+                }
+            }
+            const __half2 lo = __halves2half2(__float2half_rn(f.x), __float2half_rn(f.y)), hi = __halves2half2(__float2half_rn(f.z), __float2half_rn(f.w));
+            uint2 pk;
+            pk.x = *reinterpret_cast<const uint32_t *>(&lo); pk.y = *reinterpret_cast<const uint32_t *>(&hi);
+            *reinterpret_cast<uint2 *>(Bs + r * MMF_LD + ch * 4) = pk;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int ks = 0; ks < MMF_TK; ks += 16) {
+            uint32_t af[2][4], bf[4][2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const __half * ap = As + (wm + i * 16 + g) * MMF_LD + ks + 2 * t;
+                af[i][0] = *reinterpret_cast<const uint32_t *>(ap);
+                af[i][1] = *reinterpret_cast<const uint32_t *>(ap + 8 * MMF_LD);
+                af[i][2] = *reinterpret_cast<const uint32_t *>(ap + 8);
+                af[i][3] = *reinterpret_cast<const uint32_t *>(ap + 8 * MMF_LD + 8);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const __half * bp = Bs + (wn + j * 8 + g) * MMF_LD + ks + 2 * t;
+                bf[j][0] = *reinterpret_cast<const uint32_t *>(bp);
+                bf[j][1] = *reinterpret_cast<const uint32_t *>(bp + 8);
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                                 : "+f"(acc[i][j][0]), "+f"(acc[i][j][1]), "+f"(acc[i][j][2]), "+f"(acc[i][j][3])
+                                 : "r"(af[i][0]), "r"(af[i][1]), "r"(af[i][2]), "r"(af[i][3]), "r"(bf[j][0]), "r"(bf[j][1]));
+        }
+        __syncthreads();
+    }
+    // c0 = (row g, col 2t), c1 = (row g, col 2t+1), c2 = (row g+8, col 2t), c3 = (row g+8, col 2t+1); row -> i0, col -> i1
+    char * dbase = d.data + i2 * d.nb2 + i3 * d.nb3;
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int64_t rA = m0 + wm + i * 16 + g, rB = rA + 8, cA = n0 + wn + j * 8 + 2 * t, cB = cA + 1;
+            if (rA < M && cA < N) *reinterpret_cast<float *>(dbase + rA * d.nb0 + cA * d.nb1) = acc[i][j][0];
+            if (rA < M && cB < N) *reinterpret_cast<float *>(dbase + rA * d.nb0 + cB * d.nb1) = acc[i][j][1];
+            if (rB < M && cA < N) *reinterpret_cast<float *>(dbase + rB * d.nb0 + cA * d.nb1) = acc[i][j][2];
+            if (rB < M && cB < N) *reinterpret_cast<float *>(dbase + rB * d.nb0 + cB * d.nb1) = acc[i][j][3];
+        }
+}
+
 int op_mul_mat_f(const TV & a, const TV & b, const TV & d, cudaStream_t st) {
     const int64_t nout = nelem(d);
     if (nout <= 0) return B200_OK;
+    static const bool no_mma = getenv("B200_MMF_NO_MMA") != nullptr;  // bisect aid
+    if (!no_mma && a.type == B200_TYPE_F16 && b.ne[1] >= 16 && a.nb[0] == 2 && b.nb[0] == 4 && d.ne[2] * d.ne[3] <= 65535 && a.ne[0] > 0) {
+        const dim3 grid((unsigned) ((a.ne[1] + MMF_TM - 1) / MMF_TM), (unsigned) ((b.ne[1] + MMF_TN - 1) / MMF_TN), (unsigned) (d.ne[2] * d.ne[3]));
+        if (grid.y <= 65535) {
+            launch_pdl(mul_mat_f16_mma_kernel, grid, dim3(128), 0, st, dv(a), dv(b), dv(d));
+            return (int) cudaGetLastError();
+        }
+    }
     const unsigned grid = (unsigned) ((nout * 32 + 255) / 256);
     if (a.type == B200_TYPE_F16) launch_pdl(mul_mat_f_kernel<__half>, dim3(grid), dim3(256), 0, st, dv(a), dv(b), dv(d), nout);
     else if (a.type == B200_TYPE_F32) launch_pdl(mul_mat_f_kernel<float>, dim3(grid), dim3(256), 0, st, dv(a), dv(b), dv(d), nout);
