@@ -78,6 +78,12 @@ __device__ __forceinline__ void bulk_g2s_hint(void * smem_dst, const void * gmem
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// RULE (learned the hard way, r01): a pointer to data that a PREDECESSOR kernel writes must NOT be declared `const T * __restrict__`.
+// nvcc turns such loads into invariant ld.global.nc and is then free to hoist them ABOVE the inline-asm griddepcontrol.wait
+// (observed: the q loads of attn_scores_mma_kernel were scheduled before ACQBULK once the wait was no longer the first statement ->
+// stale activations under real overlap, i.e. CUDA-graph replay / back-to-back stream launches, while eager launches looked fine).
+// Under programmatic dependent launch the data is simply not read-only for the lifetime of the dependent grid.  Plain pointers make
+// the "memory" clobber below a real barrier.  tools/sass_pdl_audit.py lists every global load that precedes the wait in the SASS.
 // Host-side launch helper: every kernel of the decode step is launched with programmatic stream serialization so that
 // its launch latency (and, for the GEMV, its weight prefetch) overlaps the predecessor's execution.  Contract for the
 // kernels: call pdl_launch_dependents() at the top, and pdl_wait() before the first access to anything a predecessor

@@ -44,8 +44,8 @@ __device__ __forceinline__ float blk_max(float v, float * red) {
 // (reference ggml-quants.c:2555-2592 / arch/x86/quants.c:290-384) — bit-identical codes.
 // ------------------------------------------------------------------------------------------------------------------
 template <bool Q8K, int J>
-__global__ void __launch_bounds__(1024) add_rmsnorm_quant_kernel(const float * __restrict__ x, const float * __restrict__ r, const float * __restrict__ w,
-                                                                 float * __restrict__ x_out, float * __restrict__ y_out, uint8_t * __restrict__ qact,
+__global__ void __launch_bounds__(1024) add_rmsnorm_quant_kernel(const float * x, const float * r, const float * w,
+                                                                 float * x_out, float * y_out, uint8_t * qact,
                                                                  int64_t ne0, float eps, size_t col_bytes, int nsplit) {
     __shared__ float red[32];
     __shared__ unsigned long long keys[32];
@@ -65,9 +65,14 @@ __global__ void __launch_bounds__(1024) add_rmsnorm_quant_kernel(const float * _
             const int64_t e = 4 * (int64_t) t + 4 * (int64_t) T * j;
             float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
             if (e < ne0) {
-                for (int c = 0; c < nsplit; ++c) {
-                    const float4 b = *reinterpret_cast<const float4 *>(x + (int64_t) c * ne0 + e);
-                    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+                // 8 partial rows in flight at a time (a plain loop would serialise one L2 round trip per split); summed in split order
+                for (int c0 = 0; c0 < nsplit; c0 += 8) {
+                    float4 b[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        b[i] = (c0 + i < nsplit) ? *reinterpret_cast<const float4 *>(x + (int64_t) (c0 + i) * ne0 + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { a.x += b[i].x; a.y += b[i].y; a.z += b[i].z; a.w += b[i].w; }
                 }
                 if (x_out) *reinterpret_cast<float4 *>(x_out + e) = a;
             }
@@ -90,6 +95,13 @@ __global__ void __launch_bounds__(1024) add_rmsnorm_quant_kernel(const float * _
             v[j][0] = v[j][1] = v[j][2] = v[j][3] = 0.0f;
         }
     }
+    // the norm weights do not depend on the reduction: fetch them before it (one L2 round trip off the serial chain)
+    float4 wv[J];
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+        const int64_t e = 4 * (int64_t) t + 4 * (int64_t) T * j;
+        wv[j] = (e < ne0) ? *reinterpret_cast<const float4 *>(w + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     ss = blk_sum(ss, red);
     const float mean = ss / (float) ne0;
     const float scale = 1.0f / sqrtf(mean + eps);
@@ -97,7 +109,7 @@ __global__ void __launch_bounds__(1024) add_rmsnorm_quant_kernel(const float * _
     for (int j = 0; j < J; ++j) {
         const int64_t e = 4 * (int64_t) t + 4 * (int64_t) T * j;
         if (e < ne0) {
-            const float4 ww = *reinterpret_cast<const float4 *>(w + e);
+            const float4 ww = wv[j];
             v[j][0] = (v[j][0] * scale) * ww.x; v[j][1] = (v[j][1] * scale) * ww.y;
             v[j][2] = (v[j][2] * scale) * ww.z; v[j][3] = (v[j][3] * scale) * ww.w;
             if (y_out) *reinterpret_cast<float4 *>(y_out + row * ne0 + e) = make_float4(v[j][0], v[j][1], v[j][2], v[j][3]);
@@ -235,8 +247,8 @@ static int sum_partials_quant(int wtype, const float * partial, int nsplit, floa
 // RoPE(q), RoPE(k) + KV-cache append for ONE token.  grid = n_heads + kv_heads, block = head_dim/2 threads.
 // angle recurrence exactly as rope_kernel (ops.cu).  mode 0 = adjacent pairs, 2 = NEOX.
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void rope_kv_store_kernel(const float * q, float * q_out, const float * __restrict__ k, const float * __restrict__ v,
-                                     const int32_t * __restrict__ pos, const float * __restrict__ ff, __half * __restrict__ kc, __half * __restrict__ vc,
+__global__ void rope_kv_store_kernel(const float * q, float * q_out, const float * k, const float * v,
+                                     const int32_t * pos, const float * ff, __half * kc, __half * vc,
                                      int n_heads, int kv_heads, int hd, int mode, float theta_scale, int64_t k_row_stride, int64_t v_row_stride, int v_col) {
     pdl_launch_dependents();
     pdl_wait();
@@ -289,8 +301,8 @@ int rope_kv_store(float * q, const float * k, const float * v, const int32_t * p
 // sum(exp(s - max)) so that the consumer can normalise without a pass over the whole row.
 #define B200_ATTN_CH 128
 template <int HD, int GQA>
-__global__ void __launch_bounds__(256) attn_scores2_kernel(const float * __restrict__ q, const __half * __restrict__ kc, float * __restrict__ scores,
-                                                           float2 * __restrict__ part, int n_kv, int64_t k_row_stride, float scale, int64_t s_stride,
+__global__ void __launch_bounds__(256) attn_scores2_kernel(const float * q, const __half * kc, float * scores,
+                                                           float2 * part, int n_kv, int64_t k_row_stride, float scale, int64_t s_stride,
                                                            int nchunks) {
     constexpr int LPR = HD / 8;               // lanes per row
     constexpr int RPW = 32 / LPR;             // rows per warp load
@@ -354,8 +366,8 @@ __global__ void __launch_bounds__(256) attn_scores2_kernel(const float * __restr
 // softmax normalisation (from the chunk statistics) fused with out = V . P
 // grid (HD/8, kv_heads), block 256 = 8 warps, one V^T channel row per warp; P of the group's GQA heads lives in smem.
 template <int GQA>
-__global__ void __launch_bounds__(256) attn_softmax_pv_kernel(const float * __restrict__ scores, const float2 * __restrict__ part, const __half * __restrict__ vc,
-                                                              float * __restrict__ out, int n_kv, int head_dim, int64_t v_row_stride, int64_t s_stride,
+__global__ void __launch_bounds__(256) attn_softmax_pv_kernel(const float * scores, const float2 * part, const __half * vc,
+                                                              float * out, int n_kv, int head_dim, int64_t v_row_stride, int64_t s_stride,
                                                               int nchunks) {
     extern __shared__ float P[];  // [GQA][s_stride]
     __shared__ float hmax[GQA], hinv[GQA];
@@ -480,8 +492,8 @@ __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
 // scores[h][t] = scale * K[t][grp] . f16(q[h]) for the GQA heads of KV group `grp`; CTA = 128 positions, warp = 16.
 // Also emits per (head, chunk) max and sum(exp(s - max)).
 template <int HD, int GQA>
-__global__ void __launch_bounds__(256) attn_scores_mma_kernel(const float * __restrict__ q, const __half * __restrict__ kc, float * __restrict__ scores,
-                                                              float2 * __restrict__ part, int n_kv, int64_t k_row_stride, float scale, int64_t s_stride,
+__global__ void __launch_bounds__(256) attn_scores_mma_kernel(const float * q, const __half * kc, float * scores,
+                                                              float2 * part, int n_kv, int64_t k_row_stride, float scale, int64_t s_stride,
                                                               int nchunks, int preload) {
     constexpr int NU = HD / 32;  // 16-byte chunks per lane per row
     __shared__ float wmax[8][8], wsum[8][8];
@@ -565,8 +577,8 @@ __global__ void __launch_bounds__(256) attn_scores_mma_kernel(const float * __re
 // The kernel is latency-bound (few CTAs, short dependent chains), so every phase issues all of its loads up front.
 #define B200_PV_WARPS 16
 template <int GQA>
-__global__ void __launch_bounds__(B200_PV_WARPS * 32) attn_pv_mma_kernel(const float * __restrict__ scores, const float2 * __restrict__ part,
-                                                                         const __half * __restrict__ vc, float * __restrict__ out, int n_kv, int head_dim,
+__global__ void __launch_bounds__(B200_PV_WARPS * 32) attn_pv_mma_kernel(const float * scores, const float2 * part,
+                                                                         const __half * vc, float * out, int n_kv, int head_dim,
                                                                          int64_t v_row_stride, int64_t s_stride, int nchunks, int sp) {
     constexpr int NT = B200_PV_WARPS * 32;
     extern __shared__ __align__(16) unsigned char smraw[];
@@ -714,8 +726,8 @@ __global__ void __launch_bounds__(B200_PV_WARPS * 32) attn_pv_mma_kernel(const f
 // ------------------------------------------------------------------------------------------------------------------
 #define B200_PVS_ROUND 256  // positions per inner round (two 128-position k groups held in registers)
 template <int HD, int GQA>
-__global__ void __launch_bounds__(HD * 2) attn_pv_split_kernel(const float * __restrict__ scores, const float2 * __restrict__ part,
-                                                               const __half * __restrict__ vc, float * __restrict__ partial, int n_kv,
+__global__ void __launch_bounds__(HD * 2) attn_pv_split_kernel(const float * scores, const float2 * part,
+                                                               const __half * vc, float * partial, int n_kv,
                                                                int64_t v_row_stride, int64_t s_stride, int nchunks, int span, int n_heads, int preload) {
     constexpr int NT = HD * 2;
     constexpr int SP = B200_PVS_ROUND + 32;  // +64 bytes: the 8 head rows land in different bank groups (conflict-free 16-byte B loads)

@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(512) gemv_q_kernel(const GemvParams p) {
             // a group never straddles two slots (m % GROUP == 0, checked on the host)
             const int64_t slot = row0 / p.mat[0].m;
             const int64_t lr = row0 - slot * p.mat[0].m;
-            const int e = min(max(__ldg(p.ids + slot), 0), p.n_expert - 1);
+            const int e = min(max(p.ids[slot], 0), p.n_expert - 1);  // plain load: produced by the predecessor (see common.cuh, PDL rule)
             const int64_t eoff = (int64_t) e * p.expert_bytes;
             if (PAIRED) return (i < HALF) ? p.mat[0].W + eoff + (lr + i) * row_bytes : p.mat[1].W + eoff + (lr + i - HALF) * row_bytes;
             return p.mat[0].W + eoff + (lr + i) * row_bytes;

@@ -36,7 +36,7 @@ __device__ __forceinline__ float block_max(float v, float * red) {
 // ---- RMSNorm (+ weight multiply) ------------------------------------------------------------------------
 // reference: ggml_compute_forward_rms_norm_f32 ggml/src/ggml-cpu/ops.cpp:3710-3758 followed by ggml_mul
 // (RMSNorm::forward src/layers.cpp:2216-2225):  y = (x * (1/sqrt(mean(x^2)+eps))) * w
-__global__ void __launch_bounds__(1024) rms_norm_mul_kernel(const float * __restrict__ x, const float * __restrict__ w, float * __restrict__ y,
+__global__ void __launch_bounds__(1024) rms_norm_mul_kernel(const float * x, const float * w, float * y,
                                                             int64_t ne0, float eps) {
     __shared__ float red[32];
     pdl_launch_dependents();
@@ -61,7 +61,7 @@ int rms_norm_mul(const float * x, const float * w, float * y, int64_t ne0, int64
 }
 
 // ---- elementwise ----------------------------------------------------------------------------------------
-__global__ void add_kernel(const float * __restrict__ a, const float * __restrict__ b, float * __restrict__ y, int64_t n) {
+__global__ void add_kernel(const float * a, const float * b, float * y, int64_t n) {
     pdl_launch_dependents();
     pdl_wait();
     const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
@@ -73,7 +73,7 @@ int add_f32(const float * a, const float * b, float * y, int64_t n, cudaStream_t
     return (int) cudaGetLastError();
 }
 // SwiGLU of BaseMLP::forward (src/layers.cpp:2475-2483): silu(gate) * up, silu = x/(1+exp(-x)) (vec.h:1061)
-__global__ void silu_mul_kernel(const float * __restrict__ g, const float * __restrict__ u, float * __restrict__ y, int64_t n) {
+__global__ void silu_mul_kernel(const float * g, const float * u, float * y, int64_t n) {
     pdl_launch_dependents();
     pdl_wait();
     const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
@@ -94,8 +94,8 @@ struct RopeParams {
     int n_dims, mode;
     float theta_scale, freq_scale, ext_factor, attn_factor, corr0, corr1;
 };
-__global__ void rope_kernel(const float * __restrict__ x, float * __restrict__ y, const int32_t * __restrict__ pos,
-                            const float * __restrict__ ff, const RopeParams p) {
+__global__ void rope_kernel(const float * x, float * y, const int32_t * pos,
+                            const float * ff, const RopeParams p) {
     pdl_launch_dependents();
     pdl_wait();
     const int64_t t = blockIdx.x;
@@ -158,7 +158,7 @@ int rope_f32(const float * x, float * y, const int32_t * pos, const float * freq
 // ---- softmax ------------------------------------------------------------------------------------------------
 // reference: ggml_compute_forward_soft_max_f32 ggml/src/ggml-cpu/ops.cpp:5225-5335 (scale, optional mask; no ALiBi):
 // p = exp(x*scale + mask - max) / sum
-__global__ void __launch_bounds__(1024) soft_max_kernel(const float * __restrict__ x, const float * __restrict__ mask, float * __restrict__ y,
+__global__ void __launch_bounds__(1024) soft_max_kernel(const float * x, const float * mask, float * y,
                                                         int64_t ne0, float scale) {
     __shared__ float red[32];
     pdl_launch_dependents();
@@ -195,8 +195,8 @@ int soft_max_f32(const float * x, const float * mask, float * y, int64_t ne0, in
 // ---- embedding gather from a quantized table ------------------------------------------------------------------
 // reference: ggml_compute_forward_get_rows ggml/src/ggml-cpu/ops.cpp:4820 + dequantize_row_* ggml-quants.c:307/401/1352.
 // Q4_0 / Q8_0 tables are in the repacked SoA row layout (quantize.cu).
-__global__ void get_rows_kernel(int type, const uint8_t * __restrict__ table, int64_t k, const int32_t * __restrict__ ids,
-                                float * __restrict__ y) {
+__global__ void get_rows_kernel(int type, const uint8_t * table, int64_t k, const int32_t * ids,
+                                float * y) {
     pdl_launch_dependents();
     pdl_wait();
     const int64_t r = blockIdx.x;
@@ -270,7 +270,7 @@ namespace b200 {
 
 // scores[h][t] = scale * sum_d K[t][g][d] * f16(q[h][d])      grid (ceil(n_kv/TPB), kv_heads), block 256 (8 warps)
 template <int HD, int GQA>
-__global__ void __launch_bounds__(256) attn_scores_kernel(const float * __restrict__ q, const __half * __restrict__ kc, float * __restrict__ scores,
+__global__ void __launch_bounds__(256) attn_scores_kernel(const float * q, const __half * kc, float * scores,
                                                           int n_kv, int kv_heads, int64_t k_row_stride, float scale, int64_t s_stride) {
     __shared__ float qs[GQA][HD];
     pdl_launch_dependents();
@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(256) attn_scores_kernel(const float * __restri
 }
 
 // in-place softmax over scores[h][0..n_kv), result rounded through f16 (it is the f16 operand of V.P)
-__global__ void __launch_bounds__(1024) attn_softmax_kernel(float * __restrict__ scores, int n_kv, int64_t s_stride) {
+__global__ void __launch_bounds__(1024) attn_softmax_kernel(float * scores, int n_kv, int64_t s_stride) {
     __shared__ float red[32];
     pdl_launch_dependents();
     pdl_wait();
@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(1024) attn_softmax_kernel(float * __restrict__
 
 // out[h][d] = sum_t Vt[g*HD+d][t] * P[h][t]          grid (HD*kv_heads/8), block 256: one warp per channel row
 template <int GQA>
-__global__ void __launch_bounds__(256) attn_pv_kernel(const float * __restrict__ P, const __half * __restrict__ vc, float * __restrict__ out, int n_kv,
+__global__ void __launch_bounds__(256) attn_pv_kernel(const float * P, const __half * vc, float * out, int n_kv,
                                                       int head_dim, int64_t v_row_stride, int64_t s_stride) {
     pdl_launch_dependents();
     pdl_wait();
@@ -384,7 +384,7 @@ int attn_decode(const float * q, const void * kc, const void * vc, float * out, 
 }
 
 // write one token's K (row) and V (column of the transposed cache) as f16 — KVCacheAttention::save_to_cache
-__global__ void kv_store_kernel(const float * __restrict__ k, const float * __restrict__ v, __half * __restrict__ kc, __half * __restrict__ vc, int kv_hidden,
+__global__ void kv_store_kernel(const float * k, const float * v, __half * kc, __half * vc, int kv_hidden,
                                 int64_t k_row_stride, int64_t v_row_stride, int pos) {
     pdl_launch_dependents();
     pdl_wait();

@@ -136,7 +136,7 @@ int op_set_rows(const TV & s, const TV & ids, const TV & d, cudaStream_t st) {
 }
 
 // ---- SCALE (y = x*s + b, ops.cpp:4374), CLAMP, SILU, DIAG_MASK_INF on contiguous tensors -----------------------
-__global__ void scale_kernel(const float * __restrict__ x, float * __restrict__ y, int64_t n, float s, float b) {
+__global__ void scale_kernel(const float * x, float * y, int64_t n, float s, float b) {
     pdl_launch_dependents();
     pdl_wait();
     const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
@@ -147,7 +147,7 @@ int op_scale(const float * x, float * y, int64_t n, float s, float b, cudaStream
     launch_pdl(scale_kernel, dim3((unsigned) ((n + 255) / 256)), dim3(256), 0, st, x, y, n, s, b);
     return (int) cudaGetLastError();
 }
-__global__ void clamp_kernel(const float * __restrict__ x, float * __restrict__ y, int64_t n, float lo, float hi) {
+__global__ void clamp_kernel(const float * x, float * y, int64_t n, float lo, float hi) {
     pdl_launch_dependents();
     pdl_wait();
     const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
@@ -158,7 +158,7 @@ int op_clamp(const float * x, float * y, int64_t n, float lo, float hi, cudaStre
     launch_pdl(clamp_kernel, dim3((unsigned) ((n + 255) / 256)), dim3(256), 0, st, x, y, n, lo, hi);
     return (int) cudaGetLastError();
 }
-__global__ void silu_kernel(const float * __restrict__ x, float * __restrict__ y, int64_t n) {
+__global__ void silu_kernel(const float * x, float * y, int64_t n) {
     pdl_launch_dependents();
     pdl_wait();
     const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
@@ -170,7 +170,7 @@ int op_silu(const float * x, float * y, int64_t n, cudaStream_t st) {
     return (int) cudaGetLastError();
 }
 // ggml_compute_forward_diag_mask_f32: for k in z, j in rows, i >= n_past: if (i > n_past + j) -inf
-__global__ void diag_mask_inf_kernel(const float * __restrict__ x, float * __restrict__ y, int64_t ne0, int64_t ne1, int64_t n, int n_past) {
+__global__ void diag_mask_inf_kernel(const float * x, float * y, int64_t ne0, int64_t ne1, int64_t n, int n_past) {
     pdl_launch_dependents();
     pdl_wait();
     const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;

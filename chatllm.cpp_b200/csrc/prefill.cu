@@ -26,7 +26,7 @@ size_t pact_col_bytes(int wtype, int64_t k) {
 
 // one warp per 32-element block; Q8_K needs the block max over 256 -> two passes over 8 warps of a CTA
 template <bool Q8K>
-__global__ void __launch_bounds__(256) quantize_plain_kernel(const float * __restrict__ x, int64_t x_col_stride, int64_t k, uint8_t * __restrict__ pact,
+__global__ void __launch_bounds__(256) quantize_plain_kernel(const float * x, int64_t x_col_stride, int64_t k, uint8_t * pact,
                                                              size_t col_bytes) {
     __shared__ unsigned long long wkey[8];
     __shared__ float s_max;

@@ -19,8 +19,8 @@ size_t qact_col_bytes(int wtype, int64_t k) { return (size_t) act_layout(wtype =
 // ---- Q8_K: one warp-group of 256 threads per 256-element block ----------------------------------------
 // max = the element with the largest |x| (FIRST occurrence on ties, ggml-quants.c:2563-2567), iscale = -127/max,
 // q = nearest_int(iscale * x) clamped to 127 (RNE, :444-449), d = 1/iscale.
-__global__ void __launch_bounds__(256) quantize_q8_K_kernel(const float * __restrict__ x, int64_t x_col_stride, int64_t k,
-                                                            uint8_t * __restrict__ qact, size_t col_bytes) {
+__global__ void __launch_bounds__(256) quantize_q8_K_kernel(const float * x, int64_t x_col_stride, int64_t k,
+                                                            uint8_t * qact, size_t col_bytes) {
     pdl_launch_dependents();
     pdl_wait();
     const int blk = blockIdx.x;
@@ -82,8 +82,8 @@ __global__ void __launch_bounds__(256) quantize_q8_K_kernel(const float * __rest
 
 // ---- Q8_0 (x86 variant): one warp per 32-element block --------------------------------------------------
 // amax = max|x|, d = amax/127 stored as fp16, id = 127/amax (0 if amax == 0), q = RNE(x*id).
-__global__ void __launch_bounds__(256) quantize_q8_0_kernel(const float * __restrict__ x, int64_t x_col_stride, int64_t k,
-                                                            uint8_t * __restrict__ qact, size_t col_bytes) {
+__global__ void __launch_bounds__(256) quantize_q8_0_kernel(const float * x, int64_t x_col_stride, int64_t k,
+                                                            uint8_t * qact, size_t col_bytes) {
     pdl_launch_dependents();
     pdl_wait();
     const int col = blockIdx.y;
@@ -134,7 +134,7 @@ int quantize_act(int wtype, const float * x, int64_t x_col_stride, int64_t k, in
 // The mapping is per byte, so arbitrary (offset, size) windows written by ggml_backend_tensor_set
 // (1 MiB chunks, src/chat.cpp:1322-1338) can be converted independently.
 template <int QB>  // quant bytes per block: 16 (Q4_0) or 32 (Q8_0)
-__global__ void repack_bytes_kernel(const uint8_t * __restrict__ src, uint8_t * __restrict__ dst_tensor, int64_t tensor_off,
+__global__ void repack_bytes_kernel(const uint8_t * src, uint8_t * dst_tensor, int64_t tensor_off,
                                     int64_t nbytes, int64_t nb_row, bool inverse) {
     const int BB = QB + 2;
     const int64_t row_bytes = nb_row * BB;
