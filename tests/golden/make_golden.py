@@ -112,5 +112,53 @@ def main():
     print("wrote", os.path.join(HERE, "ref_vectors.npz"), {k: v.shape for k, v in out.items()})
 
 
+def main_moe():
+    """ref_moe_vectors.npz: ggml_mul_mat_id (ggml/src/ggml-cpu/ggml-cpu.c:1503-1700) and the whole sparse-MoE block of
+    GenericSparseMLP::forward / MultiMLP::forward (src/layers.cpp:3755-3880, :3674-3688), executed by the reference CPU backend."""
+    rng = np.random.default_rng(4321)
+    out = {}
+    k, m, n_expert, n_used, n_tok = 512, 32, 8, 2, 3
+    ids = np.stack([rng.choice(n_expert, size=n_used, replace=False) for _ in range(n_tok)]).astype(np.int32)
+    out["mmid_ids"] = ids
+    for t in (qf.Q4_K, qf.Q4_0, qf.Q8_0):
+        nm = qf.NAMES[t]
+        as_ = qf.random_blocks(t, n_expert * m, k, rng=rng)
+        out[f"mmid_{nm}_as"] = as_
+        for tag, nb1 in (("bcast", 1), ("slot", n_used)):
+            b = acts(rng, n_tok * nb1, k, heavy=True).reshape(n_tok, nb1, k)
+            g = rs.Graph()
+            y = g.mul_mat_id(g.input(as_.reshape(-1), t, (k, m, n_expert)), g.input(b), g.input(ids))
+            (yv,) = g.run("CPU", [(y, np.float32, (n_tok, n_used, m))], n_threads=4)
+            out[f"mmid_{nm}_{tag}_b"], out[f"mmid_{nm}_{tag}_y"] = b, yv
+
+    # the block: router -> softmax -> top-2 -> normalised weights -> experts' SwiGLU -> down -> weighted sum over the slots
+    hidden, ffn = 256, 512
+    t = qf.Q4_K
+    wr = qf.random_blocks(t, n_expert, hidden, rng=rng)
+    wg = qf.random_blocks(t, n_expert * ffn, hidden, rng=rng); wu = qf.random_blocks(t, n_expert * ffn, hidden, rng=rng)
+    wd = qf.random_blocks(t, n_expert * hidden, ffn, rng=rng)
+    x = acts(rng, 1, hidden)
+    g = rs.Graph()
+    h = g.input(x)
+    probs = g.soft_max(g.scale(g.mul_mat(g.input(wr.reshape(-1), t, (hidden, n_expert)), h), 40.0))
+    sel = g.top_k(probs, n_used)
+    w = g.reshape(g.get_rows(g.reshape(probs, (1, n_expert, 1)), sel), (n_used, 1))
+    w = g.reshape(g.div(w, g.sum_rows(w)), (1, n_used, 1))
+    h3 = g.reshape(h, (hidden, 1, 1))
+    act = g.silu(g.mul_mat_id(g.input(wg.reshape(-1), t, (hidden, ffn, n_expert)), h3, sel))
+    par = g.mul(g.mul_mat_id(g.input(wu.reshape(-1), t, (hidden, ffn, n_expert)), h3, sel), act, inplace=True)
+    experts = g.mul(g.mul_mat_id(g.input(wd.reshape(-1), t, (ffn, hidden, n_expert)), par, sel), w)
+    o = g.add(g.view(experts, (hidden, 1), nb=(hidden * n_used * 4,), offset=0), g.view(experts, (hidden, 1), nb=(hidden * n_used * 4,), offset=hidden * 4))
+    # intermediates are views / in-place results whose storage the graph allocator recycles: read them through contiguous copies
+    w_out, par_out = g.cont(w), g.cont(par)
+    selv, wv, parv, ov = g.run("CPU", [(sel, np.int32, (1, n_used)), (w_out, np.float32, (1, n_used, 1)), (par_out, np.float32, (1, n_used, ffn)),
+                                       (o, np.float32, (1, hidden))], n_threads=4)
+    out.update({"moe_wr": wr, "moe_wg": wg, "moe_wu": wu, "moe_wd": wd, "moe_x": x, "moe_sel": selv, "moe_w": wv, "moe_par": parv, "moe_out": ov})
+    np.savez_compressed(os.path.join(HERE, "ref_moe_vectors.npz"), **out)
+    print("wrote", os.path.join(HERE, "ref_moe_vectors.npz"), {k_: v.shape for k_, v in out.items()})
+
+
 if __name__ == "__main__":
-    main()
+    if "--moe-only" not in sys.argv:
+        main()
+    main_moe()

@@ -446,3 +446,29 @@ def test_mul_mat_id_paired_swiglu_vs_oracle(K, wtype, k, m):
     u = qf.port_mul_mat_id(wtype, wu, k, m, n_expert, x[None], ids[None])[0]
     ref = np.zeros_like(g); qf.port().oq_silu_mul(g.ctypes.data, u.ctypes.data, ref.ctypes.data, g.size)
     assert np.abs(y - ref).max() <= 3e-5 * np.abs(ref).max()
+
+
+GM = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_moe_vectors.npz"))
+
+
+@pytest.mark.parametrize("wtype", [qf.Q4_K, qf.Q4_0, qf.Q8_0])
+@pytest.mark.parametrize("tag", ["bcast", "slot"])
+def test_mul_mat_id_vs_reference_golden(K, wtype, tag):
+    """expert-indexed GEMV against outputs stored from the reference CPU backend's ggml_mul_mat_id (make_golden.py main_moe)"""
+    nm = qf.NAMES[wtype]
+    as_, b, ids, ref = GM[f"mmid_{nm}_as"], GM[f"mmid_{nm}_{tag}_b"], GM["mmid_ids"], GM[f"mmid_{nm}_{tag}_y"]
+    k, m, n_expert = b.shape[2], ref.shape[2], 8
+    wd = K.upload_weights(wtype, as_, k, n_expert * m)
+    for t in range(b.shape[0]):
+        y = K.mul_mat_id(wtype, wd, k, m, n_expert, _t(ids[t]), _t(b[t])).cpu().numpy()
+        assert np.abs(y - ref[t]).max() <= 2e-5 * np.abs(ref).max()
+
+
+def test_moe_experts_swiglu_vs_reference_golden(K):
+    """the paired expert launch (gate / silu / up / mul of MultiMLP::forward) against the reference's `par` tensor, experts as
+    chosen by the reference's own top_k"""
+    wg, wu, x, sel, ref = GM["moe_wg"], GM["moe_wu"], GM["moe_x"], GM["moe_sel"][0], GM["moe_par"][0]
+    hidden, ffn, n_expert = x.shape[1], ref.shape[1], 8
+    dg, du = K.upload_weights(qf.Q4_K, wg, hidden, n_expert * ffn), K.upload_weights(qf.Q4_K, wu, hidden, n_expert * ffn)
+    y = K.mul_mat_id(qf.Q4_K, dg, hidden, ffn, n_expert, _t(sel.astype(np.int32)), _t(x), w1_dev=du).cpu().numpy()
+    assert np.abs(y - ref).max() <= 3e-5 * np.abs(ref).max()

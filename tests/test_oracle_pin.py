@@ -194,3 +194,45 @@ def test_mul_mat_id_live_vs_reference_cpu_backend(t, n_tokens, broadcast):
     if broadcast:
         mine_sw = qf.port_mul_mat_id(t, as_, k, m, n_expert, b, ids[:, ::-1])
         assert np.array_equal(mine_sw, mine[:, ::-1])
+
+
+GM = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_moe_vectors.npz"))
+
+
+@pytest.mark.parametrize("t", [qf.Q4_K, qf.Q4_0, qf.Q8_0])
+@pytest.mark.parametrize("tag", ["bcast", "slot"])
+def test_mul_mat_id_vs_golden(t, tag):
+    """oq_mul_mat_id against stored outputs of the reference CPU backend (tests/golden/make_golden.py main_moe): works where
+    oracle/_ref is absent."""
+    nm = qf.NAMES[t]
+    as_, b, ids, ref = GM[f"mmid_{nm}_as"], GM[f"mmid_{nm}_{tag}_b"], GM["mmid_ids"], GM[f"mmid_{nm}_{tag}_y"]
+    y = qf.port_mul_mat_id(t, as_, b.shape[2], ref.shape[2], 8, b, ids)
+    assert np.abs(y - ref).max() <= 2e-5 * np.abs(ref).max()
+
+
+def moe_block_port(wr, wg, wu, wd, x, n_expert=8, n_used=2, t=qf.Q4_K):
+    """GenericSparseMLP::forward + MultiMLP::forward (src/layers.cpp:3755-3880, :3674-3688) for one token, composed from the
+    port's primitives: router matmul -> softmax(40 * logits) -> top-k -> normalised weights -> SwiGLU experts -> down -> sum."""
+    hidden, ffn = x.shape[1], wg.shape[0] // n_expert
+    logits = qf.port_mul_mat(t, wr, hidden, n_expert, x) * np.float32(40.0)
+    probs = np.zeros_like(logits)
+    qf.port().oq_soft_max(logits.ctypes.data, None, probs.ctypes.data, n_expert, 1, 1.0)
+    sel = np.argsort(-probs[0], kind="stable")[:n_used].astype(np.int32)
+    w = probs[0, sel]; w = (w / np.float32(w.sum(dtype=np.float32))).astype(np.float32)
+    g = qf.port_mul_mat_id(t, wg, hidden, ffn, n_expert, x[None], sel[None])[0]
+    u = qf.port_mul_mat_id(t, wu, hidden, ffn, n_expert, x[None], sel[None])[0]
+    par = np.zeros_like(g); qf.port().oq_silu_mul(g.ctypes.data, u.ctypes.data, par.ctypes.data, g.size)
+    e = qf.port_mul_mat_id(t, wd, ffn, hidden, n_expert, par[None], sel[None])[0]        # [n_used, hidden], one column per slot
+    out = (e[0] * w[0]).astype(np.float32)
+    for i in range(1, n_used):
+        out = (out + e[i] * w[i]).astype(np.float32)
+    return sel, w, par, out
+
+
+def test_sparse_moe_block_vs_golden():
+    sel, w, par, out = moe_block_port(GM["moe_wr"], GM["moe_wg"], GM["moe_wu"], GM["moe_wd"], GM["moe_x"])
+    assert set(sel.tolist()) == set(GM["moe_sel"][0].tolist())
+    order = [sel.tolist().index(e) for e in GM["moe_sel"][0].tolist()]   # the reference's top_k order of the two slots
+    assert np.abs(w[order] - GM["moe_w"].reshape(-1)).max() <= 1e-6
+    assert np.abs(par[order] - GM["moe_par"][0]).max() <= 3e-5 * np.abs(GM["moe_par"]).max()
+    assert np.abs(out - GM["moe_out"][0]).max() <= 5e-5 * np.abs(GM["moe_out"]).max()

@@ -1,0 +1,52 @@
+"""Static guard for the programmatic-dependent-launch rule (chatllm.cpp_b200/csrc/common.cuh), CPU-only: in the SASS
+of every kernel that executes griddepcontrol.wait (ACQBULK) no global load may precede the wait, except the deliberate pre-wait
+streams — the GEMV's bulk weight copies and the old K / V rows of the two split attention kernels.  A `const T * __restrict__`
+parameter on producer-written data lets nvcc hoist loads above the wait (it did, round 1); this test catches the next one at build time."""
+import os
+import re
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BUILD = os.path.join(ROOT, "chatllm.cpp_b200", "build")
+OBJS = ["fused.o", "gemv.o", "ops.o", "ops_generic.o", "quantize.o", "prefill.o"]
+
+pytestmark = pytest.mark.skipif(not shutil.which("cuobjdump") or not all(os.path.exists(os.path.join(BUILD, o)) for o in OBJS),
+                                reason="needs the built kernel objects (python -c 'import __graft_entry__ as g; g.build()') and cuobjdump")
+
+LOAD = re.compile(r"\b(LDG|LD\.E|UBLKCP|LDGSTS)")
+
+
+def kernels(obj):
+    sass = subprocess.run(["cuobjdump", "-sass", os.path.join(BUILD, obj)], capture_output=True, text=True, check=True).stdout
+    for fn in sass.split("Function : ")[1:]:
+        name = fn.split("\n", 1)[0].strip()
+        ins = [t for _, t in re.findall(r"/\*([0-9a-f]{4,})\*/\s+(.*?);", fn)]
+        yield name, ins
+
+
+@pytest.mark.parametrize("obj", OBJS)
+def test_no_producer_load_is_hoisted_above_the_pdl_wait(obj):
+    checked = 0
+    for name, ins in kernels(obj):
+        waits = [i for i, t in enumerate(ins) if "ACQBULK" in t]
+        if not waits:
+            continue
+        checked += 1
+        before = [t for t in ins[:waits[0]] if LOAD.search(t)]
+        between = [t for t in ins[waits[0]:waits[-1]] if LOAD.search(t)]
+        if "gemv_q_kernel" in name:
+            # weights only, and only through the bulk-copy engine; activations (plain LDG) come after the wait
+            assert all("UBLKCP" in t for t in before) and not between, (name, before, between)
+        elif "attn_pv_split_kernel" in name:
+            # one round of V fragments (2 k-groups x 4 chunks x 2 rows) for the splits that do not hold the newest position
+            assert len(before) <= 16 and all("LDG.E.128" in t for t in before) and not between, (name, before, between)
+        elif "attn_scores_mma_kernel" in name:
+            # K fragments between the two (mutually exclusive) waits; q strictly after
+            assert not before and len(between) <= 8 and all("LDG.E.128" in t for t in between), (name, before, between)
+        else:
+            assert not before and not between, (name, before, between)
+    if obj in ("fused.o", "gemv.o"):
+        assert checked > 0
