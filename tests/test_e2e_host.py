@@ -169,3 +169,33 @@ def test_llama3_8b_q4k_real_shape_few_layers(tmp_path):
     model = make_model(str(tmp_path), "llama3-8b", "q4_K", layers=2, max_length=512)
     rel, spread, rc, rg, _ = compare(str(tmp_path), model, 128256, prefill=100, decode=3)
     print("llama3-8b q4_K max rel", rel, "ref spread", spread, "cpu ms/tok", rc["decode_ms_median"], "gpu ms/tok", rg["decode_ms_median"])
+
+
+def _n_cuda():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:  # noqa: BLE001
+        return 0
+
+
+@pytest.mark.skipif(_n_cuda() < 2, reason="needs two GPUs (layer split across devices of the plugin)")
+@pytest.mark.parametrize("quant", ["q4_K", "q4_0"])
+def test_layer_split_across_two_devices(tmp_path, quant):
+    """`-ngl "0:1,prolog;1:1,epilog"` puts layer 0 (+ embedding) on CUDA0 and layer 1 (+ final norm, lm_head) on CUDA1,
+    weights and KV cache with them (docs/gpu.md:36-52); the hidden-state row crosses the boundary through the plugin's
+    cpy_tensor_async (event on the producer's stream, peer copy on the consumer's).  Same gates as the single-device test."""
+    model = make_model(str(tmp_path), "tiny-test", quant)
+    worst = []
+    for prefill in (5, 9):
+        for seed in (1, 3, 4):
+            cpu_dump, gpu_dump = os.path.join(str(tmp_path), "cpu.bin"), os.path.join(str(tmp_path), "gpu.bin")
+            run_host(model, "0", cpu_dump, prefill, 4, seed=seed)
+            rg, _ = run_host(model, "0:1,prolog;1:1,epilog", gpu_dump, prefill, 4, seed=seed)
+            assert rg["device0"] == "CUDA0" and rg["devices"] >= 3
+            a, b = _logits(cpu_dump, 512), _logits(gpu_dump, 512)
+            assert a.shape == b.shape == (5, 512) and np.isfinite(b).all()
+            worst.append(float(_rel(a, b).max()))
+    print("tiny-test", quant, "2-device layer split: max rel logit err per (length, seed)", worst)
+    assert max(worst) <= 3e-2, worst
+    assert sum(w <= 1e-3 for w in worst) > len(worst) // 2, worst
