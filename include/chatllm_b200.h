@@ -76,6 +76,15 @@ int b200_mul_mat_q_batched(int wtype, const void * W, int64_t k, int64_t m, cons
  *                                            — gate/up projections + SwiGLU of BaseMLP::forward (src/layers.cpp:2475-2483) */
 int b200_mul_mat_q_multi(int wtype, int mode, int nmat, const void * const * W, const int64_t * m, float * const * y, const int64_t * ldy,
                          const float * const * bias, int64_t k, const void * qact, int64_t n, void * stream);
+/* b200_mul_mat_q_multi for ONE token with a fused prologue or epilogue (OPT-IN: written at the end of round 1, not yet measured):
+ *   pro_x != NULL : activations = Q(rms_norm(pro_x) * pro_w) computed in every CTA's prologue (qact ignored; k <= 20480) — replaces the
+ *                   RMS_NORM + MUL + src1 conversion in front of the matmul (src/layers.cpp:2216-2225, ggml-cpu.c:1291-1326)
+ *   res   != NULL : y_i[r] = W_i[r,:].x (+ bias_i[r]) + res_i[r]  (mode 0; res_i may alias y_i) — the residual ADD of
+ *                   LMBlock1Forward::forward (src/layers.cpp:2719-2761) in the epilogue
+ * Exactly one of the two may be given per call. */
+int b200_gemv_fused(int wtype, int mode, int nmat, const void * const * W, const int64_t * m, float * const * y, const int64_t * ldy,
+                    const float * const * bias, const float * const * res, int64_t k, const void * qact, const float * pro_x,
+                    const float * pro_w, float pro_eps, void * stream);
 /* Expert-indexed matmul for ONE token = ggml_mul_mat_id (ggml/src/ggml.c:3225-3240; CPU ggml_compute_forward_mul_mat_id
  * ggml/src/ggml-cpu/ggml-cpu.c:1503-1700; caller MultiLinear::forward src/layers.cpp:2145-2151, MultiMLP::forward :3674-3688).
  *   W0 (and W1): stacks of n_expert matrices [m, k] in the device layout, expert e at byte offset e * m * row_bytes.
