@@ -1,7 +1,10 @@
 """OPT-IN tests (-m gpu AND B200_TEST_FUSED2=1) for the round-2 fusion written at the end of round 1 and not yet run on a GPU:
 RMSNorm + activation quantization in the consumer GEMV's prologue, residual add in the producer GEMV's epilogue
 (chatllm.cpp_b200/csrc/normquant.cuh, b200_gemv_fused, DecodeSession(fused=2): 9 launches per layer instead of 11).
-They stay out of the default suite until they have passed once on a B200:  B200_TEST_FUSED2=1 python -m pytest tests/test_fused2_optin.py -m gpu"""
+They stay out of the default suite until they have passed once on a B200:
+    B200_TEST_FUSED2=1 python -m pytest tests/test_fused2_optin.py -m gpu            # kernels + session
+    B200_FUSE2=1 python -m pytest tests/test_plugin_ops.py tests/test_e2e_host.py -m gpu   # the same fusion inside the plugin (graph_compute)
+then flip the defaults (DecodeSession(fused=2) in bench.py, B200_FUSE2 default on) and move these into the regular files."""
 import ctypes as C
 import os
 
