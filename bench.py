@@ -132,6 +132,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--tune", default="", help="ks,stages,warps,rg,grid for the GEMV pipeline (0 = default)")
     ap.add_argument("--unfused", action="store_true")
+    ap.add_argument("--fused2", action="store_true", help="opt-in step with norm+quant in the GEMV prologue / residual in the epilogue (9 launches per layer)")
     ap.add_argument("--layers", type=int, default=0, help="debug: fewer layers (result is then NOT the BASELINE config)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3)
@@ -176,7 +177,7 @@ def main():
     cfg = S.make_config(MODEL, pkg.Q4_K, layers=a.layers or None, max_len=N_PAST + 256)
     from chatllm_cpp_b200 import sharding
     lo, hi = sharding.plan_layers(cfg.layers, world)[rank]
-    sess = S.DecodeSession(cfg, seed=0, layer_lo=lo, layer_hi=hi, first=(rank == 0), last=(rank == world - 1), fused=not a.unfused)
+    sess = S.DecodeSession(cfg, seed=0, layer_lo=lo, layer_hi=hi, first=(rank == 0), last=(rank == world - 1), fused=(2 if a.fused2 else not a.unfused))
     sess.fill_kv_random(N_PAST, seed=rank)
     sess.tok.fill_(12345 % cfg.vocab)
 

@@ -1,0 +1,25 @@
+#!/bin/bash
+# First gpurun call of round 2: bring up what round 1 wrote but could not run (its B200 minutes were spent), in order of value.
+#   gpurun --timeout 900 -- 'bash tools/gpu_round2_bringup.sh'
+OUT=gpurun_out/r02_bringup
+mkdir -p $OUT
+# 1. the default suite must still be green on this box
+( timeout 300 python -m pytest tests -m gpu -x -q ) > $OUT/pytest_default.log 2>&1; echo "default: $(tail -1 $OUT/pytest_default.log)"
+# 2. opt-in fusion: kernels + session, then the same fusion inside the plugin over the whole plugin / e2e suites
+( B200_TEST_FUSED2=1 timeout 200 python -m pytest tests/test_fused2_optin.py -m gpu -q ) > $OUT/pytest_fused2.log 2>&1; echo "fused2 kernels/session: $(tail -1 $OUT/pytest_fused2.log)"
+( B200_FUSE2=1 timeout 300 python -m pytest tests/test_plugin_ops.py tests/test_e2e_host.py -m gpu -q ) > $OUT/pytest_plugin_fuse2.log 2>&1; echo "plugin B200_FUSE2=1: $(tail -1 $OUT/pytest_plugin_fuse2.log)"
+grep -E "^(FAILED|ERROR)" $OUT/pytest_fused2.log $OUT/pytest_plugin_fuse2.log | head -20
+# 3. what it buys: device-resident step and e2e, default vs opt-in
+python bench.py --no-e2e --no-cpu > $OUT/bench_default.json 2>> $OUT/bench.err; python bench.py --no-e2e --no-cpu --fused2 > $OUT/bench_fused2.json 2>> $OUT/bench.err
+python - <<'PY'
+import json
+for n in ("default", "fused2"):
+    try:
+        d = json.load(open(f"gpurun_out/r02_bringup/bench_{n}.json")); print(n, d["value"], "tok/s", d["ms_per_step"], "ms", d["gpu_launches"] // d["steps"], "launches/step")
+    except Exception as e: print(n, "failed", e)
+PY
+( timeout 200 python tools/plugin_profile.py; echo "--- B200_FUSE2=1"; timeout 200 python tools/plugin_profile.py B200_FUSE2=1 ) > $OUT/plugin_profile.txt 2>&1; grep -E "decode_ms_mean|B200PROF|---" $OUT/plugin_profile.txt | cut -c1-200 | tail -8
+# 4. 2-device layer split through the plugin (only on a --gpus 2 call)
+if [ "$(nvidia-smi -L | wc -l)" -ge 2 ]; then
+  ( B200_TEST_MULTI_GPU=1 timeout 200 python -m pytest tests/test_e2e_host.py -m gpu -q -k layer_split ) > $OUT/pytest_2gpu.log 2>&1; echo "2-GPU split: $(tail -1 $OUT/pytest_2gpu.log)"
+fi
