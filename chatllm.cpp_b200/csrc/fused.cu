@@ -852,7 +852,10 @@ static int attn_decode_mma_t(const float * q, const void * kc, const void * vc, 
     const int npos = nchunks * 128;
     const int sp = npos + 32;  // +64 bytes: the 8 head rows land in different bank groups (conflict-free 16-byte B loads)
     const size_t smem = (size_t) 8 * sp * 2 + B200_PV_WARPS * 128 * 4;
-    static size_t configured = 0;
+    static size_t configured_dev[16] = {0};  // function attributes are per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    size_t & configured = configured_dev[dev & 15];
     if (smem > configured) {
         const size_t want = smem > 160 * 1024 ? smem : 160 * 1024;
         cudaError_t e = cudaFuncSetAttribute(attn_pv_mma_kernel<GQA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) want);
@@ -877,7 +880,10 @@ static int attn_decode2_t(const float * q, const void * kc, const void * vc, flo
     dim3 g1((unsigned) nchunks, (unsigned) kv_heads);
     launch_pdl(attn_scores2_kernel<HD, GQA>, g1, dim3(256), 0, st, q, (const __half *) kc, scratch, part, n_kv, k_row_stride, scale, s_stride, nchunks);
     const size_t smem = (size_t) GQA * s_stride * 4;
-    static size_t configured = 0;
+    static size_t configured_dev[16] = {0};  // function attributes are per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    size_t & configured = configured_dev[dev & 15];
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(attn_softmax_pv_kernel<GQA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (smem > 200 * 1024 ? smem : 200 * 1024));
         if (e != cudaSuccess) return (int) e;

@@ -488,11 +488,14 @@ static int env_int(const char * name, int dflt) {
 template <class F, int RG, int NC, int MODE, int FX = 0>
 static int launch(const GemvParams & p, int warps, int grid, size_t smem_bytes, cudaStream_t st) {
     auto kern = gemv_q_kernel<F, RG, NC, MODE, FX>;
-    static size_t configured = 0;  // per template instantiation
-    if (smem_bytes > configured) {
+    static size_t configured[16] = {0};  // per template instantiation AND per device (function attributes are per device)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 15;
+    if (smem_bytes > configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_bytes);
         if (e != cudaSuccess) return (int) e;
-        configured = smem_bytes;
+        configured[dev] = smem_bytes;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned) grid);

@@ -952,6 +952,9 @@ static void b200_backend_free(ggml_backend_t backend) {
     if (bc->qact) cudaFree(bc->qact);
     if (bc->attn_scratch) cudaFree(bc->attn_scratch);
     if (bc->kv_scratch) cudaFree(bc->kv_scratch);
+    if (bc->p2p_ev) cudaEventDestroy(bc->p2p_ev);
+    if (bc->ev0) cudaEventDestroy(bc->ev0);
+    if (bc->ev1) cudaEventDestroy(bc->ev1);
     cudaStreamDestroy(bc->stream);
     delete bc;
     delete backend;
@@ -1154,9 +1157,10 @@ static int b200_count_devices() {
     for (int i = 0; i < n && kept < B200_MAX_DEVICES; ++i) {
         cudaDeviceProp prop;
         if (cudaGetDeviceProperties(&prop, i) != cudaSuccess) continue;
-        if (prop.major != 10) {  // sm_100a code only
-            GGML_LOG_WARN("b200: skipping device %d (%s, cc %d.%d): this module contains sm_100a code only\n", i, prop.name, prop.major, prop.minor);
-            continue;
+        if (prop.major != 10) {  // sm_100a code only.  Device contexts are indexed by CUDA ordinal, so enumeration stops at the first foreign device
+            GGML_LOG_WARN("b200: device %d (%s, cc %d.%d) is not sm_100: this module contains sm_100a code only; using devices 0..%d\n", i, prop.name, prop.major,
+                          prop.minor, i - 1);
+            break;
         }
         b200_device_ctx * dc = &g_dev_ctx[kept];
         dc->device = i;

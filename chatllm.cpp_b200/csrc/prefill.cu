@@ -277,7 +277,10 @@ template <int FMT, int NT>
 static int mmq_launch(const MmqParams & p, cudaStream_t st) {
     constexpr int BN = NT * 8;
     const size_t smem = 2 * (size_t) (BN * MMQ_BSTRIDE + BN * 8 * 4 + BN * 8 * 4);
-    static bool configured = false;
+    static bool configured_dev[16] = {false};  // function attributes are per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    bool & configured = configured_dev[dev & 15];
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(mmq_kernel<FMT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
         if (e != cudaSuccess) return (int) e;
