@@ -995,6 +995,19 @@ static bool b200_cpy_tensor_async(ggml_backend_t backend_src, ggml_backend_t bac
     CUDA_OK(cudaSetDevice(bs->device));
     CUDA_OK(cudaEventRecord(bs->p2p_ev, bs->stream));
     CUDA_OK(cudaSetDevice(bd->device));
+    if (bs->device != bd->device) {  // direct NVLink path for the peer copy (without it the copy is staged through host memory)
+        static bool tried[B200_MAX_DEVICES][B200_MAX_DEVICES] = {};
+        bool & t = tried[bd->device % B200_MAX_DEVICES][bs->device % B200_MAX_DEVICES];
+        if (!t) {
+            t = true;
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, bd->device, bs->device) == cudaSuccess && can) {
+                const cudaError_t e = cudaDeviceEnablePeerAccess(bs->device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) GGML_LOG_WARN("b200: peer access %d -> %d not enabled: %s\n", bd->device, bs->device, cudaGetErrorString(e));
+                cudaGetLastError();
+            }
+        }
+    }
     CUDA_OK(cudaStreamWaitEvent(bd->stream, bs->p2p_ev, 0));
     if (bs->device == bd->device) CUDA_OK(cudaMemcpyAsync(dst->data, src->data, nb, cudaMemcpyDeviceToDevice, bd->stream));
     else CUDA_OK(cudaMemcpyPeerAsync(dst->data, bd->device, src->data, bs->device, nb, bd->stream));
