@@ -59,6 +59,7 @@ def lib():
         L.b200_pact_col_bytes.argtypes = [i32, i64]; L.b200_pact_col_bytes.restype = C.c_size_t
         L.b200_quantize_plain.argtypes = [i32, vp, i64, i64, i64, vp, vp]
         L.b200_mul_mat_q_batched.argtypes = [i32, vp, i64, i64, vp, i64, vp, i64, vp, vp]
+        L.b200_mul_mat_q_batched_tc.argtypes = [vp, i64, i64, vp, i64, vp, i64, vp, vp]
         _lib = L
     return _lib
 
@@ -66,4 +67,4 @@ def lib():
 EXPORTS = ["b200_abi_version", "b200_device_sm_count", "b200_repack_weights", "b200_qact_col_bytes", "b200_quantize_act",
            "b200_mul_mat_q", "b200_mul_mat", "b200_gemv_set_tuning", "b200_rms_norm", "b200_add", "b200_silu_mul", "b200_rope",
            "b200_soft_max", "b200_get_rows", "b200_attn_decode_scratch_bytes", "b200_attn_decode", "b200_attn_decode_quant", "b200_kv_store", "b200_add_rmsnorm_quant", "b200_rope_kv_store",
-           "b200_mul_mat_q_multi", "b200_gemv_fused", "b200_mul_mat_q_id", "b200_pact_col_bytes", "b200_quantize_plain", "b200_mul_mat_q_batched"]
+           "b200_mul_mat_q_multi", "b200_gemv_fused", "b200_mul_mat_q_id", "b200_pact_col_bytes", "b200_quantize_plain", "b200_mul_mat_q_batched", "b200_mul_mat_q_batched_tc"]

@@ -79,6 +79,10 @@ int b200_mul_mat_q_batched(int wtype, const void * W, int64_t k, int64_t m, cons
     return mul_mat_q_batched(wtype, W, k, m, pact, n, y, ldy, bias, (cudaStream_t) stream);
 }
 
+int b200_mul_mat_q_batched_tc(const void * W, int64_t k, int64_t m, const void * pact, int64_t n, float * y, int64_t ldy, const float * bias, void * stream) {
+    return mul_mat_q_batched_tc(W, k, m, pact, n, y, ldy, bias, pact_col_bytes(B200_TYPE_Q4_K, k), (cudaStream_t) stream);
+}
+
 int b200_gemv_set_tuning(int ks, int stages, int warps, int rg, int grid) {
     g_tune.ks = ks; g_tune.stages = stages; g_tune.warps = warps; g_tune.rg = rg; g_tune.grid = grid;
     return B200_OK;

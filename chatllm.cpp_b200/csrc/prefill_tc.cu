@@ -1,0 +1,238 @@
+// prefill_tc.cu — prompt-sized Q4_K matmul on the 5th-generation tensor cores (tcgen05.mma kind::i8, accumulators in TMEM), EXACT.
+//
+// OPT-IN (B200_MMQ_TCGEN05=1): written at the end of round 1 after the round's B200 minutes were spent — it compiles for sm_100a
+// (SASS: UTCIMMA / UTCBAR / LDTM) but has NOT run on a GPU yet.  The default path stays prefill.cu's mma.sync kernel (≈130 TOPS
+// effective, 67 % of the prompt time, profiles/r01e_prefill_2048_launches_summary.txt).  Bring-up: tests/test_fused2_optin.py
+// (test_tcgen05_prefill_equals_mma_sync) demands BIT-identical outputs to mmq_kernel.
+//
+// Why this is exact.  Per 256-element super-block the reference computes (ggml-cpu/arch/x86/quants.c:1742-1916)
+//        y += dx·d·Σ_j sc_j Σ_{k∈j} q_k x_k  −  dx·dmin·Σ_j m_j Σ_{k∈j} x_k          (sc_j, m_j: 6-bit, q: 4-bit, x: int8 codes)
+// An int32 accumulator cannot run across sub-blocks with different sc_j — unless the scale is folded into the int8 operand:
+//        sc_j = 8·hi_j + lo_j  (hi, lo < 8)   =>   hi_j·q ≤ 105 and lo_j·q ≤ 105 fit int8,
+// so three int8 "planes" of the weight tile  A_hi = hi_j·q,  A_lo = lo_j·q,  A_m = m_j (broadcast over the sub-block)  give
+//        Σ_j sc_j Σ q x = 8·(A_hi·X) + (A_lo·X),      Σ_j m_j bsum_j = (A_m·X)
+// as three exact int32 GEMMs over K = 256, and ONE fp32 rescale per super-block — the same fp32 expression, in the same order over
+// the super-blocks, as mmq_kernel.  TMEM is read back once per K = 256 (1/256 of the MMA work on the CUDA cores).
+//
+// Round-1 shape of the kernel (deliberately the simplest correct structure; the pipelined version is DESIGN.md §7.5):
+//   CTA = 128 rows x 128 columns, 256 threads.  Per super-block: (1) every thread expands its row's nibbles into the three planes and
+//   copies its share of the int8 activation tile, both straight into the canonical no-swizzle K-major core-matrix layout
+//   (8 rows x 16 bytes per core matrix; cute/arch/mma_sm100_desc.hpp "INTERLEAVE": ((8,n),2):((1,SBO),LBO)); (2) fence.proxy.async +
+//   barrier; (3) ONE thread issues 8 k-steps x 3 planes of tcgen05.mma (M=128, N=128, K=32) and commits to an mbarrier; (4) all
+//   threads wait, tcgen05.ld their row's 64 columns of the three accumulators, rescale into 64 fp32 registers.  No overlap yet.
+#include "common.cuh"
+#include "kernels.h"
+
+#include <cstdlib>
+
+namespace b200 {
+
+#define TC_M 128
+#define TC_N 128
+#define TC_PLANE_BYTES (TC_M * 256)  // one 128 x 256-byte int8 tile
+#define TC_LBO 2048u                 // bytes between the two 16-byte K chunks of a core-matrix column: (TC_M / 8) core matrices of 128 bytes
+#define TC_SBO 128u                  // bytes between consecutive 8-row groups
+#define TC_TMEM_COLS 512             // 3 accumulators x 128 columns -> next power of two
+
+__host__ __device__ inline int64_t tc_al16(int64_t x) { return (x + 15) & ~(int64_t) 15; }
+
+struct TcParams {
+    const uint8_t * W;
+    const uint8_t * pact;
+    float * y;
+    const float * bias;
+    int64_t k, m, n, ldy;
+    int nunits;
+    size_t col_bytes;
+};
+
+// shared-memory matrix descriptor, no swizzle, K-major (mma_sm100_desc.hpp SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version = 1 [46,48), base_offset = 0, lbo_mode = 0, layout_type = SWIZZLE_NONE (0) [61,64)
+__device__ __forceinline__ uint64_t tc_desc(uint32_t saddr) {
+    return (uint64_t) ((saddr >> 4) & 0x3fffu) | ((uint64_t) ((TC_LBO >> 4) & 0x3fffu) << 16) | ((uint64_t) ((TC_SBO >> 4) & 0x3fffu) << 32) | ((uint64_t) 1 << 46);
+}
+// instruction descriptor (mma_sm100_desc.hpp InstrDescriptor): c_format S32 (2) [4,6), a_format / b_format signed 8 bit (1) [7,10) / [10,13),
+// K-major A and B, n_dim = N >> 3 [17,23), m_dim = M >> 4 [24,29)
+#define TC_IDESC ((2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t) (TC_N >> 3) << 17) | ((uint32_t) (TC_M >> 4) << 24))
+
+__device__ __forceinline__ void tc_mma_i8(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
+        "}\n" ::"r"(tmem_c),
+        "l"(da), "l"(db), "r"(TC_IDESC), "r"(accumulate), "r"(0u)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint64_t * bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, int (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+          "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+          "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// byte offset of (row-or-column i, 16-byte K chunk c) inside a 128 x 256-byte tile in the canonical no-swizzle K-major layout
+__device__ __forceinline__ uint32_t tc_off(int i, int c) { return (uint32_t) ((c * (TC_M / 8) + (i >> 3)) * 128 + (i & 7) * 16); }
+
+__global__ void __launch_bounds__(256, 1) mmq_tc_q4k_kernel(const TcParams p) {
+    extern __shared__ __align__(128) uint8_t sm[];
+    uint8_t * A_hi = sm, * A_lo = sm + TC_PLANE_BYTES, * A_m = sm + 2 * TC_PLANE_BYTES, * Bt = sm + 3 * TC_PLANE_BYTES;
+    float * dxs = reinterpret_cast<float *>(sm + 4 * TC_PLANE_BYTES);  // [128] activation scale of this super-block per column
+    __shared__ __align__(8) uint64_t mma_bar;
+    __shared__ uint32_t tmem_base_s;
+    pdl_launch_dependents();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wg = warp >> 2, q = warp & 3;  // warpgroup (K half in the expansion, column half in the epilogue), TMEM lane quarter
+    const int row = q * 32 + lane;           // this thread's row of the tile = its TMEM lane
+    const int64_t grow = min((int64_t) blockIdx.y * TC_M + row, p.m - 1);  // clamped: stores are masked
+    const int64_t col_base = (int64_t) blockIdx.x * TC_N;
+    const uint8_t * wrow = p.W + grow * (int64_t) p.nunits * 144;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t) TC_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 32) {
+        mbar_init(&mma_bar, 1);
+        fence_mbar_init();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+
+    float yacc[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) yacc[i] = 0.0f;
+    const int64_t d_off = tc_al16(p.k);  // plain activation layout (prefill.cu): qs[k] | float d[k/256] | int bs[k/32]
+
+    pdl_wait();  // the quantized activations come from the predecessor
+    for (int u = 0; u < p.nunits; ++u) {
+        // ---- (1a) weights: this thread's row, sub-blocks 4*wg .. 4*wg+3 -> three int8 planes
+        const uint8_t * blk = wrow + (size_t) u * 144;
+        const uint4 hdr = *reinterpret_cast<const uint4 *>(blk);
+        const float d_r = half_bits_to_float(hdr.x & 0xffffu), dmin_r = half_bits_to_float(hdr.x >> 16);
+        // get_scale_min_k4 (ggml-quants.c:703-711), four at a time: sub-blocks 0..3 in *_a, 4..7 in *_b
+        const uint32_t sc_a = hdr.y & 0x3f3f3f3fu, sc_b = (hdr.w & 0x0f0f0f0fu) | (((hdr.y >> 6) & 0x03030303u) << 4);
+        const uint32_t mn_a = hdr.z & 0x3f3f3f3fu, mn_b = ((hdr.w >> 4) & 0x0f0f0f0fu) | (((hdr.z >> 6) & 0x03030303u) << 4);
+        const uint32_t sc4 = wg ? sc_b : sc_a, mn4 = wg ? mn_b : mn_a;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            const int j = 4 * wg + jj;
+            const uint32_t sc = (sc4 >> (8 * jj)) & 0xffu, mn = (mn4 >> (8 * jj)) & 0xffu;
+            const uint32_t hi = sc >> 3, lo = sc & 7u, mrep = mn * 0x01010101u;
+            // nibble order (ggml-quants.c:1352-1373): 64-element group j/2 = 32 bytes; low nibbles = sub-block 2*(j/2), high = the next one
+            const uint8_t * qa = blk + 16 + (j >> 1) * 32;
+            const int sh = (j & 1) * 4;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const uint4 v = *reinterpret_cast<const uint4 *>(qa + half * 16);
+                const uint32_t n0 = (v.x >> sh) & 0x0f0f0f0fu, n1 = (v.y >> sh) & 0x0f0f0f0fu, n2 = (v.z >> sh) & 0x0f0f0f0fu, n3 = (v.w >> sh) & 0x0f0f0f0fu;
+                const uint32_t o = tc_off(row, j * 2 + half);
+                // per-byte products <= 7 * 15 = 105: no carry between the four bytes of a word
+                *reinterpret_cast<uint4 *>(A_hi + o) = make_uint4(n0 * hi, n1 * hi, n2 * hi, n3 * hi);
+                *reinterpret_cast<uint4 *>(A_lo + o) = make_uint4(n0 * lo, n1 * lo, n2 * lo, n3 * lo);
+                *reinterpret_cast<uint4 *>(A_m + o) = make_uint4(mrep, mrep, mrep, mrep);
+            }
+        }
+        // ---- (1b) activations: column (tid & 127), K chunks 8*(tid >> 7) .. +7 of this super-block
+        {
+            const int coln = tid & 127, cb = (tid >> 7) * 8;
+            const int64_t gc = min(col_base + coln, p.n - 1);
+            const uint8_t * src = p.pact + (size_t) gc * p.col_bytes + (size_t) u * 256;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4 *>(Bt + tc_off(coln, cb + c)) = *reinterpret_cast<const uint4 *>(src + (cb + c) * 16);
+            if (tid < 128) dxs[coln] = reinterpret_cast<const float *>(p.pact + (size_t) gc * p.col_bytes + d_off)[u];
+        }
+        fence_proxy_async();  // generic-proxy stores above -> visible to the tensor core's (async proxy) reads
+        __syncthreads();
+        // ---- (2) one thread issues the 24 MMAs of this super-block and commits them to the mbarrier
+        if (tid == 0) {
+            tc_fence_after();
+            const uint32_t a0 = smem_u32(A_hi), a1 = smem_u32(A_lo), a2 = smem_u32(A_m), b0 = smem_u32(Bt);
+#pragma unroll
+            for (int s = 0; s < 8; ++s) {  // k-step s = 16-byte chunks 2s, 2s+1
+                const uint32_t koff = (uint32_t) s * 2u * TC_LBO;
+                const uint64_t db = tc_desc(b0 + koff);
+                tc_mma_i8(tmem + 0 * TC_N, tc_desc(a0 + koff), db, s > 0);
+                tc_mma_i8(tmem + 1 * TC_N, tc_desc(a1 + koff), db, s > 0);
+                tc_mma_i8(tmem + 2 * TC_N, tc_desc(a2 + koff), db, s > 0);
+            }
+            tc_commit(&mma_bar);  // implies tcgen05.fence::before_thread_sync
+        }
+        // ---- (3) everyone waits for the accumulators, then reads its row: columns 64*wg .. +63 of the three planes
+        mbar_wait(&mma_bar, (uint32_t) u & 1u);
+        tc_fence_after();
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+            const int c0 = wg * 64 + ch * 32;
+            const uint32_t taddr = tmem + ((uint32_t) (q * 32) << 16) + (uint32_t) c0;
+            int hi[32], lo[32], mm[32];
+            tc_ld32(taddr + 0 * TC_N, hi);
+            tc_ld32(taddr + 1 * TC_N, lo);
+            tc_ld32(taddr + 2 * TC_N, mm);
+            tc_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const float dx = dxs[c0 + i];
+                // the same fp32 expression as mmq_kernel (prefill.cu): acc += dx*d*isum - dx*dmin*msum
+                yacc[ch * 32 + i] += dx * d_r * (float) (8 * hi[i] + lo[i]) - dx * dmin_r * (float) mm[i];
+            }
+        }
+        tc_fence_before();
+        __syncthreads();  // TMEM accumulators and the smem tiles are free for the next super-block
+    }
+    // ---- store: y is column-major (ldy); this thread owns row `grow`, columns col_base + 64*wg .. +63
+    const int64_t r = (int64_t) blockIdx.y * TC_M + row;
+    if (r < p.m) {
+        const float b = p.bias ? p.bias[r] : 0.0f;
+#pragma unroll
+        for (int i = 0; i < 64; ++i) {
+            const int64_t c = col_base + wg * 64 + i;
+            if (c < p.n) p.y[c * p.ldy + r] = yacc[i] + b;
+        }
+    }
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t) TC_TMEM_COLS) : "memory");
+}
+
+bool mmq_tc_enabled() {
+    static const bool on = getenv("B200_MMQ_TCGEN05") && atoi(getenv("B200_MMQ_TCGEN05")) != 0;
+    return on;
+}
+
+// Q4_K only; same contract as mul_mat_q_batched (prefill.cu)
+int mul_mat_q_batched_tc(const void * W, int64_t k, int64_t m, const void * pact, int64_t n, float * y, int64_t ldy, const float * bias, size_t col_bytes,
+                         cudaStream_t st) {
+    if (k <= 0 || m <= 0 || n <= 0) return B200_OK;
+    if (k % 256) return B200_ERR_UNSUPPORTED;
+    TcParams p;
+    p.W = (const uint8_t *) W; p.pact = (const uint8_t *) pact; p.y = y; p.bias = bias;
+    p.k = k; p.m = m; p.n = n; p.ldy = ldy; p.nunits = (int) (k / 256); p.col_bytes = col_bytes;
+    const size_t smem = 4 * (size_t) TC_PLANE_BYTES + TC_N * sizeof(float);
+    static bool configured_dev[16] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!configured_dev[dev & 15]) {
+        cudaError_t e = cudaFuncSetAttribute(mmq_tc_q4k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        if (e != cudaSuccess) return (int) e;
+        configured_dev[dev & 15] = true;
+    }
+    dim3 grid((unsigned) ((n + TC_N - 1) / TC_N), (unsigned) ((m + TC_M - 1) / TC_M));
+    launch_pdl(mmq_tc_q4k_kernel, grid, dim3(256), smem, st, p);
+    return (int) cudaGetLastError();
+}
+
+}  // namespace b200

@@ -116,3 +116,27 @@ def test_session_fused2_matches_fused1_and_graph_replay(wtype):
     b.logits.zero_()
     g.replay(); torch.cuda.synchronize()
     assert torch.equal(lb, b.logits)
+
+
+@pytest.mark.parametrize("k,m,n", [(256, 128, 128), (1024, 130, 64), (4096, 300, 200), (4096, 4096, 512), (14336, 512, 130)])
+def test_tcgen05_prefill_equals_mma_sync(k, m, n):
+    """csrc/prefill_tc.cu (tcgen05.mma kind::i8, three exact int8 planes) must reproduce mmq_kernel (mma.sync) BIT FOR BIT: the int32
+    super-block sums are the same integers and the fp32 rescale is the same expression in the same order.  Run under a timeout: a wrong
+    descriptor can hang the MMA barrier."""
+    import torch
+    pkg, K = _setup()
+    rng = np.random.default_rng(k + m + n)
+    pool = qf.random_blocks(qf.Q4_K, min(m, 512), k, rng=rng)
+    w = pool[rng.integers(0, pool.shape[0], m)]
+    wd = K.upload_weights(qf.Q4_K, w, k, m)
+    x = rng.standard_normal((n, k)).astype(np.float32); x[rng.random((n, k)) < 1e-3] *= 20
+    xd = _t(x)
+    L = pkg.lib()
+    pq = torch.empty(L.b200_pact_col_bytes(qf.Q4_K, k) * n, dtype=torch.uint8, device="cuda")
+    assert L.b200_quantize_plain(qf.Q4_K, xd.data_ptr(), k, k, n, pq.data_ptr(), 0) == 0
+    bias = _t(rng.standard_normal(m).astype(np.float32))
+    y0 = torch.zeros((n, m), device="cuda"); y1 = torch.full((n, m), float("nan"), device="cuda")
+    assert L.b200_mul_mat_q_batched(qf.Q4_K, wd.data_ptr(), k, m, pq.data_ptr(), n, y0.data_ptr(), m, bias.data_ptr(), 0) == 0
+    assert L.b200_mul_mat_q_batched_tc(wd.data_ptr(), k, m, pq.data_ptr(), n, y1.data_ptr(), m, bias.data_ptr(), 0) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(y0, y1), float((y0 - y1).abs().max())

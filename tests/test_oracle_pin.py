@@ -236,3 +236,47 @@ def test_sparse_moe_block_vs_golden():
     assert np.abs(w[order] - GM["moe_w"].reshape(-1)).max() <= 1e-6
     assert np.abs(par[order] - GM["moe_par"][0]).max() <= 3e-5 * np.abs(GM["moe_par"]).max()
     assert np.abs(out - GM["moe_out"][0]).max() <= 5e-5 * np.abs(GM["moe_out"]).max()
+
+
+def test_q4k_scale_split_planes_are_exact():
+    """The algebra behind csrc/prefill_tc.cu: with sc = 8*hi + lo (hi, lo < 8) the three int8 planes hi*q, lo*q (<= 105) and m give the
+    reference's per-super-block integers exactly — 8*(A_hi.X) + (A_lo.X) == sum_j sc_j sum q x and (A_m.X) == sum_j m_j bsum_j — so the
+    tensor-core result, rescaled once per super-block, equals the oracle's mul_mat up to fp32 association."""
+    rng = np.random.default_rng(99)
+    k, m, n = 1024, 24, 5
+    w = qf.random_blocks(qf.Q4_K, m, k, rng=rng)
+    x = rng.standard_normal((n, k)).astype(np.float32); x[0, 5] = 30.0
+    # activation codes exactly as the reference quantizes them (Q8_K)
+    q8 = np.zeros((n, k // 256 * 292), dtype=np.uint8)
+    for r in range(n):
+        qf.port().oq_quantize_row_q8_K_ref(x[r].ctypes.data, q8[r].ctypes.data, k)
+    qb = q8.reshape(n, k // 256, 292)
+    dx = qb[:, :, 0:4].copy().view(np.float32).reshape(n, -1)
+    xc = qb[:, :, 4:260].view(np.int8).astype(np.int32)                                   # [n, nb, 256]
+    wb = w.reshape(m, k // 256, 144)
+    d = wb[:, :, 0:2].copy().view(np.float16).astype(np.float32).reshape(m, -1)
+    dmin = wb[:, :, 2:4].copy().view(np.float16).astype(np.float32).reshape(m, -1)
+    sc8 = wb[:, :, 4:16].astype(np.int32)                                                  # 12 scale bytes (get_scale_min_k4)
+    sc = np.zeros((m, k // 256, 8), dtype=np.int32); mn = np.zeros_like(sc)
+    for j in range(8):
+        if j < 4:
+            sc[:, :, j] = sc8[:, :, j] & 63; mn[:, :, j] = sc8[:, :, j + 4] & 63
+        else:
+            sc[:, :, j] = (sc8[:, :, j + 4] & 0xF) | ((sc8[:, :, j - 4] >> 6) << 4)
+            mn[:, :, j] = (sc8[:, :, j + 4] >> 4) | ((sc8[:, :, j] >> 6) << 4)
+    qs = wb[:, :, 16:].astype(np.int32).reshape(m, k // 256, 4, 32)
+    q = np.stack([qs & 0xF, qs >> 4], axis=3).reshape(m, k // 256, 8, 32)                 # sub-block j = (group j//2, nibble j%2)
+    hi, lo = sc >> 3, sc & 7
+    A_hi, A_lo = (hi[..., None] * q), (lo[..., None] * q)
+    assert A_hi.max() <= 105 and A_lo.max() <= 105 and mn.max() <= 63                      # all three planes fit int8
+    A_m = np.broadcast_to(mn[..., None], q.shape)
+    X = xc.reshape(n, k // 256, 8, 32)
+    g_hi = np.einsum("mbjk,nbjk->nmb", A_hi, X); g_lo = np.einsum("mbjk,nbjk->nmb", A_lo, X); g_m = np.einsum("mbjk,nbjk->nmb", A_m, X)
+    isum = np.einsum("mbj,nmbj->nmb", sc, np.einsum("mbjk,nbjk->nmbj", q, X))             # the reference's integers
+    msum = np.einsum("mbj,nbj->nmb", mn, X.sum(-1))
+    assert np.array_equal(8 * g_hi + g_lo, isum) and np.array_equal(g_m, msum)
+    y = np.zeros((n, m), dtype=np.float32)
+    for b in range(k // 256):
+        y += (dx[:, None, b] * d[None, :, b]) * (8 * g_hi + g_lo)[:, :, b].astype(np.float32) - (dx[:, None, b] * dmin[None, :, b]) * g_m[:, :, b].astype(np.float32)
+    ref = qf.port_mul_mat(qf.Q4_K, w, k, m, x)
+    assert np.abs(y - ref).max() <= 2e-5 * np.abs(ref).max()

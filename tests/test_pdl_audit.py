@@ -11,7 +11,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BUILD = os.path.join(ROOT, "chatllm.cpp_b200", "build")
-OBJS = ["fused.o", "gemv.o", "ops.o", "ops_generic.o", "quantize.o", "prefill.o"]
+OBJS = ["fused.o", "gemv.o", "ops.o", "ops_generic.o", "quantize.o", "prefill.o", "prefill_tc.o"]
 
 pytestmark = pytest.mark.skipif(not shutil.which("cuobjdump") or not all(os.path.exists(os.path.join(BUILD, o)) for o in OBJS),
                                 reason="needs the built kernel objects (python -c 'import __graft_entry__ as g; g.build()') and cuobjdump")

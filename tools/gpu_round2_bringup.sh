@@ -6,7 +6,9 @@ mkdir -p $OUT
 # 1. the default suite must still be green on this box
 ( timeout 300 python -m pytest tests -m gpu -x -q ) > $OUT/pytest_default.log 2>&1; echo "default: $(tail -1 $OUT/pytest_default.log)"
 # 2. opt-in fusion: kernels + session, then the same fusion inside the plugin over the whole plugin / e2e suites
-( B200_TEST_FUSED2=1 timeout 200 python -m pytest tests/test_fused2_optin.py -m gpu -q ) > $OUT/pytest_fused2.log 2>&1; echo "fused2 kernels/session: $(tail -1 $OUT/pytest_fused2.log)"
+( B200_TEST_FUSED2=1 timeout 200 python -m pytest tests/test_fused2_optin.py -m gpu -q -k "not tcgen05" ) > $OUT/pytest_fused2.log 2>&1; echo "fused2 kernels/session: $(tail -1 $OUT/pytest_fused2.log)"
+# 2b. tcgen05 prompt matmul: its own process and a short timeout (a wrong descriptor would hang on the MMA barrier), smallest case first
+( B200_TEST_FUSED2=1 timeout 60 python -m pytest tests/test_fused2_optin.py -m gpu -q -x -k tcgen05 ) > $OUT/pytest_tcgen05.log 2>&1; echo "tcgen05 prefill: rc=$? $(tail -1 $OUT/pytest_tcgen05.log)"
 ( B200_FUSE2=1 timeout 300 python -m pytest tests/test_plugin_ops.py tests/test_e2e_host.py -m gpu -q ) > $OUT/pytest_plugin_fuse2.log 2>&1; echo "plugin B200_FUSE2=1: $(tail -1 $OUT/pytest_plugin_fuse2.log)"
 grep -E "^(FAILED|ERROR)" $OUT/pytest_fused2.log $OUT/pytest_plugin_fuse2.log | head -20
 # 3. what it buys: device-resident step and e2e, default vs opt-in
