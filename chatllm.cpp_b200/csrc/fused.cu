@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "kernels.h"
 
+#include <cooperative_groups.h>
 #include <math.h>
 #include <stdlib.h>
 
@@ -818,6 +819,194 @@ __global__ void __launch_bounds__(HD * 2) attn_pv_split_kernel(const float * sco
     if (2 * t + 1 < GQA) { po[(int64_t) (2 * t + 1) * HD + g] = c[1]; po[(int64_t) (2 * t + 1) * HD + g + 8] = c[3]; }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Cluster V.P (OPT-IN, B200_ATTN_CLUSTER=1; written at the end of round 1, not yet run on a GPU).  The position splits of one KV group
+// form a THREAD-BLOCK CLUSTER (up to 16 CTAs, non-portable size allowed on sm_100): each CTA multiplies its 512-position slab of V with
+// its slice of P exactly like attn_pv_split_kernel (16 warps: two 256-position rounds side by side, every V load in flight at once),
+// leaves its fp32 partial [GQA][HD] in its own shared memory, and after a cluster barrier rank 0 sums the partials of all ranks IN RANK
+// ORDER through distributed shared memory, writes the group's slice of the attention output and — because a KV group owns whole
+// 256-element (Q8_K) / 32-element (Q8_0) quantization blocks of that vector (GQA*HD % 256 == 0) — also its slice of the o-projection's
+// quantized activations.  The single-CTA summing/quantizing tail launch (3.4 us of the 55 us layer) disappears: attention = 2 launches.
+// Requires GQA * HD % 256 == 0 and n_kv <= 16 * 512 (longer contexts keep the scratch-partial path).
+// ------------------------------------------------------------------------------------------------------------------
+#define B200_PVC_SPAN 512
+template <int HD, int GQA, bool Q8K>
+__global__ void __launch_bounds__(HD * 4) attn_pv_cluster_kernel(const float * scores, const float2 * part, const __half * vc, float * out, uint8_t * qact,
+                                                                 int n_kv, int64_t v_row_stride, int64_t s_stride, int nchunks, int n_heads, int preload) {
+    namespace cg = cooperative_groups;
+    constexpr int NT = HD * 4;        // 2 rounds x HD/16 channel warps x 32
+    constexpr int NWC = HD / 16;      // channel warps per round
+    constexpr int SP = B200_PVC_SPAN + 32;  // row stride in halves: 64 bytes past a multiple of 128 -> conflict-free 16-byte B loads
+    constexpr int NE = GQA * HD;      // outputs of this KV group
+    static_assert(NE % 256 == 0, "a KV group must own whole quantization blocks");
+    __shared__ __align__(16) __half Ph[8 * SP];
+    __shared__ __align__(16) float part_s[NE];   // this CTA's partial [head][channel]; read by rank 0 through DSMEM
+    __shared__ float hmax[8], hinv[8];
+    __shared__ unsigned long long wkey[NT / 32];
+    __shared__ float bmaxs[NE / 256];
+    cg::cluster_group cluster = cg::this_cluster();
+    pdl_launch_dependents();
+    const int grp = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int rnd = warp / NWC, cw = warp % NWC;  // which 256-position round of the slab, which 16 channels
+    const int p_begin = blockIdx.x * B200_PVC_SPAN;
+    const int p_end = min(n_kv, p_begin + B200_PVC_SPAN);
+    for (int i = threadIdx.x; i < (8 - GQA) * SP / 2; i += NT) reinterpret_cast<uint32_t *>(Ph + GQA * SP)[i] = 0u;
+
+    const int c0 = cw * 16;
+    const __half * rowA = vc + (int64_t) (grp * HD + c0 + g) * v_row_stride;
+    const __half * rowB = rowA + 8 * v_row_stride;
+    auto ldv = [&](const __half * row, int p0) -> uint4 {
+        if (p0 >= p_end) return make_uint4(0, 0, 0, 0);
+        uint4 v = *reinterpret_cast<const uint4 *>(row + p0);
+        const int r = p_end - p0;
+        if (r < 8) {
+            uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) w[j] = (2 * j + 1 < r) ? w[j] : ((2 * j < r) ? (w[j] & 0xffffu) : 0u);
+            v = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        return v;
+    };
+    uint4 alo[2][4], ahi[2][4];
+    const int pr = p_begin + rnd * 256;  // this warp's 256 positions
+    auto load_round = [&]() {
+#pragma unroll
+        for (int s2 = 0; s2 < 2; ++s2)
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                alo[s2][u] = ldv(rowA, pr + s2 * 128 + 8 * t + 32 * u);
+                ahi[s2][u] = ldv(rowB, pr + s2 * 128 + 8 * t + 32 * u);
+            }
+    };
+    const bool early = preload && p_end < n_kv;  // only the last slab can hold the newest position (see attn_pv_split_kernel)
+    if (early) load_round();
+    pdl_wait();
+    if (!early) load_round();
+    for (int h = warp; h < GQA; h += NT / 32) {
+        const float2 * pp = part + (int64_t) (grp * GQA + h) * nchunks;
+        float mx = -INFINITY;
+        for (int i = lane; i < nchunks; i += 32) mx = fmaxf(mx, pp[i].x);
+        mx = warp_max(mx);
+        float sum = 0.0f;
+        for (int i = lane; i < nchunks; i += 32) { const float2 pv = pp[i]; sum += pv.y * expf(pv.x - mx); }
+        sum = warp_sum(sum);
+        if (lane == 0) { hmax[h] = mx; hinv[h] = 1.0f / sum; }
+    }
+    __syncthreads();
+    // ---- P of the slab: Ph[h][i] = f16(exp(s - max_h) * inv_h), zero beyond n_kv  (same expression as attn_pv_split_kernel)
+    for (int i = threadIdx.x; i < B200_PVC_SPAN; i += NT) {
+        const int pp0 = p_begin + i;
+#pragma unroll
+        for (int h = 0; h < GQA; ++h) {
+            const float e = (pp0 < p_end) ? __expf(scores[(int64_t) (grp * GQA + h) * s_stride + pp0] - hmax[h]) * hinv[h] : 0.0f;
+            Ph[h * SP + i] = __float2half_rn(e);
+        }
+    }
+    __syncthreads();
+    float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int s2 = 0; s2 < 2; ++s2) {
+        if (pr + s2 * 128 < p_end) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint4 b = *reinterpret_cast<const uint4 *>(Ph + g * SP + rnd * 256 + s2 * 128 + 8 * t + 32 * u);
+                mma16816(c, alo[s2][u].x, ahi[s2][u].x, alo[s2][u].y, ahi[s2][u].y, b.x, b.y);
+                mma16816(c, alo[s2][u].z, ahi[s2][u].z, alo[s2][u].w, ahi[s2][u].w, b.z, b.w);
+            }
+        }
+    }
+    // ---- CTA partial: round 1 deposits, round 0 adds.  c0 = (ch g, head 2t), c1 = (ch g, head 2t+1), c2 = (ch g+8, head 2t), c3 = (ch g+8, head 2t+1)
+    float * pw = part_s + c0;
+    if (rnd == 1) {
+        if (2 * t < GQA) { pw[(2 * t) * HD + g] = c[0]; pw[(2 * t) * HD + g + 8] = c[2]; }
+        if (2 * t + 1 < GQA) { pw[(2 * t + 1) * HD + g] = c[1]; pw[(2 * t + 1) * HD + g + 8] = c[3]; }
+    }
+    __syncthreads();
+    if (rnd == 0) {
+        if (2 * t < GQA) { pw[(2 * t) * HD + g] += c[0]; pw[(2 * t) * HD + g + 8] += c[2]; }
+        if (2 * t + 1 < GQA) { pw[(2 * t + 1) * HD + g] += c[1]; pw[(2 * t + 1) * HD + g + 8] += c[3]; }
+    }
+    cluster.sync();   // every rank's partial is complete and visible cluster-wide
+    if (cluster.block_rank() == 0) {
+        const unsigned nr = cluster.num_blocks();
+        const ActLayout L = act_layout(Q8K, (int64_t) n_heads * HD);
+        const int64_t ebase = (int64_t) grp * NE;   // first element of this group in the [n_heads * HD] output vector
+        for (int e0 = 0; e0 < NE; e0 += NT) {        // NT == NE for GQA = 4 (one pass); the barriers below are uniform
+            const int e = e0 + threadIdx.x;
+            const bool on = e < NE;
+            float v = 0.0f;
+            if (on) {
+                for (unsigned r = 0; r < nr; ++r) v += cluster.map_shared_rank(part_s, r)[e];   // rank order: deterministic
+                out[ebase + e] = v;
+            }
+            if (qact == nullptr) continue;
+            if (Q8K) {
+                // quantize_row_q8_K_ref (ggml-quants.c:2555-2592) as quantize_q8_K_kernel: 256 consecutive threads = one block
+                unsigned long long key = on ? (((unsigned long long) __float_as_uint(fabsf(v)) << 32) | (unsigned) (255 - (e & 255))) : 0ull;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+                    key = other > key ? other : key;
+                }
+                __syncthreads();
+                if (lane == 0) wkey[warp] = key;
+                __syncthreads();
+                const int b8 = (threadIdx.x >> 8) * 8;  // first warp of this thread's 256-element block
+                unsigned long long kk = wkey[b8];
+#pragma unroll
+                for (int w = 1; w < 8; ++w) kk = wkey[b8 + w] > kk ? wkey[b8 + w] : kk;
+                const int idx = 255 - (int) (kk & 0xffffffffu);
+                if (on && (e & 255) == idx) bmaxs[e >> 8] = v;
+                __syncthreads();
+                if (on) {
+                    const float mx = bmaxs[e >> 8];
+                    int qv = 0;
+                    float dd = 0.0f;
+                    if (mx != 0.0f) {
+                        const float iscale = __fdiv_rn(-127.f, mx);
+                        qv = min(127, __float2int_rn(__fmul_rn(iscale, v)));
+                        dd = __fdiv_rn(1.0f, iscale);
+                    }
+                    const int64_t ge = ebase + e;
+                    reinterpret_cast<int8_t *>(qact)[act_qs_off_q8k(ge)] = (int8_t) qv;
+                    int sq = qv;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+                    if (lane == 0) reinterpret_cast<int16_t *>(qact + L.bs_off)[ge >> 5] = (int16_t) sq;
+                    if ((e & 255) == 0) reinterpret_cast<float *>(qact + L.d_off)[ge >> 8] = dd;
+                }
+            } else {
+                // x86 quantize_row_q8_0 (arch/x86/quants.c:290-384) as add_rmsnorm_quant_kernel: one warp = one 32-element block
+                float amax = on ? fabsf(v) : 0.0f;
+                amax = warp_max(amax);
+                const float dv = __fdiv_rn(amax, 127.f);
+                const float id = (amax != 0.0f) ? __fdiv_rn(127.f, amax) : 0.0f;
+                const int qv = __float2int_rn(__fmul_rn(v, id));
+                int sq = qv;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+                if (on) {
+                    const int64_t ge = ebase + e;
+                    reinterpret_cast<int8_t *>(qact)[act_qs_off_q80(ge)] = (int8_t) qv;
+                    if (lane == 0) {
+                        reinterpret_cast<float *>(qact + L.d_off)[ge >> 5] = __half2float(__float2half_rn(dv));
+                        reinterpret_cast<int *>(qact + L.bs_off)[ge >> 5] = sq;
+                    }
+                }
+            }
+        }
+        // the last group also zeroes the padding of the code area (k not a multiple of 1024) so the GEMV can read it blindly
+        if (qact != nullptr && Q8K && grp == (int) gridDim.y - 1) {
+            const int64_t k = (int64_t) n_heads * HD;
+            for (int64_t e = k + threadIdx.x; e < L.qs_bytes; e += NT) reinterpret_cast<int8_t *>(qact)[act_qs_off_q8k(e)] = 0;
+        }
+    }
+    cluster.sync();   // no rank may exit while rank 0 is still reading its shared memory
+}
+
 // positions per CTA of the split V.P kernel: 256 up to 8K context (<= 32 splits), then grown in steps of 256
 static int pv_span(int n_kv) {
     int span = B200_PVS_ROUND;
@@ -838,6 +1027,38 @@ static int attn_decode_mma_t(const float * q, const void * kc, const void * vc, 
                k_row_stride, scale, s_stride, nchunks, preload);
     static const int old_pv = getenv("B200_ATTN_OLD_PV") ? atoi(getenv("B200_ATTN_OLD_PV")) : 0;  // A/B aid: the channel-split kernel
     const int n_heads = kv_heads * GQA;
+    if constexpr ((GQA * HD) % 256 == 0) {
+        static const int use_cluster = getenv("B200_ATTN_CLUSTER") ? atoi(getenv("B200_ATTN_CLUSTER")) : 0;  // OPT-IN (unmeasured): cluster V.P, no tail launch
+        const int nsplit_c = (n_kv + B200_PVC_SPAN - 1) / B200_PVC_SPAN;
+        const bool q8k = wtype == B200_TYPE_Q4_K;
+        if (use_cluster && nsplit_c <= 16 && (!qact || q8k || wtype == B200_TYPE_Q4_0 || wtype == B200_TYPE_Q8_0)) {
+            auto kern = q8k ? attn_pv_cluster_kernel<HD, GQA, true> : attn_pv_cluster_kernel<HD, GQA, false>;
+            static bool nonportable_dev[16] = {false};
+            int dev = 0;
+            cudaGetDevice(&dev);
+            if (nsplit_c > 8 && !nonportable_dev[dev & 15]) {  // clusters of 9..16 CTAs need the opt-in attribute (both quantizer variants)
+                cudaError_t e = cudaFuncSetAttribute(attn_pv_cluster_kernel<HD, GQA, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+                if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_pv_cluster_kernel<HD, GQA, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+                if (e != cudaSuccess) return (int) e;
+                nonportable_dev[dev & 15] = true;
+            }
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned) nsplit_c, (unsigned) kv_heads);
+            cfg.blockDim = dim3(HD * 4);
+            cfg.dynamicSmemBytes = 0;
+            cfg.stream = st;
+            cudaLaunchAttribute attr[2];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = (unsigned) nsplit_c; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[1].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = pdl_enabled() ? 2 : 1;
+            cudaError_t e = cudaLaunchKernelEx(&cfg, kern, (const float *) scratch, (const float2 *) part, (const __half *) vc, out, (uint8_t *) qact, n_kv, v_row_stride,
+                                               s_stride, nchunks, n_heads, preload);
+            return (int) e;
+        }
+    }
     if (!old_pv && ((int64_t) n_heads * HD) % 256 == 0 && (int64_t) n_heads * HD <= 20480) {
         const int span = pv_span(n_kv);
         const int nsplit = (n_kv + span - 1) / span;

@@ -143,3 +143,55 @@ def test_tcgen05_prefill_equals_mma_sync(k, m, n):
     print("tcgen05 vs mma.sync bit-identical:", bool(torch.equal(y0, y1)), "max abs diff", float((y0 - y1).abs().max()))
     assert torch.isfinite(y1).all()
     assert float((y0 - y1).abs().max()) <= 2e-6 * float(y0.abs().max())
+
+
+@pytest.mark.parametrize("wtype", [qf.Q4_K, qf.Q4_0])
+@pytest.mark.parametrize("heads,kvh,hd,n_kv", [(32, 8, 128, 4097), (32, 8, 128, 300), (32, 8, 128, 8192), (32, 4, 64, 777), (8, 2, 64, 1500)])
+def test_cluster_pv_equals_split_pv(wtype, heads, kvh, hd, n_kv):
+    """B200_ATTN_CLUSTER=1 (thread-block-cluster V.P with DSMEM reduction and in-cluster quantization, no tail launch) against the default
+    three-launch attention: same P, same products; only the order in which the position slabs are summed differs (512- instead of
+    256-position slabs) -> outputs within 1e-6 of the output scale, quantized codes equal except where a value sits on a rounding tie.
+    The flag is read once per process: run as  B200_ATTN_CLUSTER=1 B200_TEST_FUSED2=1 pytest -k cluster_pv  (the reference result is
+    produced by a child process without the flag)."""
+    import subprocess, sys, json, tempfile, torch
+    if not os.environ.get("B200_ATTN_CLUSTER"):
+        pytest.skip("set B200_ATTN_CLUSTER=1 for this process")
+    pkg, K = _setup()
+    code = f"""
+import os, sys, numpy as np, torch
+os.environ.pop('B200_ATTN_CLUSTER', None)
+sys.path.insert(0, {os.path.dirname(os.path.abspath(__file__))!r}); sys.path.insert(0, {os.path.dirname(os.path.dirname(os.path.abspath(__file__)))!r})
+import test_fused2_optin as T
+np.save(sys.argv[1], T.run_attn_quant({wtype}, {heads}, {kvh}, {hd}, {n_kv}))
+"""
+    with tempfile.TemporaryDirectory() as d:
+        ref_path = os.path.join(d, "ref.npy")
+        env = {k: v for k, v in os.environ.items() if k != "B200_ATTN_CLUSTER"}
+        subprocess.run([sys.executable, "-c", code, ref_path], check=True, env=env, timeout=120)
+        ref = np.load(ref_path)
+    got = run_attn_quant(wtype, heads, kvh, hd, n_kv)
+    k = heads * hd
+    assert np.abs(got[:k] - ref[:k]).max() <= 1e-6 * np.abs(ref[:k]).max()
+    assert (got[k:] != ref[k:]).mean() <= 2e-3   # quantized codes / scales / sums (as floats): ties only
+
+
+def run_attn_quant(wtype, heads, kvh, hd, n_kv):
+    """attention output (k floats) followed by the decoded qact (codes, scales, block sums) as one float array"""
+    import torch
+    import test_gpu_kernels as TG
+    pkg, K = _setup()
+    rng = np.random.default_rng(n_kv + heads + wtype)
+    max_len = ((n_kv + 255) // 256) * 256 + 256
+    kv_hidden = kvh * hd
+    kd = _t(rng.standard_normal((max_len, kv_hidden)).astype(np.float16))
+    vd = _t(rng.standard_normal((kv_hidden, max_len)).astype(np.float16))
+    qd = _t(rng.standard_normal((heads, hd)).astype(np.float32) * 2)
+    L = pkg.lib()
+    scratch = torch.empty(L.b200_attn_decode_scratch_bytes(heads, max_len) // 4 + 16, dtype=torch.float32, device="cuda")
+    out = torch.zeros((1, heads * hd), device="cuda")
+    q = torch.zeros(L.b200_qact_col_bytes(wtype, heads * hd), dtype=torch.uint8, device="cuda")
+    assert L.b200_attn_decode_quant(qd.data_ptr(), kd.data_ptr(), vd.data_ptr(), out.data_ptr(), scratch.data_ptr(), heads, kvh, hd, n_kv, kv_hidden,
+                                    max_len, 1.0 / np.sqrt(hd), wtype, q.data_ptr(), 0) == 0
+    torch.cuda.synchronize()
+    qs, d, bs = TG._decode_qact(q.cpu().numpy()[None, :], wtype, heads * hd)
+    return np.concatenate([out.cpu().numpy().reshape(-1), qs.astype(np.float32).reshape(-1), d.reshape(-1), bs.astype(np.float32).reshape(-1)])

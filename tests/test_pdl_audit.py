@@ -40,7 +40,7 @@ def test_no_producer_load_is_hoisted_above_the_pdl_wait(obj):
         if "gemv_q_kernel" in name:
             # weights only, and only through the bulk-copy engine; activations (plain LDG) come after the wait
             assert all("UBLKCP" in t for t in before) and not between, (name, before, between)
-        elif "attn_pv_split_kernel" in name:
+        elif "attn_pv_split_kernel" in name or "attn_pv_cluster_kernel" in name:
             # one round of V fragments (2 k-groups x 4 chunks x 2 rows) for the splits that do not hold the newest position
             assert len(before) <= 16 and all("LDG.E.128" in t for t in before) and not between, (name, before, between)
         elif "attn_scores_mma_kernel" in name:

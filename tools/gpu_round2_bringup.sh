@@ -10,7 +10,10 @@ mkdir -p $OUT
 # 2b. tcgen05 prompt matmul: its own process and a short timeout (a wrong descriptor would hang on the MMA barrier), smallest case first
 ( B200_TEST_FUSED2=1 timeout 60 python -m pytest tests/test_fused2_optin.py -m gpu -q -x -k tcgen05 ) > $OUT/pytest_tcgen05.log 2>&1; echo "tcgen05 prefill: rc=$? $(tail -1 $OUT/pytest_tcgen05.log)"
 ( B200_FUSE2=1 timeout 300 python -m pytest tests/test_plugin_ops.py tests/test_e2e_host.py -m gpu -q ) > $OUT/pytest_plugin_fuse2.log 2>&1; echo "plugin B200_FUSE2=1: $(tail -1 $OUT/pytest_plugin_fuse2.log)"
-grep -E "^(FAILED|ERROR)" $OUT/pytest_fused2.log $OUT/pytest_plugin_fuse2.log | head -20
+# 2c. cluster V.P (DSMEM reduction + in-cluster quantization, attention = 2 launches)
+( B200_ATTN_CLUSTER=1 B200_TEST_FUSED2=1 timeout 200 python -m pytest tests/test_fused2_optin.py tests/test_gpu_kernels.py tests/test_session.py -m gpu -q -k "cluster_pv or attn or graph_replay or decode_steps" ) > $OUT/pytest_cluster.log 2>&1; echo "cluster V.P: $(tail -1 $OUT/pytest_cluster.log)"
+B200_ATTN_CLUSTER=1 timeout 100 python tools/step_breakdown.py 2>&1 | grep attn
+grep -E "^(FAILED|ERROR)" $OUT/pytest_fused2.log $OUT/pytest_cluster.log $OUT/pytest_tcgen05.log $OUT/pytest_plugin_fuse2.log | head -20
 # 3. what it buys: device-resident step and e2e, default vs opt-in
 python bench.py --no-e2e --no-cpu > $OUT/bench_default.json 2>> $OUT/bench.err; python bench.py --no-e2e --no-cpu --fused2 > $OUT/bench_fused2.json 2>> $OUT/bench.err
 python - <<'PY'
