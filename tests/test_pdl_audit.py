@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BUILD = os.path.join(ROOT, "chatllm.cpp_b200", "build")
 OBJS = ["fused.o", "gemv.o", "ops.o", "ops_generic.o", "quantize.o", "prefill.o", "prefill_tc.o"]
 
-pytestmark = pytest.mark.skipif(not shutil.which("cuobjdump") or not all(os.path.exists(os.path.join(BUILD, o)) for o in OBJS),
+needs_objs = pytest.mark.skipif(not shutil.which("cuobjdump") or not all(os.path.exists(os.path.join(BUILD, o)) for o in OBJS),
                                 reason="needs the built kernel objects (python -c 'import __graft_entry__ as g; g.build()') and cuobjdump")
 
 LOAD = re.compile(r"\b(LDG|LD\.E|UBLKCP|LDGSTS)")
@@ -27,6 +27,7 @@ def kernels(obj):
         yield name, ins
 
 
+@needs_objs
 @pytest.mark.parametrize("obj", OBJS)
 def test_no_producer_load_is_hoisted_above_the_pdl_wait(obj):
     checked = 0
@@ -50,3 +51,22 @@ def test_no_producer_load_is_hoisted_above_the_pdl_wait(obj):
             assert not before and not between, (name, before, between)
     if obj in ("fused.o", "gemv.o"):
         assert checked > 0
+
+
+def test_tcgen05_smem_layout_matches_the_cute_canonical_layout(tmp_path):
+    """csrc/prefill_tc.cu writes its operand tiles with tc_off() and encodes LBO = 2048 / SBO = 128 by hand.  tools/cute_layout_check.cu
+    (host code, compiled against the CUTLASS/CuTe headers vendored in the image) checks both against CuTe's own canonical UMMA K-major
+    no-swizzle layout and against what cute::UMMA::make_umma_desc would derive for it."""
+    import glob
+    inc = glob.glob("/opt/prime-rl/.venv/lib/python*/site-packages/flashinfer/data/cutlass/include")
+    if not inc or not shutil.which("nvcc"):
+        pytest.skip("needs nvcc and the vendored CUTLASS headers")
+    exe = str(tmp_path / "layout_check")
+    subprocess.run(["nvcc", "-std=c++17", "-I" + inc[0], "-o", exe, os.path.join(ROOT, "tools", "cute_layout_check.cu")], check=True, capture_output=True)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
+    assert "mismatches: 0" in out
+    assert "SBO (uint128 units) = 8 " in out and "LBO (uint128 units) = 128 " in out
+    assert "offset of (row 0, k 32) = 4096 bytes" in out
+    tiled = [l for l in out.splitlines() if l.startswith("tiled")][0].split(" o ")[-1]
+    mine = [l for l in out.splitlines() if l.startswith("mine")][0].split(": ")[-1]
+    assert tiled.strip() == mine.strip(), (tiled, mine)

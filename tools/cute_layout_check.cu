@@ -1,0 +1,41 @@
+// Host-side check of csrc/prefill_tc.cu's shared-memory layout against CuTe's canonical UMMA K-major no-swizzle (INTERLEAVE) layout
+// and of the LBO / SBO values make_umma_desc would derive for it.
+#include <cstdio>
+#include <cute/tensor.hpp>
+#include <cute/atom/mma_traits_sm90_gmma.hpp>
+using namespace cute;
+
+static unsigned tc_off(int i, int c) { return (unsigned) ((c * (128 / 8) + (i >> 3)) * 128 + (i & 7) * 16); }
+
+int main() {
+    // canonical atom for int8, K-major, no swizzle: 8 rows x 16 bytes
+    auto atom = GMMA::Layout_K_INTER_Atom<int8_t>{};
+    print("atom  : "); print(atom); print("\n");
+    // our tile: 128 rows x 256 K-bytes, stored as [K chunk of 16 B][row group of 8][8 rows][16 B]
+    // build it explicitly as a CuTe layout: (row, k) -> byte offset
+    auto mine = make_layout(make_shape(make_shape(Int<8>{}, Int<16>{}), make_shape(Int<16>{}, Int<16>{})),
+                            make_stride(make_stride(Int<16>{}, Int<128>{}), make_stride(Int<1>{}, Int<2048>{})));
+    print("mine  : "); print(mine); print("\n");
+    int bad = 0;
+    for (int r = 0; r < 128; ++r)
+        for (int k = 0; k < 256; ++k) {
+            unsigned want = tc_off(r, k / 16) + (k % 16);
+            unsigned got = (unsigned) mine(r, k);
+            if (want != got) { if (bad < 5) printf("mismatch r=%d k=%d want=%u got=%u\n", r, k, want, got); ++bad; }
+        }
+    printf("tc_off vs explicit layout mismatches: %d\n", bad);
+    // what make_umma_desc<Major::K> reads off such a tensor (mma_traits_sm100.hpp): in uint128 units
+    auto u128 = recast_layout<int8_t, uint128_t>(mine);   // (128, 16) in 16-byte units
+    print("u128  : "); print(u128); print("\n");
+    auto canonical = logical_divide(u128, Tile<Layout<_8, _1>, Layout<_2, _1>>{});
+    print("canon : "); print(canonical); print("\n");
+    printf("stride<0,0> (rows inside a core matrix, must be 1 for SWIZZLE_NONE... SwizzleAtomMNSize=1) = %d\n", (int) stride<0, 0>(canonical));
+    printf("stride<0,1> -> SBO (uint128 units) = %d  => %d bytes\n", (int) stride<0, 1>(canonical), 16 * (int) stride<0, 1>(canonical));
+    printf("stride<1,0> -> LBO (uint128 units) = %d  => %d bytes\n", (int) stride<1, 0>(canonical), 16 * (int) stride<1, 0>(canonical));
+    // the k-step advance used by the kernel: descriptor start moves by 2 K-chunks = 2 * 2048 bytes per K = 32
+    printf("offset of (row 0, k 32) = %d bytes (kernel: s * 2 * TC_LBO with TC_LBO = 2048)\n", (int) mine(0, 32));
+    // compare with tiling the canonical atom to the same shape
+    auto tiled = tile_to_shape(atom, make_shape(Int<128>{}, Int<256>{}));
+    print("tiled : "); print(tiled); print("\n");
+    return 0;
+}
