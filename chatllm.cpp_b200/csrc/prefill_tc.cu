@@ -22,17 +22,11 @@
 //   threads wait, tcgen05.ld their row's 64 columns of the three accumulators, rescale into 64 fp32 registers.  No overlap yet.
 #include "common.cuh"
 #include "kernels.h"
+#include "prefill_tc_desc.h"
 
 #include <cstdlib>
 
 namespace b200 {
-
-#define TC_M 128
-#define TC_N 128
-#define TC_PLANE_BYTES (TC_M * 256)  // one 128 x 256-byte int8 tile
-#define TC_LBO 2048u                 // bytes between the two 16-byte K chunks of a core-matrix column: (TC_M / 8) core matrices of 128 bytes
-#define TC_SBO 128u                  // bytes between consecutive 8-row groups
-#define TC_TMEM_COLS 512             // 3 accumulators x 128 columns -> next power of two
 
 __host__ __device__ inline int64_t tc_al16(int64_t x) { return (x + 15) & ~(int64_t) 15; }
 
@@ -45,15 +39,6 @@ struct TcParams {
     int nunits;
     size_t col_bytes;
 };
-
-// shared-memory matrix descriptor, no swizzle, K-major (mma_sm100_desc.hpp SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
-// SBO>>4 [32,46), version = 1 [46,48), base_offset = 0, lbo_mode = 0, layout_type = SWIZZLE_NONE (0) [61,64)
-__device__ __forceinline__ uint64_t tc_desc(uint32_t saddr) {
-    return (uint64_t) ((saddr >> 4) & 0x3fffu) | ((uint64_t) ((TC_LBO >> 4) & 0x3fffu) << 16) | ((uint64_t) ((TC_SBO >> 4) & 0x3fffu) << 32) | ((uint64_t) 1 << 46);
-}
-// instruction descriptor (mma_sm100_desc.hpp InstrDescriptor): c_format S32 (2) [4,6), a_format / b_format signed 8 bit (1) [7,10) / [10,13),
-// K-major A and B, n_dim = N >> 3 [17,23), m_dim = M >> 4 [24,29)
-#define TC_IDESC ((2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t) (TC_N >> 3) << 17) | ((uint32_t) (TC_M >> 4) << 24))
 
 __device__ __forceinline__ void tc_mma_i8(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t accumulate) {
     asm volatile(
@@ -82,9 +67,6 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, int (&r)[32]) {
         : "r"(taddr));
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// byte offset of (row-or-column i, 16-byte K chunk c) inside a 128 x 256-byte tile in the canonical no-swizzle K-major layout
-__device__ __forceinline__ uint32_t tc_off(int i, int c) { return (uint32_t) ((c * (TC_M / 8) + (i >> 3)) * 128 + (i & 7) * 16); }
 
 __global__ void __launch_bounds__(256, 1) mmq_tc_q4k_kernel(const TcParams p) {
     extern __shared__ __align__(128) uint8_t sm[];

@@ -3,9 +3,9 @@
 #include <cstdio>
 #include <cute/tensor.hpp>
 #include <cute/atom/mma_traits_sm90_gmma.hpp>
+#include <cute/arch/mma_sm100_desc.hpp>
+#include "../chatllm.cpp_b200/csrc/prefill_tc_desc.h"   // tc_off, tc_desc, TC_IDESC: exactly what the kernel uses
 using namespace cute;
-
-static unsigned tc_off(int i, int c) { return (unsigned) ((c * (128 / 8) + (i >> 3)) * 128 + (i & 7) * 16); }
 
 int main() {
     // canonical atom for int8, K-major, no swizzle: 8 rows x 16 bytes
@@ -37,5 +37,14 @@ int main() {
     // compare with tiling the canonical atom to the same shape
     auto tiled = tile_to_shape(atom, make_shape(Int<128>{}, Int<256>{}));
     print("tiled : "); print(tiled); print("\n");
+    // descriptor encodings against CuTe's own bit-field unions
+    UMMA::SmemDescriptor sd;
+    sd.version_ = 1; sd.lbo_mode_ = 0; sd.layout_type_ = uint8_t(UMMA::LayoutType::SWIZZLE_NONE); sd.base_offset_ = 0;
+    const uint32_t saddr = 0x12340u;   // some 16-byte aligned shared-memory address
+    sd.start_address_ = uint16_t(saddr >> 4); sd.stride_byte_offset_ = 8; sd.leading_byte_offset_ = 128;
+    printf("smem descriptor  cute=%016llx  kernel=%016llx  %s\n", (unsigned long long) uint64_t(sd), (unsigned long long) tc_desc(saddr),
+           uint64_t(sd) == tc_desc(saddr) ? "EQUAL" : "DIFFERENT");
+    auto id = UMMA::make_instr_desc<int8_t, int8_t, int32_t, 128, 128, UMMA::Major::K, UMMA::Major::K>();
+    printf("instr descriptor cute=%08x  kernel=%08x  %s\n", uint32_t(id), (uint32_t) TC_IDESC, uint32_t(id) == (uint32_t) TC_IDESC ? "EQUAL" : "DIFFERENT");
     return 0;
 }
