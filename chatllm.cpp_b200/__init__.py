@@ -59,7 +59,7 @@ def lib():
         L.b200_pact_col_bytes.argtypes = [i32, i64]; L.b200_pact_col_bytes.restype = C.c_size_t
         L.b200_quantize_plain.argtypes = [i32, vp, i64, i64, i64, vp, vp]
         L.b200_mul_mat_q_batched.argtypes = [i32, vp, i64, i64, vp, i64, vp, i64, vp, vp]
-        L.b200_mul_mat_q_batched_tc.argtypes = [vp, i64, i64, vp, i64, vp, i64, vp, vp]
+        L.b200_mul_mat_q_batched_tc.argtypes = [i32, vp, i64, i64, vp, i64, vp, i64, vp, vp]
         _lib = L
     return _lib
 

@@ -79,8 +79,9 @@ int b200_mul_mat_q_batched(int wtype, const void * W, int64_t k, int64_t m, cons
     return mul_mat_q_batched(wtype, W, k, m, pact, n, y, ldy, bias, (cudaStream_t) stream);
 }
 
-int b200_mul_mat_q_batched_tc(const void * W, int64_t k, int64_t m, const void * pact, int64_t n, float * y, int64_t ldy, const float * bias, void * stream) {
-    return mul_mat_q_batched_tc(W, k, m, pact, n, y, ldy, bias, pact_col_bytes(B200_TYPE_Q4_K, k), (cudaStream_t) stream);
+int b200_mul_mat_q_batched_tc(int wtype, const void * W, int64_t k, int64_t m, const void * pact, int64_t n, float * y, int64_t ldy, const float * bias,
+                              void * stream) {
+    return mul_mat_q_batched_tc(wtype, W, k, m, pact, n, y, ldy, bias, pact_col_bytes(wtype, k), (cudaStream_t) stream);
 }
 
 int b200_gemv_set_tuning(int ks, int stages, int warps, int rg, int grid) {

@@ -43,8 +43,8 @@ int mul_mat_q_batched(int wtype, const void * W, int64_t k, int64_t m, const voi
 
 // ---- prefill_tc.cu: OPT-IN (B200_MMQ_TCGEN05=1) tcgen05.mma kind::i8 version of the Q4_K prompt matmul, bit-identical to mmq_kernel by construction
 bool mmq_tc_enabled();
-int mul_mat_q_batched_tc(const void * W, int64_t k, int64_t m, const void * pact, int64_t n, float * y, int64_t ldy, const float * bias, size_t col_bytes,
-                         cudaStream_t st);
+int mul_mat_q_batched_tc(int wtype, const void * W, int64_t k, int64_t m, const void * pact, int64_t n, float * y, int64_t ldy, const float * bias,
+                         size_t col_bytes, cudaStream_t st);
 
 // ---- ops.cu
 int rms_norm_mul(const float * x, const float * w, float * y, int64_t ne0, int64_t nrows, float eps, cudaStream_t st);

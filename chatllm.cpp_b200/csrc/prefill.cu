@@ -299,7 +299,7 @@ int mul_mat_q_batched(int wtype, const void * W, int64_t k, int64_t m, const voi
     MmqParams p;
     p.W = (const uint8_t *) W; p.pact = (const uint8_t *) pact; p.y = y; p.bias = bias;
     p.k = k; p.m = m; p.n = n; p.ldy = ldy; p.nunits = (int) (k / 256); p.col_bytes = pact_col_bytes(wtype, k);
-    if (wtype == B200_TYPE_Q4_K && n >= 64 && mmq_tc_enabled()) return mul_mat_q_batched_tc(W, k, m, pact, n, y, ldy, bias, p.col_bytes, st);
+    if (n >= 64 && mmq_tc_enabled()) return mul_mat_q_batched_tc(wtype, W, k, m, pact, n, y, ldy, bias, p.col_bytes, st);
     const bool wide = n > 32;
     switch (wtype) {
         case B200_TYPE_Q4_K: return wide ? mmq_launch<0, 8>(p, st) : mmq_launch<0, 4>(p, st);

@@ -40,16 +40,17 @@ struct TcParams {
     size_t col_bytes;
 };
 
-__device__ __forceinline__ void tc_mma_i8(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t accumulate) {
+__device__ __forceinline__ void tc_mma_i8_desc(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
         "}\n" ::"r"(tmem_c),
-        "l"(da), "l"(db), "r"(TC_IDESC), "r"(accumulate), "r"(0u)
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u)
         : "memory");
 }
+__device__ __forceinline__ void tc_mma_i8(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t accumulate) { tc_mma_i8_desc(tmem_c, da, db, TC_IDESC, accumulate); }
 __device__ __forceinline__ void tc_commit(uint64_t * bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -190,31 +191,157 @@ __global__ void __launch_bounds__(256, 1) mmq_tc_q4k_kernel(const TcParams p) {
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t) TC_TMEM_COLS) : "memory");
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Q4_0 / Q8_0 (one fp16 scale per 32-element block on BOTH operands): the rescale is inherently per K = 32, so the tile is
+// 128 rows x 64 columns and every k-step gets ITS OWN TMEM accumulator (8 x 64 = 512 columns): 8 independent MMAs (K = 32,
+// accumulate = false), one commit, one wait, then each thread applies  acc = fma(d_w[r][j] * d_x[c][j], (float) isum_j, acc)
+// for j = 0..7 in order — the expression and order of mmq_kernel<1|2>.  FMT 1 = Q4_0, 2 = Q8_0 (device row layout: qs[nb][QB] | d[nb]).
+// ------------------------------------------------------------------------------------------------------------------
+template <int FMT>
+__global__ void __launch_bounds__(256, 1) mmq_tc_blk32_kernel(const TcParams p) {
+    extern __shared__ __align__(128) uint8_t sm[];
+    uint8_t * At = sm, * Bt = sm + TC_PLANE_BYTES;                      // A: 128 x 256 B ; B: 64 x 256 B
+    float * dxs = reinterpret_cast<float *>(sm + TC_PLANE_BYTES + TC_N64 * 256);  // [64][8] activation block scales of this unit
+    __shared__ __align__(8) uint64_t mma_bar;
+    __shared__ uint32_t tmem_base_s;
+    constexpr int QB = (FMT == 1) ? 16 : 32;
+    pdl_launch_dependents();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wg = warp >> 2, q = warp & 3;
+    const int row = q * 32 + lane;
+    const int64_t grow = min((int64_t) blockIdx.y * TC_M + row, p.m - 1);
+    const int64_t col_base = (int64_t) blockIdx.x * TC_N64;
+    const int64_t row_bytes = (int64_t) p.nunits * (8 * QB + 16);
+    const uint8_t * wrow = p.W + grow * row_bytes;
+    const unsigned short * wd = reinterpret_cast<const unsigned short *>(wrow + (size_t) p.nunits * 8 * QB);
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t) TC_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 32) {
+        mbar_init(&mma_bar, 1);
+        fence_mbar_init();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+
+    float yacc[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) yacc[i] = 0.0f;
+    const int64_t d_off = tc_al16(p.k);  // plain activation layout: qs[k] | float d[k/32] | int bs[k/32]
+
+    pdl_wait();
+    for (int u = 0; u < p.nunits; ++u) {
+        float sw[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sw[j] = half_bits_to_float(wd[u * 8 + j]);
+        // ---- weights: this thread's row, blocks 4*wg .. 4*wg+3 -> int8 (Q4_0: nibble - 8; low nibbles = elements 0..15, ggml-quants.c:307-325)
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            const int j = 4 * wg + jj;
+            if (FMT == 1) {
+                const uint4 v = *reinterpret_cast<const uint4 *>(wrow + (size_t) (u * 8 + j) * 16);
+                *reinterpret_cast<uint4 *>(At + tc_off(row, 2 * j)) =
+                    make_uint4(__vsub4(v.x & 0x0f0f0f0fu, 0x08080808u), __vsub4(v.y & 0x0f0f0f0fu, 0x08080808u), __vsub4(v.z & 0x0f0f0f0fu, 0x08080808u),
+                               __vsub4(v.w & 0x0f0f0f0fu, 0x08080808u));
+                *reinterpret_cast<uint4 *>(At + tc_off(row, 2 * j + 1)) =
+                    make_uint4(__vsub4((v.x >> 4) & 0x0f0f0f0fu, 0x08080808u), __vsub4((v.y >> 4) & 0x0f0f0f0fu, 0x08080808u),
+                               __vsub4((v.z >> 4) & 0x0f0f0f0fu, 0x08080808u), __vsub4((v.w >> 4) & 0x0f0f0f0fu, 0x08080808u));
+            } else {
+                const uint8_t * b = wrow + (size_t) (u * 8 + j) * 32;
+                *reinterpret_cast<uint4 *>(At + tc_off(row, 2 * j)) = *reinterpret_cast<const uint4 *>(b);
+                *reinterpret_cast<uint4 *>(At + tc_off(row, 2 * j + 1)) = *reinterpret_cast<const uint4 *>(b + 16);
+            }
+        }
+        // ---- activations: column (tid & 63), K chunks 4*(tid >> 6) .. +3 ; block scales [64][8]
+        {
+            const int coln = tid & 63, cb = (tid >> 6) * 4;
+            const int64_t gc = min(col_base + coln, p.n - 1);
+            const uint8_t * src = p.pact + (size_t) gc * p.col_bytes + (size_t) u * 256;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4 *>(Bt + tc_off64(coln, cb + c)) = *reinterpret_cast<const uint4 *>(src + (cb + c) * 16);
+            for (int c = tid; c < TC_N64 * 8; c += 256) {
+                const int64_t g2 = min(col_base + (c >> 3), p.n - 1);
+                dxs[c] = reinterpret_cast<const float *>(p.pact + (size_t) g2 * p.col_bytes + d_off)[u * 8 + (c & 7)];
+            }
+        }
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            const uint32_t a0 = smem_u32(At), b0 = smem_u32(Bt);
+#pragma unroll
+            for (int s = 0; s < 8; ++s)   // block s = K chunks 2s, 2s+1 -> its own accumulator (columns 64 s .. 64 s + 63)
+                tc_mma_i8_desc(tmem + (uint32_t) s * TC_N64, tc_desc_lbo(a0 + (uint32_t) s * 2u * TC_LBO, TC_LBO), tc_desc_lbo(b0 + (uint32_t) s * 2u * TC_LBO64, TC_LBO64),
+                               TC_IDESC64, 0u);
+            tc_commit(&mma_bar);
+        }
+        mbar_wait(&mma_bar, (uint32_t) u & 1u);
+        tc_fence_after();
+        const int c0 = wg * 32;  // this thread's 32 columns of the 64-column tile
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+            int isum[32];
+            tc_ld32(tmem + ((uint32_t) (q * 32) << 16) + (uint32_t) (s * TC_N64 + c0), isum);
+            tc_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) yacc[i] = fmaf(sw[s] * dxs[(c0 + i) * 8 + s], (float) isum[i], yacc[i]);   // mmq_kernel<1|2>'s expression
+        }
+        tc_fence_before();
+        __syncthreads();
+    }
+    const int64_t r = (int64_t) blockIdx.y * TC_M + row;
+    if (r < p.m) {
+        const float b = p.bias ? p.bias[r] : 0.0f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const int64_t c = col_base + wg * 32 + i;
+            if (c < p.n) p.y[c * p.ldy + r] = yacc[i] + b;
+        }
+    }
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t) TC_TMEM_COLS) : "memory");
+}
+
 bool mmq_tc_enabled() {
     static const bool on = getenv("B200_MMQ_TCGEN05") && atoi(getenv("B200_MMQ_TCGEN05")) != 0;
     return on;
 }
 
-// Q4_K only; same contract as mul_mat_q_batched (prefill.cu)
-int mul_mat_q_batched_tc(const void * W, int64_t k, int64_t m, const void * pact, int64_t n, float * y, int64_t ldy, const float * bias, size_t col_bytes,
-                         cudaStream_t st) {
+// same contract as mul_mat_q_batched (prefill.cu)
+template <typename Kern>
+static int tc_launch(Kern kern, const TcParams & p, size_t smem, int ntile, bool * configured_dev, cudaStream_t st) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!configured_dev[dev & 15]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        if (e != cudaSuccess) return (int) e;
+        configured_dev[dev & 15] = true;
+    }
+    dim3 grid((unsigned) ((p.n + ntile - 1) / ntile), (unsigned) ((p.m + TC_M - 1) / TC_M));
+    launch_pdl(kern, grid, dim3(256), smem, st, p);
+    return (int) cudaGetLastError();
+}
+
+int mul_mat_q_batched_tc(int wtype, const void * W, int64_t k, int64_t m, const void * pact, int64_t n, float * y, int64_t ldy, const float * bias,
+                         size_t col_bytes, cudaStream_t st) {
     if (k <= 0 || m <= 0 || n <= 0) return B200_OK;
     if (k % 256) return B200_ERR_UNSUPPORTED;
     TcParams p;
     p.W = (const uint8_t *) W; p.pact = (const uint8_t *) pact; p.y = y; p.bias = bias;
     p.k = k; p.m = m; p.n = n; p.ldy = ldy; p.nunits = (int) (k / 256); p.col_bytes = col_bytes;
-    const size_t smem = 4 * (size_t) TC_PLANE_BYTES + TC_N * sizeof(float);
-    static bool configured_dev[16] = {false};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (!configured_dev[dev & 15]) {
-        cudaError_t e = cudaFuncSetAttribute(mmq_tc_q4k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-        if (e != cudaSuccess) return (int) e;
-        configured_dev[dev & 15] = true;
+    static bool cfg_k[16] = {false}, cfg_40[16] = {false}, cfg_80[16] = {false};
+    const size_t smem32 = (size_t) TC_PLANE_BYTES + TC_N64 * 256 + TC_N64 * 8 * sizeof(float);
+    switch (wtype) {
+        case B200_TYPE_Q4_K: return tc_launch(mmq_tc_q4k_kernel, p, 4 * (size_t) TC_PLANE_BYTES + TC_N * sizeof(float), TC_N, cfg_k, st);
+        case B200_TYPE_Q4_0: return tc_launch(mmq_tc_blk32_kernel<1>, p, smem32, TC_N64, cfg_40, st);
+        case B200_TYPE_Q8_0: return tc_launch(mmq_tc_blk32_kernel<2>, p, smem32, TC_N64, cfg_80, st);
+        default: return B200_ERR_UNSUPPORTED;
     }
-    dim3 grid((unsigned) ((n + TC_N - 1) / TC_N), (unsigned) ((m + TC_M - 1) / TC_M));
-    launch_pdl(mmq_tc_q4k_kernel, grid, dim3(256), smem, st, p);
-    return (int) cudaGetLastError();
 }
 
 }  // namespace b200

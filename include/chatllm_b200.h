@@ -70,11 +70,12 @@ size_t b200_pact_col_bytes(int wtype, int64_t k);
 int b200_quantize_plain(int wtype, const float * x, int64_t x_col_stride, int64_t k, int64_t n, void * pact, void * stream);
 int b200_mul_mat_q_batched(int wtype, const void * W, int64_t k, int64_t m, const void * pact, int64_t n, float * y, int64_t ldy,
                            const float * bias, void * stream);
-/* OPT-IN tcgen05 version of b200_mul_mat_q_batched for Q4_K (csrc/prefill_tc.cu: tcgen05.mma kind::i8, accumulators in TMEM; the 6-bit
- * sub-block scales are folded into three int8 weight planes so the super-block sums stay exact in int32).  Bit-identical to
- * b200_mul_mat_q_batched by construction; not yet run on a GPU (round 1) — the plugin uses it only with B200_MMQ_TCGEN05=1. */
-int b200_mul_mat_q_batched_tc(const void * W, int64_t k, int64_t m, const void * pact, int64_t n, float * y, int64_t ldy, const float * bias,
-                              void * stream);
+/* OPT-IN tcgen05 version of b200_mul_mat_q_batched (csrc/prefill_tc.cu: tcgen05.mma kind::i8, accumulators in TMEM).  Q4_K: the 6-bit
+ * sub-block scales are folded into three int8 weight planes so the super-block sums stay exact in int32; Q4_0 / Q8_0: one TMEM
+ * accumulator per 32-element block.  Same integers and the same fp32 rescale expression as b200_mul_mat_q_batched; not yet run on a
+ * GPU (round 1) — the plugin uses it only with B200_MMQ_TCGEN05=1. */
+int b200_mul_mat_q_batched_tc(int wtype, const void * W, int64_t k, int64_t m, const void * pact, int64_t n, float * y, int64_t ldy,
+                              const float * bias, void * stream);
 /* Several matrices that share the activation vector in ONE launch.
  *   mode 0 (concat, nmat <= 3): y_i[c*ldy_i + r] = W_i[r,:].x_c (+ bias_i[r])       — q/k/v projections of a layer
  *   mode 1 (paired, nmat == 2, m_0 == m_1): y_0[c*ldy_0 + r] = silu(W_0[r,:].x_c) * (W_1[r,:].x_c)

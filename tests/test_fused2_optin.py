@@ -118,8 +118,9 @@ def test_session_fused2_matches_fused1_and_graph_replay(wtype):
     assert torch.equal(lb, b.logits)
 
 
+@pytest.mark.parametrize("wtype", [qf.Q4_K, qf.Q4_0, qf.Q8_0])
 @pytest.mark.parametrize("k,m,n", [(256, 128, 128), (1024, 130, 64), (4096, 300, 200), (4096, 4096, 512), (14336, 512, 130)])
-def test_tcgen05_prefill_equals_mma_sync(k, m, n):
+def test_tcgen05_prefill_equals_mma_sync(wtype, k, m, n):
     """csrc/prefill_tc.cu (tcgen05.mma kind::i8, three exact int8 planes) must reproduce mmq_kernel (mma.sync): the int32 super-block
     sums are the same integers and the fp32 rescale is the same expression in the same order, so the two agree to fp32 rounding of
     that expression (nvcc may contract it into FMAs differently in the two kernels: a few ulp, 2e-6 allowed; bit-equality is reported).
@@ -127,18 +128,18 @@ def test_tcgen05_prefill_equals_mma_sync(k, m, n):
     import torch
     pkg, K = _setup()
     rng = np.random.default_rng(k + m + n)
-    pool = qf.random_blocks(qf.Q4_K, min(m, 512), k, rng=rng)
+    pool = qf.random_blocks(wtype, min(m, 512), k, rng=rng)
     w = pool[rng.integers(0, pool.shape[0], m)]
-    wd = K.upload_weights(qf.Q4_K, w, k, m)
+    wd = K.upload_weights(wtype, w, k, m)
     x = rng.standard_normal((n, k)).astype(np.float32); x[rng.random((n, k)) < 1e-3] *= 20
     xd = _t(x)
     L = pkg.lib()
-    pq = torch.empty(L.b200_pact_col_bytes(qf.Q4_K, k) * n, dtype=torch.uint8, device="cuda")
-    assert L.b200_quantize_plain(qf.Q4_K, xd.data_ptr(), k, k, n, pq.data_ptr(), 0) == 0
+    pq = torch.empty(L.b200_pact_col_bytes(wtype, k) * n, dtype=torch.uint8, device="cuda")
+    assert L.b200_quantize_plain(wtype, xd.data_ptr(), k, k, n, pq.data_ptr(), 0) == 0
     bias = _t(rng.standard_normal(m).astype(np.float32))
     y0 = torch.zeros((n, m), device="cuda"); y1 = torch.full((n, m), float("nan"), device="cuda")
-    assert L.b200_mul_mat_q_batched(qf.Q4_K, wd.data_ptr(), k, m, pq.data_ptr(), n, y0.data_ptr(), m, bias.data_ptr(), 0) == 0
-    assert L.b200_mul_mat_q_batched_tc(wd.data_ptr(), k, m, pq.data_ptr(), n, y1.data_ptr(), m, bias.data_ptr(), 0) == 0
+    assert L.b200_mul_mat_q_batched(wtype, wd.data_ptr(), k, m, pq.data_ptr(), n, y0.data_ptr(), m, bias.data_ptr(), 0) == 0
+    assert L.b200_mul_mat_q_batched_tc(wtype, wd.data_ptr(), k, m, pq.data_ptr(), n, y1.data_ptr(), m, bias.data_ptr(), 0) == 0
     torch.cuda.synchronize()
     print("tcgen05 vs mma.sync bit-identical:", bool(torch.equal(y0, y1)), "max abs diff", float((y0 - y1).abs().max()))
     assert torch.isfinite(y1).all()

@@ -67,7 +67,8 @@ def test_tcgen05_smem_layout_matches_the_cute_canonical_layout(tmp_path):
     assert "mismatches: 0" in out
     assert "SBO (uint128 units) = 8 " in out and "LBO (uint128 units) = 128 " in out
     assert "offset of (row 0, k 32) = 4096 bytes" in out
-    assert out.count("EQUAL") == 2 and "DIFFERENT" not in out, out   # smem descriptor and instruction descriptor bit patterns
+    assert out.count("EQUAL") == 4 and "DIFFERENT" not in out, out   # smem + instruction descriptor bit patterns, N = 128 and N = 64 tiles
+    assert "tc_off64 vs tiled canonical layout mismatches: 0" in out and "LBO (uint128 units) = 64 " in out
     tiled = [l for l in out.splitlines() if l.startswith("tiled")][0].split(" o ")[-1]
     mine = [l for l in out.splitlines() if l.startswith("mine")][0].split(": ")[-1]
     assert tiled.strip() == mine.strip(), (tiled, mine)

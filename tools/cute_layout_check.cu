@@ -46,5 +46,18 @@ int main() {
            uint64_t(sd) == tc_desc(saddr) ? "EQUAL" : "DIFFERENT");
     auto id = UMMA::make_instr_desc<int8_t, int8_t, int32_t, 128, 128, UMMA::Major::K, UMMA::Major::K>();
     printf("instr descriptor cute=%08x  kernel=%08x  %s\n", uint32_t(id), (uint32_t) TC_IDESC, uint32_t(id) == (uint32_t) TC_IDESC ? "EQUAL" : "DIFFERENT");
+    // ---- the N = 64 activation tile of the block-scaled kernels (mmq_tc_blk32_kernel)
+    auto tiled64 = tile_to_shape(atom, make_shape(Int<64>{}, Int<256>{}));
+    int bad64 = 0;
+    for (int r = 0; r < 64; ++r)
+        for (int k = 0; k < 256; ++k) bad64 += (tc_off64(r, k / 16) + (k % 16)) != (unsigned) tiled64.layout_b()(r, k);
+    printf("tc_off64 vs tiled canonical layout mismatches: %d\n", bad64);
+    auto canon64 = logical_divide(recast_layout<int8_t, uint128_t>(tiled64.layout_b()), Tile<Layout<_8, _1>, Layout<_2, _1>>{});
+    printf("N=64 tile: SBO (uint128 units) = %d , LBO (uint128 units) = %d , kernel TC_LBO64 = %u bytes\n", (int) stride<0, 1>(canon64), (int) stride<1, 0>(canon64), TC_LBO64);
+    auto id64 = UMMA::make_instr_desc<int8_t, int8_t, int32_t, 128, 64, UMMA::Major::K, UMMA::Major::K>();
+    printf("instr descriptor N=64 cute=%08x  kernel=%08x  %s\n", uint32_t(id64), (uint32_t) TC_IDESC64, uint32_t(id64) == (uint32_t) TC_IDESC64 ? "EQUAL" : "DIFFERENT");
+    sd.leading_byte_offset_ = uint16_t(stride<1, 0>(canon64));
+    printf("smem descriptor N=64 cute=%016llx  kernel=%016llx  %s\n", (unsigned long long) uint64_t(sd), (unsigned long long) tc_desc_lbo(saddr, TC_LBO64),
+           uint64_t(sd) == tc_desc_lbo(saddr, TC_LBO64) ? "EQUAL" : "DIFFERENT");
     return 0;
 }
