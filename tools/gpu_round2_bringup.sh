@@ -24,6 +24,10 @@ for n in ("default", "fused2"):
     except Exception as e: print(n, "failed", e)
 PY
 ( timeout 200 python tools/plugin_profile.py; echo "--- B200_FUSE2=1"; timeout 200 python tools/plugin_profile.py B200_FUSE2=1 ) > $OUT/plugin_profile.txt 2>&1; grep -E "decode_ms_mean|B200PROF|---" $OUT/plugin_profile.txt | cut -c1-200 | tail -8
+# 3b. GEMV residency experiment: smaller rings so two CTAs share an SM and consecutive GEMVs overlap
+for t in "16,2,8,4,0" "8,2,8,4,296" "8,3,8,4,296" "12,2,8,4,296" "8,2,4,4,592" "8,4,4,4,592"; do
+  python bench.py --no-e2e --no-cpu --steps 32 --tune $t 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('tune $t', d['value'], 'tok/s  gemv', d['roofline']['achieved'], 'GB/s')" 2>/dev/null || echo "tune $t failed"
+done | tee $OUT/gemv_tune_sweep.txt
 # 4. 2-device layer split through the plugin (only on a --gpus 2 call)
 if [ "$(nvidia-smi -L | wc -l)" -ge 2 ]; then
   ( B200_TEST_MULTI_GPU=1 timeout 200 python -m pytest tests/test_e2e_host.py -m gpu -q -k layer_split ) > $OUT/pytest_2gpu.log 2>&1; echo "2-GPU split: $(tail -1 $OUT/pytest_2gpu.log)"
