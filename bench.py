@@ -133,6 +133,7 @@ def main():
     ap.add_argument("--tune", default="", help="ks,stages,warps,rg,grid for the GEMV pipeline (0 = default)")
     ap.add_argument("--unfused", action="store_true")
     ap.add_argument("--fused2", action="store_true", help="opt-in step with norm+quant in the GEMV prologue / residual in the epilogue (9 launches per layer)")
+    ap.add_argument("--no-mk", action="store_true", help="A/B aid: the round-1 step (355 launches replayed as a CUDA graph) instead of the persistent kernel")
     ap.add_argument("--layers", type=int, default=0, help="debug: fewer layers (result is then NOT the BASELINE config)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3)
@@ -174,10 +175,15 @@ def main():
 
     if a.tune:
         pkg.lib().b200_gemv_set_tuning(*[int(v) for v in a.tune.split(",")])
-    cfg = S.make_config(MODEL, pkg.Q4_K, layers=a.layers or None, max_len=N_PAST + 256)
+    use_mk = not a.no_mk and not a.unfused and not a.fused2
+    CTX_ROOM = 1024   # the device-side greedy loop walks one position per step: warm-up + timed steps must fit behind n_past = 4096
+    if use_mk and a.warmup + a.steps + 2 > CTX_ROOM:
+        raise SystemExit(f"--warmup + --steps must stay below {CTX_ROOM - 2}")
+    cfg = S.make_config(MODEL, pkg.Q4_K, layers=a.layers or None, max_len=N_PAST + (CTX_ROOM if use_mk else 256))
     from chatllm_cpp_b200 import sharding
     lo, hi = sharding.plan_layers(cfg.layers, world)[rank]
-    sess = S.DecodeSession(cfg, seed=0, layer_lo=lo, layer_hi=hi, first=(rank == 0), last=(rank == world - 1), fused=(2 if a.fused2 else not a.unfused))
+    sess = S.DecodeSession(cfg, seed=0, layer_lo=lo, layer_hi=hi, first=(rank == 0), last=(rank == world - 1), fused=(3 if use_mk else 2 if a.fused2 else not a.unfused))
+    sess.mk_advance = True   # persistent kernel: tok <- argmax(logits), pos <- pos + 1 on the device (real greedy decoding, growing KV cache)
     sess.fill_kv_random(N_PAST, seed=rank)
     sess.tok.fill_(12345 % cfg.vocab)
 
@@ -191,6 +197,7 @@ def main():
     sampler = ClockSampler(local) if rank == 0 else None
     if world == 1:
         graph = sess.capture(N_PAST)
+        sess.pos.fill_(N_PAST)
         for _ in range(a.warmup):
             graph.replay()
         sync_all()
@@ -222,6 +229,7 @@ def main():
     if sampler and world == 1:
         t_tail = time.time() + 1.2
         while time.time() < t_tail:
+            sess.pos.fill_(N_PAST)   # keep the device-side position inside the allocated context
             for _ in range(32):
                 graph.replay()
             torch.cuda.synchronize()
@@ -285,13 +293,26 @@ def main():
                 "frac_of_nominal_8TBps": round(achieved / 8000.0, 4), "launches": len(shapes), "avg_launch_us": round(gemv_ms * 1e3 / len(shapes), 2),
                 "algorithmic_MB_per_token_shard": round(gemv_bytes / 1e6, 1), "traffic": None,
                 "share_of_step": round(gemv_ms / ms, 3)}
+    if use_mk and world == 1:
+        # the dominant kernel IS the step: one launch of decode_mk_kernel streams every weight byte of the token plus the KV cache.
+        # algorithmic bytes per launch = sum over the quantized matmuls of m*(k/256)*144 + 4k + 4m + the F16 K/V rows read
+        n_kv_mean = N_PAST + a.warmup + (a.steps + 1) / 2.0
+        mk_bytes = cfg.weight_bytes_per_token() + cfg.kv_bytes_per_token(n_kv_mean)
+        mk_ach = mk_bytes / ms / 1e6
+        roofline = {"bound": "hbm", "kernel": "decode_mk_kernel<FmtQ4K,128> (persistent, 1 launch per token)", "achieved": round(mk_ach, 1), "peak": pk["hbm_gbs"],
+                    "unit": "GB/s", "frac": round(mk_ach / pk["hbm_gbs"], 4),
+                    "peak_kind": pk_kind + " (MEASURED_PEAKS.json hbm_gbs)" if pk_kind == "measured" else "fallback",
+                    "frac_of_nominal_8TBps": round(mk_ach / 8000.0, 4), "launches": 1, "avg_launch_us": round(ms * 1e3, 2),
+                    "algorithmic_MB_per_launch": round(mk_bytes / 1e6, 1), "traffic": None, "share_of_step": 1.0, "mk": getattr(sess, "mk_info", None),
+                    "per_op_gemv_kernel_alone": {"achieved": round(achieved, 1), "frac": round(achieved / pk["hbm_gbs"], 4), "launches": len(shapes),
+                                                 "note": "round-1 gemv_q_kernel, one launch per matmul, replayed alone (the fallback path for shapes the persistent kernel declines)"}}
 
     if rank != 0:
         if dist:
             dist.destroy_process_group()
         return
     out = dict(base)
-    tok_bytes = cfg.weight_bytes_per_token() + cfg.kv_bytes_per_token(N_PAST)
+    tok_bytes = cfg.weight_bytes_per_token() + cfg.kv_bytes_per_token(N_PAST + (a.warmup + (a.steps + 1) / 2.0 if use_mk else 0))
     out.update({"value": round(value, 2), "ms_per_step": round(ms, 4), "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
                 "frac_of_hbm_roofline_whole_token": round(value * tok_bytes / 1e9 / pk["hbm_gbs"], 4),
                 "bytes_per_token_MB": round(tok_bytes / 1e6, 1)})
@@ -301,6 +322,8 @@ def main():
     # ---- e2e through the drop-in boundary (N=1 only: the reference host is a single process)
     if not a.no_e2e and world == 1 and os.path.exists(HARNESS):
         try:
+            if use_mk and sess.mk_status() != 0:
+                raise SystemExit("persistent kernel reported a grid-barrier timeout")
             del sess, graph, gg
             torch.cuda.empty_cache()
             model = ensure_model_file(a.layers)

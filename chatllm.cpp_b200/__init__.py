@@ -20,6 +20,24 @@ F32, F16, Q4_0, Q8_0, Q4_K = 0, 1, 2, 8, 12
 _lib = None
 
 
+class DecodeLayer(C.Structure):
+    """b200_decode_layer (include/chatllm_b200.h)"""
+    _fields_ = [(n, C.c_void_p) for n in ("wq", "wk", "wv", "wo", "wgate", "wup", "wdown", "bq", "bk", "bv", "attn_norm", "ffn_norm", "k_cache", "v_cache")]
+
+
+class DecodeModel(C.Structure):
+    """b200_decode_model"""
+    _fields_ = [(n, C.c_int32) for n in ("wtype", "n_layers", "hidden", "heads", "kv_heads", "head_dim", "ffn", "vocab", "rope_mode", "embed_type")] + \
+               [(n, C.c_float) for n in ("rope_theta", "eps", "attn_scale")] + [("k_row_stride", C.c_int64), ("v_row_stride", C.c_int64)] + \
+               [("layers", C.POINTER(DecodeLayer)), ("embed", C.c_void_p), ("final_norm", C.c_void_p), ("lm_head", C.c_void_p), ("rope_freq_factors", C.c_void_p)]
+
+
+class DecodeIO(C.Structure):
+    """b200_decode_io"""
+    _fields_ = [("tok", C.c_void_p), ("pos", C.c_void_p), ("n_kv", C.c_int32), ("v_col", C.c_int32), ("x", C.c_void_p), ("logits", C.c_void_p),
+                ("next_tok", C.c_void_p), ("flags", C.c_int32), ("step_begin", C.c_int32), ("step_end", C.c_int32)]
+
+
 class B200Error(RuntimeError):
     pass
 
@@ -60,6 +78,12 @@ def lib():
         L.b200_quantize_plain.argtypes = [i32, vp, i64, i64, i64, vp, vp]
         L.b200_mul_mat_q_batched.argtypes = [i32, vp, i64, i64, vp, i64, vp, i64, vp, vp]
         L.b200_mul_mat_q_batched_tc.argtypes = [i32, vp, i64, i64, vp, i64, vp, i64, vp, vp]
+        L.b200_decode_plan_create.argtypes = [C.POINTER(DecodeModel), i32, C.POINTER(i32)]; L.b200_decode_plan_create.restype = vp
+        L.b200_decode_plan_destroy.argtypes = [vp]; L.b200_decode_plan_destroy.restype = None
+        L.b200_decode_plan_set_kv.argtypes = [vp, i32, vp, vp]
+        L.b200_decode_plan_status.argtypes = [vp, vp]
+        L.b200_decode_plan_info.argtypes = [vp] + [C.POINTER(i32)] * 5
+        L.b200_decode_step.argtypes = [vp, C.POINTER(DecodeIO), vp]
         _lib = L
     return _lib
 
@@ -67,4 +91,5 @@ def lib():
 EXPORTS = ["b200_abi_version", "b200_device_sm_count", "b200_repack_weights", "b200_qact_col_bytes", "b200_quantize_act",
            "b200_mul_mat_q", "b200_mul_mat", "b200_gemv_set_tuning", "b200_rms_norm", "b200_add", "b200_silu_mul", "b200_rope",
            "b200_soft_max", "b200_get_rows", "b200_attn_decode_scratch_bytes", "b200_attn_decode", "b200_attn_decode_quant", "b200_kv_store", "b200_add_rmsnorm_quant", "b200_rope_kv_store",
-           "b200_mul_mat_q_multi", "b200_gemv_fused", "b200_mul_mat_q_id", "b200_pact_col_bytes", "b200_quantize_plain", "b200_mul_mat_q_batched", "b200_mul_mat_q_batched_tc"]
+           "b200_mul_mat_q_multi", "b200_gemv_fused", "b200_mul_mat_q_id", "b200_pact_col_bytes", "b200_quantize_plain", "b200_mul_mat_q_batched", "b200_mul_mat_q_batched_tc",
+           "b200_decode_plan_create", "b200_decode_plan_destroy", "b200_decode_plan_set_kv", "b200_decode_plan_status", "b200_decode_plan_info", "b200_decode_step"]

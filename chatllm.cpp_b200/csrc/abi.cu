@@ -159,4 +159,20 @@ int b200_kv_store(const float * k, const float * v, void * k_cache, void * v_cac
     return kv_store(k, v, k_cache, v_cache_t, kv_hidden, k_row_stride, v_row_stride, pos, (cudaStream_t) stream);
 }
 
+// ---- persistent decode kernel (decode_mk.cu).  The C structs of the header and the C++ structs of kernels.h have the same layout.
+static_assert(sizeof(b200_decode_layer) == sizeof(DecodeLayer) && sizeof(b200_decode_model) == sizeof(DecodeModel) && sizeof(b200_decode_io) == sizeof(DecodeIO),
+              "C ABI structs and kernels.h structs must match");
+void * b200_decode_plan_create(const b200_decode_model * model, int max_ctx, int * err) {
+    if (!model) { if (err) *err = B200_ERR_ARG; return nullptr; }
+    return decode_plan_create(*reinterpret_cast<const DecodeModel *>(model), max_ctx, err);
+}
+void b200_decode_plan_destroy(void * plan) { decode_plan_destroy(plan); }
+int b200_decode_plan_set_kv(void * plan, int layer, void * k_cache, void * v_cache) { return decode_plan_set_kv(plan, layer, k_cache, v_cache); }
+int b200_decode_plan_status(void * plan, void * stream) { return decode_plan_status(plan, (cudaStream_t) stream); }
+int b200_decode_plan_info(void * plan, int * grid, int * smem_bytes, int * n_steps, int * stages, int * ks) { return decode_plan_info(plan, grid, smem_bytes, n_steps, stages, ks); }
+int b200_decode_step(void * plan, const b200_decode_io * io, void * stream) {
+    if (!io) return B200_ERR_ARG;
+    return decode_step(plan, *reinterpret_cast<const DecodeIO *>(io), (cudaStream_t) stream);
+}
+
 }  // extern "C"

@@ -875,7 +875,7 @@ static int compute_node(b200_backend_ctx * bc, ggml_tensor * node) {
     switch (node->op) {
         case GGML_OP_GET_ROWS:
             if (s0->type == GGML_TYPE_F32 || s0->type == GGML_TYPE_F16) return op_get_rows_f(tv(s0), tv(s1), tv(node), st);
-            return get_rows_q((int) s0->type, s0->data, s0->ne[0], (const int32_t *) s1->data, ggml_nelements(s1), (float *) node->data, st);
+            return get_rows_q((int) s0->type, s0->data, s0->ne[0], (const int32_t *) s1->data, ggml_nelements(s1), (float *) node->data, st, s0->ne[1]);
         case GGML_OP_RMS_NORM: {
             float eps;
             memcpy(&eps, node->op_params, sizeof(float));

@@ -35,6 +35,42 @@ int mul_mat_q_id(int wtype, int paired, const void * W0, const void * W1, int64_
                  const void * qact, int act_cols, float * y, int64_t ldy, const GemvTuning * tune, cudaStream_t st);
 int sm_count();
 
+// ---- decode_mk.cu: the whole decode token of a dense Llama-family model as one persistent kernel
+struct DecodeLayer {
+    const void * wq, * wk, * wv, * wo, * wgate, * wup, * wdown;  // quantized matrices in the device layout
+    const float * bq, * bk, * bv;                                  // optional q/k/v biases (NULL)
+    const float * attn_norm, * ffn_norm;
+    void * k_cache;  // F16 [n_ctx][k_row_stride]
+    void * v_cache;  // F16 transposed [kv_hidden][v_row_stride]
+};
+struct DecodeModel {
+    int wtype, n_layers, hidden, heads, kv_heads, head_dim, ffn, vocab, rope_mode, embed_type;
+    float rope_theta, eps, attn_scale;
+    int64_t k_row_stride, v_row_stride;  // halves
+    const DecodeLayer * layers;           // HOST array of n_layers entries
+    const void * embed;                   // quantized embedding table (NULL: the caller always passes the hidden state)
+    const float * final_norm;
+    const void * lm_head;                 // NULL: the step ends with the hidden state (a layer shard that is not the last)
+    const float * rope_freq_factors;
+};
+struct DecodeIO {
+    const int32_t * tok;   // device; NULL: x holds the incoming hidden state
+    const int32_t * pos;   // device: position of this token (RoPE angle, K-cache row)
+    int n_kv;              // positions attended to, < 0: pos[0] + 1
+    int v_col;             // V-cache column of this token, < 0: pos[0]
+    float * x;             // residual stream [hidden] in/out (NULL: plan-owned)
+    float * logits;        // [vocab]
+    int32_t * next_tok;    // optional: argmax of the logits (first maximum)
+    int flags;             // bit 0: tok[0] = next_tok, pos[0] += 1 at the end (greedy decoding without the host)
+    int step_begin, step_end;  // debug: run only steps [begin, end) (0, 0 = all)
+};
+void * decode_plan_create(const DecodeModel & m, int max_ctx, int * err);
+void decode_plan_destroy(void * plan);
+int decode_plan_set_kv(void * plan, int layer, void * k_cache, void * v_cache);
+int decode_plan_status(void * plan, cudaStream_t st);
+int decode_plan_info(void * plan, int * grid, int * smem_bytes, int * n_steps, int * stages, int * ks);
+int decode_step(void * plan, const DecodeIO & io, cudaStream_t st);
+
 // ---- prefill.cu: batched (n > 8) quantized matmul on the int8 tensor cores, plain activation layout
 size_t pact_col_bytes(int wtype, int64_t k);
 int quantize_plain(int wtype, const float * x, int64_t x_col_stride, int64_t k, int64_t n, void * pact, cudaStream_t st);
@@ -54,7 +90,8 @@ int rope_f32(const float * x, float * y, const int32_t * pos, const float * freq
              int64_t x_head_stride, int64_t x_tok_stride, int64_t y_head_stride, int64_t y_tok_stride, int n_dims, int mode, int n_ctx_orig,
              float freq_base, float freq_scale, float ext_factor, float attn_factor, float beta_fast, float beta_slow, cudaStream_t st);
 int soft_max_f32(const float * x, const float * mask, float * y, int64_t ne0, int64_t nrows, float scale, cudaStream_t st);
-int get_rows_q(int type, const void * table, int64_t k, const int32_t * ids, int64_t n, float * y, cudaStream_t st);
+// n_rows > 0: ids outside [0, n_rows) produce a zero row instead of an out-of-bounds read
+int get_rows_q(int type, const void * table, int64_t k, const int32_t * ids, int64_t n, float * y, cudaStream_t st, int64_t n_rows = 0);
 size_t attn_decode_scratch_bytes(int n_heads, int n_kv);
 int attn_decode(const float * q, const void * kc, const void * vc, float * out, float * scratch, int n_heads, int kv_heads, int head_dim, int n_kv,
                 int64_t k_row_stride, int64_t v_row_stride, float scale, cudaStream_t st);

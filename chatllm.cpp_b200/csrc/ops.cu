@@ -2,6 +2,7 @@
 // embedding gather, F16 attention matmuls, KV-cache writes).  Each mirrors the arithmetic of the reference CPU
 // op (file:line cited per kernel) closely enough that decode logits agree to ~1e-5 relative.
 #include "common.cuh"
+#include "dequant.cuh"
 #include "kernels.h"
 
 #include <math.h>
@@ -195,63 +196,25 @@ int soft_max_f32(const float * x, const float * mask, float * y, int64_t ne0, in
 // ---- embedding gather from a quantized table ------------------------------------------------------------------
 // reference: ggml_compute_forward_get_rows ggml/src/ggml-cpu/ops.cpp:4820 + dequantize_row_* ggml-quants.c:307/401/1352.
 // Q4_0 / Q8_0 tables are in the repacked SoA row layout (quantize.cu).
-__global__ void get_rows_kernel(int type, const uint8_t * table, int64_t k, const int32_t * ids,
+__global__ void get_rows_kernel(int type, const uint8_t * table, int64_t k, const int32_t * ids, int64_t n_rows,
                                 float * y) {
     pdl_launch_dependents();
     pdl_wait();
     const int64_t r = blockIdx.x;
     const int64_t row = ids[r];
     float * out = y + r * k;
-    if (type == B200_TYPE_Q4_K) {
-        const uint8_t * base = table + row * (k / 256) * 144;
-        for (int64_t e = threadIdx.x; e < k; e += blockDim.x) {
-            const int64_t b = e >> 8;
-            const int w = (int) (e & 255);
-            const uint8_t * blk = base + b * 144;
-            const float d = half_bits_to_float(blk[0] | (blk[1] << 8)), dmin = half_bits_to_float(blk[2] | (blk[3] << 8));
-            const int j = w >> 5;  // sub-block
-            const uint8_t * q = blk + 4;
-            int sc, mn;
-            if (j < 4) { sc = q[j] & 63; mn = q[j + 4] & 63; }
-            else { sc = (q[j + 4] & 0xF) | ((q[j - 4] >> 6) << 4); mn = (q[j + 4] >> 4) | ((q[j] >> 6) << 4); }
-            const uint8_t byte = blk[16 + (j >> 1) * 32 + (w & 31)];
-            const int qv = (j & 1) ? (byte >> 4) : (byte & 0xF);
-            out[e] = (d * sc) * qv - (dmin * mn);
-        }
-    } else if (type == B200_TYPE_Q4_0) {
-        const int64_t nb = k / 32;
-        const uint8_t * base = table + row * nb * 18;
-        for (int64_t e = threadIdx.x; e < k; e += blockDim.x) {
-            const int64_t b = e >> 5;
-            const int w = (int) (e & 31);
-            const uint8_t * dp = base + nb * 16 + b * 2;
-            const float d = half_bits_to_float(dp[0] | (dp[1] << 8));
-            const uint8_t byte = base[b * 16 + (w & 15)];
-            const int qv = (w < 16 ? (byte & 0xF) : (byte >> 4)) - 8;
-            out[e] = qv * d;
-        }
-    } else if (type == B200_TYPE_Q8_0) {
-        const int64_t nb = k / 32;
-        const uint8_t * base = table + row * nb * 34;
-        for (int64_t e = threadIdx.x; e < k; e += blockDim.x) {
-            const int64_t b = e >> 5;
-            const uint8_t * dp = base + nb * 32 + b * 2;
-            const float d = half_bits_to_float(dp[0] | (dp[1] << 8));
-            out[e] = (float) ((const int8_t *) base)[e] * d;
-        }
-    } else if (type == B200_TYPE_F32) {
-        const float * src = (const float *) table + row * k;
-        for (int64_t e = threadIdx.x; e < k; e += blockDim.x) out[e] = src[e];
-    } else if (type == B200_TYPE_F16) {
-        const __half * src = (const __half *) table + row * k;
-        for (int64_t e = threadIdx.x; e < k; e += blockDim.x) out[e] = __half2float(src[e]);
+    if (row < 0 || (n_rows > 0 && row >= n_rows)) {  // the reference asserts 0 <= i01 < ne01 (ops.cpp get_rows); never read out of bounds
+        for (int64_t e = threadIdx.x; e < k; e += blockDim.x) out[e] = 0.0f;
+        return;
     }
+    const uint8_t * base = table + row * dequant_row_bytes(type, k);
+    for (int64_t e = threadIdx.x; e < k; e += blockDim.x) out[e] = dequant_row_elem(type, base, k, e);
 }
-int get_rows_q(int type, const void * table, int64_t k, const int32_t * ids, int64_t n, float * y, cudaStream_t st) {
+int get_rows_q(int type, const void * table, int64_t k, const int32_t * ids, int64_t n, float * y, cudaStream_t st, int64_t n_rows) {
     if (n <= 0) return B200_OK;
     if (type != B200_TYPE_Q4_K && type != B200_TYPE_Q4_0 && type != B200_TYPE_Q8_0 && type != B200_TYPE_F32 && type != B200_TYPE_F16)
         return B200_ERR_UNSUPPORTED;
-    launch_pdl(get_rows_kernel, dim3((unsigned) n), dim3(256), 0, st, type, (const uint8_t *) table, k, ids, y);
+    launch_pdl(get_rows_kernel, dim3((unsigned) n), dim3(256), 0, st, type, (const uint8_t *) table, k, ids, n_rows, y);
     return (int) cudaGetLastError();
 }
 

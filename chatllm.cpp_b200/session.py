@@ -15,7 +15,7 @@ import math
 import numpy as np
 import torch
 
-from . import F16, F32, Q4_0, Q4_K, Q8_0, lib
+from . import F16, F32, Q4_0, Q4_K, Q8_0, DecodeIO, DecodeLayer, DecodeModel, lib
 from . import kernels as K
 
 BLK = {Q4_0: (32, 18), Q8_0: (32, 34), Q4_K: (256, 144)}
@@ -126,8 +126,10 @@ class DecodeSession:
         self.scratch = torch.empty(lib().b200_attn_decode_scratch_bytes(c.heads, c.max_len) // 4, dtype=torch.float32, device="cuda")
         cbmax = max(lib().b200_qact_col_bytes(c.wtype, c.hidden), lib().b200_qact_col_bytes(c.wtype, c.ffn))
         self.qact = torch.empty(cbmax, dtype=torch.uint8, device="cuda")
+        self.next_tok = torch.zeros(1, dtype=torch.int32, device="cuda")
         self.launches_per_step = 0
         self._graph = None
+        self._plan = None
 
     # ---- one token ------------------------------------------------------------------------------------------------
     def _mm(self, w, k, m, x, out, bias=None):
@@ -274,8 +276,56 @@ class DecodeSession:
             raise RuntimeError(f"fused step failed rc={rc}")
         self.launches_per_step = n
 
+    # ---- fused=3: the whole step as ONE persistent kernel (csrc/decode_mk.cu, b200_decode_step) ----------------------------------
+    def _mk_plan(self):
+        import ctypes as C
+        c = self.cfg
+        n = len(self.layers)
+        arr = (DecodeLayer * max(n, 1))()
+        p = lambda t: 0 if t is None else t.data_ptr()
+        for i, W in enumerate(self.layers):
+            arr[i] = DecodeLayer(p(W.wq), p(W.wk), p(W.wv), p(W.wo), p(W.wgate), p(W.wup), p(W.wdown), p(W.bq), p(W.bk), p(W.bv),
+                                 p(W.attn_norm), p(W.ffn_norm), p(W.kc), p(W.vc))
+        m = DecodeModel(c.wtype, n, c.hidden, c.heads, c.kv_heads, c.head_dim, c.ffn, c.vocab, c.rope_mode, 0, c.rope_theta, c.eps, 1.0 / math.sqrt(c.head_dim),
+                        c.kv_hidden, c.max_len, arr, p(self.embed) if self.first else 0, p(self.final_norm) if self.last else 0,
+                        p(self.lm_head) if self.last else 0, 0)
+        err = C.c_int(0)
+        plan = lib().b200_decode_plan_create(C.byref(m), c.max_len, C.byref(err))
+        if not plan:
+            raise RuntimeError(f"b200_decode_plan_create failed err={err.value}")
+        self._plan = plan
+        self._plan_keep = (arr, m)
+        g, sm, ns, stg, ks = (C.c_int(0) for _ in range(5))
+        lib().b200_decode_plan_info(plan, C.byref(g), C.byref(sm), C.byref(ns), C.byref(stg), C.byref(ks))
+        self.mk_info = dict(grid=g.value, smem_bytes=sm.value, n_steps=ns.value, stages=stg.value, ks=ks.value)
+
+    def enqueue_step_mk(self, n_past=None, advance=False, step_begin=0, step_end=0):
+        """n_past is NOT needed: the kernel reads the position from self.pos on the device (one captured graph serves every position)."""
+        import ctypes as C
+        if self._plan is None:
+            self._mk_plan()
+        io = DecodeIO(self.tok.data_ptr() if self.first else 0, self.pos.data_ptr(), -1, -1, self.x.data_ptr(), self.logits.data_ptr() if self.last else 0,
+                      self.next_tok.data_ptr() if self.last else 0, 1 if advance else 0, step_begin, step_end)
+        rc = lib().b200_decode_step(self._plan, C.byref(io), torch.cuda.current_stream().cuda_stream)
+        if rc:
+            raise RuntimeError(f"b200_decode_step failed rc={rc}")
+        self.launches_per_step = 1
+
+    def mk_status(self):
+        return lib().b200_decode_plan_status(self._plan, torch.cuda.current_stream().cuda_stream) if self._plan else 0
+
+    def __del__(self):
+        try:
+            if self._plan:
+                lib().b200_decode_plan_destroy(self._plan)
+                self._plan = None
+        except Exception:  # noqa: BLE001  (interpreter shutdown)
+            pass
+
     def enqueue(self, n_past):
-        if self.fused == 2:
+        if self.fused == 3:
+            self.enqueue_step_mk(n_past, advance=getattr(self, "mk_advance", False))
+        elif self.fused == 2:
             self.enqueue_step_fused2(n_past)
         elif self.fused:
             self.enqueue_step_fused(n_past)

@@ -154,6 +154,52 @@ int b200_attn_decode_quant(const float * q, const void * k_cache, const void * v
 int b200_kv_store(const float * k, const float * v, void * k_cache, void * v_cache_t, int kv_hidden, int64_t k_row_stride,
                   int64_t v_row_stride, int pos, void * stream);
 
+/* ---- the whole decode token as ONE persistent kernel (csrc/decode_mk.cu) ------------------------------------------------------
+ * Replaces, for one token of a dense Llama-family model (RMSNorm -> q/k/v -> RoPE -> KV append -> attention -> o -> residual ->
+ * RMSNorm -> SwiGLU MLP -> residual, then final norm + lm_head), the ~1000-node graph the reference builds and schedules per token:
+ * HeterogeneousModel::forward (src/models.cpp:1399-1424) -> LMBlock1Forward::forward (src/layers.cpp:2719-2761) ->
+ * LMFinalSteps::forward (src/models.cpp:1736-1785).  One cooperative launch of one CTA per SM: every warp streams ITS rows of every
+ * quantized matmul of the token through a private bulk-copy ring that runs ahead across the grid barriers between steps, so HBM stays
+ * busy while activations are normalised / quantized and attention runs.  Same arithmetic as the per-op entry points above.
+ * All pointers inside the structs are DEVICE pointers (weights in the device layout); `layers` itself is a host array. */
+typedef struct b200_decode_layer {
+    const void * wq, * wk, * wv, * wo, * wgate, * wup, * wdown;
+    const float * bq, * bk, * bv;          /* optional q/k/v biases (NULL) */
+    const float * attn_norm, * ffn_norm;
+    void * k_cache;                        /* F16 [n_ctx][k_row_stride]            (src/layers.cpp:2933) */
+    void * v_cache;                        /* F16 transposed [kv_hidden][v_row_stride] (src/layers.cpp:2937) */
+} b200_decode_layer;
+typedef struct b200_decode_model {
+    int32_t wtype, n_layers, hidden, heads, kv_heads, head_dim, ffn, vocab, rope_mode, embed_type; /* embed_type 0: = wtype */
+    float rope_theta, eps, attn_scale;
+    int64_t k_row_stride, v_row_stride;    /* in halves, multiples of 8 */
+    const b200_decode_layer * layers;      /* HOST array [n_layers] */
+    const void * embed;                    /* quantized embedding table, NULL: callers always pass the hidden state */
+    const float * final_norm;
+    const void * lm_head;                  /* NULL: the step ends with the hidden state (a layer shard that is not the last) */
+    const float * rope_freq_factors;       /* optional [head_dim/2] */
+} b200_decode_model;
+typedef struct b200_decode_io {
+    const int32_t * tok;                   /* device; NULL: x holds the incoming hidden state */
+    const int32_t * pos;                   /* device: position of this token (RoPE angle, K-cache row) */
+    int32_t n_kv;                          /* positions attended to; < 0: pos[0] + 1 (read on the device) */
+    int32_t v_col;                         /* V-cache column of this token; < 0: pos[0] */
+    float * x;                             /* residual stream [hidden], in/out; NULL: plan-owned */
+    float * logits;                        /* [vocab] (required when the model has an lm_head) */
+    int32_t * next_tok;                    /* optional: argmax of the logits, first maximum */
+    int32_t flags;                         /* bit 0: tok[0] = next_tok, pos[0] += 1 when the step ends (greedy decoding without the host) */
+    int32_t step_begin, step_end;          /* debug: run only steps [begin, end); 0, 0 = the whole token */
+} b200_decode_io;
+/* returns NULL and *err (B200_ERR_* / cudaError_t) when the shape is not supported; max_ctx sizes the attention workspace */
+void * b200_decode_plan_create(const b200_decode_model * model, int max_ctx, int * err);
+void b200_decode_plan_destroy(void * plan);
+/* the KV cache tensors of a layer moved (they are owned by the host application) */
+int b200_decode_plan_set_kv(void * plan, int layer, void * k_cache, void * v_cache);
+/* 0 = fine, 1 = a grid barrier timed out in an earlier step (synchronizes `stream`) */
+int b200_decode_plan_status(void * plan, void * stream);
+int b200_decode_plan_info(void * plan, int * grid, int * smem_bytes, int * n_steps, int * stages, int * ks);
+int b200_decode_step(void * plan, const b200_decode_io * io, void * stream);
+
 #ifdef __cplusplus
 }
 #endif

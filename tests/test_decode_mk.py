@@ -1,0 +1,163 @@
+"""Persistent whole-token decode kernel (csrc/decode_mk.cu, b200_decode_step) — GPU tests through the C ABI.
+
+  * one launch == the same token executed step by step (debug step ranges): the cross-step weight prefetch and the grid barriers
+    change nothing, bit for bit;
+  * real Llama-3-8B layer shapes at n_past = 4096 against the oracle port's oq_layer_step on the same KV cache (teacher-forced per
+    layer: both sides get the same layer input);
+  * greedy decoding on the device (argmax + position advance inside the kernel) under CUDA-graph replay == eager host-driven steps.
+The small-shape / every-format / both-RoPE-mode comparison with the oracle is test_session.py::test_decode_steps_match_oracle[fused=3].
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import qformats as qf
+
+pytestmark = pytest.mark.gpu
+
+
+def _mods():
+    import torch
+    import __graft_entry__ as ge
+    ge.load_package()
+    from chatllm_cpp_b200 import kernels as K, session as S
+    return torch, K, S
+
+
+@pytest.mark.parametrize("wtype,hidden,heads,kvh,ffn,n_past", [
+    (qf.Q4_K, 1024, 8, 2, 2816, 300),      # head_dim 128, GQA 4, ffn not a multiple of 1024
+    (qf.Q4_0, 512, 8, 8, 1024, 17),        # head_dim 64, GQA 1
+    (qf.Q8_0, 1792, 14, 2, 4864, 1029),    # head_dim 128, GQA 7 (Qwen2.5 grouping), hidden not a multiple of 1024
+])
+def test_single_launch_equals_stepwise(wtype, hidden, heads, kvh, ffn, n_past):
+    torch, K, S = _mods()
+    cfg = S.Config(wtype, 2048, hidden, heads, kvh, 3, ffn, rope_mode=2 if wtype == qf.Q8_0 else 0, max_len=n_past + 64, bias=(wtype == qf.Q8_0))
+    sess = S.DecodeSession(cfg, seed=5, fused=3)
+    sess.fill_kv_random(n_past, seed=2)
+    kv0 = [(W.kc.clone(), W.vc.clone()) for W in sess.layers]
+    one = sess.step(11, n_past).clone()
+    x_one = sess.x.clone()
+    kv_one = [(W.kc.clone(), W.vc.clone()) for W in sess.layers]
+    assert sess.mk_status() == 0
+    for W, (k0, v0) in zip(sess.layers, kv0):
+        W.kc.copy_(k0); W.vc.copy_(v0)
+    sess.logits.zero_(); sess.x.zero_()
+    sess.tok.fill_(11); sess.pos.fill_(n_past)
+    for s in range(sess.mk_info["n_steps"]):
+        sess.enqueue_step_mk(step_begin=s, step_end=s + 1)
+    torch.cuda.synchronize()
+    assert sess.mk_status() == 0
+    assert torch.equal(one, sess.logits)
+    assert torch.equal(x_one, sess.x)
+    for W, (k1, v1) in zip(sess.layers, kv_one):
+        assert torch.equal(W.kc, k1) and torch.equal(W.vc, v1)
+    assert int(sess.next_tok.item()) == int(one.argmax().item())
+
+
+class OqLayer(C.Structure):
+    _fields_ = [("type", C.c_int), ("hidden", C.c_int), ("n_heads", C.c_int), ("n_kv_heads", C.c_int), ("head_dim", C.c_int), ("ffn", C.c_int),
+                ("max_len", C.c_int), ("rope_mode", C.c_int), ("rope_theta", C.c_float), ("eps", C.c_float),
+                ("attn_norm", C.c_void_p), ("ffn_norm", C.c_void_p),
+                ("wq", C.c_void_p), ("wk", C.c_void_p), ("wv", C.c_void_p), ("wo", C.c_void_p), ("wgate", C.c_void_p), ("wup", C.c_void_p),
+                ("wdown", C.c_void_p), ("bq", C.c_void_p), ("bk", C.c_void_p), ("bv", C.c_void_p), ("k_cache", C.c_void_p), ("v_cache", C.c_void_p)]
+
+
+def test_llama3_8b_layer_shapes_at_4096_vs_oracle():
+    """Teacher-forced per layer at the BENCHMARKED shapes (hidden 4096, 32/8 heads, ffn 14336, Q4_K) and n_past = 4096: the kernel and
+    the oracle port get the same layer input and the same 4096-position KV cache; layer outputs must agree to 1e-3 (north star)."""
+    torch, K, S = _mods()
+    wtype, hidden, heads, kvh, ffn, vocab, n_past = qf.Q4_K, 4096, 32, 8, 14336, 4096, 4096
+    hd, kv_hidden, max_len = 128, 1024, n_past + 16
+    rng = np.random.default_rng(7)
+    cfg = S.Config(wtype, vocab, hidden, heads, kvh, 2, ffn, rope_theta=500000.0, rope_mode=0, eps=1e-5, max_len=max_len)
+    host = {}
+
+    def weights(i, name, m, k):
+        if k == 0:
+            v = (1 + 0.1 * rng.standard_normal(m)).astype(np.float32)
+            host[(i, name)] = v
+            return torch.from_numpy(v).cuda()
+        w = qf.random_blocks(wtype, m, k, rng=rng)
+        host[(i, name)] = w
+        return K.upload_weights(wtype, w, k, m)
+
+    sess = S.DecodeSession(cfg, weights=weights, fused=3)
+    kcs, vcs = [], []
+    for W in sess.layers:
+        kc = (rng.standard_normal((max_len, kv_hidden)) * 0.5).astype(np.float16)
+        vc = (rng.standard_normal((kv_hidden, max_len)) * 0.5).astype(np.float16)
+        W.kc.copy_(torch.from_numpy(kc)); W.vc.copy_(torch.from_numpy(vc))
+        kcs.append(kc.view(np.uint16).copy()); vcs.append(vc.view(np.uint16).copy())
+    port = qf.port()
+    port.oq_layer_step.argtypes = [C.POINTER(OqLayer), C.c_void_p, C.c_int, C.c_int]
+    n_steps = sess.mk_info["n_steps"]
+    sess.tok.fill_(99); sess.pos.fill_(n_past)
+    sess.enqueue_step_mk(step_begin=0, step_end=1)      # embedding
+    rels = []
+    for li in range(2):
+        x_in = sess.x.cpu().numpy().copy()              # the layer input BOTH sides use
+        sess.enqueue_step_mk(step_begin=1 + 7 * li, step_end=1 + 7 * (li + 1))
+        torch.cuda.synchronize()
+        got = sess.x.cpu().numpy()[0]
+        L = OqLayer(wtype, hidden, heads, kvh, hd, ffn, max_len, 0, 500000.0, 1e-5)
+        for f, n in (("attn_norm", "attn_norm"), ("ffn_norm", "ffn_norm"), ("wq", "q"), ("wk", "k"), ("wv", "v"), ("wo", "o"), ("wgate", "gate"),
+                     ("wup", "up"), ("wdown", "down")):
+            setattr(L, f, host[(li, n)].ctypes.data)
+        L.k_cache, L.v_cache = kcs[li].ctypes.data, vcs[li].ctypes.data
+        h = x_in.copy()
+        port.oq_layer_step(C.byref(L), h.ctypes.data, n_past, 1)
+        ref = h[0]
+        rels.append(float(np.abs(got - ref).max() / np.abs(ref).max()))
+        # the appended cache row / column are the oracle's (1 f16 ulp: fp32 summation order of the k / v projections)
+        kg = sess.layers[li].kc[n_past].cpu().numpy().astype(np.float32)
+        kr = kcs[li][n_past].view(np.float16).astype(np.float32)
+        assert np.abs(kg - kr).max() <= 2e-3 * np.abs(kr).max()
+    assert sess.mk_status() == 0
+    print("layer rel errors vs oracle:", rels)
+    assert max(rels) <= 1e-3, rels
+    # final norm + lm_head against the oracle on the kernel's own hidden state
+    x_in = sess.x.cpu().numpy().copy()
+    sess.enqueue_step_mk(step_begin=n_steps - 2, step_end=n_steps)
+    torch.cuda.synchronize()
+    got = sess.logits.cpu().numpy()[0]
+    hn = np.zeros_like(x_in)
+    port.oq_rms_norm(x_in.ctypes.data, host[(-1, "final_norm")].ctypes.data, hn.ctypes.data, hidden, 1, 1e-5)
+    ref = qf.port_mul_mat(wtype, host[(-1, "lm_head")], hidden, vocab, hn, variant=1)[0]
+    assert np.abs(got - ref).max() <= 1e-4 * np.abs(ref).max()
+    assert int(sess.next_tok.item()) == int(np.argmax(got))
+
+
+def test_device_side_greedy_loop_under_graph_replay():
+    """tok <- argmax(logits), pos <- pos + 1 inside the kernel: ONE captured graph replayed K times walks K positions of a growing KV
+    cache and produces the same tokens / logits as K eager host-driven steps."""
+    torch, K, S = _mods()
+    cfg = S.Config(qf.Q4_K, 1536, 1024, 8, 2, 2, 2048, max_len=160)
+    a = S.DecodeSession(cfg, seed=9, fused=3)
+    b = S.DecodeSession(cfg, seed=9, fused=3)
+    for s in (a, b):
+        s.fill_kv_random(100, seed=4)
+    # eager, host in the loop
+    tok, toks_a, logits_a = 5, [], []
+    for pos in range(100, 108):
+        lg = a.step(tok, pos)
+        tok = int(lg.argmax().item())
+        toks_a.append(tok); logits_a.append(lg.clone())
+    # device-side loop: capture once, replay
+    b.mk_advance = True
+    b.tok.fill_(5); b.pos.fill_(100)
+    g = torch.cuda.CUDAGraph(); st = torch.cuda.Stream()
+    b.enqueue(0); torch.cuda.synchronize()            # warm-up (first-use attributes); consumes position 100
+    assert int(b.next_tok.item()) == toks_a[0] and int(b.pos.item()) == 101
+    with torch.cuda.stream(st):
+        with torch.cuda.graph(g, stream=st):
+            b.enqueue(0)
+    toks_b = [toks_a[0]]
+    for i in range(1, 8):
+        g.replay(); torch.cuda.synchronize()
+        toks_b.append(int(b.next_tok.item()))
+        assert torch.equal(b.logits, logits_a[i]), i
+    assert toks_b == toks_a and int(b.pos.item()) == 108
+    assert b.mk_status() == 0
+    for Wa, Wb in zip(a.layers, b.layers):
+        assert torch.equal(Wa.kc, Wb.kc) and torch.equal(Wa.vc, Wb.vc)

@@ -20,7 +20,7 @@ class OqLayer(C.Structure):
 
 @pytest.mark.parametrize("wtype", [qf.Q4_K, qf.Q4_0, qf.Q8_0])
 @pytest.mark.parametrize("rope_mode,bias", [(0, False), (2, True)])
-@pytest.mark.parametrize("fused", [False, True])
+@pytest.mark.parametrize("fused", [False, True, 3])
 def test_decode_steps_match_oracle(wtype, rope_mode, bias, fused):
     import torch
     import __graft_entry__ as ge
@@ -60,6 +60,8 @@ def test_decode_steps_match_oracle(wtype, rope_mode, bias, fused):
     rels = []
     for pos, tok in enumerate(toks):
         got = sess.step(tok, pos).cpu().numpy()[0]
+        if fused == 3:
+            assert sess.mk_status() == 0, "persistent kernel: a grid barrier timed out"
         h = np.zeros((1, hidden), dtype=np.float32)
         ids = np.array([tok], dtype=np.int32)
         port.oq_get_rows(wtype, host[(-1, "embed")].ctypes.data, hidden, ids.ctypes.data, 1, h.ctypes.data)
