@@ -1016,13 +1016,14 @@ static int pv_span(int n_kv) {
 
 template <int HD, int GQA>
 static int attn_decode_mma_t(const float * q, const void * kc, const void * vc, float * out, float * scratch, int n_kv, int kv_heads, int64_t k_row_stride,
-                             int64_t v_row_stride, float scale, int wtype, void * qact, cudaStream_t st) {
+                             int64_t v_row_stride, float scale, int wtype, void * qact, int preload_arg, cudaStream_t st) {
     const int64_t s_stride = (n_kv + 7) & ~7;
     const int nchunks = (n_kv + 127) / 128;
     float2 * part = reinterpret_cast<float2 *>(scratch + (int64_t) kv_heads * GQA * s_stride);
     // B200_ATTN_PRELOAD=0: every CTA waits for its predecessor before its first load (A/B aid).  Contract of the default: cache positions
     // below n_kv - 1 were written by earlier decode steps, not by the launches immediately preceding this call (include/chatllm_b200.h).
-    static const int preload = getenv("B200_ATTN_PRELOAD") ? atoi(getenv("B200_ATTN_PRELOAD")) : 1;
+    static const int preload_env = getenv("B200_ATTN_PRELOAD") ? atoi(getenv("B200_ATTN_PRELOAD")) : 1;
+    const int preload = preload_arg >= 0 ? (preload_arg && preload_env) : preload_env;  // the caller knows when older cache rows were just rewritten
     launch_pdl(attn_scores_mma_kernel<HD, GQA>, dim3((unsigned) nchunks, (unsigned) kv_heads), dim3(256), 0, st, q, (const __half *) kc, scratch, part, n_kv,
                k_row_stride, scale, s_stride, nchunks, preload);
     static const int old_pv = getenv("B200_ATTN_OLD_PV") ? atoi(getenv("B200_ATTN_OLD_PV")) : 0;  // A/B aid: the channel-split kernel
@@ -1129,7 +1130,7 @@ int attn_decode2(const float * q, const void * kc, const void * vc, float * out,
 
 // as attn_decode2, and additionally qact = the output quantized as the activations of a following matmul with weight type wtype
 int attn_decode3(const float * q, const void * kc, const void * vc, float * out, float * scratch, int n_heads, int kv_heads, int head_dim, int n_kv,
-                 int64_t k_row_stride, int64_t v_row_stride, float scale, int wtype, void * qact, cudaStream_t st) {
+                 int64_t k_row_stride, int64_t v_row_stride, float scale, int wtype, void * qact, cudaStream_t st, int preload) {
     if (n_kv <= 0) return B200_OK;
     if (n_heads % kv_heads) return B200_ERR_ARG;
     if ((k_row_stride % 8) || (v_row_stride % 8)) return B200_ERR_UNSUPPORTED;  // 16-byte row loads
@@ -1137,7 +1138,7 @@ int attn_decode3(const float * q, const void * kc, const void * vc, float * out,
     static const int no_mma = getenv("B200_ATTN_NO_MMA") ? atoi(getenv("B200_ATTN_NO_MMA")) : 0;
 #define B200_ATTN2(HD_, G_)                                                                                                                       \
     if (head_dim == HD_ && gqa == G_) {                                                                                                           \
-        if (!no_mma) return attn_decode_mma_t<HD_, G_>(q, kc, vc, out, scratch, n_kv, kv_heads, k_row_stride, v_row_stride, scale, wtype, qact, st); \
+        if (!no_mma) return attn_decode_mma_t<HD_, G_>(q, kc, vc, out, scratch, n_kv, kv_heads, k_row_stride, v_row_stride, scale, wtype, qact, preload, st); \
         const int rc_ = attn_decode2_t<HD_, G_>(q, kc, vc, out, scratch, n_kv, kv_heads, k_row_stride, v_row_stride, scale, st);                  \
         if (rc_ || !qact) return rc_;                                                                                                             \
         return quantize_act(wtype, out, (int64_t) n_heads * head_dim, (int64_t) n_heads * head_dim, 1, qact, st);                                 \

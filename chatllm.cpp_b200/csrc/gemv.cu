@@ -326,29 +326,36 @@ __global__ void __launch_bounds__(512) gemv_q_kernel(const GemvParams p) {
 // ======================================================================================================
 // host side
 // ======================================================================================================
-static int g_sms = 0;
-int sm_count() {
-    if (!g_sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (g_sms <= 0) g_sms = 148;
+int sm_count() {  // of the CURRENT device (cached per device ordinal)
+    static int sms[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int & n = sms[dev & 63];
+    if (!n) {
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
     }
-    return g_sms;
+    return n;
 }
 
 static int env_int(const char * name, int dflt) {
     const char * v = getenv(name);
     return v ? atoi(v) : dflt;
 }
+// pipeline shape defaults: the B200_GEMV_* environment is read ONCE (the plugin passes tune == NULL ~225 times per decoded token)
+static const GemvTuning & env_tuning() {
+    static const GemvTuning t = {env_int("B200_GEMV_KS", 16), env_int("B200_GEMV_STAGES", 2), env_int("B200_GEMV_WARPS", 8), env_int("B200_GEMV_RG", 4),
+                                 env_int("B200_GEMV_GRID", 0)};
+    return t;
+}
 
 template <class F, int RG, int NC, int MODE, int FX = 0>
 static int launch(const GemvParams & p, int warps, int grid, size_t smem_bytes, cudaStream_t st) {
     auto kern = gemv_q_kernel<F, RG, NC, MODE, FX>;
-    static size_t configured[16] = {0};  // per template instantiation AND per device (function attributes are per device)
+    static size_t configured[64] = {0};  // per template instantiation AND per device (function attributes are per device)
     int dev = 0;
     cudaGetDevice(&dev);
-    dev &= 15;
+    if (dev < 0 || dev >= 64) return B200_ERR_UNSUPPORTED;
     if (smem_bytes > configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_bytes);
         if (e != cudaSuccess) return (int) e;
@@ -470,11 +477,11 @@ int mul_mat_q_fused(int wtype, int mode, int nmat, const void * const * W, const
         const int nc = left >= 4 ? 4 : (left >= 2 ? 2 : 1);
 
         GemvTuning t;
-        t.rg = tune && tune->rg ? tune->rg : env_int("B200_GEMV_RG", 4);
-        t.warps = tune && tune->warps ? tune->warps : env_int("B200_GEMV_WARPS", 8);
-        t.stages = tune && tune->stages ? tune->stages : env_int("B200_GEMV_STAGES", 2);
-        t.ks = tune && tune->ks ? tune->ks : env_int("B200_GEMV_KS", 16);
-        t.grid = tune && tune->grid ? tune->grid : env_int("B200_GEMV_GRID", 0);
+        t.rg = tune && tune->rg ? tune->rg : env_tuning().rg;
+        t.warps = tune && tune->warps ? tune->warps : env_tuning().warps;
+        t.stages = tune && tune->stages ? tune->stages : env_tuning().stages;
+        t.ks = tune && tune->ks ? tune->ks : env_tuning().ks;
+        t.grid = tune && tune->grid ? tune->grid : env_tuning().grid;
         if (t.ks > nunits) t.ks = nunits;
         // few rows: keep at least one row-group per warp
         while (t.rg > 1 && m_phys < (int64_t) sms * t.warps * t.rg / 2) t.rg >>= 1;
@@ -549,11 +556,11 @@ int mul_mat_q_id(int wtype, int paired, const void * W0, const void * W1, int64_
     const int64_t m_total = (int64_t) n_ids * m, m_phys = m_total * (paired ? 2 : 1);
 
     GemvTuning t;
-    t.rg = tune && tune->rg ? tune->rg : env_int("B200_GEMV_RG", 4);
-    t.warps = tune && tune->warps ? tune->warps : env_int("B200_GEMV_WARPS", 8);
-    t.stages = tune && tune->stages ? tune->stages : env_int("B200_GEMV_STAGES", 2);
-    t.ks = tune && tune->ks ? tune->ks : env_int("B200_GEMV_KS", 16);
-    t.grid = tune && tune->grid ? tune->grid : env_int("B200_GEMV_GRID", 0);
+    t.rg = tune && tune->rg ? tune->rg : env_tuning().rg;
+    t.warps = tune && tune->warps ? tune->warps : env_tuning().warps;
+    t.stages = tune && tune->stages ? tune->stages : env_tuning().stages;
+    t.ks = tune && tune->ks ? tune->ks : env_tuning().ks;
+    t.grid = tune && tune->grid ? tune->grid : env_tuning().grid;
     if (t.ks > nunits) t.ks = nunits;
     while (t.rg > 1 && m_phys < (int64_t) sms * t.warps * t.rg / 2) t.rg >>= 1;
     if (paired && t.rg < 2) t.rg = 2;

@@ -98,6 +98,9 @@ struct b200_backend_ctx {
     const float * pn_x = nullptr, * pn_w = nullptr;
     float pn_eps = 0.0f;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // this graph rewrites OLD KV-cache rows (context shift / sliding-window roll: F16 -> F16 copies, src/layers.cpp:2999-3020, :3284-3332):
+    // the fused attention must not stream the cache before its programmatic-dependent-launch wait
+    bool kv_rewritten = false;
     double prof_host_ms = 0, prof_gpu_ms = 0, prof_sync_ms = 0;
     long long prof_graphs = 0, prof_launches0 = 0;
 };
@@ -598,7 +601,8 @@ static int try_fuse_norm(b200_backend_ctx * bc, ggml_cgraph * g, int i, int * rc
     else if (mul->src[1] == rms) w = mul->src[0];
     if (!w || !f32c(w) || ggml_nelements(w) != rms->ne[0] || !f32c(rms->src[0]) || !f32c(mul)) return 0;
     if (rms->ne[0] % 256 || rms->ne[0] > 20480) return 0;
-    if (!add && !ggml_node_has_n_uses(g, j, 1)) return 0;
+    if (!ggml_node_has_n_uses(g, j, 1) || (rms->flags & GGML_TENSOR_FLAG_OUTPUT)) return 0;  // rms->data is never written by the fused group
+    if (add && (add->flags & GGML_TENSOR_FLAG_OUTPUT) && !f32c(add)) return 0;
     // which weight type will consume the normalised activations?
     int wtype = -1;
     for (int t = j + 2; t < g->n_nodes && t < j + 12; ++t) {
@@ -656,6 +660,7 @@ static int try_fuse_bias(b200_backend_ctx * bc, ggml_cgraph * g, int i, int * rc
     if (!is_quant_mm(mm) || add->op != GGML_OP_ADD || add->src[0] != mm) return 0;
     const ggml_tensor * b = add->src[1];
     if (!f32c(b) || ggml_nelements(b) != mm->ne[0] || !f32c(add) || !ggml_are_same_shape(add, mm)) return 0;
+    if (!ggml_node_has_n_uses(g, i, 1) || (mm->flags & GGML_TENSOR_FLAG_OUTPUT)) return 0;  // mm->data is never written by the fused group
     *rc = mul_mat_quant(bc, mm->src[0], mm->src[1], (float *) add->data, (int64_t) (add->nb[1] / 4), (const float *) b->data);
     return 2;
 }
@@ -670,6 +675,8 @@ static int try_fuse_attention(b200_backend_ctx * bc, ggml_cgraph * g, int i, int
         pm->op != GGML_OP_PERMUTE || ct->op != GGML_OP_CONT)
         return 0;
     if (sc->src[0] != kq || dm->src[0] != sc || sm->src[0] != dm || sm->src[1] || sm->src[2] || pv->src[1] != sm || pm->src[0] != pv || ct->src[0] != pm) return 0;
+    for (int t = i; t <= i + 5; ++t)   // kq, sc, dm, sm, pv (and the permute view) are never materialised: they must be dead outside the group
+        if (!ggml_node_has_n_uses(g, t, 1) || (g->nodes[t]->flags & GGML_TENSOR_FLAG_OUTPUT)) return 0;
     const ggml_tensor * K = kq->src[0], * Q = kq->src[1], * V = pv->src[0];
     if (K->type != GGML_TYPE_F16 || V->type != GGML_TYPE_F16 || Q->type != GGML_TYPE_F32) return 0;
     const int64_t hd = K->ne[0], n_kv = K->ne[1], kvh = K->ne[2], heads = Q->ne[2];
@@ -711,7 +718,7 @@ static int try_fuse_attention(b200_backend_ctx * bc, ggml_cgraph * g, int i, int
         }
     }
     int r = attn_decode3((const float *) Q->data, K->data, V->data, (float *) ct->data, bc->attn_scratch, (int) heads, (int) kvh, (int) hd, (int) n_kv,
-                         (int64_t) (K->nb[1] / 2), (int64_t) (V->nb[1] / 2), scale, wtype, qo, bc->stream);
+                         (int64_t) (K->nb[1] / 2), (int64_t) (V->nb[1] / 2), scale, wtype, qo, bc->stream, bc->kv_rewritten ? 0 : 1);
     if (r == B200_ERR_UNSUPPORTED) return 0;
     *rc = r;
     bc->launches += 2;
@@ -1036,6 +1043,14 @@ static enum ggml_status b200_graph_compute(ggml_backend_t backend, ggml_cgraph *
     order_after_inputs(&g_dev_ctx[bc->device], bc->stream);
     bc->q_src = nullptr;  // nothing is known to be quantized at the start of a graph
     bc->pn_mul = nullptr;
+    bc->kv_rewritten = false;
+    for (int i = 0; i < cgraph->n_nodes; ++i) {
+        const ggml_tensor * n = cgraph->nodes[i];
+        if ((n->op == GGML_OP_CPY || n->op == GGML_OP_DUP || n->op == GGML_OP_CONT) && n->type == GGML_TYPE_F16 && n->src[0] && n->src[0]->type == GGML_TYPE_F16) {
+            bc->kv_rewritten = true;
+            break;
+        }
+    }
     static const bool trace = getenv("B200_TRACE") != nullptr;
     static const bool prof = getenv("B200_PROFILE") != nullptr;
     std::chrono::steady_clock::time_point t0;

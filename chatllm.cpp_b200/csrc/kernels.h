@@ -110,8 +110,10 @@ size_t attn_decode2_scratch_bytes(int n_heads, int n_kv);
 int attn_decode2(const float * q, const void * kc, const void * vc, float * out, float * scratch, int n_heads, int kv_heads, int head_dim, int n_kv,
                  int64_t k_row_stride, int64_t v_row_stride, float scale, cudaStream_t st);
 // + qact (may be NULL) = out quantized as the activations of a following matmul with weight type wtype (n_heads*head_dim % 256 == 0)
+// preload: 1 = K / V rows older than n_kv - 1 may be streamed before the programmatic-dependent-launch wait (they were written by
+// EARLIER decode steps), 0 = a launch just before this call may have rewritten them (cache shift), -1 = library default
 int attn_decode3(const float * q, const void * kc, const void * vc, float * out, float * scratch, int n_heads, int kv_heads, int head_dim, int n_kv,
-                 int64_t k_row_stride, int64_t v_row_stride, float scale, int wtype, void * qact, cudaStream_t st);
+                 int64_t k_row_stride, int64_t v_row_stride, float scale, int wtype, void * qact, cudaStream_t st, int preload = -1);
 
 // ---- ops_generic.cu: strided / broadcasting ops as ggml graphs present them (ne[0] fastest, nb in bytes)
 struct TV {

@@ -136,6 +136,10 @@ int quantize_act(int wtype, const float * x, int64_t x_col_stride, int64_t k, in
 template <int QB>  // quant bytes per block: 16 (Q4_0) or 32 (Q8_0)
 __global__ void repack_bytes_kernel(const uint8_t * src, uint8_t * dst_tensor, int64_t tensor_off,
                                     int64_t nbytes, int64_t nb_row, bool inverse) {
+    // launched through launch_pdl like every kernel of the library: a kernel of a PDL chain that never waits could finish while its
+    // predecessor is still running and break the transitive ordering every later kernel relies on (common.cuh)
+    pdl_launch_dependents();
+    pdl_wait();
     const int BB = QB + 2;
     const int64_t row_bytes = nb_row * BB;
     for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < nbytes; i += (int64_t) gridDim.x * blockDim.x) {

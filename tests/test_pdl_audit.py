@@ -11,12 +11,13 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BUILD = os.path.join(ROOT, "chatllm.cpp_b200", "build")
-OBJS = ["fused.o", "gemv.o", "ops.o", "ops_generic.o", "quantize.o", "prefill.o", "prefill_tc.o"]
+OBJS = ["fused.o", "gemv.o", "ops.o", "ops_generic.o", "quantize.o", "prefill.o", "prefill_tc.o", "decode_mk.o"]
 
 needs_objs = pytest.mark.skipif(not shutil.which("cuobjdump") or not all(os.path.exists(os.path.join(BUILD, o)) for o in OBJS),
                                 reason="needs the built kernel objects (python -c 'import __graft_entry__ as g; g.build()') and cuobjdump")
 
 LOAD = re.compile(r"\b(LDG|LD\.E|UBLKCP|LDGSTS)")
+STORE = re.compile(r"\b(STG|ST\.E|RED\.E|ATOMG)")
 
 
 def kernels(obj):
@@ -33,9 +34,16 @@ def test_no_producer_load_is_hoisted_above_the_pdl_wait(obj):
     checked = 0
     for name, ins in kernels(obj):
         waits = [i for i, t in enumerate(ins) if "ACQBULK" in t]
-        if not waits:
+        if "decode_mk_kernel" in name:
+            # the persistent kernel is a cooperative launch WITHOUT the programmatic-serialization attribute: plain stream order
+            assert not waits, name
             continue
+        # every other kernel is launched through launch_pdl: one that never waits could finish before its predecessor and break the
+        # transitive ordering of the chain (repack_bytes_kernel had no wait and the old audit skipped it silently)
+        assert waits, f"{name}: launched with programmatic stream serialization but never executes griddepcontrol.wait"
         checked += 1
+        stores = [t for t in ins[:waits[0]] if STORE.search(t)]
+        assert not stores, (name, "global stores before the first wait", stores)
         before = [t for t in ins[:waits[0]] if LOAD.search(t)]
         between = [t for t in ins[waits[0]:waits[-1]] if LOAD.search(t)]
         if "gemv_q_kernel" in name:
