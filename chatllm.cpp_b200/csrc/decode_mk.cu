@@ -951,6 +951,7 @@ void * decode_plan_create(const DecodeModel & m, int max_ctx, int * err) {
     pl->ws_bytes = off;
     if (cudaMalloc(&pl->ws, pl->ws_bytes) != cudaSuccess) { cudaGetLastError(); delete pl; return fail((int) cudaErrorMemoryAllocation); }
     cudaMemset(pl->ws, 0, pl->ws_bytes);  // barrier counter / argmax key / the padding of att_q start at zero
+    cudaDeviceSynchronize();               // (the first launch may be on a non-blocking stream)
     uint8_t * w = (uint8_t *) pl->ws;
     P.sync = (unsigned long long *) (w + o_sync);
     P.q = (float *) (w + o_q); P.kbuf = (float *) (w + o_k); P.vbuf = (float *) (w + o_v); P.scores = (float *) (w + o_sc);
@@ -1051,9 +1052,10 @@ int decode_step(void * h, const DecodeIO & io, cudaStream_t st) {
             if (kind == 1 || kind == 3) ph.y[0] = x;
             if (kind == 4) ph.y[0] = io.logits;
         }
-        // synchronous copies: the host vectors may be edited again right after this call
-        if (!pl->h_phases.empty()) B200_CUDA_CHECK(cudaMemcpy(pl->d_phases, pl->h_phases.data(), sizeof(MKPhase) * pl->h_phases.size(), cudaMemcpyHostToDevice));
-        if (!pl->h_kv.empty()) B200_CUDA_CHECK(cudaMemcpy(pl->d_kv, pl->h_kv.data(), sizeof(MKLayerKV) * pl->h_kv.size(), cudaMemcpyHostToDevice));
+        // in-stream copies (ordered behind a launch that may still be reading the tables); the source is pageable memory, so the runtime
+        // has taken its copy by the time the call returns and the host vectors may be edited again
+        if (!pl->h_phases.empty()) B200_CUDA_CHECK(cudaMemcpyAsync(pl->d_phases, pl->h_phases.data(), sizeof(MKPhase) * pl->h_phases.size(), cudaMemcpyHostToDevice, st));
+        if (!pl->h_kv.empty()) B200_CUDA_CHECK(cudaMemcpyAsync(pl->d_kv, pl->h_kv.data(), sizeof(MKLayerKV) * pl->h_kv.size(), cudaMemcpyHostToDevice, st));
         pl->dirty = false; pl->up_x = x; pl->up_logits = io.logits;
     }
     prm.x = x;

@@ -103,6 +103,12 @@ struct b200_backend_ctx {
     bool kv_rewritten = false;
     double prof_host_ms = 0, prof_gpu_ms = 0, prof_sync_ms = 0;
     long long prof_graphs = 0, prof_launches0 = 0;
+    // whole-token plan (try_whole_token): the persistent decode kernel's phase table + workspace, rebuilt only when the graph's weights move
+    void * mk_plan = nullptr;
+    std::vector<DecodeLayer> mk_layers;
+    DecodeModel mk_model{};
+    int mk_max_ctx = 0;
+    long long mk_tokens = 0;
 };
 
 static ggml_backend_device g_devices[B200_MAX_DEVICES];
@@ -667,7 +673,12 @@ static int try_fuse_bias(b200_backend_ctx * bc, ggml_cgraph * g, int i, int * rc
 
 static const ggml_tensor * view_root(const ggml_tensor * t);
 // decode attention: MUL_MAT(K,Q) -> SCALE -> DIAG_MASK_INF -> SOFT_MAX -> MUL_MAT(V,P) -> PERMUTE -> CONT, one query token
-static int try_fuse_attention(b200_backend_ctx * bc, ggml_cgraph * g, int i, int * rc) {
+struct AttnMatch {
+    const ggml_tensor * K, * Q, * V, * ct;
+    int64_t hd, n_kv, kvh, heads;
+    float scale;
+};
+static int match_attention(ggml_cgraph * g, int i, AttnMatch & m) {
     if (i + 6 >= g->n_nodes) return 0;
     ggml_tensor * kq = g->nodes[i], * sc = g->nodes[i + 1], * dm = g->nodes[i + 2], * sm = g->nodes[i + 3], * pv = g->nodes[i + 4], * pm = g->nodes[i + 5],
                 * ct = g->nodes[i + 6];
@@ -692,6 +703,15 @@ static int try_fuse_attention(b200_backend_ctx * bc, ggml_cgraph * g, int i, int
     if (sbias != 0.0f || smscale != 1.0f || smbias != 0.0f) return 0;
     if (dm->op_params[0] != (int32_t) (n_kv - 1)) return 0;  // the single query row sees every cached position
     if (!f32c(ct) || ct->ne[0] != hd || ct->ne[1] != heads || ggml_nelements(ct) != hd * heads) return 0;
+    m.K = K; m.Q = Q; m.V = V; m.ct = ct; m.hd = hd; m.n_kv = n_kv; m.kvh = kvh; m.heads = heads; m.scale = scale;
+    return 7;
+}
+static int try_fuse_attention(b200_backend_ctx * bc, ggml_cgraph * g, int i, int * rc) {
+    AttnMatch am;
+    if (!match_attention(g, i, am)) return 0;
+    const ggml_tensor * K = am.K, * Q = am.Q, * V = am.V, * ct = am.ct;
+    const int64_t hd = am.hd, n_kv = am.n_kv, kvh = am.kvh, heads = am.heads;
+    const float scale = am.scale;
     const size_t need = attn_decode2_scratch_bytes((int) heads, (int) n_kv) + attn_decode_scratch_bytes((int) heads, (int) n_kv);
     if (bc->attn_scratch_bytes < need) {
         CUDA_OK(cudaStreamSynchronize(bc->stream));
@@ -740,11 +760,17 @@ static bool plain_rope(const ggml_tensor * r, int64_t hd) {
     return n_dims == hd && (mode == 0 || mode == GGML_ROPE_TYPE_NEOX) && fp[1] == 1.0f && fp[2] == 0.0f && fp[3] == 1.0f &&
            (!r->src[2] || (r->src[2]->type == GGML_TYPE_F32 && ggml_is_contiguous(r->src[2])));
 }
-static int try_fuse_qkv(b200_backend_ctx * bc, ggml_cgraph * g, int i, int * rc) {
+struct QkvMatch {
+    const ggml_tensor * mm[3], * out[3], * bias[3];  // v, k, q (graph order)
+    const ggml_tensor * cpy, * sr, * rk, * rq;
+    int64_t hd, kvh, heads;
+    int idx_rq;
+};
+static int match_qkv(ggml_cgraph * g, int i, QkvMatch & qm) {
     int j = i;
     auto next_real = [&](int from) { while (from < g->n_nodes && is_view_op(g->nodes[from]->op)) ++from; return from; };
     // one projection: MUL_MAT [+ ADD bias]; returns the tensor holding the projection's result
-    const ggml_tensor * mm[3] = {nullptr, nullptr, nullptr}, * out[3], * bias[3] = {nullptr, nullptr, nullptr};
+    const ggml_tensor * mm[3] = {nullptr, nullptr, nullptr}, * out[3] = {nullptr, nullptr, nullptr}, * bias[3] = {nullptr, nullptr, nullptr};
     int idx_out[3];
     auto take_proj = [&](int s) -> bool {
         j = next_real(j);
@@ -802,6 +828,18 @@ static int try_fuse_qkv(b200_backend_ctx * bc, ggml_cgraph * g, int i, int * rc)
         mm[0]->src[0]->type != mm[2]->src[0]->type)
         return 0;
     for (int s = 0; s < 3; ++s) if (mm[s]->src[0]->ne[1] % 2) return 0;
+
+    for (int s = 0; s < 3; ++s) { qm.mm[s] = mm[s]; qm.out[s] = out[s]; qm.bias[s] = bias[s]; }
+    qm.cpy = cpy; qm.sr = sr; qm.rk = rk; qm.rq = rq; qm.hd = hd; qm.kvh = kvh; qm.heads = heads; qm.idx_rq = idx_rq;
+    return idx_rq - i + 1;
+}
+static int try_fuse_qkv(b200_backend_ctx * bc, ggml_cgraph * g, int i, int * rc) {
+    QkvMatch qm;
+    if (!match_qkv(g, i, qm)) return 0;
+    const ggml_tensor * const * mm = qm.mm, * const * out = qm.out, * const * bias = qm.bias;
+    const ggml_tensor * cpy = qm.cpy, * sr = qm.sr, * rk = qm.rk, * rq = qm.rq;
+    const int64_t hd = qm.hd, kvh = qm.kvh, heads = qm.heads;
+    const int idx_rq = qm.idx_rq;
 
     const ggml_tensor * x = mm[0]->src[1];
     const bool pro = (x == bc->pn_mul);
@@ -956,9 +994,12 @@ static void b200_backend_free(ggml_backend_t backend) {
     b200_backend_ctx * bc = (b200_backend_ctx *) backend->context;
     cudaSetDevice(bc->device);
     cudaStreamSynchronize(bc->stream);
+    if (getenv("B200_STATS"))  // tests / bench: how the graphs of this backend instance were executed
+        fprintf(stderr, "B200STATS device=%d launches=%lld fused_nodes=%lld whole_token_graphs=%lld\n", bc->device, bc->launches, bc->fused, bc->mk_tokens);
     if (bc->qact) cudaFree(bc->qact);
     if (bc->attn_scratch) cudaFree(bc->attn_scratch);
     if (bc->kv_scratch) cudaFree(bc->kv_scratch);
+    if (bc->mk_plan) decode_plan_destroy(bc->mk_plan);
     if (bc->p2p_ev) cudaEventDestroy(bc->p2p_ev);
     if (bc->ev0) cudaEventDestroy(bc->ev0);
     if (bc->ev1) cudaEventDestroy(bc->ev1);
@@ -1037,6 +1078,209 @@ static void trace_node(b200_backend_ctx * bc, int idx, const ggml_tensor * t) {
             (long long) t->ne[2], (long long) t->ne[3], s, a);
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Whole-token execution (per-token host overhead).  A one-token graph that is EXACTLY
+//     [GET_ROWS(embedding)]  N x { RMS_NORM*w -> q/k/v (+bias) -> RoPE -> KV append -> attention -> o -> +residual -> RMS_NORM*w -> SwiGLU MLP -> +residual }
+//     [RMS_NORM*w -> lm_head]
+// (what HeterogeneousModel::forward src/models.cpp:1399-1424 builds for the dense Llama family; a device's layer range of it when the
+// model is split with -ngl "0:16;1:16") is not walked node by node: the weights / caches / io pointers are collected into a
+// b200_decode_model and the token runs as ONE launch of the persistent kernel (decode_mk.cu) — the reference's answer to the same
+// overhead is CUDA-graph capture of the node launches (ggml-cuda.cu:2875-3071, :3993-4089).  The plan (device tables + workspace) is
+// cached and rebuilt only when a weight / cache pointer changes; only n_kv and the token / position / logits pointers vary per token.
+// Anything that does not match exactly (prompt batches, MoE, sliding-window caches, context shifts, YaRN, eval callbacks that cut
+// the graph) falls back to the per-node path below.  B200_NO_MK=1 disables it.
+// ------------------------------------------------------------------------------------------------------------
+static bool norm_pair(ggml_cgraph * g, int i_rms, int i_mul, const ggml_tensor ** w, float * eps) {
+    const ggml_tensor * rms = g->nodes[i_rms], * mul = g->nodes[i_mul];
+    if (rms->op != GGML_OP_RMS_NORM || mul->op != GGML_OP_MUL) return false;
+    const ggml_tensor * ww = mul->src[0] == rms ? mul->src[1] : (mul->src[1] == rms ? mul->src[0] : nullptr);
+    if (!ww || !f32c(ww) || ggml_nelements(ww) != rms->ne[0] || !f32c(rms->src[0]) || !f32c(mul) || ggml_nrows(rms) != 1) return false;
+    if (!ggml_node_has_n_uses(g, i_rms, 1) || (rms->flags & GGML_TENSOR_FLAG_OUTPUT) || (mul->flags & GGML_TENSOR_FLAG_OUTPUT)) return false;
+    memcpy(eps, rms->op_params, sizeof(float));
+    *w = ww;
+    return true;
+}
+static bool try_whole_token(b200_backend_ctx * bc, ggml_cgraph * g, int * rc) {
+    static const bool off = getenv("B200_NO_MK") && atoi(getenv("B200_NO_MK")) != 0;
+    if (off || !fusion_enabled() || bc->kv_rewritten || g->n_nodes < 20) return false;
+    const int n = g->n_nodes;
+    auto next_real = [&](int from) { while (from < n && (is_view_op(g->nodes[from]->op) || ggml_is_empty(g->nodes[from]))) ++from; return from; };
+    int i = next_real(0);
+    if (i >= n) return false;
+    const ggml_tensor * embed = nullptr, * tok = nullptr, * cur = nullptr;
+    if (g->nodes[i]->op == GGML_OP_GET_ROWS) {
+        const ggml_tensor * gr = g->nodes[i];
+        if (!b200_supports_op_impl(nullptr, gr) || !ggml_is_quantized(gr->src[0]->type) || ggml_nelements(gr->src[1]) != 1 || !f32c(gr)) return false;
+        embed = gr->src[0]; tok = gr->src[1]; cur = gr;
+        i = next_real(i + 1);
+    }
+    std::vector<DecodeLayer> layers;
+    DecodeModel M{};
+    const ggml_tensor * pos = nullptr, * x_in = nullptr, * x_out = nullptr, * logits = nullptr, * ff = nullptr;
+    int64_t n_kv = -1;
+    bool first = true;
+    while (i < n) {
+        // ---- RMS_NORM * w of the hidden state
+        const int i_rms = i, i_mul = next_real(i + 1);
+        if (i_mul >= n) return false;
+        const ggml_tensor * w1 = nullptr;
+        float eps = 0.0f;
+        if (!norm_pair(g, i_rms, i_mul, &w1, &eps)) return false;
+        const ggml_tensor * xs = view_root(g->nodes[i_rms]->src[0]);
+        if (cur) { if (xs != cur) return false; } else { cur = x_in = xs; }
+        const ggml_tensor * nrm = g->nodes[i_mul];
+        const int64_t hidden = nrm->ne[0];
+        if (first) { M.hidden = (int) hidden; M.eps = eps; } else if (hidden != M.hidden || eps != M.eps) return false;
+        int j = next_real(i_mul + 1);
+        if (j >= n) return false;
+        QkvMatch qm;
+        const int nq = match_qkv(g, j, qm);
+        if (!nq) {
+            // ---- head: lm_head . (final norm), and nothing after it
+            const ggml_tensor * mm = g->nodes[j];
+            if (!is_quant_mm(mm) || view_root(mm->src[1]) != nrm || mm->src[1]->ne[1] != 1 || mm->src[1]->ne[0] != hidden || next_real(j + 1) < n) return false;
+            if (ggml_node_get_use_count(g, i_mul) != 1) return false;
+            M.final_norm = (const float *) w1->data; M.lm_head = mm->src[0]->data; M.vocab = (int) mm->src[0]->ne[1];
+            if ((int) mm->src[0]->type != M.wtype && !layers.empty()) return false;
+            if (layers.empty()) M.wtype = (int) mm->src[0]->type;
+            logits = mm;
+            i = n;
+            break;
+        }
+        // ---- q/k/v + RoPE + KV append
+        if (qm.mm[0]->src[1] != nrm || ggml_node_get_use_count(g, i_mul) != 3) return false;
+        const int wtype = (int) qm.mm[0]->src[0]->type;
+        float fp[6];
+        memcpy(fp, (const int32_t *) qm.rq->op_params + 5, sizeof(fp));
+        const int rope_mode = qm.rq->op_params[2];
+        if (first) {
+            M.wtype = wtype; M.heads = (int) qm.heads; M.kv_heads = (int) qm.kvh; M.head_dim = (int) qm.hd; M.rope_mode = rope_mode == 0 ? 0 : 2; M.rope_theta = fp[0];
+            pos = qm.rk->src[1]; ff = qm.rk->src[2];
+        } else if (wtype != M.wtype || qm.heads != M.heads || qm.kvh != M.kv_heads || qm.hd != M.head_dim || (rope_mode == 0 ? 0 : 2) != M.rope_mode || fp[0] != M.rope_theta ||
+                   qm.rk->src[1]->data != pos->data || (qm.rk->src[2] ? qm.rk->src[2]->data : nullptr) != (ff ? ff->data : nullptr))
+            return false;
+        if (ggml_nelements(qm.rk->src[1]) != 1 || qm.heads * qm.hd != hidden) return false;
+        for (int s = 0; s < 3; ++s) if (qm.mm[s]->src[0]->ne[0] != hidden) return false;
+        j = next_real(j + nq);
+        // ---- attention over the cache that was just appended to
+        AttnMatch am;
+        if (j >= n || !match_attention(g, j, am)) return false;
+        if (view_root(am.Q) != view_root(qm.rq) || am.hd != qm.hd || am.kvh != qm.kvh || am.heads != qm.heads) return false;
+        if (am.K->data != qm.sr->data || am.K->nb[1] != qm.sr->nb[1]) return false;                       // K view starts at cache row 0
+        if ((const char *) qm.cpy->data != (const char *) am.V->data + (am.n_kv - 1) * 2 || qm.cpy->nb[1] != am.V->nb[1]) return false;  // V column n_kv - 1
+        if (first) { n_kv = am.n_kv; M.attn_scale = am.scale; M.k_row_stride = (int64_t) (am.K->nb[1] / 2); M.v_row_stride = (int64_t) (am.V->nb[1] / 2); }
+        else if (am.n_kv != n_kv || am.scale != M.attn_scale || (int64_t) (am.K->nb[1] / 2) != M.k_row_stride || (int64_t) (am.V->nb[1] / 2) != M.v_row_stride) return false;
+        j = next_real(j + 7);
+        // ---- o projection + residual
+        if (j >= n) return false;
+        const ggml_tensor * o = g->nodes[j];
+        if (!is_quant_mm(o) || (int) o->src[0]->type != wtype || view_root(o->src[1]) != am.ct || o->src[1]->ne[1] != 1 || o->src[0]->ne[0] != hidden || o->src[0]->ne[1] != hidden ||
+            !ggml_node_has_n_uses(g, j, 1))
+            return false;
+        int ja = next_real(j + 1);
+        if (ja >= n) return false;
+        const ggml_tensor * add1 = g->nodes[ja];
+        if (add1->op != GGML_OP_ADD || !f32c(add1) || ggml_nelements(add1) != hidden) return false;
+        if (!((add1->src[0] == o && view_root(add1->src[1]) == cur) || (add1->src[1] == o && view_root(add1->src[0]) == cur))) return false;
+        // ---- RMS_NORM * w -> SwiGLU MLP -> + residual
+        const int i_rms2 = next_real(ja + 1), i_mul2 = next_real(i_rms2 + 1);
+        if (i_mul2 >= n) return false;
+        const ggml_tensor * w2 = nullptr;
+        float eps2 = 0.0f;
+        if (!norm_pair(g, i_rms2, i_mul2, &w2, &eps2) || eps2 != M.eps || view_root(g->nodes[i_rms2]->src[0]) != add1 || ggml_node_get_use_count(g, i_mul2) != 2) return false;
+        const ggml_tensor * nrm2 = g->nodes[i_mul2];
+        j = next_real(i_mul2 + 1);
+        if (j + 3 >= n) return false;
+        const ggml_tensor * gate = g->nodes[j], * act = g->nodes[j + 1], * up = g->nodes[j + 2], * gu = g->nodes[j + 3];
+        if (!is_quant_mm(gate) || !is_quant_mm(up) || act->op != GGML_OP_UNARY || ggml_get_unary_op(act) != GGML_UNARY_OP_SILU || gu->op != GGML_OP_MUL) return false;
+        if (act->src[0] != gate || gate->src[1] != nrm2 || up->src[1] != nrm2 || (int) gate->src[0]->type != wtype || (int) up->src[0]->type != wtype ||
+            !ggml_are_same_shape(gate->src[0], up->src[0]) || gate->src[0]->ne[0] != hidden)
+            return false;
+        if (!((gu->src[0] == act && gu->src[1] == up) || (gu->src[1] == act && gu->src[0] == up))) return false;
+        if (!f32c(gu) || !ggml_node_has_n_uses(g, j, 1) || !ggml_node_has_n_uses(g, j + 1, 1) || !ggml_node_has_n_uses(g, j + 2, 1) || !ggml_node_has_n_uses(g, j + 3, 1)) return false;
+        const int64_t ffn = gate->src[0]->ne[1];
+        if (first) M.ffn = (int) ffn; else if (ffn != M.ffn) return false;
+        j = next_real(j + 4);
+        if (j >= n) return false;
+        const ggml_tensor * down = g->nodes[j];
+        if (!is_quant_mm(down) || (int) down->src[0]->type != wtype || view_root(down->src[1]) != gu || down->src[1]->ne[1] != 1 || down->src[0]->ne[0] != ffn ||
+            down->src[0]->ne[1] != hidden || !ggml_node_has_n_uses(g, j, 1))
+            return false;
+        ja = next_real(j + 1);
+        if (ja >= n) return false;
+        const ggml_tensor * add2 = g->nodes[ja];
+        if (add2->op != GGML_OP_ADD || !f32c(add2) || ggml_nelements(add2) != hidden) return false;
+        if (!((add2->src[0] == down && add2->src[1] == add1) || (add2->src[1] == down && add2->src[0] == add1))) return false;
+        DecodeLayer L{};
+        L.wq = qm.mm[2]->src[0]->data; L.wk = qm.mm[1]->src[0]->data; L.wv = qm.mm[0]->src[0]->data; L.wo = o->src[0]->data;
+        L.wgate = gate->src[0]->data; L.wup = up->src[0]->data; L.wdown = down->src[0]->data;
+        L.bq = qm.bias[2] ? (const float *) qm.bias[2]->data : nullptr; L.bk = qm.bias[1] ? (const float *) qm.bias[1]->data : nullptr;
+        L.bv = qm.bias[0] ? (const float *) qm.bias[0]->data : nullptr;
+        L.attn_norm = (const float *) w1->data; L.ffn_norm = (const float *) w2->data;
+        L.k_cache = am.K->data; L.v_cache = am.V->data;
+        if (qm.mm[2]->src[0]->ne[1] != hidden || qm.mm[1]->src[0]->ne[1] != qm.kvh * qm.hd || qm.mm[0]->src[0]->ne[1] != qm.kvh * qm.hd) return false;
+        layers.push_back(L);
+        cur = x_out = add2;
+        first = false;
+        i = next_real(ja + 1);
+    }
+    if (layers.empty()) return false;
+    // ---- plan: reuse while nothing the tables point at has moved
+    M.n_layers = (int) layers.size();
+    M.embed = embed ? embed->data : nullptr;
+    M.embed_type = embed ? (int) embed->type : 0;
+    M.rope_freq_factors = ff ? (const float *) ff->data : nullptr;
+    M.layers = nullptr;
+    const int max_ctx = (int) M.v_row_stride;
+    if (n_kv > max_ctx) return false;
+    bool same = bc->mk_plan && bc->mk_layers.size() == layers.size() && bc->mk_max_ctx == max_ctx;
+    if (same) {
+        DecodeModel a = bc->mk_model, b = M;
+        a.layers = b.layers = nullptr;
+        same = memcmp(&a, &b, sizeof(DecodeModel)) == 0;
+    }
+    if (same) {
+        for (size_t l = 0; l < layers.size() && same; ++l) {
+            DecodeLayer a = bc->mk_layers[l], b = layers[l];
+            if (a.k_cache != b.k_cache || a.v_cache != b.v_cache) { decode_plan_set_kv(bc->mk_plan, (int) l, b.k_cache, b.v_cache); bc->mk_layers[l].k_cache = b.k_cache; bc->mk_layers[l].v_cache = b.v_cache; a = bc->mk_layers[l]; }
+            same = memcmp(&a, &b, sizeof(DecodeLayer)) == 0;
+        }
+    }
+    if (!same) {
+        if (bc->mk_plan) { CUDA_OK(cudaStreamSynchronize(bc->stream)); decode_plan_destroy(bc->mk_plan); bc->mk_plan = nullptr; }
+        M.layers = layers.data();
+        int err = 0;
+        bc->mk_plan = decode_plan_create(M, max_ctx, &err);
+        if (!bc->mk_plan) {
+            static bool warned = false;
+            if (!warned) { GGML_LOG_INFO("b200: persistent decode kernel declined this model (err %d): per-node path\n", err); warned = true; }
+            return false;
+        }
+        bc->mk_layers = layers; bc->mk_model = M; bc->mk_model.layers = nullptr; bc->mk_max_ctx = max_ctx;
+    }
+    // ---- one launch.  The residual stream lives in the tensor a later split / the host reads (layer-split models), else in the plan.
+    DecodeIO io{};
+    io.tok = tok ? (const int32_t *) tok->data : nullptr;
+    io.pos = (const int32_t *) pos->data;
+    io.n_kv = (int) n_kv;
+    io.v_col = (int) n_kv - 1;
+    io.x = nullptr;
+    if (!logits) io.x = (float *) x_out->data;
+    else if (x_in) io.x = (float *) x_in->data;   // the incoming copy of a layer-split boundary is updated in place
+    if (x_in && io.x != (float *) x_in->data) {
+        const cudaError_t e = cudaMemcpyAsync(io.x, x_in->data, (size_t) M.hidden * 4, cudaMemcpyDeviceToDevice, bc->stream);
+        if (e != cudaSuccess) { *rc = (int) e; return true; }
+        bc->launches++;
+    }
+    io.logits = logits ? (float *) logits->data : nullptr;
+    io.next_tok = nullptr; io.flags = 0; io.step_begin = io.step_end = 0;
+    *rc = decode_step(bc->mk_plan, io, bc->stream);
+    bc->launches++;
+    bc->fused += n;
+    bc->mk_tokens++;
+    return true;
+}
+
 static enum ggml_status b200_graph_compute(ggml_backend_t backend, ggml_cgraph * cgraph) {
     b200_backend_ctx * bc = (b200_backend_ctx *) backend->context;
     CUDA_OK(cudaSetDevice(bc->device));
@@ -1059,7 +1303,13 @@ static enum ggml_status b200_graph_compute(ggml_backend_t backend, ggml_cgraph *
         t0 = std::chrono::steady_clock::now();
         cudaEventRecord(bc->ev0, bc->stream);
     }
-    for (int i = 0; i < cgraph->n_nodes; ++i) {
+    int rc_mk = 0;
+    const bool whole = !trace && try_whole_token(bc, cgraph, &rc_mk);
+    if (whole && rc_mk != 0) {
+        GGML_LOG_ERROR("b200: persistent decode kernel failed rc=%d%s\n", rc_mk, rc_mk > 0 ? cudaGetErrorString((cudaError_t) rc_mk) : "");
+        return GGML_STATUS_FAILED;
+    }
+    for (int i = whole ? cgraph->n_nodes : 0; i < cgraph->n_nodes; ++i) {
         ggml_tensor * node = cgraph->nodes[i];
         if (is_view_op(node->op) || ggml_is_empty(node)) continue;
         int rc = 0;

@@ -179,8 +179,7 @@ def _n_cuda():
         return 0
 
 
-@pytest.mark.skipif(_n_cuda() < 2 or not os.environ.get("B200_TEST_MULTI_GPU"),
-                    reason="needs two GPUs and B200_TEST_MULTI_GPU=1 (the plugin's peer-copy path has not been run on a 2-GPU box yet: opt-in)")
+@pytest.mark.skipif(_n_cuda() < 2, reason="needs two GPUs")
 @pytest.mark.parametrize("quant", ["q4_K", "q4_0"])
 def test_layer_split_across_two_devices(tmp_path, quant):
     """`-ngl "0:1,prolog;1:1,epilog"` puts layer 0 (+ embedding) on CUDA0 and layer 1 (+ final norm, lm_head) on CUDA1,
@@ -200,3 +199,30 @@ def test_layer_split_across_two_devices(tmp_path, quant):
     print("tiny-test", quant, "2-device layer split: max rel logit err per (length, seed)", worst)
     assert max(worst) <= 3e-2, worst
     assert sum(w <= 1e-3 for w in worst) > len(worst) // 2, worst
+
+
+def _stats(err):
+    line = [l for l in err.splitlines() if l.startswith("B200STATS")]
+    assert line, err[-1500:]
+    return {k: int(v) for k, v in (kv.split("=") for kv in line[0].split()[1:])}
+
+
+@pytest.mark.parametrize("arch,quant", [("tiny-test", "q4_K"), ("tiny-test", "q8_0"), ("qwen2-test", "q4_0")])
+def test_decode_graphs_run_as_one_persistent_launch(tmp_path, arch, quant):
+    """every one-token graph of a dense Llama-family model is executed by the plugin as ONE launch of the persistent
+    decode kernel (try_whole_token in ggml-b200.cu), and gives the logits of the node-by-node path (B200_NO_MK=1) and of the CPU."""
+    model = make_model(str(tmp_path), arch, quant)
+    d = str(tmp_path)
+    decode = 12
+    r1, e1 = run_host(model, "all", os.path.join(d, "mk.bin"), 5, decode, extra_env={"B200_STATS": "1"})
+    r0, e0 = run_host(model, "all", os.path.join(d, "nomk.bin"), 5, decode, extra_env={"B200_STATS": "1", "B200_NO_MK": "1"})
+    run_host(model, "0", os.path.join(d, "cpu.bin"), 5, decode)
+    s1, s0 = _stats(e1), _stats(e0)
+    assert s1["whole_token_graphs"] >= decode, s1          # (the harness' 1-token probe call is one more)
+    assert s0["whole_token_graphs"] == 0 and s1["launches"] < s0["launches"], (s0, s1)
+    a, b, c = _logits(os.path.join(d, "mk.bin"), 512), _logits(os.path.join(d, "nomk.bin"), 512), _logits(os.path.join(d, "cpu.bin"), 512)
+    assert np.isfinite(a).all()
+    rel_cpu, rel_nomk = _rel(c, a), _rel(b, a)
+    print(arch, quant, "persistent kernel vs CPU", rel_cpu, "vs node-by-node", rel_nomk)
+    assert np.median(rel_cpu) <= 1e-3 and rel_cpu.max() <= 3e-2, rel_cpu
+    assert np.median(rel_nomk) <= 1e-3 and rel_nomk.max() <= 3e-2, rel_nomk
