@@ -122,8 +122,209 @@ def cpu_reference_arm(steps, warmup, probe=(8, 16, 32, 64, 128)):
                       f"(best of a probe over {list(tried)} threads on {cores} host cores)"}
 
 
+def clocks_during(fn, idx=0, min_s=1.0):
+    """run fn() repeatedly for >= min_s while sampling nvidia-smi clocks; returns the clocks dict"""
+    import torch
+    s = ClockSampler(idx); s.start()
+    t_end = time.time() + min_s
+    while time.time() < t_end:
+        fn()
+        torch.cuda.synchronize()
+    return s.stop()
+
+
+def run_config3(a):
+    """BASELINE.json configs[2]: Qwen2.5-7B Q4_0, prefill 2048 + decode 512, 1 x B200.
+    value  = decode tokens/s over 512 greedy steps after position 2048 (persistent kernel, device-resident);
+    prefill = the prompt's quantized matmuls (28 layers x 7 matrices at n = 2048 columns: 2*n*sum(m*k) = 28.96 TFLOP) through
+              b200_quantize_plain + b200_mul_mat_q_batched, timed with CUDA events -> TFLOP/s vs the measured bf16 tensor peak (roofline);
+    e2e    = the unmodified chatllm host through libggml-cuda.so: real 2048-token prompt, then 512 decode steps."""
+    import torch
+    import __graft_entry__ as ge
+    pkg = ge.load_package(); L = pkg.lib()
+    from chatllm_cpp_b200 import session as S
+    torch.cuda.set_device(0)
+    model, wtype, P, D = "qwen2.5-7b", pkg.Q4_0, 2048, 512
+    cfg = S.make_config(model, wtype, layers=a.layers or None, max_len=P + D + 64)
+    sess = S.DecodeSession(cfg, seed=0, fused=3)
+    sess.fill_kv_random(P, seed=1)
+    sess.mk_advance = True
+    sess.tok.fill_(12345 % cfg.vocab)
+    graph = sess.capture(P)
+    sess.pos.fill_(P)
+    for _ in range(max(a.warmup, 3)):
+        graph.replay()
+    torch.cuda.synchronize()
+    sess.pos.fill_(P)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(D):
+        graph.replay()
+    e1.record(); torch.cuda.synchronize()
+    dec_ms = e0.elapsed_time(e1) / D
+    pk, pk_kind = peaks()
+    tok_bytes = cfg.weight_bytes_per_token() + cfg.kv_bytes_per_token(P + D / 2)
+    # ---- prefill matmuls (the tensor-core path), every layer's own weights: working set 4 GB >> L2
+    st = torch.cuda.current_stream().cuda_stream
+    n = P
+    xs = {k: torch.randn((n, k), device="cuda") for k in (cfg.hidden, cfg.ffn)}
+    pact = {k: torch.empty(L.b200_pact_col_bytes(wtype, k) * n, dtype=torch.uint8, device="cuda") for k in xs}
+    ybuf = torch.empty(n * max(cfg.ffn, cfg.hidden), dtype=torch.float32, device="cuda")
+    shapes = []
+    for W in sess.layers:
+        shapes += [(W.wq, cfg.hidden, cfg.hidden), (W.wk, cfg.hidden, cfg.kv_hidden), (W.wv, cfg.hidden, cfg.kv_hidden), (W.wo, cfg.hidden, cfg.hidden),
+                   (W.wgate, cfg.hidden, cfg.ffn), (W.wup, cfg.hidden, cfg.ffn), (W.wdown, cfg.ffn, cfg.hidden)]
+    tc = os.environ.get("B200_MMQ_TCGEN05", "1") != "0"
+    mm = L.b200_mul_mat_q_batched_tc if tc else L.b200_mul_mat_q_batched
+
+    def prefill_mm():
+        rc = 0
+        for k in xs:
+            rc |= L.b200_quantize_plain(wtype, xs[k].data_ptr(), k, k, n, pact[k].data_ptr(), st)
+        for (w, k, m) in shapes:
+            rc |= mm(wtype, w.data_ptr(), k, m, pact[k].data_ptr(), n, ybuf.data_ptr(), m, 0, st)
+        if rc:
+            raise RuntimeError(f"prefill matmul failed rc={rc}")
+    for _ in range(2):
+        prefill_mm()
+    torch.cuda.synchronize()
+    reps = 3
+    e0.record()
+    for _ in range(reps):
+        prefill_mm()
+    e1.record(); torch.cuda.synchronize()
+    pf_ms = e0.elapsed_time(e1) / reps
+    flop = 2.0 * n * sum(m * k for (_, k, m) in shapes)
+    tfl = flop / pf_ms / 1e9
+    clocks = clocks_during(lambda: prefill_mm(), 0, 1.0)
+    out = {"metric": "decode tokens/s after a 2048-token prompt (Q4_0 Qwen2.5-7B); prefill tensor-pipe %", "value": round(1000.0 / dec_ms, 2), "unit": "tokens/s",
+           "n_gpus": 1, "steps": D, "warmup": max(a.warmup, 3), "ms_per_step": round(dec_ms, 4), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+           "dtype": "int8 x int4 -> int32 dot, fp32 scales/accumulate", "data": "synthetic (seeded random valid Q4_0 blocks, random F16 KV cache)",
+           "config": {"workload": "Qwen2.5-7B Q4_0 prefill 2048 + decode 512, 1 x B200 (BASELINE.json configs[2])", "n_past": P, "decode_steps": D,
+                      "l2": "inputs (4.2 GB per token / per prompt pass) exceed L2; no flush needed"},
+           "gpu_launches": D, "clocks": clocks,
+           "frac_of_hbm_roofline_whole_token": round(1000.0 / dec_ms * tok_bytes / 1e9 / pk["hbm_gbs"], 4),
+           "roofline": {"bound": "tensor", "kernel": ("mmq_tc_kernel (tcgen05.mma kind::i8)" if tc else "mmq_kernel (mma.sync m16n8k32.s8)"), "achieved": round(tfl, 1),
+                        "peak": pk.get("bf16_tflops_sustained", pk["bf16_tflops"]), "unit": "TFLOP/s",
+                        "frac": round(tfl / pk.get("bf16_tflops_sustained", pk["bf16_tflops"]), 4), "peak_kind": pk_kind + " bf16 dense sustained (int8 peak is higher)",
+                        "algorithmic_TFLOP_per_pass": round(flop / 1e12, 2), "ms_per_pass": round(pf_ms, 2), "launches": len(shapes), "traffic": None,
+                        "prompt_tokens_per_s_matmuls_only": round(n / pf_ms * 1e3, 1)}}
+    if not a.no_e2e and os.path.exists(HARNESS):
+        try:
+            del sess, graph
+            torch.cuda.empty_cache()
+            path = f"/tmp/b200_{model}_q4_0{'_L%d' % a.layers if a.layers else ''}.bin"
+            if not os.path.exists(path):
+                cmd = [sys.executable, os.path.join(ROOT, "tools", "make_model.py"), "--arch", model, "--quant", "q4_0", "--out", path + ".tmp", "--max_length", str(P + D + 64)]
+                if a.layers:
+                    cmd += ["--layers", str(a.layers)]
+                subprocess.run(cmd, check=True, capture_output=True)
+                os.replace(path + ".tmp", path)
+            cmdl = [HARNESS, "--model", path, "--ggml_dir", RUNDIR, "--ngl", "all", "--threads", "16", "--prefill", str(P), "--batch", str(P), "--decode", str(D),
+                    "--max_length", str(P + D + 64), "--skip", "3"]
+            p = subprocess.run(cmdl, capture_output=True, text=True, timeout=3000)
+            r = json.loads(p.stdout.strip().splitlines()[-1])
+            out["e2e"] = {"value": round(1000.0 / r["decode_ms_mean_after_skip"], 2), "unit": "tokens/s", "ms_per_step": round(r["decode_ms_mean_after_skip"], 4),
+                          "h2d_bytes_per_step": 4 + 4 * cfg.layers, "d2h_bytes_per_step": 4 * cfg.vocab,
+                          "prefill": {"tokens": P, "ms": r["prefill_ms"], "tokens_per_s": round(P / r["prefill_ms"] * 1e3, 1)},
+                          "path": "unmodified chatllm host -> libggml-cuda.so (one-token graphs run as one persistent-kernel launch)"}
+        except Exception as ex:  # noqa: BLE001
+            out["e2e"] = {"value": None, "error": str(ex)[-300:]}
+    print(json.dumps(out))
+
+
+def run_config5(a):
+    """BASELINE.json configs[4]: Mixtral-8x7B Q4_K MoE decode, 1 x B200 (26 GB resident, 7.17 GB streamed per token).
+    The model runs through the drop-in boundary (router -> top-2 -> expert-indexed GEMV, MODE 2 / 3 of gemv.cu): `value` is the unmodified
+    host's decode loop (the only whole-model MoE driver in this repo), and the roofline is the expert-indexed GEMV kernel on the real
+    shapes, replayed alone with CUDA events."""
+    import torch
+    import __graft_entry__ as ge
+    pkg = ge.load_package(); L = pkg.lib()
+    torch.cuda.set_device(0)
+    wtype, hidden, ffn, n_exp, top, layers = pkg.Q4_K, 4096, 14336, 8, 2, (a.layers or 32)
+    st = torch.cuda.current_stream().cuda_stream
+    gen = torch.Generator(device="cuda"); gen.manual_seed(0)
+    from chatllm_cpp_b200 import session as S
+    # expert stacks of `rot` layers (each 3 x 8 x 33 MB = 793 MB) so that the replayed stream never sits in L2
+    rot = 4
+    stacks = [(S.synth_weights_device(wtype, n_exp * ffn, hidden, gen), S.synth_weights_device(wtype, n_exp * ffn, hidden, gen),
+               S.synth_weights_device(wtype, n_exp * hidden, ffn, gen)) for _ in range(rot)]
+    ids = torch.tensor([3, 6], dtype=torch.int32, device="cuda")
+    xq = torch.empty(L.b200_qact_col_bytes(wtype, hidden), dtype=torch.uint8, device="cuda")
+    gq = torch.empty(L.b200_qact_col_bytes(wtype, ffn) * top, dtype=torch.uint8, device="cuda")
+    x = torch.randn((1, hidden), device="cuda"); gx = torch.randn((top, ffn), device="cuda")
+    L.b200_quantize_act(wtype, x.data_ptr(), hidden, hidden, 1, xq.data_ptr(), st)
+    L.b200_quantize_act(wtype, gx.data_ptr(), ffn, ffn, top, gq.data_ptr(), st)
+    yg = torch.empty((top, ffn), dtype=torch.float32, device="cuda"); yd = torch.empty((top, hidden), dtype=torch.float32, device="cuda")
+
+    def moe_layers():
+        rc = 0
+        for i in range(layers):
+            wg, wu, wd = stacks[i % rot]
+            rc |= L.b200_mul_mat_q_id(wtype, 1, wg.data_ptr(), wu.data_ptr(), hidden, ffn, n_exp, ids.data_ptr(), top, xq.data_ptr(), 1, yg.data_ptr(), ffn, st)
+            rc |= L.b200_mul_mat_q_id(wtype, 0, wd.data_ptr(), 0, ffn, hidden, n_exp, ids.data_ptr(), top, gq.data_ptr(), top, yd.data_ptr(), hidden, st)
+        if rc:
+            raise RuntimeError(f"mul_mat_q_id failed rc={rc}")
+    moe_layers(); torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph(); gs = torch.cuda.Stream()
+    with torch.cuda.stream(gs):
+        with torch.cuda.graph(g, stream=gs):
+            moe_layers()
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 10
+    e0.record()
+    for _ in range(reps):
+        g.replay()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    exp_bytes = layers * top * (2 * ffn * (hidden // 256) * 144 + hidden * (ffn // 256) * 144)
+    pk, pk_kind = peaks()
+    ach = exp_bytes / ms / 1e6
+    clocks = clocks_during(lambda: g.replay(), 0, 1.0)
+    out = {"metric": "decode tokens/s (Q4_K Mixtral-8x7B, top-2 of 8 experts)", "value": None, "unit": "tokens/s", "n_gpus": 1, "steps": a.steps, "warmup": max(a.warmup, 3),
+           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int8 x int4 -> int32 dot, fp32 scales/accumulate",
+           "data": "synthetic (seeded random valid Q4_K blocks)",
+           "config": {"workload": "Mixtral-8x7B Q4_K MoE decode, 1 x B200 (BASELINE.json configs[4])", "l2": "expert stacks of 4 layers rotate (3.2 GB) in the kernel-only leg; whole model 26 GB in the e2e leg"},
+           "clocks": clocks, "gpu_launches": 2 * layers * reps,
+           "roofline": {"bound": "hbm", "kernel": "gemv_q_kernel<FmtQ4K, MODE 2/3> (expert-indexed, ids on device)", "achieved": round(ach, 1), "peak": pk["hbm_gbs"], "unit": "GB/s",
+                        "frac": round(ach / pk["hbm_gbs"], 4), "peak_kind": pk_kind, "launches": 2 * layers, "avg_launch_us": round(ms * 1e3 / (2 * layers), 2),
+                        "algorithmic_MB_per_token_experts": round(exp_bytes / 1e6, 1), "traffic": None}}
+    if not a.no_e2e and os.path.exists(HARNESS):
+        try:
+            del stacks
+            torch.cuda.empty_cache()
+            path = f"/tmp/b200_mixtral-8x7b_q4_K{'_L%d' % a.layers if a.layers else ''}.bin"
+            if not os.path.exists(path):
+                cmd = [sys.executable, os.path.join(ROOT, "tools", "make_model.py"), "--arch", "mixtral-8x7b", "--quant", "q4_K", "--out", path + ".tmp", "--max_length", "1024"]
+                if a.layers:
+                    cmd += ["--layers", str(a.layers)]
+                subprocess.run(cmd, check=True, capture_output=True)
+                os.replace(path + ".tmp", path)
+            cmdl = [HARNESS, "--model", path, "--ggml_dir", RUNDIR, "--ngl", "all", "--threads", "16", "--prefill", "64", "--batch", "64", "--decode", str(a.warmup + a.steps),
+                    "--max_length", "1024", "--skip", str(a.warmup)]
+            env = dict(os.environ); env["B200_STATS"] = "1"
+            p = subprocess.run(cmdl, capture_output=True, text=True, timeout=3000, env=env)
+            r = json.loads(p.stdout.strip().splitlines()[-1])
+            e_ms = r["decode_ms_mean_after_skip"]
+            tok_bytes = 7171.1e6 + 2 * 1024 * 2 * 64 * 32
+            out["value"] = round(1000.0 / e_ms, 2); out["ms_per_step"] = round(e_ms, 4)
+            out["frac_of_hbm_roofline_whole_token"] = round(1000.0 / e_ms * tok_bytes / 1e9 / pk["hbm_gbs"], 4)
+            out["e2e"] = {"value": round(1000.0 / e_ms, 2), "unit": "tokens/s", "ms_per_step": round(e_ms, 4), "h2d_bytes_per_step": 4 + 4 * 32, "d2h_bytes_per_step": 4 * 32000,
+                          "load_ms": r.get("load_ms"), "path": "unmodified chatllm host -> libggml-cuda.so (node-by-node path with fusion: MoE is not a persistent-kernel shape yet)",
+                          "n_past": "64..", "stats": [l for l in p.stderr.splitlines() if l.startswith("B200STATS")][:1]}
+        except Exception as ex:  # noqa: BLE001
+            out["e2e"] = {"value": None, "error": str(ex)[-300:]}
+    print(json.dumps(out))
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--config", default="llama3-8b-q4_K-decode4096", choices=["llama3-8b-q4_K-decode4096", "qwen2.5-7b-q4_0-prefill2048", "mixtral-8x7b-q4_K-decode"],
+                    help="default = the headline (BASELINE.json configs[1]); the other two print the secondary lines for configs[2] / configs[4]")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=64)
     ap.add_argument("--warmup", type=int, default=5)
@@ -134,16 +335,21 @@ def main():
     ap.add_argument("--unfused", action="store_true")
     ap.add_argument("--fused2", action="store_true", help="opt-in step with norm+quant in the GEMV prologue / residual in the epilogue (9 launches per layer)")
     ap.add_argument("--no-mk", action="store_true", help="A/B aid: the round-1 step (355 launches replayed as a CUDA graph) instead of the persistent kernel")
+    ap.add_argument("--no-peer", action="store_true", help="multi-GPU A/B aid: hand the hidden row over with torch.distributed send/recv instead of NVLink mailboxes")
     ap.add_argument("--layers", type=int, default=0, help="debug: fewer layers (result is then NOT the BASELINE config)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3)
+    if a.config != "llama3-8b-q4_K-decode4096" and a.impl == "ours":
+        if int(os.environ.get("RANK", "0")) == 0:
+            (run_config3 if a.config.startswith("qwen") else run_config5)(a)
+        return
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     base = {"metric": "decode tokens/s @4096ctx (Q4_K Llama-3-8B)", "unit": "tokens/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int8 x int4 -> int32 dot, fp32 scales/accumulate",
             "data": "synthetic (seeded random valid Q4_K blocks, random F16 KV cache; no checkpoints offline)",
             "config": {"workload": "Llama-3-8B Q4_K single-token decode at n_past=4096 (BASELINE.json configs[1])", "n_past": N_PAST,
-                       "parallelism": "1 GPU" if a.gpus == 1 else f"layer-sharded x{a.gpus} (KV sharded by layer, NCCL send/recv of the hidden row)",
+                       "parallelism": "1 GPU" if a.gpus == 1 else f"layer-sharded x{a.gpus} (KV sharded by layer; hidden row / next token stored into the next rank's CUDA-IPC mailbox over NVLink by the persistent kernel, flag spin on the receiver)",
                        "l2": "inputs (4.76 GB per token) exceed L2; no flush needed"}}
 
     if a.impl == "reference":
@@ -209,6 +415,28 @@ def main():
         e1.record()
         sync_all()
         torch.cuda.cudart().cudaProfilerStop()
+    elif use_mk and not a.no_peer:
+        # layer-sharded: every rank replays ONE graph per token; the hidden row / next token move between the persistent kernels through
+        # NVLink-mapped mailboxes (sharding.PeerRing) — no host, no NCCL on the data path
+        ring = sharding.PeerRing(rank, world, cfg.hidden, pkg.lib())
+        sess.ring = ring
+        if rank == 0:
+            ring.view("tok", "<i4").fill_(12345 % cfg.vocab)
+        sess.pos.fill_(N_PAST)
+        sync_all()
+        graph = sess.capture(N_PAST)           # one eager step (a real token: every rank does it) + capture
+        sess.pos.fill_(N_PAST + 1)
+        for _ in range(a.warmup):
+            graph.replay()
+        sync_all()
+        if sampler: sampler.start()
+        e0.record()
+        for _ in range(a.steps):
+            graph.replay()
+        e1.record()
+        sync_all()
+        if sess.mk_status() != 0:
+            raise SystemExit(f"rank {rank}: persistent kernel reported a timeout (barrier or peer flag)")
     else:
         pipe = sharding.Pipeline(rank, world, sess.x, lambda _x: sess.enqueue(N_PAST), tok_buf=sess.tok)
         one_step = pipe.step

@@ -35,7 +35,9 @@ class DecodeModel(C.Structure):
 class DecodeIO(C.Structure):
     """b200_decode_io"""
     _fields_ = [("tok", C.c_void_p), ("pos", C.c_void_p), ("n_kv", C.c_int32), ("v_col", C.c_int32), ("x", C.c_void_p), ("logits", C.c_void_p),
-                ("next_tok", C.c_void_p), ("flags", C.c_int32), ("step_begin", C.c_int32), ("step_end", C.c_int32)]
+                ("next_tok", C.c_void_p), ("flags", C.c_int32), ("step_begin", C.c_int32), ("step_end", C.c_int32),
+                ("wait_flag", C.c_void_p), ("send_x", C.c_void_p), ("send_flag", C.c_void_p), ("send_tok", C.c_void_p), ("wait_offset", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 class B200Error(RuntimeError):
@@ -84,6 +86,11 @@ def lib():
         L.b200_decode_plan_status.argtypes = [vp, vp]
         L.b200_decode_plan_info.argtypes = [vp] + [C.POINTER(i32)] * 5
         L.b200_decode_step.argtypes = [vp, C.POINTER(DecodeIO), vp]
+        L.b200_decode_plan_times.argtypes = [vp, vp, i32, vp]
+        L.b200_ipc_alloc.argtypes = [C.c_size_t, C.POINTER(vp), vp]
+        L.b200_ipc_open.argtypes = [vp, C.POINTER(vp)]
+        L.b200_ipc_close.argtypes = [vp]
+        L.b200_ipc_free.argtypes = [vp]
         _lib = L
     return _lib
 
@@ -92,4 +99,4 @@ EXPORTS = ["b200_abi_version", "b200_device_sm_count", "b200_repack_weights", "b
            "b200_mul_mat_q", "b200_mul_mat", "b200_gemv_set_tuning", "b200_rms_norm", "b200_add", "b200_silu_mul", "b200_rope",
            "b200_soft_max", "b200_get_rows", "b200_attn_decode_scratch_bytes", "b200_attn_decode", "b200_attn_decode_quant", "b200_kv_store", "b200_add_rmsnorm_quant", "b200_rope_kv_store",
            "b200_mul_mat_q_multi", "b200_gemv_fused", "b200_mul_mat_q_id", "b200_pact_col_bytes", "b200_quantize_plain", "b200_mul_mat_q_batched", "b200_mul_mat_q_batched_tc",
-           "b200_decode_plan_create", "b200_decode_plan_destroy", "b200_decode_plan_set_kv", "b200_decode_plan_status", "b200_decode_plan_info", "b200_decode_step"]
+           "b200_decode_plan_create", "b200_decode_plan_destroy", "b200_decode_plan_set_kv", "b200_decode_plan_status", "b200_decode_plan_info", "b200_decode_plan_times", "b200_decode_step", "b200_ipc_alloc", "b200_ipc_open", "b200_ipc_close", "b200_ipc_free"]

@@ -3,6 +3,7 @@
 #include "common.cuh"
 #include "kernels.h"
 
+#include <cstring>
 #include <mutex>
 
 using namespace b200;
@@ -170,9 +171,33 @@ void b200_decode_plan_destroy(void * plan) { decode_plan_destroy(plan); }
 int b200_decode_plan_set_kv(void * plan, int layer, void * k_cache, void * v_cache) { return decode_plan_set_kv(plan, layer, k_cache, v_cache); }
 int b200_decode_plan_status(void * plan, void * stream) { return decode_plan_status(plan, (cudaStream_t) stream); }
 int b200_decode_plan_info(void * plan, int * grid, int * smem_bytes, int * n_steps, int * stages, int * ks) { return decode_plan_info(plan, grid, smem_bytes, n_steps, stages, ks); }
+int b200_decode_plan_times(void * plan, long long * out, int cap, void * stream) { return decode_plan_times(plan, out, cap, (cudaStream_t) stream); }
 int b200_decode_step(void * plan, const b200_decode_io * io, void * stream) {
     if (!io) return B200_ERR_ARG;
     return decode_step(plan, *reinterpret_cast<const DecodeIO *>(io), (cudaStream_t) stream);
 }
+
+int b200_ipc_alloc(size_t bytes, void ** dptr, void * handle64) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    if (!dptr || !handle64 || bytes == 0) return B200_ERR_ARG;
+    void * p = nullptr;
+    B200_CUDA_CHECK(cudaMalloc(&p, bytes));
+    B200_CUDA_CHECK(cudaMemset(p, 0, bytes));
+    B200_CUDA_CHECK(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); return (int) e; }
+    memcpy(handle64, &h, 64);
+    *dptr = p;
+    return B200_OK;
+}
+int b200_ipc_open(const void * handle64, void ** dptr) {
+    if (!dptr || !handle64) return B200_ERR_ARG;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    return (int) cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess);
+}
+int b200_ipc_close(void * dptr) { return (int) cudaIpcCloseMemHandle(dptr); }
+int b200_ipc_free(void * dptr) { return (int) cudaFree(dptr); }
 
 }  // extern "C"

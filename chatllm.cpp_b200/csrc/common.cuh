@@ -74,6 +74,11 @@ __device__ __forceinline__ void bulk_g2s_hint(void * smem_dst, const void * gmem
                  : "memory");
 }
 
+// bulk prefetch global -> L2 (TMA engine, fire and forget; size and address multiples of 16 bytes)
+__device__ __forceinline__ void bulk_prefetch_l2(const void * gmem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
+}
+
 // ---- programmatic dependent launch -----------------------------------------------------------------
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }

@@ -43,7 +43,7 @@ constexpr int MK_PV_SP = MK_PV_ROUND + 32;
 enum : int { MK_PRO_COPY = 0, MK_PRO_NORM = 1, MK_PRO_QUANT = 2 };
 enum : int { MK_EPI_STORE = 0, MK_EPI_RESID = 1, MK_EPI_SWIGLU = 2, MK_EPI_STORE_ARGMAX = 3 };
 // step kinds inside a layer (7 per layer): 0 qkv, 1 scores, 2 pv, 3 tail, 4 o, 5 gate/up, 6 down
-enum : int { MK_FLAG_ADVANCE = 1 };
+enum : int { MK_FLAG_ADVANCE = 1, MK_FLAG_ADVANCE_POS = 2 };
 
 struct MKPhase {  // one quantized-matmul phase; table built on the host, read-only on the device
     const uint8_t * W[3];
@@ -80,6 +80,12 @@ struct MKParams {
     float * x;
     int32_t * next_tok;
     int has_head, flags;
+    // layer-sharded multi-GPU hand-off over NVLink peer memory (all NULL on one GPU)
+    const unsigned long long * wait_flag;  // LOCAL flag a peer raises when this launch's input (hidden row / token) has arrived
+    int wait_offset;                       // proceed when *wait_flag >= launches completed so far + wait_offset
+    float * send_x;                        // PEER: the next shard's residual-stream buffer
+    unsigned long long * send_flag;        // PEER: its wait_flag
+    int32_t * send_tok;                    // PEER (last shard): the first shard's token buffer
     // workspace
     unsigned long long * sync;  // [0] barrier counter, [1] base of the next launch, [2] argmax key, [3] status
     float * q, * kbuf, * vbuf, * scores, * partial, * gate;
@@ -88,8 +94,20 @@ struct MKParams {
     int64_t s_stride;
     int max_tiles;
     int step_begin, step_end;
+    long long * times;  // profiling aid (B200_MK_TIMES=1): SM clock of CTA 0 at kernel start and after every step's barrier
     int ks, stages;
     uint32_t act_bytes, stage_bytes;
+    int kv_prefetch;     // pull the layer's K / V rows into L2 during its q/k/v projection
+    int l2_ahead;        // items per warp pulled into L2 ahead of the shared-memory ring (0 = off)
+    uint32_t tab_bytes;  // > 0: both tables live at the start of dynamic shared memory
+    int merged_tail;     // the last V.P CTA of a KV group sums + quantizes the group's slice (no separate tail step)
+};
+
+// the phase table / KV-cache table as the device code sees them: copied into shared memory at kernel start when they fit (a first-touch
+// miss on a table entry costs a DRAM round trip behind ~20 MB of queued weight requests — it used to stall every warp at every phase change)
+struct MKTabs {
+    const MKPhase * ph;
+    const MKLayerKV * kv;
 };
 
 // ---- loads of data produced by OTHER CTAs of this launch: L2 only (never a stale L1 line) ----------------------------------------
@@ -101,6 +119,14 @@ __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long
     unsigned long long v;
     asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long * p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long * p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t;
@@ -114,8 +140,9 @@ __device__ __forceinline__ void grid_barrier(const MKParams & p, unsigned long l
     __syncthreads();
     if (threadIdx.x == 0) {
         target += gridDim.x;
-        __threadfence();
-        atomicAdd(p.sync, 1ull);
+        // release-arrive: orders every write this CTA made before the bar.sync above (cumulativity) ahead of the increment; measured on the
+        // B200 (tools/mk_microbench.cu) 0.4 us cheaper than __threadfence() + atomicAdd
+        asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(p.sync) : "memory");
         const unsigned long long t0 = globaltimer_ns();
         unsigned spins = 0;
         while (ld_acquire_u64(p.sync) < target) {
@@ -124,9 +151,8 @@ __device__ __forceinline__ void grid_barrier(const MKParams & p, unsigned long l
                 if (globaltimer_ns() - t0 > 2000000000ull) { atomicExch(p.sync + 3, 1ull); break; }
             }
         }
-        __threadfence();
     }
-    __syncthreads();
+    __syncthreads();  // data of other CTAs is read with ld.global.cg (L2) after this point: no stale L1 line can be hit
 }
 
 // block sum in double (blockDim.x == 256); red: 8 doubles of shared memory
@@ -144,110 +170,105 @@ __device__ __forceinline__ double block_sum_f64(double v, double * red) {
     return t;
 }
 
-// ---- activation quantization into a column (shared or global memory); values come from `val(e)` (4 consecutive elements) ----------
-// Same expressions as normquant.cuh / quantize.cu (reference ggml-quants.c:2555-2592, arch/x86/quants.c:290-384): bit-identical codes.
-// blockDim.x == 256; [e_begin, e_end) multiples of 256, e_begin a multiple of 1024.
-template <bool Q8K, int NR>
-__device__ __forceinline__ void quantize_rounds(uint8_t * base, const ActLayout & L, int64_t e_base, int64_t e_end, const float4 (&pre)[NR], NormQuantSmem & sm) {
-    const int t = threadIdx.x;
-    const int lane = t & 31, warp = t >> 5;
+// ---- activation quantization into a column (shared or global memory), one WARP per 256-element block ----------------------------------
+// Same expressions as quantize.cu / normquant.cuh (reference quantize_row_q8_K_ref ggml-quants.c:2555-2592, x86 quantize_row_q8_0
+// arch/x86/quants.c:290-384): bit-identical codes.  Lane l of the warp owns elements [4l, 4l+4) and [128+4l, 128+4l+4) of its block, so
+// the block maximum / the 32-element sums are warp shuffles: NO block-wide barrier (the round-1 prologue's 3 barriers per 1024 elements
+// made it cost ~6 us per GEMV, gpurun_out/r02_bringup).
+template <bool Q8K>
+__device__ __forceinline__ void quantize_block_warp(uint8_t * base, const ActLayout & L, int64_t blk, const float4 & a, const float4 & b) {
+    const int lane = threadIdx.x & 31;
+    const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    const int64_t e0 = blk * 256 + 4 * lane, e1 = e0 + 128;
+    if (Q8K) {
+        // first-occurrence argmax |v| over the block: key = (|v| bits, 255 - index)
+        unsigned long long key = 0ull;
 #pragma unroll
-    for (int r = 0; r < NR; ++r) {
-        if (e_base + 1024 * r < e_end) {  // uniform over the block
-            const int64_t e = e_base + 1024 * r + 4 * t;
-            const bool on = e < e_end;
-            const float v[4] = {pre[r].x, pre[r].y, pre[r].z, pre[r].w};
-            if (Q8K) {
-                float * dd = (float *) (base + L.d_off);
-                int16_t * bs = (int16_t *) (base + L.bs_off);
-                unsigned long long key = 0ull;
-                if (on) {
+        for (int i = 0; i < 8; ++i) {
+            const int idx = (i < 4) ? 4 * lane + i : 128 + 4 * lane + (i - 4);
+            const unsigned long long kk = ((unsigned long long) __float_as_uint(fabsf(v[i])) << 32) | (unsigned) (255 - idx);
+            key = kk > key ? kk : key;
+        }
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const unsigned long long kk = ((unsigned long long) __float_as_uint(fabsf(v[i])) << 32) | (unsigned) (255 - (4 * (t & 63) + i));
-                        key = kk > key ? kk : key;
-                    }
-                }
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+            key = other > key ? other : key;
+        }
+        const int idx = 255 - (int) (key & 0xffffffffu);
+        const int sel = ((idx >> 7) << 2) | (idx & 3);  // which of this lane's 8 values, if this lane owns idx
+        float cand = v[0];
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
-                    key = other > key ? other : key;
-                }
-                __syncthreads();
-                if (lane == 0) sm.keys[warp] = key;
-                __syncthreads();
-                const unsigned long long k2 = sm.keys[warp ^ 1];
-                key = k2 > key ? k2 : key;
-                const int idx = 255 - (int) (key & 0xffffffffu);
-                if (on && (idx >> 2) == (t & 63)) sm.bmax[t >> 6] = v[idx & 3];
-                __syncthreads();
-                if (on) {
-                    const float mx = sm.bmax[t >> 6];
-                    int q[4] = {0, 0, 0, 0};
-                    float dv = 0.0f;
-                    if (mx != 0.0f) {
-                        const float iscale = __fdiv_rn(-127.f, mx);
+        for (int i = 1; i < 8; ++i) cand = (sel == i) ? v[i] : cand;
+        const float mx = __shfl_sync(0xffffffffu, cand, (idx & 127) >> 2);
+        int q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        float dv = 0.0f;
+        if (mx != 0.0f) {
+            const float iscale = __fdiv_rn(-127.f, mx);
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) q[i] = min(127, __float2int_rn(__fmul_rn(iscale, v[i])));
-                        dv = __fdiv_rn(1.0f, iscale);
-                    }
-                    const uint32_t packed = (uint32_t) (q[0] & 0xff) | ((uint32_t) (q[1] & 0xff) << 8) | ((uint32_t) (q[2] & 0xff) << 16) | ((uint32_t) (q[3] & 0xff) << 24);
-                    *reinterpret_cast<uint32_t *>(base + act_qs_off_q8k(e)) = packed;
-                    int s = q[0] + q[1] + q[2] + q[3];
-                    s += __shfl_xor_sync(0xffffffffu, s, 1);
-                    s += __shfl_xor_sync(0xffffffffu, s, 2);
-                    s += __shfl_xor_sync(0xffffffffu, s, 4);
-                    if ((t & 7) == 0) bs[e >> 5] = (int16_t) s;
-                    if ((t & 63) == 0) dd[e >> 8] = dv;
-                }
-            } else {
-                float * dd = (float *) (base + L.d_off);
-                int * bs = (int *) (base + L.bs_off);
-                float amax = on ? fmaxf(fmaxf(fabsf(v[0]), fabsf(v[1])), fmaxf(fabsf(v[2]), fabsf(v[3]))) : 0.0f;
-                amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
-                amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
-                amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 4));
-                const float dv = __fdiv_rn(amax, 127.f);
-                const float id = (amax != 0.0f) ? __fdiv_rn(127.f, amax) : 0.0f;
-                int q[4];
+            for (int i = 0; i < 8; ++i) q[i] = min(127, __float2int_rn(__fmul_rn(iscale, v[i])));
+            dv = __fdiv_rn(1.0f, iscale);
+        }
+        *reinterpret_cast<uint32_t *>(base + act_qs_off_q8k(e0)) = (uint32_t) (q[0] & 0xff) | ((uint32_t) (q[1] & 0xff) << 8) | ((uint32_t) (q[2] & 0xff) << 16) | ((uint32_t) (q[3] & 0xff) << 24);
+        *reinterpret_cast<uint32_t *>(base + act_qs_off_q8k(e1)) = (uint32_t) (q[4] & 0xff) | ((uint32_t) (q[5] & 0xff) << 8) | ((uint32_t) (q[6] & 0xff) << 16) | ((uint32_t) (q[7] & 0xff) << 24);
+        int s0 = q[0] + q[1] + q[2] + q[3], s1 = q[4] + q[5] + q[6] + q[7];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) q[i] = __float2int_rn(__fmul_rn(v[i], id));
-                int s = q[0] + q[1] + q[2] + q[3];
-                s += __shfl_xor_sync(0xffffffffu, s, 1);
-                s += __shfl_xor_sync(0xffffffffu, s, 2);
-                s += __shfl_xor_sync(0xffffffffu, s, 4);
-                if (on) {
-                    const uint32_t packed = (uint32_t) (q[0] & 0xff) | ((uint32_t) (q[1] & 0xff) << 8) | ((uint32_t) (q[2] & 0xff) << 16) | ((uint32_t) (q[3] & 0xff) << 24);
-                    *reinterpret_cast<uint32_t *>(base + act_qs_off_q80(e)) = packed;
-                    if ((t & 7) == 0) { dd[e >> 5] = __half2float(__float2half_rn(dv)); bs[e >> 5] = s; }
-                }
-            }
+        for (int o = 1; o < 8; o <<= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
+        int16_t * bs = (int16_t *) (base + L.bs_off);
+        if ((lane & 7) == 0) { bs[e0 >> 5] = (int16_t) s0; bs[e1 >> 5] = (int16_t) s1; }
+        if (lane == 0) ((float *) (base + L.d_off))[blk] = dv;
+    } else {
+        float * dd = (float *) (base + L.d_off);
+        int * bs = (int *) (base + L.bs_off);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {  // two independent 32-element blocks per 8-lane group
+            const float * w = v + 4 * h;
+            const int64_t e = h ? e1 : e0;
+            float amax = fmaxf(fmaxf(fabsf(w[0]), fabsf(w[1])), fmaxf(fabsf(w[2]), fabsf(w[3])));
+            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
+            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 4));
+            const float dv = __fdiv_rn(amax, 127.f);
+            const float id = (amax != 0.0f) ? __fdiv_rn(127.f, amax) : 0.0f;
+            int q[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) q[i] = __float2int_rn(__fmul_rn(w[i], id));
+            int sq = q[0] + q[1] + q[2] + q[3];
+            sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+            sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+            sq += __shfl_xor_sync(0xffffffffu, sq, 4);
+            *reinterpret_cast<uint32_t *>(base + act_qs_off_q80(e)) = (uint32_t) (q[0] & 0xff) | ((uint32_t) (q[1] & 0xff) << 8) | ((uint32_t) (q[2] & 0xff) << 16) | ((uint32_t) (q[3] & 0xff) << 24);
+            if ((lane & 7) == 0) { dd[e >> 5] = __half2float(__float2half_rn(dv)); bs[e >> 5] = sq; }
         }
     }
 }
 
-// values from `val(e)` (4 consecutive elements), NR rounds of 1024 elements loaded before any of them is quantized (one L2 round trip per
-// NR rounds instead of one per round: the serial rounds of the round-1 prologue cost ~6 us per GEMV, gpurun_out/r02_bringup)
-template <bool Q8K, int NR, class ValFn>
-__device__ __forceinline__ void quantize_range(uint8_t * base, int64_t k, int64_t e_begin, int64_t e_end, ValFn val, NormQuantSmem & sm) {
+// blocks [blk_begin, blk_end) of a k-element column spread over the CTA's warps; val(e) returns 4 consecutive elements.  NP blocks per warp
+// are loaded before any of them is quantized (one L2 round trip per NP blocks).
+template <bool Q8K, int NP, class ValFn>
+__device__ __forceinline__ void quantize_blocks(uint8_t * base, int64_t k, int blk_begin, int blk_end, ValFn val) {
     const ActLayout L = act_layout(Q8K, k);
-    for (int64_t eb = e_begin; eb < e_end; eb += 1024 * NR) {
-        float4 pre[NR];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int b0 = blk_begin + warp; b0 < blk_end; b0 += MK_WARPS * NP) {
+        float4 pa[NP], pb[NP];
 #pragma unroll
-        for (int r = 0; r < NR; ++r) {
-            const int64_t e = eb + 1024 * r + 4 * threadIdx.x;
-            pre[r] = (e < e_end) ? val(e) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r = 0; r < NP; ++r) {
+            const int blk = b0 + MK_WARPS * r;
+            if (blk < blk_end) { pa[r] = val((int64_t) blk * 256 + 4 * lane); pb[r] = val((int64_t) blk * 256 + 128 + 4 * lane); }
         }
-        quantize_rounds<Q8K, NR>(base, L, eb, e_end, pre, sm);
+#pragma unroll
+        for (int r = 0; r < NP; ++r) {
+            const int blk = b0 + MK_WARPS * r;
+            if (blk < blk_end) quantize_block_warp<Q8K>(base, L, blk, pa[r], pb[r]);
+        }
     }
 }
 
 // ---- the per-warp weight pipeline -----------------------------------------------------------------------------------------------
 struct MKCursor {
-    int ph;      // current phase (== ph_end: exhausted)
-    int it;      // next item of this warp in the phase
-    int nitems;
-    int r0, r1;  // this warp's logical rows
+    int ph;         // current phase (== ph_end: exhausted)
+    int grp, seg;   // next item: row group of this warp, k-segment of the group (advanced incrementally: no divisions on the issue path)
+    int ngrp;
+    int r0, r1;     // this warp's logical rows
     int nseg, nunits, ks;
     int nmat, paired;
     int m0, m1;
@@ -256,26 +277,39 @@ struct MKCursor {
     const uint8_t * W2;
 };
 
-__device__ __forceinline__ void cursor_seek(MKCursor & c, const MKParams & p, int ph, int ph_end, int64_t gw, int64_t GW) {
+__device__ __forceinline__ void cursor_seek(MKCursor & c, const MKParams & p, const MKTabs & T, int ph, int ph_end, unsigned gw, unsigned GW) {
     for (; ph < ph_end; ++ph) {
-        const MKPhase * P = p.phases + ph;
-        const int m_total = __ldg(&P->m_total);
-        const int paired = __ldg(&P->paired);
+        const MKPhase * P = T.ph + ph;
+        const unsigned m_total = (unsigned) P->m_total;   // m_total * GW < 2^32 (checked on the host): 32-bit divisions only
+        const int paired = P->paired;
         const int group = paired ? MK_RG / 2 : MK_RG;
-        const int r0 = (int) ((int64_t) m_total * gw / GW), r1 = (int) ((int64_t) m_total * (gw + 1) / GW);
+        const int r0 = (int) (m_total * gw / GW), r1 = (int) (m_total * (gw + 1) / GW);
         if (r1 <= r0) continue;
-        c.nunits = __ldg(&P->k) / 256;
+        c.nunits = P->k / 256;
         c.ks = min(p.ks, c.nunits);
         c.nseg = (c.nunits + c.ks - 1) / c.ks;
         c.r0 = r0; c.r1 = r1;
-        c.nitems = ((r1 - r0 + group - 1) / group) * c.nseg;
-        c.nmat = __ldg(&P->nmat); c.paired = paired;
-        c.m0 = __ldg(&P->m[0]); c.m1 = __ldg(&P->m[1]);
+        c.ngrp = (r1 - r0 + group - 1) / group;
+        c.nmat = P->nmat; c.paired = paired;
+        c.m0 = P->m[0]; c.m1 = P->m[1];
         c.W0 = P->W[0]; c.W1 = P->W[1]; c.W2 = P->W[2];
-        c.it = 0;
+        c.grp = 0; c.seg = 0;
         break;
     }
     c.ph = ph;
+}
+// next item of a REGISTER cursor
+__device__ __forceinline__ void cursor_next(MKCursor & c, const MKParams & p, const MKTabs & T, int ph_end, unsigned gw, unsigned GW) {
+    if (++c.seg == c.nseg) { c.seg = 0; ++c.grp; }
+    if (c.grp >= c.ngrp) cursor_seek(c, p, T, c.ph + 1, ph_end, gw, GW);
+}
+// next item of a SHARED-MEMORY cursor (one per warp): every lane computes the same new state from what it read, lane 0 stores it
+__device__ __forceinline__ void cursor_next_shared(MKCursor & c, const MKParams & p, const MKTabs & T, int ph_end, unsigned gw, unsigned GW) {
+    MKCursor t = c;
+    __syncwarp();
+    cursor_next(t, p, T, ph_end, gw, GW);
+    if ((threadIdx.x & 31) == 0) c = t;
+    __syncwarp();
 }
 
 // global pointer of stage row i (0 .. RG-1) of the group whose first logical row is row0
@@ -292,47 +326,57 @@ __device__ __forceinline__ const uint8_t * cursor_row_src(const MKCursor & c, in
     return c.W0 + (int64_t) r * row_bytes;
 }
 
-// lane 0: bulk copies of item c.it into stage `st` (completing on `bar`)
-template <class F>
+// !PREFETCH (lane 0 only): one bulk copy into the ring, completing on `bar`.  PREFETCH (ALL lanes): the same bytes pulled into L2 only, one
+// 128-byte line per lane and instruction (LSU prefetches: a bulk prefetch would queue in the SM's in-order TMA unit ahead of the demand copies)
+template <bool PREFETCH>
+__device__ __forceinline__ void mk_copy(void * smem_dst, const uint8_t * gmem_src, uint32_t bytes, uint64_t * bar, uint64_t pol) {
+    if (PREFETCH) {
+        for (uint32_t off = (threadIdx.x & 31) * 128u; off < bytes; off += 32u * 128u) asm volatile("prefetch.global.L2 [%0];" ::"l"(gmem_src + off));
+    } else {
+        bulk_g2s_hint(smem_dst, gmem_src, bytes, bar, pol);
+    }
+}
+
+// the bulk copies of the cursor's current item into stage `st` (completing on `bar`) — or, PREFETCH, the same byte ranges into L2
+template <class F, bool PREFETCH = false>
 __device__ __forceinline__ void issue_item(const MKCursor & c, uint8_t * st, uint64_t * bar, uint64_t pol) {
     constexpr int UNIT = F::A_UNIT + F::B_UNIT;
     constexpr int HALF = MK_RG / 2;
     const int group = c.paired ? HALF : MK_RG;
-    const int grp = c.it / c.nseg, seg = c.it - grp * c.nseg;
-    const int row0 = c.r0 + grp * group;
+    const int row0 = c.r0 + c.grp * group;
     const int nlog = min(group, c.r1 - row0);
     const int64_t row_bytes = (int64_t) c.nunits * UNIT;
     if (c.nseg == 1) {  // whole rows: row r of the stage at st + r * row_bytes (A part then B part, as in HBM)
         if (c.paired) {
             const uint32_t bytes = (uint32_t) (nlog * row_bytes);
-            mbar_arrive_expect_tx(bar, 2 * bytes);
-            bulk_g2s_hint(st, cursor_row_src<UNIT>(c, row0, 0), bytes, bar, pol);
-            bulk_g2s_hint(st + (size_t) HALF * row_bytes, cursor_row_src<UNIT>(c, row0, HALF), bytes, bar, pol);
+            if (!PREFETCH) mbar_arrive_expect_tx(bar, 2 * bytes);
+            mk_copy<PREFETCH>(st, cursor_row_src<UNIT>(c, row0, 0), bytes, bar, pol);
+            mk_copy<PREFETCH>(st + (size_t) HALF * row_bytes, cursor_row_src<UNIT>(c, row0, HALF), bytes, bar, pol);
         } else {
             const uint8_t * first = cursor_row_src<UNIT>(c, row0, 0);
-            const uint8_t * last = cursor_row_src<UNIT>(c, row0, nlog - 1);
+            const uint8_t * last = (c.nmat > 1) ? cursor_row_src<UNIT>(c, row0, nlog - 1) : first + (int64_t) (nlog - 1) * row_bytes;
             if (last == first + (int64_t) (nlog - 1) * row_bytes) {  // the group lies in one matrix: one copy
                 const uint32_t bytes = (uint32_t) (nlog * row_bytes);
-                mbar_arrive_expect_tx(bar, bytes);
-                bulk_g2s_hint(st, first, bytes, bar, pol);
+                if (!PREFETCH) mbar_arrive_expect_tx(bar, bytes);
+                mk_copy<PREFETCH>(st, first, bytes, bar, pol);
             } else {
-                mbar_arrive_expect_tx(bar, (uint32_t) (nlog * row_bytes));
-                for (int r = 0; r < nlog; ++r) bulk_g2s_hint(st + (size_t) r * row_bytes, cursor_row_src<UNIT>(c, row0, r), (uint32_t) row_bytes, bar, pol);
+                if (!PREFETCH) mbar_arrive_expect_tx(bar, (uint32_t) (nlog * row_bytes));
+                for (int r = 0; r < nlog; ++r) mk_copy<PREFETCH>(st + (size_t) r * row_bytes, cursor_row_src<UNIT>(c, row0, r), (uint32_t) row_bytes, bar, pol);
             }
         }
     } else {  // k-segment: A parts [RG][ks * A_UNIT], then B parts [RG][ks * B_UNIT]
-        const int u0 = seg * c.ks;
+        const int u0 = c.seg * c.ks;
         const int nu = min(c.ks, c.nunits - u0);
         const int nrows = c.paired ? 2 * nlog : nlog;
         const uint32_t rsA = c.ks * F::A_UNIT, rsB = c.ks * F::B_UNIT, offB = MK_RG * c.ks * F::A_UNIT;
-        mbar_arrive_expect_tx(bar, (uint32_t) nrows * nu * UNIT);
+        if (!PREFETCH) mbar_arrive_expect_tx(bar, (uint32_t) nrows * nu * UNIT);
         for (int r = 0; r < MK_RG; ++r) {
             const bool valid = c.paired ? ((r < HALF ? r : r - HALF) < nlog) : (r < nlog);
             if (!valid) continue;
             const uint8_t * grow = cursor_row_src<UNIT>(c, row0, r);
-            bulk_g2s_hint(st + (size_t) r * rsA, grow + (size_t) u0 * F::A_UNIT, (uint32_t) nu * F::A_UNIT, bar, pol);
+            mk_copy<PREFETCH>(st + (size_t) r * rsA, grow + (size_t) u0 * F::A_UNIT, (uint32_t) nu * F::A_UNIT, bar, pol);
             if (F::B_UNIT)
-                bulk_g2s_hint(st + offB + (size_t) r * rsB, grow + (size_t) c.nunits * F::A_UNIT + (size_t) u0 * F::B_UNIT, (uint32_t) nu * F::B_UNIT, bar, pol);
+                mk_copy<PREFETCH>(st + offB + (size_t) r * rsB, grow + (size_t) c.nunits * F::A_UNIT + (size_t) u0 * F::B_UNIT, (uint32_t) nu * F::B_UNIT, bar, pol);
         }
     }
 }
@@ -340,56 +384,79 @@ __device__ __forceinline__ void issue_item(const MKCursor & c, uint8_t * st, uin
 struct MKRing {
     uint8_t * ring;   // this warp's stages
     uint64_t * bars;  // this warp's full barriers
-    unsigned iss_seq, con_seq;
+    int iss_stage;            // stage the next issued item goes to
+    int con_stage;            // stage of the next consumed item ...
+    uint32_t con_parity;      // ... and the mbarrier phase parity it completes
     uint64_t pol;
 };
+__device__ __forceinline__ void ring_issue_advance(MKRing & rg, int stages) { if (++rg.iss_stage == stages) rg.iss_stage = 0; }
+__device__ __forceinline__ void ring_consume_advance(MKRing & rg, int stages) { if (++rg.con_stage == stages) { rg.con_stage = 0; rg.con_parity ^= 1u; } }
 
 // ---- one GEMV step: stage the activations (prologue), then consume this warp's items of phase `ph` ---------------------------------
 template <class F>
-__device__ __forceinline__ void gemv_step(const MKParams & p, int ph, int ph_end, MKCursor & con, MKCursor & iss, MKRing & rg, uint8_t * act_s,
-                                          NormQuantSmem & nq, int64_t gw, int64_t GW, bool argmax = false) {
+__device__ __forceinline__ void gemv_step(const MKParams & p, const MKTabs & T, int ph, int ph_end, MKCursor & con, MKCursor & iss, MKCursor & pre, MKRing & rg, uint8_t * act_s,
+                                          NormQuantSmem & nq, unsigned gw, unsigned GW, bool argmax = false) {
     constexpr int UNIT = F::A_UNIT + F::B_UNIT;
     constexpr int HALF = MK_RG / 2;
     constexpr int LPU = F::LPU;
     constexpr int UPS = 32 / LPU;
-    const MKPhase * P = p.phases + ph;
+    const MKPhase * P = T.ph + ph;
     const int lane = threadIdx.x & 31;
-    const int k = __ldg(&P->k);
-    const int pro = __ldg(&P->pro);
+    const int k = P->k;
+    // pull the norm weights of the next two phases into L2 now (16 KB each, first touched by all 148 CTAs at once otherwise)
+    if (threadIdx.x == 0) {
+        for (int nx = ph + 1; nx <= ph + 2 && nx < p.n_phases; ++nx) {
+            const MKPhase * N = T.ph + nx;
+            if (N->pro == MK_PRO_NORM && (int) blockIdx.x < N->k / 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(N->pro_w + (size_t) blockIdx.x * 32));
+        }
+    }
+    const int pro = P->pro;
     const ActLayout L = act_layout(F::Q8K, k);
 
     // ---- prologue: the quantized activation column of this phase in shared memory
+    const long long t_pro0 = p.times ? clock64() : 0;
     if (pro == MK_PRO_COPY) {
         const uint8_t * src = P->pro_q;
         const int n16 = (int) (L.col_bytes >> 4);
         for (int i = threadIdx.x; i < n16; i += MK_THREADS) reinterpret_cast<uint4 *>(act_s)[i] = ldcg_u4(src + (size_t) i * 16);
     } else {
         const float * x = P->pro_x;
+        const int nblk = k / 256;
         if (pro == MK_PRO_NORM) {
             // y = rms_norm(x) * w.  Sum of squares exactly as the CPU does it (ops.cpp:3736-3741): float products accumulated in DOUBLE,
             // mean rounded to float — a fp32 tree reduction can differ in the last bit of `scale`, which flips activation codes downstream.
             const float * w = P->pro_w;
-            if (k <= 5 * 1024) {  // every element of the row lives in registers: one L2 round trip for x and w together
-                float4 xv[5], wv[5];
+            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+            if (nblk <= 3 * MK_WARPS) {  // k <= 6144: every element of the row lives in registers, one L2 round trip for x and w together
+                float4 xa[3], xb[3], wa[3], wb[3];
 #pragma unroll
-                for (int r = 0; r < 5; ++r) {
-                    const int64_t e = 1024 * r + 4 * threadIdx.x;
-                    xv[r] = (e < k) ? ldcg_f4(x + e) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    wv[r] = (e < k) ? __ldg(reinterpret_cast<const float4 *>(w + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int r = 0; r < 3; ++r) {
+                    const int blk = warp + MK_WARPS * r;
+                    const int64_t e = (int64_t) blk * 256 + 4 * lane;
+                    const bool on = blk < nblk;
+                    xa[r] = on ? ldcg_f4(x + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    xb[r] = on ? ldcg_f4(x + e + 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    wa[r] = on ? __ldg(reinterpret_cast<const float4 *>(w + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    wb[r] = on ? __ldg(reinterpret_cast<const float4 *>(w + e + 128)) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
                 double ss = 0.0;
 #pragma unroll
-                for (int r = 0; r < 5; ++r) {
-                    ss += (double) __fmul_rn(xv[r].x, xv[r].x); ss += (double) __fmul_rn(xv[r].y, xv[r].y);
-                    ss += (double) __fmul_rn(xv[r].z, xv[r].z); ss += (double) __fmul_rn(xv[r].w, xv[r].w);
+                for (int r = 0; r < 3; ++r) {
+                    ss += (double) __fmul_rn(xa[r].x, xa[r].x); ss += (double) __fmul_rn(xa[r].y, xa[r].y); ss += (double) __fmul_rn(xa[r].z, xa[r].z); ss += (double) __fmul_rn(xa[r].w, xa[r].w);
+                    ss += (double) __fmul_rn(xb[r].x, xb[r].x); ss += (double) __fmul_rn(xb[r].y, xb[r].y); ss += (double) __fmul_rn(xb[r].z, xb[r].z); ss += (double) __fmul_rn(xb[r].w, xb[r].w);
                 }
                 ss = block_sum_f64(ss, reinterpret_cast<double *>(nq.red));
                 const float mean = (float) (ss / (double) k);
                 const float scale = 1.0f / sqrtf(mean + p.eps);
 #pragma unroll
-                for (int r = 0; r < 5; ++r)
-                    xv[r] = make_float4((xv[r].x * scale) * wv[r].x, (xv[r].y * scale) * wv[r].y, (xv[r].z * scale) * wv[r].z, (xv[r].w * scale) * wv[r].w);
-                quantize_rounds<F::Q8K, 5>(act_s, L, 0, k, xv, nq);
+                for (int r = 0; r < 3; ++r) {
+                    const int blk = warp + MK_WARPS * r;
+                    if (blk < nblk) {
+                        const float4 ya = make_float4((xa[r].x * scale) * wa[r].x, (xa[r].y * scale) * wa[r].y, (xa[r].z * scale) * wa[r].z, (xa[r].w * scale) * wa[r].w);
+                        const float4 yb = make_float4((xb[r].x * scale) * wb[r].x, (xb[r].y * scale) * wb[r].y, (xb[r].z * scale) * wb[r].z, (xb[r].w * scale) * wb[r].w);
+                        quantize_block_warp<F::Q8K>(act_s, L, blk, ya, yb);
+                    }
+                }
             } else {
                 double ss = 0.0;
                 for (int64_t e = 4 * (int64_t) threadIdx.x; e < k; e += 4 * MK_THREADS) {
@@ -399,23 +466,24 @@ __device__ __forceinline__ void gemv_step(const MKParams & p, int ph, int ph_end
                 ss = block_sum_f64(ss, reinterpret_cast<double *>(nq.red));
                 const float mean = (float) (ss / (double) k);
                 const float scale = 1.0f / sqrtf(mean + p.eps);
-                quantize_range<F::Q8K, 4>(act_s, k, 0, k, [&](int64_t e) {
+                quantize_blocks<F::Q8K, 2>(act_s, k, 0, nblk, [&](int64_t e) {
                     const float4 a = ldcg_f4(x + e);
                     const float4 ww = __ldg(reinterpret_cast<const float4 *>(w + e));
                     return make_float4((a.x * scale) * ww.x, (a.y * scale) * ww.y, (a.z * scale) * ww.z, (a.w * scale) * ww.w);
-                }, nq);
+                });
             }
         } else {
-            quantize_range<F::Q8K, 8>(act_s, k, 0, k, [&](int64_t e) { return ldcg_f4(x + e); }, nq);
+            quantize_blocks<F::Q8K, 4>(act_s, k, 0, nblk, [&](int64_t e) { return ldcg_f4(x + e); });
         }
         if (F::Q8K) {  // zero the padding of the last (partial) 1024-element group so the main loop can read it blindly
             for (int64_t e = k + 4 * (int64_t) threadIdx.x; e < L.qs_bytes; e += 4 * MK_THREADS) *reinterpret_cast<uint32_t *>(act_s + act_qs_off_q8k(e)) = 0u;
         }
     }
     __syncthreads();
+    const long long t_pro = p.times ? clock64() - t_pro0 : 0;
     if (con.ph != ph) return;  // this warp owns no row of the phase
 
-    const int epi = argmax ? (int) MK_EPI_STORE_ARGMAX : __ldg(&P->epi);
+    const int epi = argmax ? (int) MK_EPI_STORE_ARGMAX : P->epi;
     const int g = lane % LPU, ul = lane / LPU;
     const bool PAIRED = con.paired != 0;
     const int group = PAIRED ? HALF : MK_RG;
@@ -425,13 +493,14 @@ __device__ __forceinline__ void gemv_step(const MKParams & p, int ph, int ph_end
     const uint32_t offB = whole ? con.nunits * F::A_UNIT : MK_RG * con.ks * F::A_UNIT;
     float best = -INFINITY;
     int best_i = 0;
+    const bool prof = p.times != nullptr && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1) && (threadIdx.x >> 5) == 3;
+    long long t_wait = 0, t_comp = 0, t_iss = 0, t_mark = prof ? clock64() : 0;
+    int n_it = 0;
 
     float acc[MK_RG];
-    while (con.it < con.nitems) {
-        const int s = rg.con_seq % p.stages;
-        const uint32_t parity = (rg.con_seq / p.stages) & 1u;
-        const int grp = con.it / con.nseg, seg = con.it - grp * con.nseg;
-        const int row0 = con.r0 + grp * group;
+    while (con.ph == ph) {
+        const int seg = con.seg;
+        const int row0 = con.r0 + con.grp * group;
         const int nlog = min(group, con.r1 - row0);
         const int u0 = seg * con.ks;
         const int nu = min(con.ks, con.nunits - u0);
@@ -439,30 +508,54 @@ __device__ __forceinline__ void gemv_step(const MKParams & p, int ph, int ph_end
 #pragma unroll
             for (int r = 0; r < MK_RG; ++r) acc[r] = 0.0f;
         }
-        mbar_wait(&rg.bars[s], parity);
-        const uint8_t * st = rg.ring + (size_t) s * p.stage_bytes;
-        for (int u = ul; u < nu; u += UPS) {
-            typename F::Act A;
-            F::load_act(act_s, L, u0 + u, g, A);
+        mbar_wait(&rg.bars[rg.con_stage], rg.con_parity);
+        if (prof) { const long long t = clock64(); t_wait += t - t_mark; t_mark = t; ++n_it; }
+        const uint8_t * st = rg.ring + (size_t) rg.con_stage * p.stage_bytes;
+        if (nlog == group) {
+            // full group (the common case): straight-line code, the four rows' loads and dot products interleave freely
+            for (int u = ul; u < nu; u += UPS) {
+                typename F::Act A;
+                F::load_act(act_s, L, u0 + u, g, A);
 #pragma unroll
-            for (int r = 0; r < MK_RG; ++r) {
-                const bool valid = PAIRED ? ((r < HALF ? r : r - HALF) < nlog) : (r < nlog);
-                if (valid) {
-                    typename F::Wt Wr;
-                    F::load_w(st + (size_t) r * rsA, st + offB + (size_t) r * rsB, u, g, Wr);
-                    acc[r] = F::dot(Wr, A, acc[r]);
+                for (int r = 0; r < MK_RG; r += 2) {  // two rows in flight: their shared-memory loads overlap the other's dp4a chains
+                    typename F::Wt Wa, Wb;
+                    F::load_w(st + (size_t) r * rsA, st + offB + (size_t) r * rsB, u, g, Wa);
+                    F::load_w(st + (size_t) (r + 1) * rsA, st + offB + (size_t) (r + 1) * rsB, u, g, Wb);
+                    acc[r] = F::dot(Wa, A, acc[r]);
+                    acc[r + 1] = F::dot(Wb, A, acc[r + 1]);
+                }
+            }
+        } else {
+            for (int u = ul; u < nu; u += UPS) {
+                typename F::Act A;
+                F::load_act(act_s, L, u0 + u, g, A);
+#pragma unroll
+                for (int r = 0; r < MK_RG; ++r) {
+                    const bool valid = PAIRED ? ((r < HALF ? r : r - HALF) < nlog) : (r < nlog);
+                    if (valid) {
+                        typename F::Wt Wr;
+                        F::load_w(st + (size_t) r * rsA, st + offB + (size_t) r * rsB, u, g, Wr);
+                        acc[r] = F::dot(Wr, A, acc[r]);
+                    }
                 }
             }
         }
         __syncwarp();
+        if (prof) { const long long t = clock64(); t_comp += t - t_mark; t_mark = t; }
+        ring_consume_advance(rg, p.stages);
         // the stage is free again: refill it with this warp's next item (possibly of a later phase)
         if (iss.ph < ph_end) {
-            if (lane == 0) issue_item<F>(iss, rg.ring + (size_t) (rg.iss_seq % p.stages) * p.stage_bytes, &rg.bars[rg.iss_seq % p.stages], rg.pol);
-            rg.iss_seq++;
-            if (++iss.it >= iss.nitems) cursor_seek(iss, p, iss.ph + 1, ph_end, gw, GW);
+            if (lane == 0) issue_item<F>(iss, rg.ring + (size_t) rg.iss_stage * p.stage_bytes, &rg.bars[rg.iss_stage], rg.pol);
+            ring_issue_advance(rg, p.stages);
+            cursor_next_shared(iss, p, T, ph_end, gw, GW);
         }
-        rg.con_seq++;
-        con.it++;
+        // ... and keep HBM busy further ahead than shared memory can hold: the item l2_ahead positions later goes to L2 now, so the stream
+        // does not stop while this warp sits at a grid barrier or quantizes activations (the ring alone covers ~3 us)
+        if (p.l2_ahead > 0 && pre.ph < ph_end) {
+            issue_item<F, true>(pre, nullptr, nullptr, 0);
+            cursor_next_shared(pre, p, T, ph_end, gw, GW);
+        }
+        if (prof) { const long long t = clock64(); t_iss += t - t_mark; t_mark = t; }
 
         if (seg == con.nseg - 1) {
 #pragma unroll
@@ -495,6 +588,7 @@ __device__ __forceinline__ void gemv_step(const MKParams & p, int ph, int ph_end
                 }
             }
         }
+        cursor_next(con, p, T, ph_end, gw, GW);
     }
     if (epi == MK_EPI_STORE_ARGMAX && lane == 0 && best > -INFINITY) {
         // order-preserving key: larger value first, then the SMALLER index (the host's argmax keeps the first maximum)
@@ -502,7 +596,10 @@ __device__ __forceinline__ void gemv_step(const MKParams & p, int ph, int ph_end
         const uint32_t ord = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
         atomicMax(p.sync + 2, ((unsigned long long) ord << 32) | (unsigned) (0xffffffffu - (unsigned) best_i));
     }
-    cursor_seek(con, p, ph + 1, ph_end, gw, GW);
+    if (prof && lane == 0) {
+        long long * a = p.times + 1 + 7 * p.n_layers + 3 + ((blockIdx.x ? 5 : 0) + (ph == 4 * p.n_layers ? 4 : (ph & 3))) * 8;
+        a[0] += t_wait; a[1] += t_comp; a[2] += t_iss; a[3] += n_it; a[4] += 1; a[5] += t_pro;
+    }
 }
 
 // ---- attention -------------------------------------------------------------------------------------------------------------------
@@ -515,7 +612,7 @@ __device__ __forceinline__ void mk_mma16816(float (&c)[4], uint32_t a0, uint32_t
 // scores[h][t] = scale * K[t][grp] . f16(rope(q[h]))  per (16-position tile, KV group) unit, one unit per warp at a time; also the per
 // (head, tile) max and sum(exp(s - max)).  The warp that owns the tile of the NEW position first ropes k and appends the K-cache row.
 template <int HD>
-__device__ __forceinline__ void scores_step(const MKParams & p, int layer, int n_kv, int kpos, uint8_t * sm) {
+__device__ __forceinline__ void scores_step(const MKParams & p, const MKTabs & T, int layer, int n_kv, int kpos, uint8_t * sm) {
     constexpr int NU = HD / 32;
     constexpr int HP = HD / 2;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -532,17 +629,42 @@ __device__ __forceinline__ void scores_step(const MKParams & p, int layer, int n
         cs[i] = make_float2(cosf(th), sinf(th));
     }
     __syncthreads();
-    for (int idx = threadIdx.x; idx < p.heads * HP; idx += MK_THREADS) {
-        const int h = idx / HP, i = idx - h * HP;
-        const int i0 = (p.rope_mode == 0) ? 2 * i : i, i1 = (p.rope_mode == 0) ? 2 * i + 1 : i + HP;
-        const float x0 = ldcg_f(p.q + (int64_t) h * HD + i0), x1 = ldcg_f(p.q + (int64_t) h * HD + i1);
-        const float c = cs[i].x, s = cs[i].y;
-        qh[h * HD + i0] = __float2half_rn(x0 * c - x1 * s);
-        qh[h * HD + i1] = __float2half_rn(x0 * s + x1 * c);
+    {
+        // RoPE(q) -> f16 in shared memory; every load of the thread is issued before the first one is used (one L2 round trip, not eight)
+        constexpr int NPT = 8;   // pairs per thread issued together: covers hidden <= 4096 (the loop below takes the rest)
+        float x0[NPT], x1[NPT];
+        const int total = p.heads * HP;
+#pragma unroll
+        for (int j = 0; j < NPT; ++j) {
+            const int idx = threadIdx.x + j * MK_THREADS;
+            if (idx < total) {
+                const int h = idx / HP, i = idx - h * HP;
+                const int i0 = (p.rope_mode == 0) ? 2 * i : i, i1 = (p.rope_mode == 0) ? 2 * i + 1 : i + HP;
+                x0[j] = ldcg_f(p.q + (int64_t) h * HD + i0); x1[j] = ldcg_f(p.q + (int64_t) h * HD + i1);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < NPT; ++j) {
+            const int idx = threadIdx.x + j * MK_THREADS;
+            if (idx < total) {
+                const int h = idx / HP, i = idx - h * HP;
+                const int i0 = (p.rope_mode == 0) ? 2 * i : i, i1 = (p.rope_mode == 0) ? 2 * i + 1 : i + HP;
+                const float c = cs[i].x, sn = cs[i].y;
+                qh[h * HD + i0] = __float2half_rn(x0[j] * c - x1[j] * sn);
+                qh[h * HD + i1] = __float2half_rn(x0[j] * sn + x1[j] * c);
+            }
+        }
+        for (int idx = threadIdx.x + NPT * MK_THREADS; idx < total; idx += MK_THREADS) {  // hidden > 4096
+            const int h = idx / HP, i = idx - h * HP;
+            const int i0 = (p.rope_mode == 0) ? 2 * i : i, i1 = (p.rope_mode == 0) ? 2 * i + 1 : i + HP;
+            const float a = ldcg_f(p.q + (int64_t) h * HD + i0), b = ldcg_f(p.q + (int64_t) h * HD + i1);
+            qh[h * HD + i0] = __float2half_rn(a * cs[i].x - b * cs[i].y);
+            qh[h * HD + i1] = __float2half_rn(a * cs[i].y + b * cs[i].x);
+        }
     }
     __syncthreads();
 
-    __half * kc = p.kv[layer].kc;
+    __half * kc = T.kv[layer].kc;
     const int ntiles = (n_kv + 15) / 16;
     const int total = ntiles * p.kv_heads;
     const int ustride = gridDim.x * MK_WARPS;
@@ -627,10 +749,38 @@ __device__ __forceinline__ int mk_pv_span(int n_kv, int per_grp) {
     return span < 16 ? 16 : span;
 }
 
+// att[e] = sum_split partial[split][e] (in split order) for the 256-element blocks [blk_begin, blk_end), quantized as the o-projection's
+// activations into global memory (one warp per block)
+template <bool Q8K>
+__device__ __forceinline__ void sum_partials_quantize(const MKParams & p, int nsplit, int blk_begin, int blk_end) {
+    const int64_t ne = (int64_t) p.heads * p.head_dim;
+    quantize_blocks<Q8K, 1>(p.att_q, ne, blk_begin, blk_end, [&](int64_t e) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int c0 = 0; c0 < nsplit; c0 += 8) {  // 8 partial rows in flight at a time; summed in split order
+            float4 b[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) b[i] = (c0 + i < nsplit) ? ldcg_f4(p.partial + (int64_t) (c0 + i) * ne + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { a.x += b[i].x; a.y += b[i].y; a.z += b[i].z; a.w += b[i].w; }
+        }
+        return a;
+    });
+}
+// separate tail step (KV groups that do not own whole 256-element blocks, e.g. GQA 7 x 128): CTA b takes 8 blocks
+template <bool Q8K>
+__device__ __forceinline__ void tail_step(const MKParams & p, int n_kv) {
+    const int nblk = p.heads * p.head_dim / 256;
+    const int b0 = (int) blockIdx.x * MK_WARPS;
+    if (b0 >= nblk) return;
+    const int per_grp = max(1, (int) gridDim.x / p.kv_heads);
+    const int span = mk_pv_span(n_kv, per_grp);
+    sum_partials_quantize<Q8K>(p, (n_kv + span - 1) / span, b0, min(nblk, b0 + MK_WARPS));
+}
+
 // partial[split][h][d] = sum over the split's positions of Vt[grp*HD + d][t] * P[h][t],  P = f16(exp(s - max_h) / sum_h) with the GLOBAL
 // max / sum of the row (from the per-tile statistics).  The CTA whose span holds the new position first appends the V-cache column.
-template <int HD>
-__device__ __forceinline__ void pv_step(const MKParams & p, int layer, int n_kv, int kpos, int v_col, uint8_t * sm) {
+template <int HD, bool Q8K>
+__device__ __forceinline__ void pv_step(const MKParams & p, const MKTabs & T, int layer, int n_kv, int kpos, int v_col, uint8_t * sm) {
     constexpr int MW = HD / 16;  // warps that own 16 channels each
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
@@ -647,7 +797,7 @@ __device__ __forceinline__ void pv_step(const MKParams & p, int layer, int n_kv,
     const int p_begin = split * span, p_end = min(n_kv, p_begin + span);
     for (int i = threadIdx.x; i < (8 - gqa) * MK_PV_SP / 2; i += MK_THREADS) reinterpret_cast<uint32_t *>(Ph + gqa * MK_PV_SP)[i] = 0u;
 
-    __half * vc = p.kv[layer].vc;
+    __half * vc = T.kv[layer].vc;
     const int c0 = warp * 16;
     const __half * rowA = vc + (int64_t) (grp * HD + c0 + g) * p.v_row_stride;
     const __half * rowB = rowA + 8 * p.v_row_stride;
@@ -683,13 +833,26 @@ __device__ __forceinline__ void pv_step(const MKParams & p, int layer, int n_kv,
     };
     load_round(p_begin);  // DRAM loads first, the (L2-resident) statistics and scores behind them
     for (int h = warp; h < gqa; h += MK_WARPS) {
+        // global max / sum of the row from the per-tile statistics: each lane folds its tiles (8 loads in flight at a time) into a running
+        // (max, sum), then the warp combines the 32 pairs
         const float2 * pp = p.part + (int64_t) (grp * gqa + h) * p.max_tiles;
-        float mx = -INFINITY;
-        for (int i = lane; i < ntiles; i += 32) mx = fmaxf(mx, __ldcg(pp + i).x);
-        mx = warp_max(mx);
-        float sum = 0.0f;
-        for (int i = lane; i < ntiles; i += 32) { const float2 pv = __ldcg(pp + i); sum += pv.y * expf(pv.x - mx); }
-        sum = warp_sum(sum);
+        float m_l = -INFINITY, s_l = 0.0f;
+        for (int i0 = lane; i0 < ntiles; i0 += 32 * 8) {
+            float2 st[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) st[j] = (i0 + 32 * j < ntiles) ? __ldcg(pp + i0 + 32 * j) : make_float2(-INFINITY, 0.0f);
+            float mc = m_l;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) mc = fmaxf(mc, st[j].x);
+            if (mc > -INFINITY) {
+                float sc = (m_l > -INFINITY) ? s_l * expf(m_l - mc) : 0.0f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) sc += (st[j].x > -INFINITY) ? st[j].y * expf(st[j].x - mc) : 0.0f;
+                m_l = mc; s_l = sc;
+            }
+        }
+        const float mx = warp_max(m_l);
+        const float sum = warp_sum((m_l > -INFINITY) ? s_l * expf(m_l - mx) : 0.0f);
         if (lane == 0) { hmax[h] = mx; hinv[h] = 1.0f / sum; }
     }
     __syncthreads();
@@ -726,29 +889,44 @@ __device__ __forceinline__ void pv_step(const MKParams & p, int layer, int n_kv,
         if (2 * t < gqa) { po[(int64_t) (2 * t) * HD + g] = c[0]; po[(int64_t) (2 * t) * HD + g + 8] = c[2]; }
         if (2 * t + 1 < gqa) { po[(int64_t) (2 * t + 1) * HD + g] = c[1]; po[(int64_t) (2 * t + 1) * HD + g + 8] = c[3]; }
     }
+    if (p.merged_tail) {
+        // the LAST split of this KV group to finish sums the group's partials (in split order: deterministic whoever does it) and emits the
+        // quantized activations of the o-projection for the group's slice — the separate tail step and its grid barrier disappear
+        int * flag = reinterpret_cast<int *>(hinv + 8);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            const unsigned long long old = atomicAdd(p.sync + 8 + grp, 1ull);
+            const int last = old == (unsigned long long) (nsplit - 1);
+            if (last) { p.sync[8 + grp] = 0ull; __threadfence(); }
+            flag[0] = last;
+        }
+        __syncthreads();
+        if (flag[0]) {
+            const int bpg = gqa * HD / 256;
+            sum_partials_quantize<Q8K>(p, nsplit, grp * bpg, (grp + 1) * bpg);
+        }
+    }
 }
 
-// att[e] = sum_split partial[split][e] (in split order), quantized as the o-projection's activations into global memory
-template <bool Q8K>
-__device__ __forceinline__ void tail_step(const MKParams & p, int n_kv, NormQuantSmem & nq) {
-    const int64_t ne = (int64_t) p.heads * p.head_dim;
-    const int nchunk = (int) ((ne + 1023) / 1024);
-    if ((int) blockIdx.x >= nchunk) return;
-    const int per_grp = max(1, (int) gridDim.x / p.kv_heads);
-    const int span = mk_pv_span(n_kv, per_grp);
-    const int nsplit = (n_kv + span - 1) / span;
-    const int64_t e0 = (int64_t) blockIdx.x * 1024, e1 = min(ne, e0 + 1024);
-    quantize_range<Q8K, 1>(p.att_q, ne, e0, e1, [&](int64_t e) {
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int c0 = 0; c0 < nsplit; c0 += 8) {  // 8 partial rows in flight at a time; summed in split order
-            float4 b[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) b[i] = (c0 + i < nsplit) ? ldcg_f4(p.partial + (int64_t) (c0 + i) * ne + e) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { a.x += b[i].x; a.y += b[i].y; a.z += b[i].z; a.w += b[i].w; }
-        }
-        return a;
-    }, nq);
+// pull this layer's K rows and V channel rows [0, n_kv) into L2 while the q/k/v projection streams its weights: the attention steps are
+// latency chains and would otherwise start with a DRAM round trip behind ~20 MB of queued weight requests
+__device__ __forceinline__ void prefetch_kv_l2(const MKParams & p, const MKTabs & T, int layer, int n_kv) {
+    const int kv_hidden = p.kv_heads * p.head_dim;
+    const uint8_t * kc = reinterpret_cast<const uint8_t *>(T.kv[layer].kc);
+    const uint8_t * vc = reinterpret_cast<const uint8_t *>(T.kv[layer].vc);
+    const int64_t gtid = (int64_t) blockIdx.x * MK_THREADS + threadIdx.x, gthreads = (int64_t) gridDim.x * MK_THREADS;
+    // one 128-byte line per thread and instruction (LSU prefetches; 16.8 MB at 4K context = 3-4 per thread)
+    const int64_t klines_row = ((int64_t) kv_hidden * 2 + 127) / 128;
+    for (int64_t i = gtid; i < (int64_t) n_kv * klines_row; i += gthreads) {
+        const int64_t r = i / klines_row, l = i - r * klines_row;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(kc + r * p.k_row_stride * 2 + l * 128));
+    }
+    const int64_t vlines_row = ((int64_t) n_kv * 2 + 127) / 128;
+    for (int64_t i = gtid; i < (int64_t) kv_hidden * vlines_row; i += gthreads) {
+        const int64_t r = i / vlines_row, l = i - r * vlines_row;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(vc + r * p.v_row_stride * 2 + l * 128));
+    }
 }
 
 // ---- the kernel -----------------------------------------------------------------------------------------------------------------
@@ -763,11 +941,24 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mk_kernel(const MKParams
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ NormQuantSmem nq;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint8_t * act_s = smem;
+    // dynamic shared memory: [phase table | KV table] [activation column / attention scratch] [mbarriers] [8 warps x stages x stage]
+    MKTabs T{p.phases, p.kv};
+    if (p.tab_bytes) {
+        const size_t nph = (size_t) p.n_phases * sizeof(MKPhase), nkv = (size_t) p.n_layers * sizeof(MKLayerKV);
+        unsigned long long * dst = reinterpret_cast<unsigned long long *>(smem);
+        const unsigned long long * s0 = reinterpret_cast<const unsigned long long *>(p.phases), * s1 = reinterpret_cast<const unsigned long long *>(p.kv);
+        for (size_t i = threadIdx.x; i < nph / 8; i += MK_THREADS) dst[i] = s0[i];
+        for (size_t i = threadIdx.x; i < nkv / 8; i += MK_THREADS) dst[nph / 8 + i] = s1[i];
+        T.ph = reinterpret_cast<const MKPhase *>(smem);
+        T.kv = reinterpret_cast<const MKLayerKV *>(smem + nph);
+        __syncthreads();
+    }
+    uint8_t * act_s = smem + p.tab_bytes;
     MKRing rg;
-    rg.bars = reinterpret_cast<uint64_t *>(smem + p.act_bytes) + (size_t) warp * p.stages;
-    rg.ring = smem + p.act_bytes + al16((int64_t) MK_WARPS * p.stages * 8) + (size_t) warp * p.stages * p.stage_bytes;
-    rg.iss_seq = rg.con_seq = 0;
+    rg.bars = reinterpret_cast<uint64_t *>(act_s + p.act_bytes) + (size_t) warp * p.stages;
+    rg.ring = act_s + p.act_bytes + al16((int64_t) MK_WARPS * p.stages * 8) + (size_t) warp * p.stages * p.stage_bytes;
+    rg.iss_stage = rg.con_stage = 0;
+    rg.con_parity = 0;
     rg.pol = 0;
     if (lane == 0) {
         for (int s = 0; s < p.stages; ++s) mbar_init(&rg.bars[s], 1);
@@ -776,23 +967,50 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mk_kernel(const MKParams
     }
     __syncwarp();
 
-    const int64_t gw = (int64_t) blockIdx.x * MK_WARPS + warp, GW = (int64_t) gridDim.x * MK_WARPS;
+    const unsigned gw = blockIdx.x * MK_WARPS + warp, GW = gridDim.x * MK_WARPS;
     const int ph_begin = mk_phases_before(p.step_begin), ph_end = min(p.n_phases, mk_phases_before(p.step_end));
-    MKCursor con, iss;
-    cursor_seek(con, p, ph_begin, ph_end, gw, GW);
-    iss = con;
+    // the consume cursor lives in registers (hot loop); the issue / L2-prefetch cursors are only touched around a bulk copy and live in shared
+    // memory (every lane reads the same words; lane 0 writes), which keeps the kernel under the 255-register ceiling
+    __shared__ MKCursor s_iss[MK_WARPS], s_pre[MK_WARPS];
+    MKCursor con;
+    MKCursor & iss = s_iss[warp];
+    MKCursor & pre = s_pre[warp];
+    cursor_seek(con, p, T, ph_begin, ph_end, gw, GW);
+    if (lane == 0) iss = con;
+    __syncwarp();
     for (int i = 0; i < p.stages && iss.ph < ph_end; ++i) {
-        if (lane == 0) issue_item<F>(iss, rg.ring + (size_t) (rg.iss_seq % p.stages) * p.stage_bytes, &rg.bars[rg.iss_seq % p.stages], rg.pol);
-        rg.iss_seq++;
-        if (++iss.it >= iss.nitems) cursor_seek(iss, p, iss.ph + 1, ph_end, gw, GW);
+        if (lane == 0) issue_item<F>(iss, rg.ring + (size_t) rg.iss_stage * p.stage_bytes, &rg.bars[rg.iss_stage], rg.pol);
+        ring_issue_advance(rg, p.stages);
+        cursor_next_shared(iss, p, T, ph_end, gw, GW);
+    }
+    if (lane == 0) pre = iss;  // the L2 prefetch cursor runs l2_ahead items in front of the ring's issue cursor
+    __syncwarp();
+    for (int i = 0; i < p.l2_ahead && pre.ph < ph_end; ++i) {
+        issue_item<F, true>(pre, nullptr, nullptr, 0);
+        cursor_next_shared(pre, p, T, ph_end, gw, GW);
     }
 
-    const int kpos = p.pos[0];
+    // layer-sharded multi-GPU: the previous shard (or, for the first shard, the last one with the next token) raises our flag through
+    // NVLink when this launch's input is in place.  The weight rings above are already streaming while we wait.
+    const unsigned long long seq = p.sync[4];  // launches of this plan completed so far
+    if (p.wait_flag) {
+        if (threadIdx.x == 0) {
+            const unsigned long long want = seq + (unsigned long long) p.wait_offset;
+            const unsigned long long t0 = globaltimer_ns();
+            unsigned spins = 0;
+            while (ld_acquire_sys_u64(p.wait_flag) < want) {
+                if ((++spins & 1023u) == 0 && globaltimer_ns() - t0 > 20000000000ull) { atomicExch(p.sync + 3, 2ull); break; }
+            }
+        }
+        __syncthreads();
+    }
+    const int kpos = __ldcg(p.pos);
     const int n_kv = p.n_kv_arg >= 0 ? p.n_kv_arg : kpos + 1;
     const int v_col = p.v_col_arg >= 0 ? p.v_col_arg : kpos;
     unsigned long long bar_target = p.sync[1];  // value of the counter when this launch started (written by the previous launch's last CTA 0)
     const int step_head = 1 + 7 * p.n_layers;
 
+    if (p.times && blockIdx.x == 0 && threadIdx.x == 0) p.times[0] = clock64();
     for (int s = p.step_begin; s < p.step_end; ++s) {
         // which quantized-matmul phase (if any) this step is: one call site for the GEMV keeps the kernel small
         int gph = -1, layer = 0, kind = -1;
@@ -802,18 +1020,20 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mk_kernel(const MKParams
             if (kind == 0) gph = 4 * layer; else if (kind >= 4) gph = 4 * layer + kind - 3;
         }
         if (gph >= 0) {
-            gemv_step<F>(p, gph, ph_end, con, iss, rg, act_s, nq, gw, GW, s == step_head && p.next_tok != nullptr);
+            if (kind == 0 && p.kv_prefetch) prefetch_kv_l2(p, T, layer, n_kv);
+            gemv_step<F>(p, T, gph, ph_end, con, iss, pre, rg, act_s, nq, gw, GW, s == step_head && p.next_tok != nullptr);
         } else if (s == 0) {
             if (p.embed) {  // Embedding::forward (src/layers.cpp:2038-2067): x = dequant(table[tok])
-                const int64_t row = p.tok[0];
+                const int64_t row = __ldcg(p.tok);  // (a peer may have just written it)
                 const uint8_t * base = p.embed + row * dequant_row_bytes(p.embed_type, p.hidden);
                 for (int64_t e = (int64_t) blockIdx.x * MK_THREADS + threadIdx.x; e < p.hidden; e += (int64_t) gridDim.x * MK_THREADS)
                     p.x[e] = dequant_row_elem(p.embed_type, base, p.hidden, e);
             }
         } else if (s == step_head + 1) {
+            int idx = 0;
             if (p.has_head && p.next_tok && blockIdx.x == 0 && threadIdx.x == 0) {
                 const unsigned long long key = __ldcg(p.sync + 2);
-                const int idx = (int) (0xffffffffu - (unsigned) (key & 0xffffffffu));
+                idx = (int) (0xffffffffu - (unsigned) (key & 0xffffffffu));
                 p.next_tok[0] = idx;
                 p.sync[2] = 0ull;
                 if (p.flags & MK_FLAG_ADVANCE) {
@@ -821,17 +1041,35 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mk_kernel(const MKParams
                     const_cast<int32_t *>(p.pos)[0] = kpos + 1;
                 }
             }
+            // ---- hand-off to the next shard: the hidden row (or, from the last shard, the next token) is stored straight into the peer's
+            // memory over NVLink, then its flag is raised with a system-scope release (the grid barrier before this step made every
+            // CTA's writes to x visible to this CTA)
+            if (blockIdx.x == 0 && (p.send_x || p.send_tok)) {
+                if (p.send_x) {
+                    for (int e = 4 * threadIdx.x; e < p.hidden; e += 4 * MK_THREADS) *reinterpret_cast<float4 *>(p.send_x + e) = ldcg_f4(p.x + e);
+                }
+                if (p.send_tok && threadIdx.x == 0) p.send_tok[0] = idx;
+                __threadfence_system();
+                __syncthreads();
+                if (threadIdx.x == 0 && p.send_flag) st_release_sys_u64(p.send_flag, seq + 1);
+            }
+            if (blockIdx.x == 0 && threadIdx.x == 0 && (p.flags & MK_FLAG_ADVANCE_POS) && !(p.flags & MK_FLAG_ADVANCE)) const_cast<int32_t *>(p.pos)[0] = kpos + 1;
         } else if (kind == 1) {
-            scores_step<HD>(p, layer, n_kv, kpos, act_s);
+            scores_step<HD>(p, T, layer, n_kv, kpos, act_s);
         } else if (kind == 2) {
-            pv_step<HD>(p, layer, n_kv, kpos, v_col, act_s);
+            pv_step<HD, F::Q8K>(p, T, layer, n_kv, kpos, v_col, act_s);
         } else if (kind == 3) {
-            tail_step<F::Q8K>(p, n_kv, nq);
+            if (p.merged_tail) continue;  // done by the last V.P CTA of every KV group: no step, no barrier
+            tail_step<F::Q8K>(p, n_kv);
         }
         if (s + 1 < p.step_end) grid_barrier(p, bar_target);
+        if (p.times && blockIdx.x == 0 && threadIdx.x == 0) p.times[1 + s - p.step_begin] = clock64();
     }
     // the counter value the next launch starts from (every CTA read sync[1] before its first barrier, which CTA 0 has passed)
-    if (blockIdx.x == 0 && threadIdx.x == 0 && p.step_end - p.step_begin > 1) p.sync[1] = bar_target;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && p.step_end - p.step_begin > 1) {
+        p.sync[1] = bar_target;
+        if (p.step_begin == 0 && p.step_end == step_head + 2) p.sync[4] = seq + 1;  // a whole token completed
+    }
 }
 
 // ======================================================================================================
@@ -922,6 +1160,7 @@ void * decode_plan_create(const DecodeModel & m, int max_ctx, int * err) {
         return fail(B200_ERR_UNSUPPORTED);
     if (m.n_layers > 0 && !m.layers) return fail(B200_ERR_ARG);
     if (m.lm_head && (m.vocab <= 0 || !m.final_norm)) return fail(B200_ERR_ARG);
+    if ((int64_t) std::max(std::max(m.vocab, m.ffn), m.hidden + 2 * m.kv_heads * m.head_dim) * 148 * MK_WARPS >= ((int64_t) 1 << 32)) return fail(B200_ERR_UNSUPPORTED);
     DecodePlan * pl = new DecodePlan;
     cudaGetDevice(&pl->device);
     pl->wtype = m.wtype;
@@ -945,9 +1184,10 @@ void * decode_plan_create(const DecodeModel & m, int max_ctx, int * err) {
     const size_t acb_h = qact_col_bytes(m.wtype, m.hidden);
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~(size_t) 255; return o; };
-    const size_t o_sync = take(64), o_q = take((size_t) m.hidden * 4), o_k = take((size_t) kv_hidden * 4), o_v = take((size_t) kv_hidden * 4),
+    const size_t o_sync = take(1024), o_q = take((size_t) m.hidden * 4), o_k = take((size_t) kv_hidden * 4), o_v = take((size_t) kv_hidden * 4),
                  o_sc = take((size_t) m.heads * s_stride * 4), o_part = take((size_t) m.heads * max_tiles * 8),
-                 o_partial = take((size_t) per_grp * m.hidden * 4), o_attq = take(acb_h), o_gate = take((size_t) m.ffn * 4), o_x = take((size_t) m.hidden * 4);
+                 o_partial = take((size_t) per_grp * m.hidden * 4), o_attq = take(acb_h), o_gate = take((size_t) m.ffn * 4), o_x = take((size_t) m.hidden * 4),
+                 o_times = take((size_t) (1 + 7 * m.n_layers + 3 + 80) * 8);
     pl->ws_bytes = off;
     if (cudaMalloc(&pl->ws, pl->ws_bytes) != cudaSuccess) { cudaGetLastError(); delete pl; return fail((int) cudaErrorMemoryAllocation); }
     cudaMemset(pl->ws, 0, pl->ws_bytes);  // barrier counter / argmax key / the padding of att_q start at zero
@@ -958,6 +1198,7 @@ void * decode_plan_create(const DecodeModel & m, int max_ctx, int * err) {
     P.part = (float2 *) (w + o_part); P.partial = (float *) (w + o_partial); P.att_q = w + o_attq; P.gate = (float *) (w + o_gate);
     P.x = (float *) (w + o_x);  // default residual stream (the caller may pass its own)
     P.s_stride = s_stride; P.max_tiles = max_tiles;
+    P.times = mk_env_int("B200_MK_TIMES", 0) ? (long long *) (w + o_times) : nullptr;
 
     // ---- phase table (pro_x / the residual y / the logits pointer are filled in by plan_upload)
     auto mat = [](MKPhase & ph, int i, const void * W, float * y, const float * bias, int mm) { ph.W[i] = (const uint8_t *) W; ph.y[i] = y; ph.bias[i] = bias; ph.m[i] = mm; };
@@ -993,18 +1234,26 @@ void * decode_plan_create(const DecodeModel & m, int max_ctx, int * err) {
     P.phases = pl->d_phases; P.kv = pl->d_kv;
 
     // ---- shared-memory layout: [activation column / attention scratch][mbarriers][8 warps x stages x stage]
+    P.l2_ahead = mk_env_int("B200_MK_L2AHEAD", 0);
+    P.kv_prefetch = mk_env_int("B200_MK_KVPREFETCH", 1);
     P.ks = mk_env_int("B200_MK_KS", 16);
     P.stages = mk_env_int("B200_MK_STAGES", 2);
     if (P.ks < 1) P.ks = 1;
     if (P.stages < 1) P.stages = 1;
     const size_t act_need = std::max(qact_col_bytes(m.wtype, m.hidden), qact_col_bytes(m.wtype, m.ffn));
-    const size_t attn_need = std::max((size_t) m.heads * m.head_dim * 2 + (size_t) m.head_dim * 4, (size_t) 8 * MK_PV_SP * 2 + 64);
+    const size_t attn_need = std::max((size_t) m.heads * m.head_dim * 2 + (size_t) m.head_dim * 4, (size_t) 8 * MK_PV_SP * 2 + 128);
+    P.merged_tail = ((m.heads / m.kv_heads) * m.head_dim) % 256 == 0 && mk_env_int("B200_MK_MERGED_TAIL", 1) ? 1 : 0;
+    if (m.kv_heads > 100) P.merged_tail = 0;
+    {   // both tables in shared memory when they leave room for a 2-stage ring
+        const size_t tb = ((size_t) P.n_phases * sizeof(MKPhase) + (size_t) m.n_layers * sizeof(MKLayerKV) + 127) & ~(size_t) 127;
+        P.tab_bytes = (tb <= 48 * 1024 && mk_env_int("B200_MK_TAB_SMEM", 1)) ? (uint32_t) tb : 0;
+    }
     P.act_bytes = (uint32_t) ((std::max(act_need, attn_need) + 127) & ~(size_t) 127);
     auto smem_for = [&]() {
         P.stage_bytes = (uint32_t) (MK_RG * P.ks * unit);
-        return (size_t) P.act_bytes + (size_t) al16((int64_t) MK_WARPS * P.stages * 8) + (size_t) MK_WARPS * P.stages * P.stage_bytes;
+        return (size_t) P.tab_bytes + (size_t) P.act_bytes + (size_t) al16((int64_t) MK_WARPS * P.stages * 8) + (size_t) MK_WARPS * P.stages * P.stage_bytes;
     };
-    const size_t limit = 226 * 1024;
+    const size_t limit = 224 * 1024;  // + ~1.5 KB static
     while (smem_for() > limit && P.stages > 2) P.stages--;
     while (smem_for() > limit && P.ks > 1) P.ks = (P.ks + 1) / 2;
     if (smem_for() > limit) { decode_plan_destroy(pl); return fail(B200_ERR_UNSUPPORTED); }
@@ -1030,7 +1279,7 @@ int decode_plan_status(void * h, cudaStream_t st) {
     if (!pl) return B200_ERR_ARG;
     unsigned long long s[4] = {0, 0, 0, 0};
     if (cudaMemcpyAsync(s, pl->prm.sync, sizeof(s), cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) return (int) cudaGetLastError();
-    if (s[3] != 0) { cudaMemsetAsync(pl->prm.sync, 0, 64, st); cudaStreamSynchronize(st); }
+    if (s[3] != 0) { cudaMemsetAsync(pl->prm.sync, 0, 1024, st); cudaStreamSynchronize(st); }
     return (int) s[3];
 }
 
@@ -1062,11 +1311,23 @@ int decode_step(void * h, const DecodeIO & io, cudaStream_t st) {
     if (!io.tok) prm.embed = nullptr;  // the caller provides the hidden state in x (a later layer shard)
     prm.tok = io.tok; prm.pos = io.pos; prm.n_kv_arg = io.n_kv; prm.v_col_arg = io.v_col;
     prm.next_tok = io.next_tok; prm.flags = io.flags;
+    prm.wait_flag = (const unsigned long long *) io.wait_flag; prm.wait_offset = io.wait_offset;
+    prm.send_x = io.send_x; prm.send_flag = (unsigned long long *) io.send_flag; prm.send_tok = io.send_tok;
     const int last = 1 + 7 * prm.n_layers + 2;
     prm.step_begin = io.step_begin > 0 ? io.step_begin : 0;
     prm.step_end = (io.step_end > 0 && io.step_end < last) ? io.step_end : last;
     if (prm.step_begin >= prm.step_end) return B200_OK;
     return (int) mk_launch(*pl, prm, st);
+}
+
+// profiling aid: SM-clock stamps of the last whole-token launch (needs B200_MK_TIMES=1 at plan creation); returns the number of stamps
+int decode_plan_times(void * h, long long * out, int cap, cudaStream_t st) {
+    DecodePlan * pl = (DecodePlan *) h;
+    if (!pl || !pl->prm.times) return 0;
+    const int n = 1 + 7 * pl->prm.n_layers + 3 + 80;
+    const int c = n < cap ? n : cap;
+    if (cudaMemcpyAsync(out, pl->prm.times, (size_t) c * 8, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) return 0;
+    return c;
 }
 
 int decode_plan_info(void * h, int * grid, int * smem_bytes, int * n_steps, int * stages, int * ks) {

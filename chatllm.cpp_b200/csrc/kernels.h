@@ -63,6 +63,12 @@ struct DecodeIO {
     int32_t * next_tok;    // optional: argmax of the logits (first maximum)
     int flags;             // bit 0: tok[0] = next_tok, pos[0] += 1 at the end (greedy decoding without the host)
     int step_begin, step_end;  // debug: run only steps [begin, end) (0, 0 = all)
+    // layer-sharded multi-GPU hand-off through NVLink peer memory (see include/chatllm_b200.h); all NULL / 0 on one GPU
+    const void * wait_flag;
+    float * send_x;
+    void * send_flag;
+    int32_t * send_tok;
+    int wait_offset, reserved;
 };
 void * decode_plan_create(const DecodeModel & m, int max_ctx, int * err);
 void decode_plan_destroy(void * plan);
@@ -70,6 +76,7 @@ int decode_plan_set_kv(void * plan, int layer, void * k_cache, void * v_cache);
 int decode_plan_status(void * plan, cudaStream_t st);
 int decode_plan_info(void * plan, int * grid, int * smem_bytes, int * n_steps, int * stages, int * ks);
 int decode_step(void * plan, const DecodeIO & io, cudaStream_t st);
+int decode_plan_times(void * plan, long long * out, int cap, cudaStream_t st);
 
 // ---- prefill.cu: batched (n > 8) quantized matmul on the int8 tensor cores, plain activation layout
 size_t pact_col_bytes(int wtype, int64_t k);

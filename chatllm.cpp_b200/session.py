@@ -304,8 +304,14 @@ class DecodeSession:
         import ctypes as C
         if self._plan is None:
             self._mk_plan()
-        io = DecodeIO(self.tok.data_ptr() if self.first else 0, self.pos.data_ptr(), -1, -1, self.x.data_ptr(), self.logits.data_ptr() if self.last else 0,
-                      self.next_tok.data_ptr() if self.last else 0, 1 if advance else 0, step_begin, step_end)
+        ring = getattr(self, "ring", None)   # sharding.PeerRing: the hidden row / token arrive in (and leave through) NVLink-mapped mailboxes
+        x_ptr = ring.x_ptr if ring is not None and not self.first else self.x.data_ptr()
+        tok_ptr = (ring.tok_ptr if ring is not None and ring.world > 1 else self.tok.data_ptr()) if self.first else 0
+        pio = ring.io if ring is not None else {}
+        flags = (1 if advance else 0) if not pio else 2   # sharded: every rank advances its own position; the token travels through the ring
+        io = DecodeIO(tok_ptr, self.pos.data_ptr(), -1, -1, x_ptr, self.logits.data_ptr() if self.last else 0,
+                      self.next_tok.data_ptr() if self.last else 0, flags, step_begin, step_end,
+                      pio.get("wait_flag", 0), pio.get("send_x", 0), pio.get("send_flag", 0), pio.get("send_tok", 0), pio.get("wait_offset", 0), 0)
         rc = lib().b200_decode_step(self._plan, C.byref(io), torch.cuda.current_stream().cuda_stream)
         if rc:
             raise RuntimeError(f"b200_decode_step failed rc={rc}")

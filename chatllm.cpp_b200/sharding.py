@@ -1,7 +1,12 @@
 """Layer sharding for multi-GPU decode (BASELINE.json configs[3]): the path is one sequential stream, so it is split BY
 LAYER exactly like the reference's `-ngl "0:16;1:16"` (docs/gpu.md:36-52, src/backend.cpp:578-652): rank r owns a contiguous
 layer range with its weights and its KV-cache shard; the single [hidden] F32 row is handed to the next rank with
-torch.distributed send/recv (NCCL on GPUs, gloo in the CPU tests).  No collective is needed anywhere else."""
+torch.distributed send/recv (gloo in the CPU tests, and the fallback on GPUs).  No collective is needed anywhere else.
+
+On GPUs the hand-off does not go through the host at all (PeerRing): every rank exports a small device mailbox with CUDA IPC, maps its
+successor's, and the persistent decode kernel of rank r stores the hidden row straight into rank r+1's mailbox over NVLink and raises
+its flag; rank r+1's kernel — already launched, its weight rings already streaming — spins on that LOCAL flag.  The last rank returns
+the next token to rank 0 the same way.  Each rank just replays one CUDA graph per token (include/chatllm_b200.h, b200_decode_io)."""
 import torch.distributed as dist
 
 
@@ -43,3 +48,75 @@ class Pipeline:
         """consume the token of the final step so no message is left in flight"""
         if self.world > 1 and self.tok is not None and self.rank == 0 and self.steps > 0:
             dist.recv(self.tok, src=self.world - 1)
+
+
+def mailbox_layout(hidden):
+    """byte offsets inside a rank's device mailbox: the incoming hidden row, the flag raised when it has arrived, and (rank 0) the
+    incoming next token with its flag.  Flags are 64-bit launch counters, never reset."""
+    x_bytes = hidden * 4
+    return dict(x=0, x_flag=x_bytes, tok_flag=x_bytes + 8, tok=x_bytes + 16, bytes=x_bytes + 64)
+
+
+def ring_io(rank, world, hidden, base_self, base_next):
+    """b200_decode_io hand-off fields of `rank` (device addresses): what it waits on in its own mailbox and where it stores its result
+    in the mailbox of rank (rank + 1) % world.  Rank 0 waits for the token of the PREVIOUS step (wait_offset 0), later ranks for the
+    hidden row of THIS step (wait_offset 1); the last rank sends the token to rank 0 instead of a hidden row."""
+    if world == 1:
+        return {}
+    L = mailbox_layout(hidden)
+    io = dict(wait_flag=base_self + (L["tok_flag"] if rank == 0 else L["x_flag"]), wait_offset=0 if rank == 0 else 1, send_x=0, send_tok=0)
+    if rank < world - 1:
+        io.update(send_x=base_next + L["x"], send_flag=base_next + L["x_flag"])
+    else:
+        io.update(send_tok=base_next + L["tok"], send_flag=base_next + L["tok_flag"])
+    return io
+
+
+class PeerRing:
+    """CUDA-IPC mailboxes of a layer-sharded decode (one process per GPU, torch.distributed only for the one-time handle exchange)."""
+
+    def __init__(self, rank, world, hidden, lib):
+        import ctypes as C
+        self.rank, self.world, self.hidden, self.lib = rank, world, hidden, lib
+        L = mailbox_layout(hidden)
+        self.base, self.next_base = C.c_void_p(0), C.c_void_p(0)
+        handle = C.create_string_buffer(64)
+        rc = lib.b200_ipc_alloc(L["bytes"], C.byref(self.base), handle)
+        if rc:
+            raise RuntimeError(f"b200_ipc_alloc failed rc={rc}")
+        self.layout = L
+        if world > 1:
+            handles = [None] * world
+            dist.all_gather_object(handles, bytes(handle.raw))
+            nxt = C.create_string_buffer(handles[(rank + 1) % world], 64)
+            rc = lib.b200_ipc_open(nxt, C.byref(self.next_base))
+            if rc:
+                raise RuntimeError(f"b200_ipc_open failed rc={rc} (peer access between the GPUs of this node is required)")
+        self.io = ring_io(rank, world, hidden, self.base.value, self.next_base.value or 0)
+
+    def view(self, name, dtype="<f4", count=None):
+        """zero-copy torch view of a mailbox field (host-side initialisation / inspection)"""
+        import torch
+
+        class _CAI:
+            pass
+        o = _CAI()
+        n = count if count is not None else (self.hidden if name == "x" else 1)
+        o.__cuda_array_interface__ = dict(shape=(n,), typestr=dtype, data=(self.base.value + self.layout[name], False), version=3)
+        return torch.as_tensor(o, device="cuda")
+
+    @property
+    def x_ptr(self):
+        return self.base.value + self.layout["x"]
+
+    @property
+    def tok_ptr(self):
+        return self.base.value + self.layout["tok"]
+
+    def close(self):
+        if self.next_base.value:
+            self.lib.b200_ipc_close(self.next_base)
+            self.next_base.value = None
+        if self.base.value:
+            self.lib.b200_ipc_free(self.base)
+            self.base.value = None

@@ -187,8 +187,20 @@ typedef struct b200_decode_io {
     float * x;                             /* residual stream [hidden], in/out; NULL: plan-owned */
     float * logits;                        /* [vocab] (required when the model has an lm_head) */
     int32_t * next_tok;                    /* optional: argmax of the logits, first maximum */
-    int32_t flags;                         /* bit 0: tok[0] = next_tok, pos[0] += 1 when the step ends (greedy decoding without the host) */
+    int32_t flags;                         /* bit 0: tok[0] = next_tok, pos[0] += 1 when the step ends (greedy decoding without the host);
+                                              bit 1: pos[0] += 1 only (a shard that does not own the token) */
     int32_t step_begin, step_end;          /* debug: run only steps [begin, end); 0, 0 = the whole token */
+    /* Layer-sharded multi-GPU (the reference copies the hidden row with cpy_tensor_async + events,
+     * ggml/src/ggml-cuda/ggml-cuda.cu:2806-2866): one process per GPU, each running its layer range with this entry point.  The kernel
+     * waits (after starting its weight streams) until the 64-bit LOCAL flag `wait_flag` reaches <launches of this plan completed so far> +
+     * wait_offset, and when the token is done stores the hidden row into `send_x` / the next token into `send_tok` — PEER memory of the
+     * next shard, mapped with b200_ipc_open — and raises the peer's flag `send_flag` to <launches completed> + 1 (system-scope release).
+     * First shard: wait_flag = its token flag, wait_offset 0;  later shards: wait_flag = their x flag, wait_offset 1. */
+    const void * wait_flag;
+    float * send_x;
+    void * send_flag;
+    int32_t * send_tok;
+    int32_t wait_offset, reserved;
 } b200_decode_io;
 /* returns NULL and *err (B200_ERR_* / cudaError_t) when the shape is not supported; max_ctx sizes the attention workspace */
 void * b200_decode_plan_create(const b200_decode_model * model, int max_ctx, int * err);
@@ -198,7 +210,15 @@ int b200_decode_plan_set_kv(void * plan, int layer, void * k_cache, void * v_cac
 /* 0 = fine, 1 = a grid barrier timed out in an earlier step (synchronizes `stream`) */
 int b200_decode_plan_status(void * plan, void * stream);
 int b200_decode_plan_info(void * plan, int * grid, int * smem_bytes, int * n_steps, int * stages, int * ks);
+/* profiling aid (B200_MK_TIMES=1 when the plan is created): SM-clock stamps at kernel start and after every step of the last launch */
+int b200_decode_plan_times(void * plan, long long * out, int cap, void * stream);
 int b200_decode_step(void * plan, const b200_decode_io * io, void * stream);
+/* Device memory that another PROCESS on the same node can map (cudaIpc*): hidden-row / flag / token mailboxes of the sharded decode.
+ * b200_ipc_alloc: cudaMalloc + zero-fill + export a 64-byte handle;  b200_ipc_open: map a peer's handle (peer access enabled lazily). */
+int b200_ipc_alloc(size_t bytes, void ** dptr, void * handle64);
+int b200_ipc_open(const void * handle64, void ** dptr);
+int b200_ipc_close(void * dptr);
+int b200_ipc_free(void * dptr);
 
 #ifdef __cplusplus
 }

@@ -26,9 +26,9 @@ def _mods():
 
 
 @pytest.mark.parametrize("wtype,hidden,heads,kvh,ffn,n_past", [
-    (qf.Q4_K, 1024, 8, 2, 2816, 300),      # head_dim 128, GQA 4, ffn not a multiple of 1024
-    (qf.Q4_0, 512, 8, 8, 1024, 17),        # head_dim 64, GQA 1
-    (qf.Q8_0, 1792, 14, 2, 4864, 1029),    # head_dim 128, GQA 7 (Qwen2.5 grouping), hidden not a multiple of 1024
+    (qf.Q4_K, 1024, 8, 2, 2816, 296),      # head_dim 128, GQA 4, ffn not a multiple of 1024
+    (qf.Q4_0, 512, 8, 8, 1024, 16),        # head_dim 64, GQA 1
+    (qf.Q8_0, 1792, 14, 2, 4864, 1032),    # head_dim 128, GQA 7 (Qwen2.5 grouping), hidden not a multiple of 1024
 ])
 def test_single_launch_equals_stepwise(wtype, hidden, heads, kvh, ffn, n_past):
     torch, K, S = _mods()
@@ -91,12 +91,16 @@ def test_llama3_8b_layer_shapes_at_4096_vs_oracle():
         kcs.append(kc.view(np.uint16).copy()); vcs.append(vc.view(np.uint16).copy())
     port = qf.port()
     port.oq_layer_step.argtypes = [C.POINTER(OqLayer), C.c_void_p, C.c_int, C.c_int]
-    n_steps = sess.mk_info["n_steps"]
     sess.tok.fill_(99); sess.pos.fill_(n_past)
-    sess.enqueue_step_mk(step_begin=0, step_end=1)      # embedding
+    sess.enqueue_step_mk(step_begin=0, step_end=1)      # embedding (the first call builds the plan)
+    n_steps = sess.mk_info["n_steps"]
     rels = []
     for li in range(2):
-        x_in = sess.x.cpu().numpy().copy()              # the layer input BOTH sides use
+        # the layer input BOTH sides use: an O(1) hidden state (the dequantized embedding row of the synthetic table is ~0.02, which makes
+        # the softmax uniform over 4097 positions — every P value then sits on the same f16 rounding boundary and a 1-ulp exp difference
+        # moves all of them together; real hidden states are O(1))
+        x_in = rng.standard_normal((1, hidden)).astype(np.float32)
+        sess.x.copy_(torch.from_numpy(x_in))
         sess.enqueue_step_mk(step_begin=1 + 7 * li, step_end=1 + 7 * (li + 1))
         torch.cuda.synchronize()
         got = sess.x.cpu().numpy()[0]
@@ -108,7 +112,9 @@ def test_llama3_8b_layer_shapes_at_4096_vs_oracle():
         h = x_in.copy()
         port.oq_layer_step(C.byref(L), h.ctypes.data, n_past, 1)
         ref = h[0]
-        rels.append(float(np.abs(got - ref).max() / np.abs(ref).max()))
+        # error relative to what the LAYER adds to the residual stream (stricter than relative to the O(1) stream itself)
+        rels.append(float(np.abs(got - ref).max() / np.abs(ref - x_in[0]).max()))
+        print("layer", li, "max err / max |layer delta| vs oracle:", rels[-1], " (max |delta|", float(np.abs(ref - x_in[0]).max()), ")")
         # the appended cache row / column are the oracle's (1 f16 ulp: fp32 summation order of the k / v projections)
         kg = sess.layers[li].kc[n_past].cpu().numpy().astype(np.float32)
         kr = kcs[li][n_past].view(np.float16).astype(np.float32)

@@ -70,3 +70,26 @@ def test_two_rank_pipeline_matches_sequential():
     for layer in range(n_layers):
         ref.mul_(1.5).add_(float(layer))
     assert torch.equal(got, ref)
+
+
+def test_ring_io_flags_are_consistent():
+    """PeerRing address arithmetic (no GPU): whatever flag / buffer rank r sends to is exactly what rank (r + 1) % world waits on / reads."""
+    import __graft_entry__ as ge
+    ge.load_package()
+    from chatllm_cpp_b200 import sharding
+    hidden = 4096
+    L = sharding.mailbox_layout(hidden)
+    assert L["x_flag"] % 8 == 0 and L["tok_flag"] % 8 == 0 and L["tok"] % 4 == 0 and L["bytes"] >= L["tok"] + 4
+    assert sharding.ring_io(0, 1, hidden, 1 << 20, 0) == {}
+    for world in (2, 4, 8):
+        bases = [(r + 1) << 24 for r in range(world)]
+        ios = [sharding.ring_io(r, world, hidden, bases[r], bases[(r + 1) % world]) for r in range(world)]
+        for r in range(world):
+            nxt = (r + 1) % world
+            assert ios[r]["send_flag"] == ios[nxt]["wait_flag"], (world, r)
+            if r < world - 1:
+                assert ios[r]["send_x"] == bases[nxt] + L["x"] and ios[r]["send_tok"] == 0
+            else:
+                assert ios[r]["send_tok"] == bases[0] + L["tok"] and ios[r]["send_x"] == 0
+        # rank 0 starts step t when the token of step t-1 has arrived (offset 0); rank r > 0 needs the hidden row of step t itself (offset 1)
+        assert [io["wait_offset"] for io in ios] == [0] + [1] * (world - 1)
