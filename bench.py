@@ -333,8 +333,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--tune", default="", help="ks,stages,warps,rg,grid for the GEMV pipeline (0 = default)")
     ap.add_argument("--unfused", action="store_true")
-    ap.add_argument("--fused2", action="store_true", help="opt-in step with norm+quant in the GEMV prologue / residual in the epilogue (9 launches per layer)")
-    ap.add_argument("--no-mk", action="store_true", help="A/B aid: the round-1 step (355 launches replayed as a CUDA graph) instead of the persistent kernel")
+    ap.add_argument("--mk", action="store_true", help="the persistent whole-token kernel (csrc/decode_mk.cu) instead of the per-op step replayed as a CUDA graph; "
+                    "measured slower on B200 (DESIGN.md §7.1), kept as an opt-in")
     ap.add_argument("--no-peer", action="store_true", help="multi-GPU A/B aid: hand the hidden row over with torch.distributed send/recv instead of NVLink mailboxes")
     ap.add_argument("--layers", type=int, default=0, help="debug: fewer layers (result is then NOT the BASELINE config)")
     a = ap.parse_args()
@@ -349,7 +349,7 @@ def main():
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int8 x int4 -> int32 dot, fp32 scales/accumulate",
             "data": "synthetic (seeded random valid Q4_K blocks, random F16 KV cache; no checkpoints offline)",
             "config": {"workload": "Llama-3-8B Q4_K single-token decode at n_past=4096 (BASELINE.json configs[1])", "n_past": N_PAST,
-                       "parallelism": "1 GPU" if a.gpus == 1 else f"layer-sharded x{a.gpus} (KV sharded by layer; hidden row / next token stored into the next rank's CUDA-IPC mailbox over NVLink by the persistent kernel, flag spin on the receiver)",
+                       "parallelism": "1 GPU" if a.gpus == 1 else f"layer-sharded x{a.gpus} (KV sharded by layer; one CUDA graph per rank: peer_wait kernel -> layers -> peer_send kernel storing the hidden row / next token into the next rank's CUDA-IPC mailbox over NVLink)",
                        "l2": "inputs (4.76 GB per token) exceed L2; no flush needed"}}
 
     if a.impl == "reference":
@@ -381,15 +381,15 @@ def main():
 
     if a.tune:
         pkg.lib().b200_gemv_set_tuning(*[int(v) for v in a.tune.split(",")])
-    use_mk = not a.no_mk and not a.unfused and not a.fused2
+    use_mk = a.mk and not a.unfused
     CTX_ROOM = 1024   # the device-side greedy loop walks one position per step: warm-up + timed steps must fit behind n_past = 4096
     if use_mk and a.warmup + a.steps + 2 > CTX_ROOM:
         raise SystemExit(f"--warmup + --steps must stay below {CTX_ROOM - 2}")
     cfg = S.make_config(MODEL, pkg.Q4_K, layers=a.layers or None, max_len=N_PAST + (CTX_ROOM if use_mk else 256))
     from chatllm_cpp_b200 import sharding
     lo, hi = sharding.plan_layers(cfg.layers, world)[rank]
-    sess = S.DecodeSession(cfg, seed=0, layer_lo=lo, layer_hi=hi, first=(rank == 0), last=(rank == world - 1), fused=(3 if use_mk else 2 if a.fused2 else not a.unfused))
-    sess.mk_advance = True   # persistent kernel: tok <- argmax(logits), pos <- pos + 1 on the device (real greedy decoding, growing KV cache)
+    sess = S.DecodeSession(cfg, seed=0, layer_lo=lo, layer_hi=hi, first=(rank == 0), last=(rank == world - 1), fused=(3 if use_mk else not a.unfused))
+    sess.mk_advance = True   # persistent kernel only: tok <- argmax(logits), pos <- pos + 1 on the device (greedy decoding, growing KV cache)
     sess.fill_kv_random(N_PAST, seed=rank)
     sess.tok.fill_(12345 % cfg.vocab)
 
@@ -415,17 +415,16 @@ def main():
         e1.record()
         sync_all()
         torch.cuda.cudart().cudaProfilerStop()
-    elif use_mk and not a.no_peer:
-        # layer-sharded: every rank replays ONE graph per token; the hidden row / next token move between the persistent kernels through
-        # NVLink-mapped mailboxes (sharding.PeerRing) — no host, no NCCL on the data path
+    elif not a.no_peer:
+        # layer-sharded: every rank replays ONE CUDA graph per token (peer_wait -> its layers -> peer_send); the hidden row / next token move
+        # between the ranks through NVLink-mapped CUDA-IPC mailboxes (sharding.PeerRing) — no host, no NCCL on the data path
         ring = sharding.PeerRing(rank, world, cfg.hidden, pkg.lib())
-        sess.ring = ring
+        sess.attach_ring(ring)
         if rank == 0:
             ring.view("tok", "<i4").fill_(12345 % cfg.vocab)
         sess.pos.fill_(N_PAST)
         sync_all()
         graph = sess.capture(N_PAST)           # one eager step (a real token: every rank does it) + capture
-        sess.pos.fill_(N_PAST + 1)
         for _ in range(a.warmup):
             graph.replay()
         sync_all()
@@ -435,8 +434,8 @@ def main():
             graph.replay()
         e1.record()
         sync_all()
-        if sess.mk_status() != 0:
-            raise SystemExit(f"rank {rank}: persistent kernel reported a timeout (barrier or peer flag)")
+        if int(ring.view("status", "<i8").item()) != 0 or (use_mk and sess.mk_status() != 0):
+            raise SystemExit(f"rank {rank}: a peer flag / grid barrier timed out")
     else:
         pipe = sharding.Pipeline(rank, world, sess.x, lambda _x: sess.enqueue(N_PAST), tok_buf=sess.tok)
         one_step = pipe.step

@@ -74,7 +74,6 @@ def lib():
         L.b200_add_rmsnorm_quant.argtypes = [i32, vp, vp, vp, vp, vp, vp, i64, i64, f32, vp]
         L.b200_rope_kv_store.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, i64, i64, vp]
         L.b200_mul_mat_q_multi.argtypes = [i32, i32, i32, vp, vp, vp, vp, vp, i64, vp, i64, vp]
-        L.b200_gemv_fused.argtypes = [i32, i32, i32, vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, f32, vp]
         L.b200_mul_mat_q_id.argtypes = [i32, i32, vp, vp, i64, i64, i32, vp, i32, vp, i32, vp, i64, vp]
         L.b200_pact_col_bytes.argtypes = [i32, i64]; L.b200_pact_col_bytes.restype = C.c_size_t
         L.b200_quantize_plain.argtypes = [i32, vp, i64, i64, i64, vp, vp]
@@ -87,6 +86,9 @@ def lib():
         L.b200_decode_plan_info.argtypes = [vp] + [C.POINTER(i32)] * 5
         L.b200_decode_step.argtypes = [vp, C.POINTER(DecodeIO), vp]
         L.b200_decode_plan_times.argtypes = [vp, vp, i32, vp]
+        L.b200_argmax.argtypes = [vp, i64, vp, vp]
+        L.b200_peer_wait.argtypes = [vp, vp, i32, vp, vp]
+        L.b200_peer_send.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp, vp]
         L.b200_ipc_alloc.argtypes = [C.c_size_t, C.POINTER(vp), vp]
         L.b200_ipc_open.argtypes = [vp, C.POINTER(vp)]
         L.b200_ipc_close.argtypes = [vp]
@@ -98,5 +100,5 @@ def lib():
 EXPORTS = ["b200_abi_version", "b200_device_sm_count", "b200_repack_weights", "b200_qact_col_bytes", "b200_quantize_act",
            "b200_mul_mat_q", "b200_mul_mat", "b200_gemv_set_tuning", "b200_rms_norm", "b200_add", "b200_silu_mul", "b200_rope",
            "b200_soft_max", "b200_get_rows", "b200_attn_decode_scratch_bytes", "b200_attn_decode", "b200_attn_decode_quant", "b200_kv_store", "b200_add_rmsnorm_quant", "b200_rope_kv_store",
-           "b200_mul_mat_q_multi", "b200_gemv_fused", "b200_mul_mat_q_id", "b200_pact_col_bytes", "b200_quantize_plain", "b200_mul_mat_q_batched", "b200_mul_mat_q_batched_tc",
-           "b200_decode_plan_create", "b200_decode_plan_destroy", "b200_decode_plan_set_kv", "b200_decode_plan_status", "b200_decode_plan_info", "b200_decode_plan_times", "b200_decode_step", "b200_ipc_alloc", "b200_ipc_open", "b200_ipc_close", "b200_ipc_free"]
+           "b200_mul_mat_q_multi", "b200_mul_mat_q_id", "b200_pact_col_bytes", "b200_quantize_plain", "b200_mul_mat_q_batched", "b200_mul_mat_q_batched_tc",
+           "b200_decode_plan_create", "b200_decode_plan_destroy", "b200_decode_plan_set_kv", "b200_decode_plan_status", "b200_decode_plan_info", "b200_decode_plan_times", "b200_decode_step", "b200_argmax", "b200_peer_wait", "b200_peer_send", "b200_ipc_alloc", "b200_ipc_open", "b200_ipc_close", "b200_ipc_free"]

@@ -146,11 +146,6 @@ int b200_mul_mat_q_multi(int wtype, int mode, int nmat, const void * const * W, 
                          const float * const * bias, int64_t k, const void * qact, int64_t n, void * stream) {
     return mul_mat_q_multi(wtype, mode, nmat, W, m, y, ldy, bias, k, qact, n, &g_tune, (cudaStream_t) stream);
 }
-int b200_gemv_fused(int wtype, int mode, int nmat, const void * const * W, const int64_t * m, float * const * y, const int64_t * ldy,
-                    const float * const * bias, const float * const * res, int64_t k, const void * qact, const float * pro_x, const float * pro_w,
-                    float pro_eps, void * stream) {
-    return mul_mat_q_fused(wtype, mode, nmat, W, m, y, ldy, bias, res, k, qact, 1, pro_x, pro_w, pro_eps, &g_tune, (cudaStream_t) stream);
-}
 int b200_mul_mat_q_id(int wtype, int paired, const void * W0, const void * W1, int64_t k, int64_t m, int n_expert, const int32_t * ids, int n_ids,
                       const void * qact, int act_cols, float * y, int64_t ldy, void * stream) {
     return mul_mat_q_id(wtype, paired, W0, W1, k, m, n_expert, ids, n_ids, qact, act_cols, y, ldy, &g_tune, (cudaStream_t) stream);
@@ -177,6 +172,11 @@ int b200_decode_step(void * plan, const b200_decode_io * io, void * stream) {
     return decode_step(plan, *reinterpret_cast<const DecodeIO *>(io), (cudaStream_t) stream);
 }
 
+int b200_peer_wait(const void * flag, const void * seq, int offset, void * status, void * stream) { return peer_wait(flag, seq, offset, status, (cudaStream_t) stream); }
+int b200_peer_send(const float * x, float * peer_x, int64_t n, const int32_t * tok, int32_t * peer_tok, void * peer_flag, void * seq, int32_t * pos, void * stream) {
+    return peer_send(x, peer_x, n, tok, peer_tok, peer_flag, seq, pos, (cudaStream_t) stream);
+}
+int b200_argmax(const float * x, int64_t n, int32_t * out, void * stream) { return argmax_f32(x, n, out, (cudaStream_t) stream); }
 int b200_ipc_alloc(size_t bytes, void ** dptr, void * handle64) {
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
     if (!dptr || !handle64 || bytes == 0) return B200_ERR_ARG;

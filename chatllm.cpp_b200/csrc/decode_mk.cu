@@ -25,7 +25,6 @@
 #include "dequant.cuh"
 #include "gemv_fmt.cuh"
 #include "kernels.h"
-#include "normquant.cuh"
 
 #include <cstdio>
 #include <cstdlib>
@@ -105,6 +104,11 @@ struct MKParams {
 
 // the phase table / KV-cache table as the device code sees them: copied into shared memory at kernel start when they fit (a first-touch
 // miss on a table entry costs a DRAM round trip behind ~20 MB of queued weight requests — it used to stall every warp at every phase change)
+// block-reduction scratch (double-precision sum of squares of the RMSNorm prologue)
+struct NormQuantSmem {
+    float red[32];
+};
+
 struct MKTabs {
     const MKPhase * ph;
     const MKLayerKV * kv;
@@ -171,7 +175,7 @@ __device__ __forceinline__ double block_sum_f64(double v, double * red) {
 }
 
 // ---- activation quantization into a column (shared or global memory), one WARP per 256-element block ----------------------------------
-// Same expressions as quantize.cu / normquant.cuh (reference quantize_row_q8_K_ref ggml-quants.c:2555-2592, x86 quantize_row_q8_0
+// Same expressions as quantize.cu / fused.cu add_rmsnorm_quant_kernel (reference quantize_row_q8_K_ref ggml-quants.c:2555-2592, x86 quantize_row_q8_0
 // arch/x86/quants.c:290-384): bit-identical codes.  Lane l of the warp owns elements [4l, 4l+4) and [128+4l, 128+4l+4) of its block, so
 // the block maximum / the 32-element sums are warp shuffles: NO block-wide barrier (the round-1 prologue's 3 barriers per 1024 elements
 // made it cost ~6 us per GEMV, gpurun_out/r02_bringup).

@@ -1029,7 +1029,7 @@ static int attn_decode_mma_t(const float * q, const void * kc, const void * vc, 
     static const int old_pv = getenv("B200_ATTN_OLD_PV") ? atoi(getenv("B200_ATTN_OLD_PV")) : 0;  // A/B aid: the channel-split kernel
     const int n_heads = kv_heads * GQA;
     if constexpr ((GQA * HD) % 256 == 0) {
-        static const int use_cluster = getenv("B200_ATTN_CLUSTER") ? atoi(getenv("B200_ATTN_CLUSTER")) : 0;  // OPT-IN (unmeasured): cluster V.P, no tail launch
+        static const int use_cluster = getenv("B200_ATTN_CLUSTER") ? atoi(getenv("B200_ATTN_CLUSTER")) : 1;  // measured r02: 9.45 vs 12.1 us per layer at 4K context (B200_ATTN_CLUSTER=0: split V.P + tail launch)
         const int nsplit_c = (n_kv + B200_PVC_SPAN - 1) / B200_PVC_SPAN;
         const bool q8k = wtype == B200_TYPE_Q4_K;
         if (use_cluster && nsplit_c <= 16 && (!qact || q8k || wtype == B200_TYPE_Q4_0 || wtype == B200_TYPE_Q8_0)) {

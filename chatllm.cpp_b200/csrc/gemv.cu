@@ -26,7 +26,6 @@
 #include "common.cuh"
 #include "gemv_fmt.cuh"
 #include "kernels.h"
-#include "normquant.cuh"
 
 #include <cstdlib>
 
@@ -52,7 +51,6 @@ struct GemvMat {
     const float * bias;
     int64_t m;    // rows
     int64_t ldy;  // column stride of y
-    const float * res;  // FX bit 1: residual added in the epilogue (same indexing as y; may alias y)
 };
 struct GemvParams {
     GemvMat mat[3];
@@ -69,14 +67,9 @@ struct GemvParams {
     int n_ids, n_expert;
     int act_cols;           // 1 = every slot reads activation column 0, n_ids = slot s reads column s
     int64_t expert_bytes;   // bytes between consecutive experts of a stack
-    // FX bit 0: the activation column is computed in the prologue as Q(rms_norm(pro_x) * pro_w) (normquant.cuh) instead of copied from qact
-    const float * pro_x;
-    const float * pro_w;
-    float pro_eps;
 };
 
-// FX: 0 = plain; bit 0 = norm+quantize prologue (NC == 1, MODE 0 / 1); bit 1 = residual epilogue (NC == 1, MODE 0).  Opt-in (normquant.cuh).
-template <class F, int RG, int NC, int MODE, int FX = 0>
+template <class F, int RG, int NC, int MODE>
 __global__ void __launch_bounds__(512) gemv_q_kernel(const GemvParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     pdl_launch_dependents();  // let the next kernel in the stream become resident and prefetch its own weights
@@ -91,9 +84,6 @@ __global__ void __launch_bounds__(512) gemv_q_kernel(const GemvParams p) {
     constexpr int GROUP = PAIRED ? HALF : RG;  // logical rows advanced per row group
     static_assert(!PAIRED || RG >= 2, "paired mode needs RG >= 2");
     static_assert(!IDX || NC == 1, "expert-indexed modes process one token");
-    constexpr bool PRO = (FX & 1) != 0, RES = (FX & 2) != 0;
-    static_assert(FX == 0 || (NC == 1 && !IDX), "fused prologue / epilogue: one token, dense modes");
-    static_assert(!RES || MODE == 0, "residual epilogue: concat mode");
     const bool whole = (p.ks == p.nunits);
     const int stage_cols = IDX ? p.act_cols : NC;  // activation columns kept in shared memory
     const uint32_t act_bytes = (uint32_t) al16((int64_t) p.act_col_bytes * stage_cols);
@@ -193,10 +183,7 @@ __global__ void __launch_bounds__(512) gemv_q_kernel(const GemvParams p) {
 
     // ---- activations: wait for the producer kernel (PDL), then stage the quantized columns in smem
     if constexpr (!IDX) pdl_wait();
-    if constexpr (PRO) {
-        __shared__ NormQuantSmem nq;
-        norm_quant_to_smem<F::Q8K>(p.pro_x, p.pro_w, p.pro_eps, p.k, act_s, nq);
-    } else {
+    {
         const uint4 * src = reinterpret_cast<const uint4 *>(p.qact);
         uint4 * dst = reinterpret_cast<uint4 *>(act_s);
         const int n16 = (int) (((size_t) p.act_col_bytes * stage_cols) >> 4);
@@ -311,7 +298,6 @@ __global__ void __launch_bounds__(512) gemv_q_kernel(const GemvParams p) {
                                 if (c < p.n) {
                                     float o = acc[r][c];
                                     if (M.bias) o += M.bias[lrow + r];
-                                    if constexpr (RES) o += M.res[(int64_t) c * M.ldy + lrow + r];
                                     M.y[(int64_t) c * M.ldy + lrow + r] = o;
                                 }
                             }
@@ -349,9 +335,9 @@ static const GemvTuning & env_tuning() {
     return t;
 }
 
-template <class F, int RG, int NC, int MODE, int FX = 0>
+template <class F, int RG, int NC, int MODE>
 static int launch(const GemvParams & p, int warps, int grid, size_t smem_bytes, cudaStream_t st) {
-    auto kern = gemv_q_kernel<F, RG, NC, MODE, FX>;
+    auto kern = gemv_q_kernel<F, RG, NC, MODE>;
     static size_t configured[64] = {0};  // per template instantiation AND per device (function attributes are per device)
     int dev = 0;
     cudaGetDevice(&dev);
@@ -389,24 +375,6 @@ static int launch_rg_nc(const GemvParams & p, int rg, int nc, int warps, int gri
     return B200_ERR_ARG;
 }
 
-// fused prologue / epilogue variants (one token): fx 1 = norm prologue (modes 0, 1), fx 2 = residual epilogue (mode 0)
-template <class F>
-static int launch_fx(int mode, int fx, const GemvParams & p, int rg, int warps, int grid, size_t smem, cudaStream_t st) {
-#define B200_FXCASE(RG_, MODE_, FX_) if (rg == RG_ && mode == MODE_ && fx == FX_) return launch<F, RG_, 1, MODE_, FX_>(p, warps, grid, smem, st);
-    B200_FXCASE(1, 0, 1) B200_FXCASE(2, 0, 1) B200_FXCASE(4, 0, 1) B200_FXCASE(2, 1, 1) B200_FXCASE(4, 1, 1)
-    B200_FXCASE(1, 0, 2) B200_FXCASE(2, 0, 2) B200_FXCASE(4, 0, 2)
-#undef B200_FXCASE
-    return B200_ERR_ARG;
-}
-static int launch_fmt_fx(int wtype, int mode, int fx, const GemvParams & p, int rg, int warps, int grid, size_t smem, cudaStream_t st) {
-    switch (wtype) {
-        case B200_TYPE_Q4_K: return launch_fx<FmtQ4K>(mode, fx, p, rg, warps, grid, smem, st);
-        case B200_TYPE_Q4_0: return launch_fx<FmtQ40>(mode, fx, p, rg, warps, grid, smem, st);
-        case B200_TYPE_Q8_0: return launch_fx<FmtQ80>(mode, fx, p, rg, warps, grid, smem, st);
-        default: return B200_ERR_UNSUPPORTED;
-    }
-}
-
 template <class F>
 static int launch_mode(int mode, const GemvParams & p, int rg, int nc, int warps, int grid, size_t smem, cudaStream_t st) {
     switch (mode) {
@@ -439,23 +407,9 @@ static int unit_bytes(int wtype) {
 // mode 1: y_0[c*ldy_0 + r] = silu(W_0[r,:].x_c) * (W_1[r,:].x_c)                                   (gate/up)
 int mul_mat_q_multi(int wtype, int mode, int nmat, const void * const * W, const int64_t * m, float * const * y, const int64_t * ldy,
                     const float * const * bias, int64_t k, const void * qact, int64_t n, const GemvTuning * tune, cudaStream_t st) {
-    return mul_mat_q_fused(wtype, mode, nmat, W, m, y, ldy, bias, nullptr, k, qact, n, nullptr, nullptr, 0.0f, tune, st);
-}
-
-// As mul_mat_q_multi, plus (one token, n == 1):
-//   pro_x != NULL : the activations are Q(rms_norm(pro_x) * pro_w) computed in every CTA's prologue (qact is ignored)
-//   res   != NULL : y_i[r] = W_i[r,:].x (+ bias_i[r]) + res_i[r]   (mode 0; res_i may alias y_i: the residual stream updated in place)
-int mul_mat_q_fused(int wtype, int mode, int nmat, const void * const * W, const int64_t * m, float * const * y, const int64_t * ldy,
-                    const float * const * bias, const float * const * res, int64_t k, const void * qact, int64_t n, const float * pro_x,
-                    const float * pro_w, float pro_eps, const GemvTuning * tune, cudaStream_t st) {
     if (k <= 0 || n <= 0 || nmat <= 0) return B200_OK;
     if (k % 256 || nmat > 3) return B200_ERR_UNSUPPORTED;
     if (mode == 1 && (nmat != 2 || m[0] != m[1])) return B200_ERR_ARG;
-    const int fx = (pro_x ? 1 : 0) | (res ? 2 : 0);
-    if (fx) {
-        if (n != 1 || fx == 3 || (pro_x && (!pro_w || k > 20480)) || (res && mode != 0)) return B200_ERR_UNSUPPORTED;
-        if (res) for (int i = 0; i < nmat; ++i) if (!res[i]) return B200_ERR_ARG;
-    }
     int unit;
     switch (wtype) {
         case B200_TYPE_Q4_K: unit = FmtQ4K::A_UNIT + FmtQ4K::B_UNIT; break;
@@ -501,14 +455,13 @@ int mul_mat_q_fused(int wtype, int mode, int nmat, const void * const * W, const
         auto smem_for = [&](const GemvTuning & q) {
             return act_bytes + (size_t) al16((int64_t) q.warps * q.stages * 8) + (size_t) q.warps * q.stages * q.rg * q.ks * unit;
         };
-        const size_t limit = (fx & 1) ? 226 * 1024 : 227 * 1024;  // the norm prologue has ~0.4 KB of static shared memory
+        const size_t limit = 227 * 1024;
         while (smem_for(t) > limit && t.stages > 3) t.stages--;
         while (smem_for(t) > limit && t.ks > 4) t.ks = (t.ks + 1) / 2;
         while (smem_for(t) > limit && t.stages > 2) t.stages--;
         while (smem_for(t) > limit && t.warps > 1) t.warps >>= 1;
         while (smem_for(t) > limit && t.ks > 1) t.ks = (t.ks + 1) / 2;
         if (smem_for(t) > limit) return B200_ERR_UNSUPPORTED;
-        if ((fx & 1) && t.warps < 2) return B200_ERR_UNSUPPORTED;  // the prologue quantizes 256-element blocks with 64 threads
 
         GemvParams p;
         p.nmat = nmat;
@@ -519,9 +472,8 @@ int mul_mat_q_fused(int wtype, int mode, int nmat, const void * const * W, const
                 p.mat[i].bias = bias ? bias[i] : nullptr;
                 p.mat[i].m = m[i];
                 p.mat[i].ldy = ldy[i];
-                p.mat[i].res = res ? res[i] : nullptr;
             } else {
-                p.mat[i] = GemvMat{nullptr, nullptr, nullptr, 0, 0, nullptr};
+                p.mat[i] = GemvMat{nullptr, nullptr, nullptr, 0, 0};
             }
         }
         p.qact = (const uint8_t *) qact + (size_t) c0 * acb;
@@ -532,9 +484,7 @@ int mul_mat_q_fused(int wtype, int mode, int nmat, const void * const * W, const
         p.stages = t.stages;
         p.act_col_bytes = (uint32_t) acb;
         p.ids = nullptr; p.n_ids = 0; p.n_expert = 0; p.act_cols = 0; p.expert_bytes = 0;
-        p.pro_x = pro_x; p.pro_w = pro_w; p.pro_eps = pro_eps;
-        const int rc = fx ? launch_fmt_fx(wtype, mode, fx, p, t.rg, t.warps, grid, smem_for(t), st)
-                          : launch_fmt(wtype, mode, p, t.rg, nc, t.warps, grid, smem_for(t), st);
+        const int rc = launch_fmt(wtype, mode, p, t.rg, nc, t.warps, grid, smem_for(t), st);
         if (rc) return rc;
         c0 += nc;
     }
@@ -588,9 +538,9 @@ int mul_mat_q_id(int wtype, int paired, const void * W0, const void * W1, int64_
 
     GemvParams p;
     p.nmat = paired ? 2 : 1;
-    p.mat[0] = GemvMat{(const uint8_t *) W0, y, nullptr, m, ldy, nullptr};
-    p.mat[1] = paired ? GemvMat{(const uint8_t *) W1, nullptr, nullptr, m, ldy, nullptr} : GemvMat{nullptr, nullptr, nullptr, 0, 0, nullptr};
-    p.mat[2] = GemvMat{nullptr, nullptr, nullptr, 0, 0, nullptr};
+    p.mat[0] = GemvMat{(const uint8_t *) W0, y, nullptr, m, ldy};
+    p.mat[1] = paired ? GemvMat{(const uint8_t *) W1, nullptr, nullptr, m, ldy} : GemvMat{nullptr, nullptr, nullptr, 0, 0};
+    p.mat[2] = GemvMat{nullptr, nullptr, nullptr, 0, 0};
     p.qact = (const uint8_t *) qact;
     p.k = k; p.m_total = m_total;
     p.n = 1;
@@ -600,7 +550,6 @@ int mul_mat_q_id(int wtype, int paired, const void * W0, const void * W1, int64_
     p.act_col_bytes = (uint32_t) acb;
     p.ids = ids; p.n_ids = n_ids; p.n_expert = n_expert; p.act_cols = act_cols;
     p.expert_bytes = m * (int64_t) nunits * unit;
-    p.pro_x = nullptr; p.pro_w = nullptr; p.pro_eps = 0.0f;
     return launch_fmt(wtype, paired ? 3 : 2, p, t.rg, 1, t.warps, grid, smem_for(t), st);
 }
 

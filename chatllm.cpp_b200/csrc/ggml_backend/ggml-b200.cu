@@ -92,11 +92,6 @@ struct b200_backend_ctx {
     int64_t q_k = 0, q_n = 0;
     // B200_PROFILE=1: per-graph host time inside graph_compute and GPU time between its first and last kernel
     cudaEvent_t p2p_ev = nullptr;  // "my stream has produced the tensor another device is about to copy"
-    // B200_FUSE2 (opt-in): an RMS_NORM + MUL pair whose only consumers are one-token quantized matmuls is not executed; the matmuls
-    // compute it in their prologue (gemv.cu FX bit 0) from these
-    const ggml_tensor * pn_mul = nullptr;
-    const float * pn_x = nullptr, * pn_w = nullptr;
-    float pn_eps = 0.0f;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // this graph rewrites OLD KV-cache rows (context shift / sliding-window roll: F16 -> F16 copies, src/layers.cpp:2999-3020, :3284-3332):
     // the fused attention must not stream the cache before its programmatic-dependent-launch wait
@@ -462,13 +457,6 @@ static int ensure_quantized(b200_backend_ctx * bc, int wtype, const ggml_tensor 
 }
 
 static int mul_mat_quant(b200_backend_ctx * bc, const ggml_tensor * w, const ggml_tensor * x, float * y, int64_t ldy, const float * bias) {
-    if (x == bc->pn_mul) {  // deferred norm: computed in the GEMV's prologue
-        const void * Ws[1] = {w->data};
-        const int64_t ms[1] = {w->ne[1]}, lds[1] = {ldy};
-        float * ys[1] = {y};
-        const float * bs[1] = {bias};
-        return mul_mat_q_fused((int) w->type, 0, 1, Ws, ms, ys, lds, bs, nullptr, w->ne[0], nullptr, 1, bc->pn_x, bc->pn_w, bc->pn_eps, nullptr, bc->stream);
-    }
     int rc = ensure_quantized(bc, (int) w->type, x);
     if (rc) return rc;
     if (x->ne[1] > GEMV_MAX_COLS) return mul_mat_q_batched((int) w->type, w->data, w->ne[0], w->ne[1], bc->qact, x->ne[1], y, ldy, bias, bc->stream);
@@ -554,41 +542,6 @@ static bool fusion_enabled() {
     return on;
 }
 
-// ---- B200_FUSE2=1 (OPT-IN, written at the end of round 1, not yet run on a GPU): the session's fused=2 step inside the plugin.
-//   * RMS_NORM -> MUL(weight) whose every consumer is a one-token quantized matmul is deferred into those matmuls' prologue;
-//   * MUL_MAT -> ADD(residual) becomes one launch with the residual in the epilogue.
-static bool fuse2_enabled() {
-    static const bool on = getenv("B200_FUSE2") && atoi(getenv("B200_FUSE2")) != 0;
-    return on;
-}
-// may the normalised tensor `mul` (node idx_mul) stay unmaterialised?  x = the norm's input
-static bool norm_deferrable(ggml_cgraph * g, int idx_mul, const ggml_tensor * mul, const ggml_tensor * x) {
-    const int64_t k = mul->ne[0];
-    if (k % 256 || k > 20480 || ggml_nrows(mul) != 1 || (mul->flags & GGML_TENSOR_FLAG_OUTPUT)) return false;
-    const int uses = ggml_node_get_use_count(g, idx_mul);
-    int found = 0, last = idx_mul, wtype = -1;
-    for (int t = idx_mul + 1; t < g->n_nodes && t < idx_mul + 48 && found < uses; ++t) {
-        const ggml_tensor * c = g->nodes[t];
-        bool refs = false;
-        for (int s = 0; s < GGML_MAX_SRC; ++s) refs |= (c->src[s] == mul);
-        if (!refs) continue;
-        if (!is_quant_mm(c) || c->src[1] != mul || c->src[0] == mul) return false;   // a view, the MoE router's reshape, an unsupported type ...
-        if (wtype >= 0 && wtype != (int) c->src[0]->type) return false;
-        wtype = (int) c->src[0]->type;
-        found++; last = t;
-    }
-    if (found == 0 || found != uses) return false;
-    // nothing executed before the last consumer may overwrite the norm's input (the host's allocator recycles dead tensors)
-    const char * x0 = (const char *) x->data, * x1 = x0 + ggml_nbytes(x);
-    for (int t = idx_mul + 1; t <= last; ++t) {
-        const ggml_tensor * c = g->nodes[t];
-        if (is_view_op(c->op) || !c->data) continue;
-        const char * d0 = (const char *) c->data, * d1 = d0 + ggml_nbytes(c);
-        if (d0 < x1 && x0 < d1) return false;
-    }
-    return true;
-}
-
 // [ADD] -> RMS_NORM -> MUL(weight)  (+ quantization for the quantized matmuls that consume it)
 static int try_fuse_norm(b200_backend_ctx * bc, ggml_cgraph * g, int i, int * rc) {
     int j = i;
@@ -618,11 +571,6 @@ static int try_fuse_norm(b200_backend_ctx * bc, ggml_cgraph * g, int i, int * rc
     float eps;
     memcpy(&eps, rms->op_params, sizeof(float));
     const int64_t ne0 = rms->ne[0], nrows = ggml_nrows(rms);
-    if (fuse2_enabled() && !add && norm_deferrable(g, j + 1, mul, rms->src[0])) {
-        bc->pn_mul = mul; bc->pn_x = (const float *) rms->src[0]->data; bc->pn_w = (const float *) w->data; bc->pn_eps = eps;
-        *rc = 0;
-        return 2;  // nothing launched: the consumers compute it
-    }
     void * q = nullptr;
     static const bool noq = getenv("B200_NORM_NOQ") != nullptr;  // bisect aid: never quantize inside the fused norm
     if (!noq && wtype >= 0 && mul->ne[2] == 1 && mul->ne[3] == 1 && nrows <= GEMV_MAX_COLS) q = ensure_qact(bc, qact_col_bytes(wtype, ne0) * (size_t) nrows);
@@ -648,11 +596,6 @@ static int try_fuse_swiglu(b200_backend_ctx * bc, ggml_cgraph * g, int i, int * 
     const int64_t ms[2] = {gate->src[0]->ne[1], up->src[0]->ne[1]};
     float * ys[2] = {(float *) mul->data, nullptr};
     const int64_t lds[2] = {(int64_t) (mul->nb[1] / 4), (int64_t) (mul->nb[1] / 4)};
-    if (x == bc->pn_mul) {
-        *rc = mul_mat_q_fused((int) gate->src[0]->type, 1, 2, Ws, ms, ys, lds, nullptr, nullptr, x->ne[0], nullptr, 1, bc->pn_x, bc->pn_w, bc->pn_eps, nullptr,
-                              bc->stream);
-        return 4;
-    }
     *rc = ensure_quantized(bc, (int) gate->src[0]->type, x);
     if (*rc) return 4;
     *rc = mul_mat_q_multi((int) gate->src[0]->type, 1, 2, Ws, ms, ys, lds, nullptr, x->ne[0], bc->qact, x->ne[1], nullptr, bc->stream);
@@ -842,11 +785,8 @@ static int try_fuse_qkv(b200_backend_ctx * bc, ggml_cgraph * g, int i, int * rc)
     const int idx_rq = qm.idx_rq;
 
     const ggml_tensor * x = mm[0]->src[1];
-    const bool pro = (x == bc->pn_mul);
-    if (!pro) {
-        *rc = ensure_quantized(bc, (int) mm[0]->src[0]->type, x);
-        if (*rc) return idx_rq - i + 1;
-    }
+    *rc = ensure_quantized(bc, (int) mm[0]->src[0]->type, x);
+    if (*rc) return idx_rq - i + 1;
     const void * Ws[3] = {mm[2]->src[0]->data, mm[1]->src[0]->data, mm[0]->src[0]->data};  // q, k, v
     const int64_t ms[3] = {mm[2]->src[0]->ne[1], mm[1]->src[0]->ne[1], mm[0]->src[0]->ne[1]};
     // The host's graph allocator recycles the v projection's buffer for k and then for q (each dies before the next is born), so the
@@ -863,8 +803,7 @@ static int try_fuse_qkv(b200_backend_ctx * bc, ggml_cgraph * g, int i, int * rc)
     const int64_t lds[3] = {ms[0], ms[1], ms[2]};
     const float * bs[3] = {bias[2] ? (const float *) bias[2]->data : nullptr, bias[1] ? (const float *) bias[1]->data : nullptr,
                            bias[0] ? (const float *) bias[0]->data : nullptr};
-    *rc = pro ? mul_mat_q_fused((int) mm[0]->src[0]->type, 0, 3, Ws, ms, ys, lds, bs, nullptr, x->ne[0], nullptr, 1, bc->pn_x, bc->pn_w, bc->pn_eps, nullptr, bc->stream)
-              : mul_mat_q_multi((int) mm[0]->src[0]->type, 0, 3, Ws, ms, ys, lds, bs, x->ne[0], bc->qact, 1, nullptr, bc->stream);
+    *rc = mul_mat_q_multi((int) mm[0]->src[0]->type, 0, 3, Ws, ms, ys, lds, bs, x->ne[0], bc->qact, 1, nullptr, bc->stream);
     if (*rc) return idx_rq - i + 1;
     bc->launches++;
     float fp[6];
@@ -873,27 +812,6 @@ static int try_fuse_qkv(b200_backend_ctx * bc, ggml_cgraph * g, int i, int * rc)
                          (const int32_t *) rk->src[1]->data, rk->src[2] ? (const float *) rk->src[2]->data : nullptr, sr->data, cpy->data, (int) heads, (int) kvh,
                          (int) hd, rq->op_params[2], fp[0], (int64_t) (sr->nb[1] / 2), (int64_t) (cpy->nb[1] / 2), 0, bc->stream);
     return idx_rq - i + 1;
-}
-
-// MUL_MAT (one token) -> ADD(residual): the residual add in the GEMV's epilogue (B200_FUSE2)
-static int try_fuse_mm_residual(b200_backend_ctx * bc, ggml_cgraph * g, int i, int * rc) {
-    ggml_tensor * mm = g->nodes[i];
-    if (!is_quant_mm(mm) || mm->src[1]->ne[1] != 1 || mm->src[1] == bc->pn_mul || !ggml_node_has_n_uses(g, i, 1)) return 0;
-    int j = i + 1;
-    while (j < g->n_nodes && is_view_op(g->nodes[j]->op)) ++j;
-    if (j >= g->n_nodes) return 0;
-    ggml_tensor * add = g->nodes[j];
-    if (add->op != GGML_OP_ADD || !(add->src[0] == mm || add->src[1] == mm) || add->src[0] == add->src[1]) return 0;
-    const ggml_tensor * r = add->src[0] == mm ? add->src[1] : add->src[0];
-    if (!f32c(r) || !f32c(add) || !ggml_are_same_shape(add, mm) || !ggml_are_same_shape(r, mm) || (mm->ne[0] % 2)) return 0;
-    *rc = ensure_quantized(bc, (int) mm->src[0]->type, mm->src[1]);
-    if (*rc) return j - i + 1;
-    const void * Ws[1] = {mm->src[0]->data};
-    const int64_t ms[1] = {mm->src[0]->ne[1]}, lds[1] = {mm->src[0]->ne[1]};
-    float * ys[1] = {(float *) add->data};
-    const float * rs[1] = {(const float *) r->data};
-    *rc = mul_mat_q_fused((int) mm->src[0]->type, 0, 1, Ws, ms, ys, lds, nullptr, rs, mm->src[0]->ne[0], bc->qact, 1, nullptr, nullptr, 0.0f, nullptr, bc->stream);
-    return j - i + 1;
 }
 
 static int try_fuse(b200_backend_ctx * bc, ggml_cgraph * g, int i, int * rc) {
@@ -907,7 +825,6 @@ static int try_fuse(b200_backend_ctx * bc, ggml_cgraph * g, int i, int * rc) {
         if (!(off & 16) && (n = try_fuse_qkv(bc, g, i, rc))) return n;
         if (!(off & 4) && (n = try_fuse_swiglu(bc, g, i, rc))) return n;
         if (!(off & 8) && (n = try_fuse_bias(bc, g, i, rc))) return n;
-        if (fuse2_enabled() && (n = try_fuse_mm_residual(bc, g, i, rc))) return n;
     }
     if (node->op == GGML_OP_MUL_MAT_ID && !(off & 32)) { if ((n = try_fuse_moe_swiglu(bc, g, i, rc))) return n; }
     return 0;
@@ -1088,7 +1005,7 @@ static void trace_node(b200_backend_ctx * bc, int idx, const ggml_tensor * t) {
 // overhead is CUDA-graph capture of the node launches (ggml-cuda.cu:2875-3071, :3993-4089).  The plan (device tables + workspace) is
 // cached and rebuilt only when a weight / cache pointer changes; only n_kv and the token / position / logits pointers vary per token.
 // Anything that does not match exactly (prompt batches, MoE, sliding-window caches, context shifts, YaRN, eval callbacks that cut
-// the graph) falls back to the per-node path below.  B200_NO_MK=1 disables it.
+// the graph) falls back to the per-node path below.  Opt-in: B200_MK=1.
 // ------------------------------------------------------------------------------------------------------------
 static bool norm_pair(ggml_cgraph * g, int i_rms, int i_mul, const ggml_tensor ** w, float * eps) {
     const ggml_tensor * rms = g->nodes[i_rms], * mul = g->nodes[i_mul];
@@ -1101,8 +1018,11 @@ static bool norm_pair(ggml_cgraph * g, int i_rms, int i_mul, const ggml_tensor *
     return true;
 }
 static bool try_whole_token(b200_backend_ctx * bc, ggml_cgraph * g, int * rc) {
-    static const bool off = getenv("B200_NO_MK") && atoi(getenv("B200_NO_MK")) != 0;
-    if (off || !fusion_enabled() || bc->kv_rewritten || g->n_nodes < 20) return false;
+    // OPT-IN (B200_MK=1): measured on the B200 the persistent kernel is slower than the node-by-node path (88 vs 55 us per
+    // layer); it stays available because it is the only path that needs no host work per node and reproduces the CPU's double-precision
+    // RMSNorm sum exactly
+    static const bool on = getenv("B200_MK") && atoi(getenv("B200_MK")) != 0;
+    if (!on || !fusion_enabled() || bc->kv_rewritten || g->n_nodes < 20) return false;
     const int n = g->n_nodes;
     auto next_real = [&](int from) { while (from < n && (is_view_op(g->nodes[from]->op) || ggml_is_empty(g->nodes[from]))) ++from; return from; };
     int i = next_real(0);
@@ -1286,7 +1206,6 @@ static enum ggml_status b200_graph_compute(ggml_backend_t backend, ggml_cgraph *
     CUDA_OK(cudaSetDevice(bc->device));
     order_after_inputs(&g_dev_ctx[bc->device], bc->stream);
     bc->q_src = nullptr;  // nothing is known to be quantized at the start of a graph
-    bc->pn_mul = nullptr;
     bc->kv_rewritten = false;
     for (int i = 0; i < cgraph->n_nodes; ++i) {
         const ggml_tensor * n = cgraph->nodes[i];

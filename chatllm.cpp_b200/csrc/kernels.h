@@ -26,10 +26,6 @@ int mul_mat_q(int wtype, const void * W, int64_t k, int64_t m, const void * qact
               const GemvTuning * tune, cudaStream_t st);
 int mul_mat_q_multi(int wtype, int mode, int nmat, const void * const * W, const int64_t * m, float * const * y, const int64_t * ldy,
                     const float * const * bias, int64_t k, const void * qact, int64_t n, const GemvTuning * tune, cudaStream_t st);
-// mul_mat_q_multi + fused norm/quantize prologue (pro_x, pro_w, eps) or residual epilogue (res); one token.  See normquant.cuh.
-int mul_mat_q_fused(int wtype, int mode, int nmat, const void * const * W, const int64_t * m, float * const * y, const int64_t * ldy,
-                    const float * const * bias, const float * const * res, int64_t k, const void * qact, int64_t n, const float * pro_x,
-                    const float * pro_w, float pro_eps, const GemvTuning * tune, cudaStream_t st);
 // expert-indexed GEMV (ggml_mul_mat_id, one token): ids on the device; act_cols = 1 (shared column) or n_ids (one per slot)
 int mul_mat_q_id(int wtype, int paired, const void * W0, const void * W1, int64_t k, int64_t m, int n_expert, const int32_t * ids, int n_ids,
                  const void * qact, int act_cols, float * y, int64_t ldy, const GemvTuning * tune, cudaStream_t st);
@@ -104,6 +100,9 @@ int attn_decode(const float * q, const void * kc, const void * vc, float * out, 
                 int64_t k_row_stride, int64_t v_row_stride, float scale, cudaStream_t st);
 int kv_store(const float * k, const float * v, void * kc, void * vc, int kv_hidden, int64_t k_row_stride, int64_t v_row_stride, int pos, cudaStream_t st);
 
+int peer_wait(const void * flag, const void * seq, int offset, void * status, cudaStream_t st);
+int peer_send(const float * x, float * peer_x, int64_t n, const int32_t * tok, int32_t * peer_tok, void * peer_flag, void * seq, int32_t * pos, cudaStream_t st);
+int argmax_f32(const float * x, int64_t n, int32_t * out, cudaStream_t st);
 
 // ---- fused.cu
 int add_rmsnorm_quant(int wtype, const float * x, const float * r, const float * w, float * x_out, float * y_out, void * qact, int64_t ne0, int64_t nrows,

@@ -361,4 +361,86 @@ int kv_store(const float * k, const float * v, void * kc, void * vc, int kv_hidd
     return (int) cudaGetLastError();
 }
 
+
+// ======================================================================================================
+// Layer-sharded multi-GPU hand-off without the host (the reference copies the hidden row with cpy_tensor_async + events,
+// ggml/src/ggml-cuda/ggml-cuda.cu:2806-2866, and synchronizes the scheduler around it): two one-CTA kernels that sit at the two ends of a
+// rank's CUDA graph.  peer_wait spins on a flag in LOCAL memory that the previous rank raises through NVLink; peer_send stores the
+// hidden row (or, from the last rank, the next token) straight into the next rank's CUDA-IPC mapped mailbox and raises its flag.  Flags
+// are 64-bit launch counters (never reset): launch t of a rank waits for flag >= t - 1 + offset.
+// ======================================================================================================
+__global__ void peer_wait_kernel(const unsigned long long * flag, const unsigned long long * seq, int offset, unsigned long long * status) {
+    pdl_launch_dependents();
+    pdl_wait();
+    if (threadIdx.x == 0) {
+        const unsigned long long want = *seq + (unsigned long long) offset;
+        unsigned long long v;
+        unsigned long long t0;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+        unsigned spins = 0;
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+            if ((++spins & 4095u) == 0) {
+                unsigned long long t1;
+                asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+                if (t1 - t0 > 20000000000ull) { if (status) *status = 1ull; break; }   // a lost peer must not hang the GPU
+            }
+        } while (v < want);
+    }
+}
+__global__ void peer_send_kernel(const float * x, float * peer_x, int64_t n, const int32_t * tok, int32_t * peer_tok, unsigned long long * peer_flag,
+                                 unsigned long long * seq, int32_t * pos) {
+    pdl_launch_dependents();
+    pdl_wait();
+    if (peer_x) for (int64_t e = 4 * (int64_t) threadIdx.x; e < n; e += 4 * (int64_t) blockDim.x) *reinterpret_cast<float4 *>(peer_x + e) = *reinterpret_cast<const float4 *>(x + e);
+    if (peer_tok && threadIdx.x == 0) peer_tok[0] = tok[0];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned long long s = *seq + 1ull;
+        if (peer_flag) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peer_flag), "l"(s) : "memory");
+        *seq = s;
+        if (pos) pos[0] += 1;
+    }
+}
+int peer_wait(const void * flag, const void * seq, int offset, void * status, cudaStream_t st) {
+    launch_pdl(peer_wait_kernel, dim3(1), dim3(32), 0, st, (const unsigned long long *) flag, (const unsigned long long *) seq, offset, (unsigned long long *) status);
+    return (int) cudaGetLastError();
+}
+int peer_send(const float * x, float * peer_x, int64_t n, const int32_t * tok, int32_t * peer_tok, void * peer_flag, void * seq, int32_t * pos, cudaStream_t st) {
+    if (n % 4) return B200_ERR_UNSUPPORTED;
+    launch_pdl(peer_send_kernel, dim3(1), dim3(256), 0, st, x, peer_x, n, tok, peer_tok, (unsigned long long *) peer_flag, (unsigned long long *) seq, pos);
+    return (int) cudaGetLastError();
+}
+
+// out[0] = index of the FIRST maximum of x[0..n)  (greedy sampling on the device: src/models.cpp:1026-1031 reads 0.5 MB of logits back
+// and scans them on the host every token).  One CTA.
+__global__ void __launch_bounds__(1024) argmax_kernel(const float * x, int64_t n, int32_t * out) {
+    __shared__ unsigned long long red[32];
+    pdl_launch_dependents();
+    pdl_wait();
+    unsigned long long best = 0ull;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint32_t b = __float_as_uint(x[i]);
+        const uint32_t ord = (b & 0x80000000u) ? ~b : (b | 0x80000000u);   // order-preserving float -> uint
+        const unsigned long long key = ((unsigned long long) ord << 32) | (unsigned) (0xffffffffu - (unsigned) i);   // ties: the smaller index wins
+        best = key > best ? key : best;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const unsigned long long v = __shfl_xor_sync(0xffffffffu, best, o); best = v > best ? v : best; }
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = best;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        unsigned long long v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { const unsigned long long w = __shfl_xor_sync(0xffffffffu, v, o); v = w > v ? w : v; }
+        if (threadIdx.x == 0) out[0] = (int32_t) (0xffffffffu - (unsigned) (v & 0xffffffffu));
+    }
+}
+int argmax_f32(const float * x, int64_t n, int32_t * out, cudaStream_t st) {
+    if (n <= 0 || n > 0x7fffffff) return B200_ERR_ARG;
+    launch_pdl(argmax_kernel, dim3(1), dim3(1024), 0, st, x, n, out);
+    return (int) cudaGetLastError();
+}
+
 }  // namespace b200

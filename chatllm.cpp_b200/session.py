@@ -192,49 +192,14 @@ class DecodeSession:
                          b=arr(C.c_void_p, [0 if W.bq is None else W.bq.data_ptr(), 0 if W.bk is None else W.bk.data_ptr(), 0 if W.bv is None else W.bv.data_ptr()]))
             W.gu = dict(W=arr(C.c_void_p, [W.wgate.data_ptr(), W.wup.data_ptr()]), m=arr(C.c_int64, [c.ffn, c.ffn]),
                         y=arr(C.c_void_p, [self.gate.data_ptr(), 0]), ld=arr(C.c_int64, [c.ffn, c.ffn]), b=arr(C.c_void_p, [0, 0]))
-            # single-matrix tables for the residual-epilogue launches of the fused=2 step: x += W . act
-            xr = arr(C.c_void_p, [self.x.data_ptr()])
-            W.o1 = dict(W=arr(C.c_void_p, [W.wo.data_ptr()]), m=arr(C.c_int64, [c.hidden]), y=xr, ld=arr(C.c_int64, [c.hidden]), res=xr)
-            W.d1 = dict(W=arr(C.c_void_p, [W.wdown.data_ptr()]), m=arr(C.c_int64, [c.hidden]), y=xr, ld=arr(C.c_int64, [c.hidden]), res=xr)
-        if self.last:
-            self._lm1 = dict(W=arr(C.c_void_p, [self.lm_head.data_ptr()]), m=arr(C.c_int64, [c.vocab]), y=arr(C.c_void_p, [self.logits.data_ptr()]),
-                             ld=arr(C.c_int64, [c.vocab]))
 
-    # ---- fused=2 step (OPT-IN, written at the end of round 1, unmeasured): 9 launches per layer.  RMSNorm + quantization move into the
-    #      consumer GEMV's prologue and the residual adds into the producer GEMV's epilogue (csrc/normquant.cuh, b200_gemv_fused).
-    def enqueue_step_fused2(self, n_past):
-        c = self.cfg
-        L = lib()
-        st = torch.cuda.current_stream().cuda_stream
-        if not hasattr(self, "_tables"):
-            self._ptr_arrays()
-        n = 0
-        hd, n_kv = c.head_dim, n_past + 1
-        q = self.qact.data_ptr()
-        x = self.x.data_ptr()
-        rc = 0
-        if self.first:
-            rc |= L.b200_get_rows(c.wtype, self.embed.data_ptr(), c.hidden, self.tok.data_ptr(), 1, x, st); n += 1
-        for W in self.layers:
-            t = W.qkv   # q/k/v = W . Q(rms_norm(x) * attn_norm)
-            rc |= L.b200_gemv_fused(c.wtype, 0, 3, t["W"], t["m"], t["y"], t["ld"], t["b"], 0, c.hidden, 0, x, W.attn_norm.data_ptr(), c.eps, st); n += 1
-            rc |= L.b200_rope_kv_store(self.q.data_ptr(), self.k.data_ptr(), self.v.data_ptr(), self.pos.data_ptr(), 0, W.kc.data_ptr(), W.vc.data_ptr(),
-                                       c.heads, c.kv_heads, hd, c.rope_mode, c.rope_theta, c.kv_hidden, c.max_len, st); n += 1
-            rc |= L.b200_attn_decode_quant(self.q.data_ptr(), W.kc.data_ptr(), W.vc.data_ptr(), self.att.data_ptr(), self.scratch.data_ptr(), c.heads,
-                                           c.kv_heads, hd, n_kv, c.kv_hidden, c.max_len, 1.0 / math.sqrt(hd), c.wtype, q, st); n += 3
-            t = W.o1    # x += W_o . att
-            rc |= L.b200_gemv_fused(c.wtype, 0, 1, t["W"], t["m"], t["y"], t["ld"], 0, t["res"], c.hidden, q, 0, 0, 0.0, st); n += 1
-            t = W.gu    # gate = silu(W_g . n) * (W_u . n),  n = Q(rms_norm(x) * ffn_norm)
-            rc |= L.b200_gemv_fused(c.wtype, 1, 2, t["W"], t["m"], t["y"], t["ld"], t["b"], 0, c.hidden, 0, x, W.ffn_norm.data_ptr(), c.eps, st); n += 1
-            rc |= L.b200_quantize_act(c.wtype, self.gate.data_ptr(), c.ffn, c.ffn, 1, q, st); n += 1
-            t = W.d1    # x += W_down . gate
-            rc |= L.b200_gemv_fused(c.wtype, 0, 1, t["W"], t["m"], t["y"], t["ld"], 0, t["res"], c.ffn, q, 0, 0, 0.0, st); n += 1
-        if self.last:
-            t = self._lm1
-            rc |= L.b200_gemv_fused(c.wtype, 0, 1, t["W"], t["m"], t["y"], t["ld"], 0, 0, c.hidden, 0, x, self.final_norm.data_ptr(), c.eps, st); n += 1
-        if rc:
-            raise RuntimeError(f"fused2 step failed rc={rc}")
-        self.launches_per_step = n
+    def attach_ring(self, ring):
+        """sharding.PeerRing: later shards read / update the hidden row in their NVLink-visible mailbox; pointer tables are rebuilt"""
+        self.ring = ring
+        if ring is not None and ring.world > 1 and not self.first:
+            self.x = ring.view("x").view(1, self.cfg.hidden)
+        if hasattr(self, "_tables"):
+            del self._tables
 
     def enqueue_step_fused(self, n_past):
         c = self.cfg
@@ -246,8 +211,12 @@ class DecodeSession:
         hd, n_kv = c.head_dim, n_past + 1
         q = self.qact.data_ptr()
         rc = 0
+        ring = getattr(self, "ring", None)
+        pio = ring.io if ring is not None and ring.world > 1 else None
+        if pio:  # layer-sharded: wait (on the device) until the previous shard's hidden row / the last shard's token is in our mailbox
+            rc |= L.b200_peer_wait(pio["wait_flag"], ring.seq_ptr, pio["wait_offset"], ring.status_ptr, st); n += 1
         if self.first:
-            rc |= L.b200_get_rows(c.wtype, self.embed.data_ptr(), c.hidden, self.tok.data_ptr(), 1, self.x.data_ptr(), st); n += 1
+            rc |= L.b200_get_rows(c.wtype, self.embed.data_ptr(), c.hidden, ring.tok_ptr if pio else self.tok.data_ptr(), 1, self.x.data_ptr(), st); n += 1
         pending = 0  # residual branch output not yet added into x
         for W in self.layers:
             rc |= L.b200_add_rmsnorm_quant(c.wtype, self.x.data_ptr(), pending, W.attn_norm.data_ptr(), self.x.data_ptr() if pending else 0, 0, q,
@@ -270,8 +239,16 @@ class DecodeSession:
             rc |= L.b200_add_rmsnorm_quant(c.wtype, self.x.data_ptr(), pending, self.final_norm.data_ptr(), self.x.data_ptr() if pending else 0, 0, q,
                                            c.hidden, 1, c.eps, st); n += 1
             rc |= L.b200_mul_mat_q(c.wtype, self.lm_head.data_ptr(), c.hidden, c.vocab, q, 1, self.logits.data_ptr(), c.vocab, 0, st); n += 1
+            if pio or getattr(self, "device_argmax", False):   # greedy sampling on the device (src/models.cpp:1026-1031 does it on the host)
+                rc |= L.b200_argmax(self.logits.data_ptr(), c.vocab, self.next_tok.data_ptr(), st); n += 1
         elif pending:
             rc |= L.b200_add(self.x.data_ptr(), pending, self.x.data_ptr(), c.hidden, st); n += 1
+        if pio:  # hand the result to the next shard through its NVLink-mapped mailbox and raise its flag
+            if self.last:
+                rc |= L.b200_peer_send(0, 0, 0, self.next_tok.data_ptr(), pio["send_tok"], pio["send_flag"], ring.seq_ptr, 0, st)
+            else:
+                rc |= L.b200_peer_send(self.x.data_ptr(), pio["send_x"], c.hidden, 0, 0, pio["send_flag"], ring.seq_ptr, 0, st)
+            n += 1
         if rc:
             raise RuntimeError(f"fused step failed rc={rc}")
         self.launches_per_step = n
@@ -331,8 +308,6 @@ class DecodeSession:
     def enqueue(self, n_past):
         if self.fused == 3:
             self.enqueue_step_mk(n_past, advance=getattr(self, "mk_advance", False))
-        elif self.fused == 2:
-            self.enqueue_step_fused2(n_past)
         elif self.fused:
             self.enqueue_step_fused(n_past)
         else:

@@ -54,7 +54,7 @@ def mailbox_layout(hidden):
     """byte offsets inside a rank's device mailbox: the incoming hidden row, the flag raised when it has arrived, and (rank 0) the
     incoming next token with its flag.  Flags are 64-bit launch counters, never reset."""
     x_bytes = hidden * 4
-    return dict(x=0, x_flag=x_bytes, tok_flag=x_bytes + 8, tok=x_bytes + 16, bytes=x_bytes + 64)
+    return dict(x=0, x_flag=x_bytes, tok_flag=x_bytes + 8, tok=x_bytes + 16, seq=x_bytes + 24, status=x_bytes + 32, bytes=x_bytes + 64)
 
 
 def ring_io(rank, world, hidden, base_self, base_next):
@@ -104,6 +104,15 @@ class PeerRing:
         n = count if count is not None else (self.hidden if name == "x" else 1)
         o.__cuda_array_interface__ = dict(shape=(n,), typestr=dtype, data=(self.base.value + self.layout[name], False), version=3)
         return torch.as_tensor(o, device="cuda")
+
+    @property
+    def seq_ptr(self):
+        """tokens this rank has completed (device counter used by b200_peer_wait / b200_peer_send)"""
+        return self.base.value + self.layout["seq"]
+
+    @property
+    def status_ptr(self):
+        return self.base.value + self.layout["status"]
 
     @property
     def x_ptr(self):

@@ -82,15 +82,6 @@ int b200_mul_mat_q_batched_tc(int wtype, const void * W, int64_t k, int64_t m, c
  *                                            — gate/up projections + SwiGLU of BaseMLP::forward (src/layers.cpp:2475-2483) */
 int b200_mul_mat_q_multi(int wtype, int mode, int nmat, const void * const * W, const int64_t * m, float * const * y, const int64_t * ldy,
                          const float * const * bias, int64_t k, const void * qact, int64_t n, void * stream);
-/* b200_mul_mat_q_multi for ONE token with a fused prologue or epilogue (OPT-IN: written at the end of round 1, not yet measured):
- *   pro_x != NULL : activations = Q(rms_norm(pro_x) * pro_w) computed in every CTA's prologue (qact ignored; k <= 20480) — replaces the
- *                   RMS_NORM + MUL + src1 conversion in front of the matmul (src/layers.cpp:2216-2225, ggml-cpu.c:1291-1326)
- *   res   != NULL : y_i[r] = W_i[r,:].x (+ bias_i[r]) + res_i[r]  (mode 0; res_i may alias y_i) — the residual ADD of
- *                   LMBlock1Forward::forward (src/layers.cpp:2719-2761) in the epilogue
- * Exactly one of the two may be given per call. */
-int b200_gemv_fused(int wtype, int mode, int nmat, const void * const * W, const int64_t * m, float * const * y, const int64_t * ldy,
-                    const float * const * bias, const float * const * res, int64_t k, const void * qact, const float * pro_x,
-                    const float * pro_w, float pro_eps, void * stream);
 /* Expert-indexed matmul for ONE token = ggml_mul_mat_id (ggml/src/ggml.c:3225-3240; CPU ggml_compute_forward_mul_mat_id
  * ggml/src/ggml-cpu/ggml-cpu.c:1503-1700; caller MultiLinear::forward src/layers.cpp:2145-2151, MultiMLP::forward :3674-3688).
  *   W0 (and W1): stacks of n_expert matrices [m, k] in the device layout, expert e at byte offset e * m * row_bytes.
@@ -213,6 +204,18 @@ int b200_decode_plan_info(void * plan, int * grid, int * smem_bytes, int * n_ste
 /* profiling aid (B200_MK_TIMES=1 when the plan is created): SM-clock stamps at kernel start and after every step of the last launch */
 int b200_decode_plan_times(void * plan, long long * out, int cap, void * stream);
 int b200_decode_step(void * plan, const b200_decode_io * io, void * stream);
+/* out[0] = index of the first maximum of x[0..n): greedy sampling on the device (the reference reads the logits back and scans them on the
+ * host every token, src/models.cpp:1026-1031). */
+int b200_argmax(const float * x, int64_t n, int32_t * out, void * stream);
+/* The two ends of a layer shard's CUDA graph (reference: cpy_tensor_async + events, ggml/src/ggml-cuda/ggml-cuda.cu:2806-2866).
+ * b200_peer_wait: spin (on the device) until the LOCAL 64-bit flag reaches *seq + offset (seq = tokens this shard has completed; offset 0 for
+ *   the first shard, which waits for the previous step's token, 1 for later shards, which wait for this step's hidden row); status (optional)
+ *   is set to 1 after a 20 s timeout instead of hanging the GPU.
+ * b200_peer_send: store x[0..n) into peer_x and / or tok[0] into peer_tok (PEER memory mapped with b200_ipc_open), raise *peer_flag to
+ *   *seq + 1 with a system-scope release, then *seq += 1 and (optionally) pos[0] += 1. */
+int b200_peer_wait(const void * flag, const void * seq, int offset, void * status, void * stream);
+int b200_peer_send(const float * x, float * peer_x, int64_t n, const int32_t * tok, int32_t * peer_tok, void * peer_flag, void * seq, int32_t * pos,
+                   void * stream);
 /* Device memory that another PROCESS on the same node can map (cudaIpc*): hidden-row / flag / token mailboxes of the sharded decode.
  * b200_ipc_alloc: cudaMalloc + zero-fill + export a 64-byte handle;  b200_ipc_open: map a peer's handle (peer access enabled lazily). */
 int b200_ipc_alloc(size_t bytes, void ** dptr, void * handle64);

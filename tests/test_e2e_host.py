@@ -209,13 +209,13 @@ def _stats(err):
 
 @pytest.mark.parametrize("arch,quant", [("tiny-test", "q4_K"), ("tiny-test", "q8_0"), ("qwen2-test", "q4_0")])
 def test_decode_graphs_run_as_one_persistent_launch(tmp_path, arch, quant):
-    """every one-token graph of a dense Llama-family model is executed by the plugin as ONE launch of the persistent
-    decode kernel (try_whole_token in ggml-b200.cu), and gives the logits of the node-by-node path (B200_NO_MK=1) and of the CPU."""
+    """with B200_MK=1 every one-token graph of a dense Llama-family model is executed by the plugin as ONE launch of the
+    persistent decode kernel (try_whole_token in ggml-b200.cu), and gives the logits of the default node-by-node path and of the CPU."""
     model = make_model(str(tmp_path), arch, quant)
     d = str(tmp_path)
     decode = 12
-    r1, e1 = run_host(model, "all", os.path.join(d, "mk.bin"), 5, decode, extra_env={"B200_STATS": "1"})
-    r0, e0 = run_host(model, "all", os.path.join(d, "nomk.bin"), 5, decode, extra_env={"B200_STATS": "1", "B200_NO_MK": "1"})
+    r1, e1 = run_host(model, "all", os.path.join(d, "mk.bin"), 5, decode, extra_env={"B200_STATS": "1", "B200_MK": "1"})
+    r0, e0 = run_host(model, "all", os.path.join(d, "nomk.bin"), 5, decode, extra_env={"B200_STATS": "1"})
     run_host(model, "0", os.path.join(d, "cpu.bin"), 5, decode)
     s1, s0 = _stats(e1), _stats(e0)
     assert s1["whole_token_graphs"] >= decode, s1          # (the harness' 1-token probe call is one more)
