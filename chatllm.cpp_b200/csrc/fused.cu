@@ -1016,7 +1016,7 @@ static int pv_span(int n_kv) {
 
 template <int HD, int GQA>
 static int attn_decode_mma_t(const float * q, const void * kc, const void * vc, float * out, float * scratch, int n_kv, int kv_heads, int64_t k_row_stride,
-                             int64_t v_row_stride, float scale, int wtype, void * qact, int preload_arg, cudaStream_t st) {
+                             int64_t v_row_stride, float scale, int wtype, void * qact, int preload_arg, int cluster_arg, cudaStream_t st) {
     const int64_t s_stride = (n_kv + 7) & ~7;
     const int nchunks = (n_kv + 127) / 128;
     float2 * part = reinterpret_cast<float2 *>(scratch + (int64_t) kv_heads * GQA * s_stride);
@@ -1032,7 +1032,7 @@ static int attn_decode_mma_t(const float * q, const void * kc, const void * vc, 
         static const int use_cluster = getenv("B200_ATTN_CLUSTER") ? atoi(getenv("B200_ATTN_CLUSTER")) : 1;  // measured r02: 9.45 vs 12.1 us per layer at 4K context (B200_ATTN_CLUSTER=0: split V.P + tail launch)
         const int nsplit_c = (n_kv + B200_PVC_SPAN - 1) / B200_PVC_SPAN;
         const bool q8k = wtype == B200_TYPE_Q4_K;
-        if (use_cluster && nsplit_c <= 16 && (!qact || q8k || wtype == B200_TYPE_Q4_0 || wtype == B200_TYPE_Q8_0)) {
+        if ((cluster_arg >= 0 ? cluster_arg : use_cluster) && nsplit_c <= 16 && (!qact || q8k || wtype == B200_TYPE_Q4_0 || wtype == B200_TYPE_Q8_0)) {
             auto kern = q8k ? attn_pv_cluster_kernel<HD, GQA, true> : attn_pv_cluster_kernel<HD, GQA, false>;
             static bool nonportable_dev[16] = {false};
             int dev = 0;
@@ -1130,7 +1130,7 @@ int attn_decode2(const float * q, const void * kc, const void * vc, float * out,
 
 // as attn_decode2, and additionally qact = the output quantized as the activations of a following matmul with weight type wtype
 int attn_decode3(const float * q, const void * kc, const void * vc, float * out, float * scratch, int n_heads, int kv_heads, int head_dim, int n_kv,
-                 int64_t k_row_stride, int64_t v_row_stride, float scale, int wtype, void * qact, cudaStream_t st, int preload) {
+                 int64_t k_row_stride, int64_t v_row_stride, float scale, int wtype, void * qact, cudaStream_t st, int preload, int cluster) {
     if (n_kv <= 0) return B200_OK;
     if (n_heads % kv_heads) return B200_ERR_ARG;
     if ((k_row_stride % 8) || (v_row_stride % 8)) return B200_ERR_UNSUPPORTED;  // 16-byte row loads
@@ -1138,7 +1138,7 @@ int attn_decode3(const float * q, const void * kc, const void * vc, float * out,
     static const int no_mma = getenv("B200_ATTN_NO_MMA") ? atoi(getenv("B200_ATTN_NO_MMA")) : 0;
 #define B200_ATTN2(HD_, G_)                                                                                                                       \
     if (head_dim == HD_ && gqa == G_) {                                                                                                           \
-        if (!no_mma) return attn_decode_mma_t<HD_, G_>(q, kc, vc, out, scratch, n_kv, kv_heads, k_row_stride, v_row_stride, scale, wtype, qact, preload, st); \
+        if (!no_mma) return attn_decode_mma_t<HD_, G_>(q, kc, vc, out, scratch, n_kv, kv_heads, k_row_stride, v_row_stride, scale, wtype, qact, preload, cluster, st); \
         const int rc_ = attn_decode2_t<HD_, G_>(q, kc, vc, out, scratch, n_kv, kv_heads, k_row_stride, v_row_stride, scale, st);                  \
         if (rc_ || !qact) return rc_;                                                                                                             \
         return quantize_act(wtype, out, (int64_t) n_heads * head_dim, (int64_t) n_heads * head_dim, 1, qact, st);                                 \

@@ -615,6 +615,13 @@ static int try_fuse_bias(b200_backend_ctx * bc, ggml_cgraph * g, int i, int * rc
 }
 
 static const ggml_tensor * view_root(const ggml_tensor * t);
+// The cluster V.P kernel wins under CUDA-graph replay (bench `value`: 9.45 vs 12.1 us per layer) but measured r02 it made the plugin's
+// stream-launched decode step 2x slower end to end (5.17 vs 2.49 ms per token): cluster launches from the host are expensive, so the
+// plugin keeps the three-launch attention unless B200_ATTN_CLUSTER=1 is set explicitly.
+static int plugin_attn_cluster() {
+    static const int v = getenv("B200_ATTN_CLUSTER") ? (atoi(getenv("B200_ATTN_CLUSTER")) != 0) : 0;
+    return v;
+}
 // decode attention: MUL_MAT(K,Q) -> SCALE -> DIAG_MASK_INF -> SOFT_MAX -> MUL_MAT(V,P) -> PERMUTE -> CONT, one query token
 struct AttnMatch {
     const ggml_tensor * K, * Q, * V, * ct;
@@ -629,8 +636,8 @@ static int match_attention(ggml_cgraph * g, int i, AttnMatch & m) {
         pm->op != GGML_OP_PERMUTE || ct->op != GGML_OP_CONT)
         return 0;
     if (sc->src[0] != kq || dm->src[0] != sc || sm->src[0] != dm || sm->src[1] || sm->src[2] || pv->src[1] != sm || pm->src[0] != pv || ct->src[0] != pm) return 0;
-    for (int t = i; t <= i + 5; ++t)   // kq, sc, dm, sm, pv (and the permute view) are never materialised: they must be dead outside the group
-        if (!ggml_node_has_n_uses(g, t, 1) || (g->nodes[t]->flags & GGML_TENSOR_FLAG_OUTPUT)) return 0;
+    for (int t = i; t <= i + 5; ++t)   // kq, sc, dm, sm, pv (and the permute view) are never materialised: they must be dead outside the group.
+        if (ggml_node_get_use_count(g, t) != 1 || (g->nodes[t]->flags & GGML_TENSOR_FLAG_OUTPUT)) return 0;   // (the host builds scale / mask / soft_max in place: they ARE views, so ggml_node_has_n_uses would refuse them)
     const ggml_tensor * K = kq->src[0], * Q = kq->src[1], * V = pv->src[0];
     if (K->type != GGML_TYPE_F16 || V->type != GGML_TYPE_F16 || Q->type != GGML_TYPE_F32) return 0;
     const int64_t hd = K->ne[0], n_kv = K->ne[1], kvh = K->ne[2], heads = Q->ne[2];
@@ -681,7 +688,7 @@ static int try_fuse_attention(b200_backend_ctx * bc, ggml_cgraph * g, int i, int
         }
     }
     int r = attn_decode3((const float *) Q->data, K->data, V->data, (float *) ct->data, bc->attn_scratch, (int) heads, (int) kvh, (int) hd, (int) n_kv,
-                         (int64_t) (K->nb[1] / 2), (int64_t) (V->nb[1] / 2), scale, wtype, qo, bc->stream, bc->kv_rewritten ? 0 : 1);
+                         (int64_t) (K->nb[1] / 2), (int64_t) (V->nb[1] / 2), scale, wtype, qo, bc->stream, bc->kv_rewritten ? 0 : 1, plugin_attn_cluster());
     if (r == B200_ERR_UNSUPPORTED) return 0;
     *rc = r;
     bc->launches += 2;
@@ -1017,7 +1024,10 @@ static bool norm_pair(ggml_cgraph * g, int i_rms, int i_mul, const ggml_tensor *
     *w = ww;
     return true;
 }
+// B200_MK_DEBUG=1: say where a graph stopped matching the whole-token template
+#define MKFAIL() do { if (mk_dbg) fprintf(stderr, "b200: whole-token template: no match at %s:%d (node %d of %d)\n", __FILE__, __LINE__, i, g->n_nodes); return false; } while (0)
 static bool try_whole_token(b200_backend_ctx * bc, ggml_cgraph * g, int * rc) {
+    static const bool mk_dbg = getenv("B200_MK_DEBUG") != nullptr;
     // OPT-IN (B200_MK=1): measured on the B200 the persistent kernel is slower than the node-by-node path (88 vs 55 us per
     // layer); it stays available because it is the only path that needs no host work per node and reproduces the CPU's double-precision
     // RMSNorm sum exactly
@@ -1026,11 +1036,11 @@ static bool try_whole_token(b200_backend_ctx * bc, ggml_cgraph * g, int * rc) {
     const int n = g->n_nodes;
     auto next_real = [&](int from) { while (from < n && (is_view_op(g->nodes[from]->op) || ggml_is_empty(g->nodes[from]))) ++from; return from; };
     int i = next_real(0);
-    if (i >= n) return false;
+    if (i >= n) MKFAIL();
     const ggml_tensor * embed = nullptr, * tok = nullptr, * cur = nullptr;
     if (g->nodes[i]->op == GGML_OP_GET_ROWS) {
         const ggml_tensor * gr = g->nodes[i];
-        if (!b200_supports_op_impl(nullptr, gr) || !ggml_is_quantized(gr->src[0]->type) || ggml_nelements(gr->src[1]) != 1 || !f32c(gr)) return false;
+        if (!b200_supports_op_impl(nullptr, gr) || !ggml_is_quantized(gr->src[0]->type) || ggml_nelements(gr->src[1]) != 1 || !f32c(gr)) MKFAIL();
         embed = gr->src[0]; tok = gr->src[1]; cur = gr;
         i = next_real(i + 1);
     }
@@ -1042,33 +1052,33 @@ static bool try_whole_token(b200_backend_ctx * bc, ggml_cgraph * g, int * rc) {
     while (i < n) {
         // ---- RMS_NORM * w of the hidden state
         const int i_rms = i, i_mul = next_real(i + 1);
-        if (i_mul >= n) return false;
+        if (i_mul >= n) MKFAIL();
         const ggml_tensor * w1 = nullptr;
         float eps = 0.0f;
-        if (!norm_pair(g, i_rms, i_mul, &w1, &eps)) return false;
+        if (!norm_pair(g, i_rms, i_mul, &w1, &eps)) MKFAIL();
         const ggml_tensor * xs = view_root(g->nodes[i_rms]->src[0]);
-        if (cur) { if (xs != cur) return false; } else { cur = x_in = xs; }
+        if (cur) { if (xs != cur) MKFAIL(); } else { cur = x_in = xs; }
         const ggml_tensor * nrm = g->nodes[i_mul];
         const int64_t hidden = nrm->ne[0];
-        if (first) { M.hidden = (int) hidden; M.eps = eps; } else if (hidden != M.hidden || eps != M.eps) return false;
+        if (first) { M.hidden = (int) hidden; M.eps = eps; } else if (hidden != M.hidden || eps != M.eps) MKFAIL();
         int j = next_real(i_mul + 1);
-        if (j >= n) return false;
+        if (j >= n) MKFAIL();
         QkvMatch qm;
         const int nq = match_qkv(g, j, qm);
         if (!nq) {
             // ---- head: lm_head . (final norm), and nothing after it
             const ggml_tensor * mm = g->nodes[j];
-            if (!is_quant_mm(mm) || view_root(mm->src[1]) != nrm || mm->src[1]->ne[1] != 1 || mm->src[1]->ne[0] != hidden || next_real(j + 1) < n) return false;
-            if (ggml_node_get_use_count(g, i_mul) != 1) return false;
+            if (!is_quant_mm(mm) || view_root(mm->src[1]) != nrm || mm->src[1]->ne[1] != 1 || mm->src[1]->ne[0] != hidden || next_real(j + 1) < n) MKFAIL();
+            if (ggml_node_get_use_count(g, i_mul) != 1) MKFAIL();
             M.final_norm = (const float *) w1->data; M.lm_head = mm->src[0]->data; M.vocab = (int) mm->src[0]->ne[1];
-            if ((int) mm->src[0]->type != M.wtype && !layers.empty()) return false;
+            if ((int) mm->src[0]->type != M.wtype && !layers.empty()) MKFAIL();
             if (layers.empty()) M.wtype = (int) mm->src[0]->type;
             logits = mm;
             i = n;
             break;
         }
         // ---- q/k/v + RoPE + KV append
-        if (qm.mm[0]->src[1] != nrm || ggml_node_get_use_count(g, i_mul) != 3) return false;
+        if (qm.mm[0]->src[1] != nrm || ggml_node_get_use_count(g, i_mul) != 3) MKFAIL();
         const int wtype = (int) qm.mm[0]->src[0]->type;
         float fp[6];
         memcpy(fp, (const int32_t *) qm.rq->op_params + 5, sizeof(fp));
@@ -1077,60 +1087,62 @@ static bool try_whole_token(b200_backend_ctx * bc, ggml_cgraph * g, int * rc) {
             M.wtype = wtype; M.heads = (int) qm.heads; M.kv_heads = (int) qm.kvh; M.head_dim = (int) qm.hd; M.rope_mode = rope_mode == 0 ? 0 : 2; M.rope_theta = fp[0];
             pos = qm.rk->src[1]; ff = qm.rk->src[2];
         } else if (wtype != M.wtype || qm.heads != M.heads || qm.kvh != M.kv_heads || qm.hd != M.head_dim || (rope_mode == 0 ? 0 : 2) != M.rope_mode || fp[0] != M.rope_theta ||
-                   qm.rk->src[1]->data != pos->data || (qm.rk->src[2] ? qm.rk->src[2]->data : nullptr) != (ff ? ff->data : nullptr))
-            return false;
-        if (ggml_nelements(qm.rk->src[1]) != 1 || qm.heads * qm.hd != hidden) return false;
-        for (int s = 0; s < 3; ++s) if (qm.mm[s]->src[0]->ne[0] != hidden) return false;
+                   (qm.rk->src[2] ? qm.rk->src[2]->data : nullptr) != (ff ? ff->data : nullptr))
+            MKFAIL();   // (every layer has its own `pos` tensor, src/layers.cpp:2360-2366; all hold n_past = n_kv - 1, which the mask parameter of each layer's attention confirms)
+        if (ggml_nelements(qm.rk->src[1]) != 1 || qm.heads * qm.hd != hidden) MKFAIL();
+        for (int s = 0; s < 3; ++s) if (qm.mm[s]->src[0]->ne[0] != hidden) MKFAIL();
         j = next_real(j + nq);
         // ---- attention over the cache that was just appended to
         AttnMatch am;
-        if (j >= n || !match_attention(g, j, am)) return false;
-        if (view_root(am.Q) != view_root(qm.rq) || am.hd != qm.hd || am.kvh != qm.kvh || am.heads != qm.heads) return false;
-        if (am.K->data != qm.sr->data || am.K->nb[1] != qm.sr->nb[1]) return false;                       // K view starts at cache row 0
-        if ((const char *) qm.cpy->data != (const char *) am.V->data + (am.n_kv - 1) * 2 || qm.cpy->nb[1] != am.V->nb[1]) return false;  // V column n_kv - 1
+        if (j >= n || !match_attention(g, j, am)) MKFAIL();
+        if (view_root(am.Q) != view_root(qm.rq) || am.hd != qm.hd || am.kvh != qm.kvh || am.heads != qm.heads) MKFAIL();
+        if (am.K->data != qm.sr->data || am.K->nb[1] != qm.sr->nb[1]) MKFAIL();                       // K view starts at cache row 0
+        if ((const char *) qm.cpy->data != (const char *) am.V->data + (am.n_kv - 1) * 2 || qm.cpy->nb[1] != am.V->nb[1]) MKFAIL();  // V column n_kv - 1
         if (first) { n_kv = am.n_kv; M.attn_scale = am.scale; M.k_row_stride = (int64_t) (am.K->nb[1] / 2); M.v_row_stride = (int64_t) (am.V->nb[1] / 2); }
-        else if (am.n_kv != n_kv || am.scale != M.attn_scale || (int64_t) (am.K->nb[1] / 2) != M.k_row_stride || (int64_t) (am.V->nb[1] / 2) != M.v_row_stride) return false;
+        else if (am.n_kv != n_kv || am.scale != M.attn_scale || (int64_t) (am.K->nb[1] / 2) != M.k_row_stride || (int64_t) (am.V->nb[1] / 2) != M.v_row_stride) MKFAIL();
         j = next_real(j + 7);
         // ---- o projection + residual
-        if (j >= n) return false;
+        if (j >= n) MKFAIL();
         const ggml_tensor * o = g->nodes[j];
         if (!is_quant_mm(o) || (int) o->src[0]->type != wtype || view_root(o->src[1]) != am.ct || o->src[1]->ne[1] != 1 || o->src[0]->ne[0] != hidden || o->src[0]->ne[1] != hidden ||
             !ggml_node_has_n_uses(g, j, 1))
-            return false;
+            MKFAIL();
         int ja = next_real(j + 1);
-        if (ja >= n) return false;
+        if (ja >= n) MKFAIL();
         const ggml_tensor * add1 = g->nodes[ja];
-        if (add1->op != GGML_OP_ADD || !f32c(add1) || ggml_nelements(add1) != hidden) return false;
-        if (!((add1->src[0] == o && view_root(add1->src[1]) == cur) || (add1->src[1] == o && view_root(add1->src[0]) == cur))) return false;
+        if (add1->op != GGML_OP_ADD || !f32c(add1) || ggml_nelements(add1) != hidden) MKFAIL();
+        if (!((add1->src[0] == o && view_root(add1->src[1]) == cur) || (add1->src[1] == o && view_root(add1->src[0]) == cur))) MKFAIL();
         // ---- RMS_NORM * w -> SwiGLU MLP -> + residual
         const int i_rms2 = next_real(ja + 1), i_mul2 = next_real(i_rms2 + 1);
-        if (i_mul2 >= n) return false;
+        if (i_mul2 >= n) MKFAIL();
         const ggml_tensor * w2 = nullptr;
         float eps2 = 0.0f;
-        if (!norm_pair(g, i_rms2, i_mul2, &w2, &eps2) || eps2 != M.eps || view_root(g->nodes[i_rms2]->src[0]) != add1 || ggml_node_get_use_count(g, i_mul2) != 2) return false;
+        if (!norm_pair(g, i_rms2, i_mul2, &w2, &eps2) || eps2 != M.eps || view_root(g->nodes[i_rms2]->src[0]) != add1 || ggml_node_get_use_count(g, i_mul2) != 2) MKFAIL();
         const ggml_tensor * nrm2 = g->nodes[i_mul2];
         j = next_real(i_mul2 + 1);
-        if (j + 3 >= n) return false;
+        if (j + 3 >= n) MKFAIL();
         const ggml_tensor * gate = g->nodes[j], * act = g->nodes[j + 1], * up = g->nodes[j + 2], * gu = g->nodes[j + 3];
-        if (!is_quant_mm(gate) || !is_quant_mm(up) || act->op != GGML_OP_UNARY || ggml_get_unary_op(act) != GGML_UNARY_OP_SILU || gu->op != GGML_OP_MUL) return false;
+        if (!is_quant_mm(gate) || !is_quant_mm(up) || act->op != GGML_OP_UNARY || ggml_get_unary_op(act) != GGML_UNARY_OP_SILU || gu->op != GGML_OP_MUL) MKFAIL();
         if (act->src[0] != gate || gate->src[1] != nrm2 || up->src[1] != nrm2 || (int) gate->src[0]->type != wtype || (int) up->src[0]->type != wtype ||
             !ggml_are_same_shape(gate->src[0], up->src[0]) || gate->src[0]->ne[0] != hidden)
-            return false;
-        if (!((gu->src[0] == act && gu->src[1] == up) || (gu->src[1] == act && gu->src[0] == up))) return false;
-        if (!f32c(gu) || !ggml_node_has_n_uses(g, j, 1) || !ggml_node_has_n_uses(g, j + 1, 1) || !ggml_node_has_n_uses(g, j + 2, 1) || !ggml_node_has_n_uses(g, j + 3, 1)) return false;
+            MKFAIL();
+        if (!((gu->src[0] == act && gu->src[1] == up) || (gu->src[1] == act && gu->src[0] == up))) MKFAIL();
+        if (!f32c(gu) || !ggml_node_has_n_uses(g, j, 1) || !ggml_node_has_n_uses(g, j + 2, 1)) MKFAIL();
+        for (int t2 = j + 1; t2 <= j + 3; t2 += 2)   // the activation and the product may be built in place (views): use count + output flag only
+            if (ggml_node_get_use_count(g, t2) != 1 || (g->nodes[t2]->flags & GGML_TENSOR_FLAG_OUTPUT)) MKFAIL();
         const int64_t ffn = gate->src[0]->ne[1];
-        if (first) M.ffn = (int) ffn; else if (ffn != M.ffn) return false;
+        if (first) M.ffn = (int) ffn; else if (ffn != M.ffn) MKFAIL();
         j = next_real(j + 4);
-        if (j >= n) return false;
+        if (j >= n) MKFAIL();
         const ggml_tensor * down = g->nodes[j];
         if (!is_quant_mm(down) || (int) down->src[0]->type != wtype || view_root(down->src[1]) != gu || down->src[1]->ne[1] != 1 || down->src[0]->ne[0] != ffn ||
             down->src[0]->ne[1] != hidden || !ggml_node_has_n_uses(g, j, 1))
-            return false;
+            MKFAIL();
         ja = next_real(j + 1);
-        if (ja >= n) return false;
+        if (ja >= n) MKFAIL();
         const ggml_tensor * add2 = g->nodes[ja];
-        if (add2->op != GGML_OP_ADD || !f32c(add2) || ggml_nelements(add2) != hidden) return false;
-        if (!((add2->src[0] == down && add2->src[1] == add1) || (add2->src[1] == down && add2->src[0] == add1))) return false;
+        if (add2->op != GGML_OP_ADD || !f32c(add2) || ggml_nelements(add2) != hidden) MKFAIL();
+        if (!((add2->src[0] == down && add2->src[1] == add1) || (add2->src[1] == down && add2->src[0] == add1))) MKFAIL();
         DecodeLayer L{};
         L.wq = qm.mm[2]->src[0]->data; L.wk = qm.mm[1]->src[0]->data; L.wv = qm.mm[0]->src[0]->data; L.wo = o->src[0]->data;
         L.wgate = gate->src[0]->data; L.wup = up->src[0]->data; L.wdown = down->src[0]->data;
@@ -1138,13 +1150,13 @@ static bool try_whole_token(b200_backend_ctx * bc, ggml_cgraph * g, int * rc) {
         L.bv = qm.bias[0] ? (const float *) qm.bias[0]->data : nullptr;
         L.attn_norm = (const float *) w1->data; L.ffn_norm = (const float *) w2->data;
         L.k_cache = am.K->data; L.v_cache = am.V->data;
-        if (qm.mm[2]->src[0]->ne[1] != hidden || qm.mm[1]->src[0]->ne[1] != qm.kvh * qm.hd || qm.mm[0]->src[0]->ne[1] != qm.kvh * qm.hd) return false;
+        if (qm.mm[2]->src[0]->ne[1] != hidden || qm.mm[1]->src[0]->ne[1] != qm.kvh * qm.hd || qm.mm[0]->src[0]->ne[1] != qm.kvh * qm.hd) MKFAIL();
         layers.push_back(L);
         cur = x_out = add2;
         first = false;
         i = next_real(ja + 1);
     }
-    if (layers.empty()) return false;
+    if (layers.empty()) MKFAIL();
     // ---- plan: reuse while nothing the tables point at has moved
     M.n_layers = (int) layers.size();
     M.embed = embed ? embed->data : nullptr;
@@ -1200,6 +1212,8 @@ static bool try_whole_token(b200_backend_ctx * bc, ggml_cgraph * g, int * rc) {
     bc->mk_tokens++;
     return true;
 }
+
+#undef MKFAIL
 
 static enum ggml_status b200_graph_compute(ggml_backend_t backend, ggml_cgraph * cgraph) {
     b200_backend_ctx * bc = (b200_backend_ctx *) backend->context;

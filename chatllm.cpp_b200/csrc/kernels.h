@@ -119,7 +119,8 @@ int attn_decode2(const float * q, const void * kc, const void * vc, float * out,
 // preload: 1 = K / V rows older than n_kv - 1 may be streamed before the programmatic-dependent-launch wait (they were written by
 // EARLIER decode steps), 0 = a launch just before this call may have rewritten them (cache shift), -1 = library default
 int attn_decode3(const float * q, const void * kc, const void * vc, float * out, float * scratch, int n_heads, int kv_heads, int head_dim, int n_kv,
-                 int64_t k_row_stride, int64_t v_row_stride, float scale, int wtype, void * qact, cudaStream_t st, int preload = -1);
+                 int64_t k_row_stride, int64_t v_row_stride, float scale, int wtype, void * qact, cudaStream_t st, int preload = -1, int cluster = -1);
+// cluster: 1 = thread-block-cluster V.P (2 launches), 0 = split V.P + tail launch (3 launches), -1 = library default (B200_ATTN_CLUSTER, on)
 
 // ---- ops_generic.cu: strided / broadcasting ops as ggml graphs present them (ne[0] fastest, nb in bytes)
 struct TV {
