@@ -145,17 +145,20 @@ def run_config3(a):
     from chatllm_cpp_b200 import session as S
     torch.cuda.set_device(0)
     model, wtype, P, D = "qwen2.5-7b", pkg.Q4_0, 2048, 512
+    if os.environ.get("B200_CFG3_MODEL"):   # e.g. "llama3-8b:q4_K": the same measurement on another architecture / format
+        model, qn = os.environ["B200_CFG3_MODEL"].split(":")
+        wtype = {"q4_K": pkg.Q4_K, "q4_0": pkg.Q4_0, "q8_0": pkg.Q8_0}[qn]
     cfg = S.make_config(model, wtype, layers=a.layers or None, max_len=P + D + 64)
-    sess = S.DecodeSession(cfg, seed=0, fused=3)
-    sess.fill_kv_random(P, seed=1)
+    sess = S.DecodeSession(cfg, seed=0, fused=(3 if a.mk else True))
+    sess.fill_kv_random(P + D, seed=1)
     sess.mk_advance = True
     sess.tok.fill_(12345 % cfg.vocab)
-    graph = sess.capture(P)
-    sess.pos.fill_(P)
+    graph = sess.capture(P + D // 2)      # the per-op step is captured at the middle position of the 512-token decode (its grids depend on n_kv)
+    sess.pos.fill_(P if a.mk else P + D // 2)
     for _ in range(max(a.warmup, 3)):
         graph.replay()
     torch.cuda.synchronize()
-    sess.pos.fill_(P)
+    sess.pos.fill_(P if a.mk else P + D // 2)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(D):
@@ -174,7 +177,7 @@ def run_config3(a):
     for W in sess.layers:
         shapes += [(W.wq, cfg.hidden, cfg.hidden), (W.wk, cfg.hidden, cfg.kv_hidden), (W.wv, cfg.hidden, cfg.kv_hidden), (W.wo, cfg.hidden, cfg.hidden),
                    (W.wgate, cfg.hidden, cfg.ffn), (W.wup, cfg.hidden, cfg.ffn), (W.wdown, cfg.ffn, cfg.hidden)]
-    tc = os.environ.get("B200_MMQ_TCGEN05", "1") != "0"
+    tc = os.environ.get("B200_MMQ_TCGEN05", "1") != "0"   # default: the tcgen05 kernel (the library default)
     mm = L.b200_mul_mat_q_batched_tc if tc else L.b200_mul_mat_q_batched
 
     def prefill_mm():
@@ -202,7 +205,7 @@ def run_config3(a):
            "dtype": "int8 x int4 -> int32 dot, fp32 scales/accumulate", "data": "synthetic (seeded random valid Q4_0 blocks, random F16 KV cache)",
            "config": {"workload": "Qwen2.5-7B Q4_0 prefill 2048 + decode 512, 1 x B200 (BASELINE.json configs[2])", "n_past": P, "decode_steps": D,
                       "l2": "inputs (4.2 GB per token / per prompt pass) exceed L2; no flush needed"},
-           "gpu_launches": D, "clocks": clocks,
+           "gpu_launches": D * sess.launches_per_step, "clocks": clocks,
            "frac_of_hbm_roofline_whole_token": round(1000.0 / dec_ms * tok_bytes / 1e9 / pk["hbm_gbs"], 4),
            "roofline": {"bound": "tensor", "kernel": ("mmq_tc_kernel (tcgen05.mma kind::i8)" if tc else "mmq_kernel (mma.sync m16n8k32.s8)"), "achieved": round(tfl, 1),
                         "peak": pk.get("bf16_tflops_sustained", pk["bf16_tflops"]), "unit": "TFLOP/s",
@@ -227,7 +230,7 @@ def run_config3(a):
             out["e2e"] = {"value": round(1000.0 / r["decode_ms_mean_after_skip"], 2), "unit": "tokens/s", "ms_per_step": round(r["decode_ms_mean_after_skip"], 4),
                           "h2d_bytes_per_step": 4 + 4 * cfg.layers, "d2h_bytes_per_step": 4 * cfg.vocab,
                           "prefill": {"tokens": P, "ms": r["prefill_ms"], "tokens_per_s": round(P / r["prefill_ms"] * 1e3, 1)},
-                          "path": "unmodified chatllm host -> libggml-cuda.so (one-token graphs run as one persistent-kernel launch)"}
+                          "path": "unmodified chatllm host -> libggml-cuda.so"}
         except Exception as ex:  # noqa: BLE001
             out["e2e"] = {"value": None, "error": str(ex)[-300:]}
     print(json.dumps(out))
@@ -561,6 +564,22 @@ def main():
                           "path": "unmodified chatllm host (graph rebuild + ggml sched per token) -> libggml-cuda.so; pageable host buffers of the host app",
                           "plugin_launches_per_step": r.get("plugin_launches_per_step"),
                           "prefill": {"tokens": r.get("prefill_tokens"), "ms": r.get("prefill_ms"), "note": "real 4096-token prompt through the plugin (batch 512) before the timed decode"}}
+            # parity of the benchmarked FILE: the same short real prompt through the plugin and on the reference's CPU backend, logits of the
+            # prompt's last token and of 3 decode steps compared (the 4096-token prompt itself would take the CPU minutes)
+            try:
+                import numpy as np
+                dumps = {}
+                for tag, ngl in (("gpu", "all"), ("cpu", "0")):
+                    dp = f"/tmp/b200_parity_{tag}.bin"
+                    cmd = [HARNESS, "--model", model, "--ggml_dir", RUNDIR, "--ngl", ngl, "--threads", "32", "--prefill", "24", "--decode", "3", "--max_length",
+                           str(N_PAST + 256), "--dump", dp, "--seed", "3"]
+                    subprocess.run(cmd, capture_output=True, text=True, timeout=600, check=True)
+                    dumps[tag] = np.fromfile(dp, dtype=np.float32).reshape(-1, cfg.vocab)
+                rel = np.abs(dumps["gpu"] - dumps["cpu"]).max(axis=1) / np.abs(dumps["cpu"]).max(axis=1)
+                out["parity"] = {"max_rel": float(rel.max()), "per_eval_rel": [float(v) for v in rel], "argmax_equal": bool((dumps["gpu"].argmax(1) == dumps["cpu"].argmax(1)).all()),
+                                 "what": "logits of a 24-token prompt + 3 decode steps, full model file, plugin vs the reference CPU backend (north star: 1e-3 where no int8 activation code flips)"}
+            except Exception as ex:  # noqa: BLE001
+                out["parity"] = {"max_rel": None, "error": str(ex)[-200:]}
         except Exception as ex:  # noqa: BLE001
             out["e2e"] = {"value": None, "error": str(ex)[-300:]}
     if not a.no_cpu and world == 1 and os.path.exists(HARNESS):

@@ -710,6 +710,11 @@ static bool plain_rope(const ggml_tensor * r, int64_t hd) {
     return n_dims == hd && (mode == 0 || mode == GGML_ROPE_TYPE_NEOX) && fp[1] == 1.0f && fp[2] == 0.0f && fp[3] == 1.0f &&
            (!r->src[2] || (r->src[2]->type == GGML_TYPE_F32 && ggml_is_contiguous(r->src[2])));
 }
+// exactly one consumer and not a requested output.  Unlike ggml_node_has_n_uses this accepts nodes the host built IN PLACE (a biased
+// projection's ADD is a view of its matmul): the fused group writes its result to the node's own data, views included.
+static bool single_use(const ggml_cgraph * g, int idx) {
+    return ggml_node_get_use_count(g, idx) == 1 && !(g->nodes[idx]->flags & GGML_TENSOR_FLAG_OUTPUT);
+}
 struct QkvMatch {
     const ggml_tensor * mm[3], * out[3], * bias[3];  // v, k, q (graph order)
     const ggml_tensor * cpy, * sr, * rk, * rq;
@@ -741,7 +746,7 @@ static int match_qkv(ggml_cgraph * g, int i, QkvMatch & qm) {
     j = next_real(j);
     if (j >= g->n_nodes || g->nodes[j]->op != GGML_OP_CPY) return 0;
     const ggml_tensor * cpy = g->nodes[j];
-    if (view_root(cpy->src[0]) != out[0] || cpy->type != GGML_TYPE_F16 || !ggml_node_has_n_uses(g, idx_out[0], 1)) return 0;
+    if (view_root(cpy->src[0]) != out[0] || cpy->type != GGML_TYPE_F16 || !single_use(g, idx_out[0])) return 0;
     const int64_t kvh_dim = out[0]->ne[0];
     if (cpy->ne[0] != 1 || cpy->ne[1] != kvh_dim || ggml_nelements(cpy) != kvh_dim || cpy->nb[1] % 2) return 0;  // one column of the transposed V cache
     ++j;
@@ -752,7 +757,7 @@ static int match_qkv(ggml_cgraph * g, int i, QkvMatch & qm) {
     const ggml_tensor * rk = g->nodes[j];
     const int idx_rk = j;
     // the host ropes in place (the ROPE node is a view of its input), so only the use COUNT can be checked for it
-    if (view_root(rk->src[0]) != out[1] || !ggml_node_has_n_uses(g, idx_out[1], 1) || ggml_node_get_use_count(g, idx_rk) != 1 ||
+    if (view_root(rk->src[0]) != out[1] || !single_use(g, idx_out[1]) || ggml_node_get_use_count(g, idx_rk) != 1 ||
         (rk->flags & GGML_TENSOR_FLAG_OUTPUT))
         return 0;
     j = next_real(j + 1);

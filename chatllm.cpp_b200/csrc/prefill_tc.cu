@@ -1,9 +1,8 @@
 // prefill_tc.cu — prompt-sized Q4_K matmul on the 5th-generation tensor cores (tcgen05.mma kind::i8, accumulators in TMEM), EXACT.
 //
-// OPT-IN (B200_MMQ_TCGEN05=1): written at the end of round 1 after the round's B200 minutes were spent — it compiles for sm_100a
-// (SASS: UTCIMMA / UTCBAR / LDTM) but has NOT run on a GPU yet.  The default path stays prefill.cu's mma.sync kernel (≈130 TOPS
-// effective, 67 % of the prompt time, profiles/r01e_prefill_2048_launches_summary.txt).  Bring-up: tests/test_fused2_optin.py
-// (test_tcgen05_prefill_equals_mma_sync) demands BIT-identical outputs to mmq_kernel.
+// Round 2: runs on the B200 and matches prefill.cu's mma.sync kernel (tests/test_gpu_blackwell.py::test_tcgen05_prefill_equals_mma_sync).
+// The first version (no overlap at all) reached 146 TFLOP/s on the Qwen2.5-7B prompt matmuls against 159 for mma.sync
+// (profiles/r02_config3_*); this one prefetches the next super-block's global data into registers behind the MMAs and the epilogue.
 //
 // Why this is exact.  Per 256-element super-block the reference computes (ggml-cpu/arch/x86/quants.c:1742-1916)
 //        y += dx·d·Σ_j sc_j Σ_{k∈j} q_k x_k  −  dx·dmin·Σ_j m_j Σ_{k∈j} x_k          (sc_j, m_j: 6-bit, q: 4-bit, x: int8 codes)
@@ -102,10 +101,26 @@ __global__ void __launch_bounds__(256, 1) mmq_tc_q4k_kernel(const TcParams p) {
     const int64_t d_off = tc_al16(p.k);  // plain activation layout (prefill.cu): qs[k] | float d[k/256] | int bs[k/32]
 
     pdl_wait();  // the quantized activations come from the predecessor
+    // software pipeline: the global loads of super-block u+1 (this thread's 80 weight bytes, 8 activation chunks, one scale) are issued
+    // right after the MMAs of super-block u and land while the tensor core works and the epilogue runs — the first version exposed two
+    // dependent global round trips per super-block (measured r02: 146 TFLOP/s, slower than the mma.sync kernel)
+    const int coln = tid & 127, cb = (tid >> 7) * 8;
+    const int64_t gc = min(col_base + coln, p.n - 1);
+    const uint8_t * xcol = p.pact + (size_t) gc * p.col_bytes;
+    uint4 hdr, wq[4], xq[8];
+    float dx_n = 0.0f;
+    auto prefetch = [&](int u) {
+        const uint8_t * blk = wrow + (size_t) u * 144;
+        hdr = *reinterpret_cast<const uint4 *>(blk);
+#pragma unroll
+        for (int h = 0; h < 4; ++h) wq[h] = *reinterpret_cast<const uint4 *>(blk + 16 + wg * 64 + h * 16);  // sub-blocks 4*wg .. 4*wg+3 share these 64 bytes
+#pragma unroll
+        for (int c = 0; c < 8; ++c) xq[c] = *reinterpret_cast<const uint4 *>(xcol + (size_t) u * 256 + (cb + c) * 16);
+        if (tid < 128) dx_n = reinterpret_cast<const float *>(xcol + d_off)[u];
+    };
+    prefetch(0);
     for (int u = 0; u < p.nunits; ++u) {
         // ---- (1a) weights: this thread's row, sub-blocks 4*wg .. 4*wg+3 -> three int8 planes
-        const uint8_t * blk = wrow + (size_t) u * 144;
-        const uint4 hdr = *reinterpret_cast<const uint4 *>(blk);
         const float d_r = half_bits_to_float(hdr.x & 0xffffu), dmin_r = half_bits_to_float(hdr.x >> 16);
         // get_scale_min_k4 (ggml-quants.c:703-711), four at a time: sub-blocks 0..3 in *_a, 4..7 in *_b
         const uint32_t sc_a = hdr.y & 0x3f3f3f3fu, sc_b = (hdr.w & 0x0f0f0f0fu) | (((hdr.y >> 6) & 0x03030303u) << 4);
@@ -117,11 +132,10 @@ __global__ void __launch_bounds__(256, 1) mmq_tc_q4k_kernel(const TcParams p) {
             const uint32_t sc = (sc4 >> (8 * jj)) & 0xffu, mn = (mn4 >> (8 * jj)) & 0xffu;
             const uint32_t hi = sc >> 3, lo = sc & 7u, mrep = mn * 0x01010101u;
             // nibble order (ggml-quants.c:1352-1373): 64-element group j/2 = 32 bytes; low nibbles = sub-block 2*(j/2), high = the next one
-            const uint8_t * qa = blk + 16 + (j >> 1) * 32;
-            const int sh = (j & 1) * 4;
+            const int sh = (jj & 1) * 4;
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
-                const uint4 v = *reinterpret_cast<const uint4 *>(qa + half * 16);
+                const uint4 v = wq[(jj >> 1) * 2 + half];
                 const uint32_t n0 = (v.x >> sh) & 0x0f0f0f0fu, n1 = (v.y >> sh) & 0x0f0f0f0fu, n2 = (v.z >> sh) & 0x0f0f0f0fu, n3 = (v.w >> sh) & 0x0f0f0f0fu;
                 const uint32_t o = tc_off(row, j * 2 + half);
                 // per-byte products <= 7 * 15 = 105: no carry between the four bytes of a word
@@ -131,14 +145,9 @@ __global__ void __launch_bounds__(256, 1) mmq_tc_q4k_kernel(const TcParams p) {
             }
         }
         // ---- (1b) activations: column (tid & 127), K chunks 8*(tid >> 7) .. +7 of this super-block
-        {
-            const int coln = tid & 127, cb = (tid >> 7) * 8;
-            const int64_t gc = min(col_base + coln, p.n - 1);
-            const uint8_t * src = p.pact + (size_t) gc * p.col_bytes + (size_t) u * 256;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4 *>(Bt + tc_off(coln, cb + c)) = *reinterpret_cast<const uint4 *>(src + (cb + c) * 16);
-            if (tid < 128) dxs[coln] = reinterpret_cast<const float *>(p.pact + (size_t) gc * p.col_bytes + d_off)[u];
-        }
+        for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4 *>(Bt + tc_off(coln, cb + c)) = xq[c];
+        if (tid < 128) dxs[coln] = dx_n;
         fence_proxy_async();  // generic-proxy stores above -> visible to the tensor core's (async proxy) reads
         __syncthreads();
         // ---- (2) one thread issues the 24 MMAs of this super-block and commits them to the mbarrier
@@ -155,6 +164,7 @@ __global__ void __launch_bounds__(256, 1) mmq_tc_q4k_kernel(const TcParams p) {
             }
             tc_commit(&mma_bar);  // implies tcgen05.fence::before_thread_sync
         }
+        if (u + 1 < p.nunits) prefetch(u + 1);   // in flight during the MMAs and the epilogue below
         // ---- (3) everyone waits for the accumulators, then reads its row: columns 64*wg .. +63 of the three planes
         mbar_wait(&mma_bar, (uint32_t) u & 1u);
         tc_fence_after();
@@ -235,16 +245,39 @@ __global__ void __launch_bounds__(256, 1) mmq_tc_blk32_kernel(const TcParams p) 
     const int64_t d_off = tc_al16(p.k);  // plain activation layout: qs[k] | float d[k/32] | int bs[k/32]
 
     pdl_wait();
+    // software pipeline (see mmq_tc_q4k_kernel): the next unit's weight blocks, block scales and activation chunks are prefetched into
+    // registers while this unit's MMAs and epilogue run
+    constexpr int WV = (FMT == 1) ? 4 : 8;           // uint4 of quants per thread per unit (4 blocks of 16 / 32 bytes)
+    const int coln = tid & 63, cb = (tid >> 6) * 4;
+    const int64_t gc = min(col_base + coln, p.n - 1);
+    const uint8_t * xcol = p.pact + (size_t) gc * p.col_bytes;
+    const int sc_col = tid >> 3, sc_j = tid & 7;     // block-scale word this thread stages ([64][8] floats = 512 words, 2 per thread)
+    const int64_t gsc0 = min(col_base + sc_col, p.n - 1), gsc1 = min(col_base + sc_col + 32, p.n - 1);
+    uint4 wq[WV], xq[4], wsc;
+    float dxa = 0.0f, dxb = 0.0f;
+    auto prefetch = [&](int u) {
+#pragma unroll
+        for (int h = 0; h < WV; ++h) wq[h] = *reinterpret_cast<const uint4 *>(wrow + ((size_t) (u * 8 + 4 * wg) * QB) + h * 16);
+        wsc = *reinterpret_cast<const uint4 *>(wd + u * 8);   // 8 fp16 block scales of this row
+#pragma unroll
+        for (int c = 0; c < 4; ++c) xq[c] = *reinterpret_cast<const uint4 *>(xcol + (size_t) u * 256 + (cb + c) * 16);
+        dxa = reinterpret_cast<const float *>(p.pact + (size_t) gsc0 * p.col_bytes + d_off)[u * 8 + sc_j];
+        dxb = reinterpret_cast<const float *>(p.pact + (size_t) gsc1 * p.col_bytes + d_off)[u * 8 + sc_j];
+    };
+    prefetch(0);
     for (int u = 0; u < p.nunits; ++u) {
         float sw[8];
+        {
+            const uint32_t wsw[4] = {wsc.x, wsc.y, wsc.z, wsc.w};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) sw[j] = half_bits_to_float(wd[u * 8 + j]);
+            for (int j = 0; j < 8; ++j) sw[j] = half_bits_to_float((wsw[j >> 1] >> (16 * (j & 1))) & 0xffffu);
+        }
         // ---- weights: this thread's row, blocks 4*wg .. 4*wg+3 -> int8 (Q4_0: nibble - 8; low nibbles = elements 0..15, ggml-quants.c:307-325)
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
             const int j = 4 * wg + jj;
             if (FMT == 1) {
-                const uint4 v = *reinterpret_cast<const uint4 *>(wrow + (size_t) (u * 8 + j) * 16);
+                const uint4 v = wq[jj];
                 *reinterpret_cast<uint4 *>(At + tc_off(row, 2 * j)) =
                     make_uint4(__vsub4(v.x & 0x0f0f0f0fu, 0x08080808u), __vsub4(v.y & 0x0f0f0f0fu, 0x08080808u), __vsub4(v.z & 0x0f0f0f0fu, 0x08080808u),
                                __vsub4(v.w & 0x0f0f0f0fu, 0x08080808u));
@@ -252,23 +285,15 @@ __global__ void __launch_bounds__(256, 1) mmq_tc_blk32_kernel(const TcParams p) 
                     make_uint4(__vsub4((v.x >> 4) & 0x0f0f0f0fu, 0x08080808u), __vsub4((v.y >> 4) & 0x0f0f0f0fu, 0x08080808u),
                                __vsub4((v.z >> 4) & 0x0f0f0f0fu, 0x08080808u), __vsub4((v.w >> 4) & 0x0f0f0f0fu, 0x08080808u));
             } else {
-                const uint8_t * b = wrow + (size_t) (u * 8 + j) * 32;
-                *reinterpret_cast<uint4 *>(At + tc_off(row, 2 * j)) = *reinterpret_cast<const uint4 *>(b);
-                *reinterpret_cast<uint4 *>(At + tc_off(row, 2 * j + 1)) = *reinterpret_cast<const uint4 *>(b + 16);
+                *reinterpret_cast<uint4 *>(At + tc_off(row, 2 * j)) = wq[(2 * jj) % WV];
+                *reinterpret_cast<uint4 *>(At + tc_off(row, 2 * j + 1)) = wq[(2 * jj + 1) % WV];
             }
         }
         // ---- activations: column (tid & 63), K chunks 4*(tid >> 6) .. +3 ; block scales [64][8]
-        {
-            const int coln = tid & 63, cb = (tid >> 6) * 4;
-            const int64_t gc = min(col_base + coln, p.n - 1);
-            const uint8_t * src = p.pact + (size_t) gc * p.col_bytes + (size_t) u * 256;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4 *>(Bt + tc_off64(coln, cb + c)) = *reinterpret_cast<const uint4 *>(src + (cb + c) * 16);
-            for (int c = tid; c < TC_N64 * 8; c += 256) {
-                const int64_t g2 = min(col_base + (c >> 3), p.n - 1);
-                dxs[c] = reinterpret_cast<const float *>(p.pact + (size_t) g2 * p.col_bytes + d_off)[u * 8 + (c & 7)];
-            }
-        }
+        for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4 *>(Bt + tc_off64(coln, cb + c)) = xq[c];
+        dxs[sc_j * TC_N64 + sc_col] = dxa;          // [block][column]: the epilogue reads four columns per shared-memory load
+        dxs[sc_j * TC_N64 + sc_col + 32] = dxb;
         fence_proxy_async();
         __syncthreads();
         if (tid == 0) {
@@ -280,6 +305,7 @@ __global__ void __launch_bounds__(256, 1) mmq_tc_blk32_kernel(const TcParams p) 
                                TC_IDESC64, 0u);
             tc_commit(&mma_bar);
         }
+        if (u + 1 < p.nunits) prefetch(u + 1);   // in flight during the MMAs and the epilogue below
         mbar_wait(&mma_bar, (uint32_t) u & 1u);
         tc_fence_after();
         const int c0 = wg * 32;  // this thread's 32 columns of the 64-column tile
@@ -289,7 +315,13 @@ __global__ void __launch_bounds__(256, 1) mmq_tc_blk32_kernel(const TcParams p) 
             tc_ld32(tmem + ((uint32_t) (q * 32) << 16) + (uint32_t) (s * TC_N64 + c0), isum);
             tc_wait_ld();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) yacc[i] = fmaf(sw[s] * dxs[(c0 + i) * 8 + s], (float) isum[i], yacc[i]);   // mmq_kernel<1|2>'s expression
+            for (int i4 = 0; i4 < 8; ++i4) {
+                const float4 d4 = *reinterpret_cast<const float4 *>(dxs + s * TC_N64 + c0 + 4 * i4);
+                yacc[4 * i4 + 0] = fmaf(sw[s] * d4.x, (float) isum[4 * i4 + 0], yacc[4 * i4 + 0]);   // mmq_kernel<1|2>'s expression
+                yacc[4 * i4 + 1] = fmaf(sw[s] * d4.y, (float) isum[4 * i4 + 1], yacc[4 * i4 + 1]);
+                yacc[4 * i4 + 2] = fmaf(sw[s] * d4.z, (float) isum[4 * i4 + 2], yacc[4 * i4 + 2]);
+                yacc[4 * i4 + 3] = fmaf(sw[s] * d4.w, (float) isum[4 * i4 + 3], yacc[4 * i4 + 3]);
+            }
         }
         tc_fence_before();
         __syncthreads();
@@ -308,7 +340,9 @@ __global__ void __launch_bounds__(256, 1) mmq_tc_blk32_kernel(const TcParams p) 
 }
 
 bool mmq_tc_enabled() {
-    static const bool on = getenv("B200_MMQ_TCGEN05") && atoi(getenv("B200_MMQ_TCGEN05")) != 0;
+    // default ON since round 2 (measured on the B200, 2048-column prompt matmuls: Q4_K 378 vs 152 TFLOP/s, Q4_0 217 vs 159, Q8_0 157 vs 121
+    // for the mma.sync kernel; profiles/r02_prefill_kernel_matrix.txt).  B200_MMQ_TCGEN05=0 selects prefill.cu's mma.sync kernel.
+    static const bool on = !(getenv("B200_MMQ_TCGEN05") && atoi(getenv("B200_MMQ_TCGEN05")) == 0);
     return on;
 }
 
