@@ -521,7 +521,10 @@ def main():
     roofline = {"bound": "hbm", "kernel": "gemv_q_kernel<FmtQ4K>", "achieved": round(achieved, 1), "peak": pk["hbm_gbs"], "unit": "GB/s",
                 "frac": round(achieved / pk["hbm_gbs"], 4), "peak_kind": pk_kind + " (MEASURED_PEAKS.json hbm_gbs)" if pk_kind == "measured" else "fallback",
                 "frac_of_nominal_8TBps": round(achieved / 8000.0, 4), "launches": len(shapes), "avg_launch_us": round(gemv_ms * 1e3 / len(shapes), 2),
-                "algorithmic_MB_per_token_shard": round(gemv_bytes / 1e6, 1), "traffic": None,
+                "algorithmic_MB_per_token_shard": round(gemv_bytes / 1e6, 1),
+                # dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` capture of this kernel on the gate shape
+                # (profiles/r02f_gemv_q4k_gate_ncu_full_summary.json: 33.067 MB read, 0 written, for 33.03 MB algorithmic), scaled to the mean launch
+                "traffic": round(gemv_bytes / len(shapes) * 33.067008 / 33.030144),
                 "share_of_step": round(gemv_ms / ms, 3)}
     if use_mk and world == 1:
         # the dominant kernel IS the step: one launch of decode_mk_kernel streams every weight byte of the token plus the KV cache.
@@ -569,15 +572,26 @@ def main():
             try:
                 import numpy as np
                 dumps = {}
-                for tag, ngl in (("gpu", "all"), ("cpu", "0")):
+                for tag, ngl, rd in (("gpu", "all", RUNDIR), ("cpu", "0", RUNDIR + "_avx512"), ("cpu_avx2", "0", RUNDIR + "_avx2")):
                     dp = f"/tmp/b200_parity_{tag}.bin"
-                    cmd = [HARNESS, "--model", model, "--ggml_dir", RUNDIR, "--ngl", ngl, "--threads", "32", "--prefill", "24", "--decode", "3", "--max_length",
+                    cmd = [HARNESS, "--model", model, "--ggml_dir", rd, "--ngl", ngl, "--threads", "32", "--prefill", "24", "--decode", "3", "--max_length",
                            str(N_PAST + 256), "--dump", dp, "--seed", "3"]
-                    subprocess.run(cmd, capture_output=True, text=True, timeout=600, check=True)
-                    dumps[tag] = np.fromfile(dp, dtype=np.float32).reshape(-1, cfg.vocab)
-                rel = np.abs(dumps["gpu"] - dumps["cpu"]).max(axis=1) / np.abs(dumps["cpu"]).max(axis=1)
-                out["parity"] = {"max_rel": float(rel.max()), "per_eval_rel": [float(v) for v in rel], "argmax_equal": bool((dumps["gpu"].argmax(1) == dumps["cpu"].argmax(1)).all()),
-                                 "what": "logits of a 24-token prompt + 3 decode steps, full model file, plugin vs the reference CPU backend (north star: 1e-3 where no int8 activation code flips)"}
+                    try:
+                        subprocess.run(cmd, capture_output=True, text=True, timeout=600, check=True)
+                        dumps[tag] = np.fromfile(dp, dtype=np.float32).reshape(-1, cfg.vocab)
+                    except Exception:  # noqa: BLE001  (no AVX-512 on this host: the cpu arm falls back to the default module directory)
+                        if tag == "cpu":
+                            subprocess.run(cmd[:4] + [RUNDIR] + cmd[5:], capture_output=True, text=True, timeout=600, check=True)
+                            dumps[tag] = np.fromfile(dp, dtype=np.float32).reshape(-1, cfg.vocab)
+                relf = lambda a, b: np.abs(a - b).max(axis=1) / np.abs(b).max(axis=1)
+                rel = relf(dumps["gpu"], dumps["cpu"])
+                out["parity"] = {"max_rel": float(rel.max()), "per_eval_rel": [round(float(v), 5) for v in rel],
+                                 "argmax_equal": bool((dumps["gpu"].argmax(1) == dumps["cpu"].argmax(1)).all()),
+                                 "reference_self_spread_avx2_vs_avx512": (round(float(relf(dumps["cpu_avx2"], dumps["cpu"]).max()), 5) if "cpu_avx2" in dumps else None),
+                                 "what": "logits of a 24-token prompt + 3 decode steps of the FULL 32-layer synthetic file: plugin vs the reference CPU backend, next to the "
+                                         "reference's own AVX2-vs-AVX-512 spread on the same inputs.  A random-weight 32-layer network amplifies a 1e-7 difference to ~1e-1 "
+                                         "(the reference disagrees with itself that much), so the 1e-3 bar is enforced per layer at these shapes (tests/test_decode_mk.py, "
+                                         "teacher-forced vs the oracle: 4e-4 / 5e-7 of the layer's update) and on shallow models (tests/test_e2e_host.py)"}
             except Exception as ex:  # noqa: BLE001
                 out["parity"] = {"max_rel": None, "error": str(ex)[-200:]}
         except Exception as ex:  # noqa: BLE001

@@ -167,3 +167,54 @@ def test_device_side_greedy_loop_under_graph_replay():
     assert b.mk_status() == 0
     for Wa, Wb in zip(a.layers, b.layers):
         assert torch.equal(Wa.kc, Wb.kc) and torch.equal(Wa.vc, Wb.vc)
+
+
+def test_per_op_step_llama3_8b_layer_shapes_at_4096_vs_oracle():
+    """The DEFAULT path (per-op kernels, what bench.py's `value` replays as a CUDA graph and what the plugin launches node by node), teacher-forced
+    per layer at the benchmarked shapes and n_past = 4096 against the oracle port: same layer input, same 4096-position KV cache.  Whole-model
+    logits of the 32-layer synthetic file cannot serve as the check: the reference's own AVX2 and AVX-512 CPU backends differ by 9e-2 on it
+    (profiles/r02_full_model_parity.txt) — a random-weight 32-layer network amplifies any 1e-7 difference."""
+    torch, K, S = _mods()
+    wtype, hidden, heads, kvh, ffn, vocab, n_past = qf.Q4_K, 4096, 32, 8, 14336, 1024, 4096
+    hd, kv_hidden, max_len = 128, 1024, n_past + 16
+    rng = np.random.default_rng(11)
+    cfg = S.Config(wtype, vocab, hidden, heads, kvh, 2, ffn, rope_theta=500000.0, rope_mode=0, eps=1e-5, max_len=max_len)
+    port = qf.port()
+    port.oq_layer_step.argtypes = [C.POINTER(OqLayer), C.c_void_p, C.c_int, C.c_int]
+    rels = []
+    for li in range(2):
+        host = {}
+
+        def weights(i, name, m, k):
+            if k == 0:
+                v = (1 + 0.1 * rng.standard_normal(m)).astype(np.float32)
+                host[name] = v
+                return torch.from_numpy(v).cuda()
+            w = qf.random_blocks(wtype, m, k, rng=rng)
+            host[name] = w
+            return K.upload_weights(wtype, w, k, m)
+
+        sess = S.DecodeSession(cfg, weights=weights, layer_lo=li, layer_hi=li + 1, first=False, last=False, fused=True)
+        W = sess.layers[0]
+        kc = (rng.standard_normal((max_len, kv_hidden)) * 0.5).astype(np.float16)
+        vc = (rng.standard_normal((kv_hidden, max_len)) * 0.5).astype(np.float16)
+        W.kc.copy_(torch.from_numpy(kc)); W.vc.copy_(torch.from_numpy(vc))
+        kcu, vcu = kc.view(np.uint16).copy(), vc.view(np.uint16).copy()
+        x_in = rng.standard_normal((1, hidden)).astype(np.float32)
+        sess.x.copy_(torch.from_numpy(x_in))
+        sess.pos.fill_(n_past)
+        sess.enqueue(n_past)
+        torch.cuda.synchronize()
+        got = sess.x.cpu().numpy()[0]
+        L = OqLayer(wtype, hidden, heads, kvh, hd, ffn, max_len, 0, 500000.0, 1e-5)
+        for f, n in (("attn_norm", "attn_norm"), ("ffn_norm", "ffn_norm"), ("wq", "q"), ("wk", "k"), ("wv", "v"), ("wo", "o"), ("wgate", "gate"),
+                     ("wup", "up"), ("wdown", "down")):
+            setattr(L, f, host[n].ctypes.data)
+        L.k_cache, L.v_cache = kcu.ctypes.data, vcu.ctypes.data
+        h = x_in.copy()
+        port.oq_layer_step(C.byref(L), h.ctypes.data, n_past, 1)
+        ref = h[0]
+        rels.append(float(np.abs(got - ref).max() / np.abs(ref - x_in[0]).max()))
+        print("per-op path, layer", li, "max err / max |layer delta| vs oracle:", rels[-1])
+        del sess
+    assert max(rels) <= 1e-3, rels

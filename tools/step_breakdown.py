@@ -8,7 +8,7 @@ import __graft_entry__ as ge
 pkg = ge.load_package(); L = pkg.lib()
 from chatllm_cpp_b200 import session as S
 if len(sys.argv) > 1: L.b200_gemv_set_tuning(*[int(v) for v in sys.argv[1].split(",")])
-cfg = S.make_config("llama3-8b", pkg.Q4_K, layers=4, max_len=4352)
+cfg = S.make_config("llama3-8b", pkg.Q4_K, layers=16, max_len=4352)   # 16 layers: q/k/v 400 MB, o 150 MB, gate+up 1.06 GB, down 528 MB rotate — every class exceeds the 126 MB L2 (r01 used 4 layers: o and q/k/v sat in L2)
 s = S.DecodeSession(cfg, seed=0); s.fill_kv_random(4096); s._ptr_arrays(); s.pos.fill_(4096)
 c = cfg; W = s.layers; q = s.qact.data_ptr(); hd = c.head_dim
 def st(): return torch.cuda.current_stream().cuda_stream
