@@ -263,6 +263,7 @@ def run_config5(a):
 
     def moe_layers():
         rc = 0
+        st = torch.cuda.current_stream().cuda_stream   # (the capture stream while the graph is being recorded)
         for i in range(layers):
             wg, wu, wd = stacks[i % rot]
             rc |= L.b200_mul_mat_q_id(wtype, 1, wg.data_ptr(), wu.data_ptr(), hidden, ffn, n_exp, ids.data_ptr(), top, xq.data_ptr(), 1, yg.data_ptr(), ffn, st)

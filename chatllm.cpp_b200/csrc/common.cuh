@@ -126,6 +126,21 @@ __device__ __forceinline__ float warp_max(float v) {
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
+// block-wide sum in DOUBLE (blockDim.x <= 1024; red: 32 doubles of shared memory).  The RMSNorm kernels accumulate the sum of squares
+// exactly as the CPU does (float products added in double, ggml-cpu/ops.cpp:3736-3741): a fp32 tree reduction can differ in the last
+// bit of `scale`, which moves EVERY normalised element by an ulp and flips int8 activation codes that sit on a rounding boundary.
+__device__ __forceinline__ double block_sum_double(double v, double * red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int w = 0; w < nw; ++w) t += red[w];
+    __syncthreads();
+    return t;
+}
 __device__ __forceinline__ float half_bits_to_float(uint32_t h16) { return __half2float(__ushort_as_half((unsigned short) h16)); }
 
 }  // namespace b200

@@ -48,7 +48,7 @@ template <bool Q8K, int J>
 __global__ void __launch_bounds__(1024) add_rmsnorm_quant_kernel(const float * x, const float * r, const float * w,
                                                                  float * x_out, float * y_out, uint8_t * qact,
                                                                  int64_t ne0, float eps, size_t col_bytes, int nsplit) {
-    __shared__ float red[32];
+    __shared__ double red[32];
     __shared__ unsigned long long keys[32];
     __shared__ float bmax[16];
     pdl_launch_dependents();
@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(1024) add_rmsnorm_quant_kernel(const float * x
     const int64_t row = blockIdx.x;
     const float * xr = x + row * ne0;
     float v[J][4];
-    float ss = 0.0f;
+    double ss = 0.0;   // float products accumulated in double, like the CPU (common.cuh block_sum_double)
     if (nsplit > 0) {
         // reduction tail of the split decode attention (attn_pv_split_kernel): x = nsplit partial rows of ne0 floats, summed in
         // split order; no normalisation.  x_out receives the sum, qact its quantization (the o-projection's activations).
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(1024) add_rmsnorm_quant_kernel(const float * x
             }
             if (x_out) *reinterpret_cast<float4 *>(x_out + row * ne0 + e) = a;
             v[j][0] = a.x; v[j][1] = a.y; v[j][2] = a.z; v[j][3] = a.w;
-            ss = fmaf(a.x, a.x, ss); ss = fmaf(a.y, a.y, ss); ss = fmaf(a.z, a.z, ss); ss = fmaf(a.w, a.w, ss);
+            ss += (double) __fmul_rn(a.x, a.x); ss += (double) __fmul_rn(a.y, a.y); ss += (double) __fmul_rn(a.z, a.z); ss += (double) __fmul_rn(a.w, a.w);
         } else {
             v[j][0] = v[j][1] = v[j][2] = v[j][3] = 0.0f;
         }
@@ -103,8 +103,8 @@ __global__ void __launch_bounds__(1024) add_rmsnorm_quant_kernel(const float * x
         const int64_t e = 4 * (int64_t) t + 4 * (int64_t) T * j;
         wv[j] = (e < ne0) ? *reinterpret_cast<const float4 *>(w + e) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    ss = blk_sum(ss, red);
-    const float mean = ss / (float) ne0;
+    ss = block_sum_double(ss, red);
+    const float mean = (float) (ss / (double) ne0);
     const float scale = 1.0f / sqrtf(mean + eps);
 #pragma unroll
     for (int j = 0; j < J; ++j) {

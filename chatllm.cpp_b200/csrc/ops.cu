@@ -39,15 +39,15 @@ __device__ __forceinline__ float block_max(float v, float * red) {
 // (RMSNorm::forward src/layers.cpp:2216-2225):  y = (x * (1/sqrt(mean(x^2)+eps))) * w
 __global__ void __launch_bounds__(1024) rms_norm_mul_kernel(const float * x, const float * w, float * y,
                                                             int64_t ne0, float eps) {
-    __shared__ float red[32];
+    __shared__ double red[32];
     pdl_launch_dependents();
     pdl_wait();
     const float * xr = x + (int64_t) blockIdx.x * ne0;
     float * yr = y + (int64_t) blockIdx.x * ne0;
-    float s = 0.0f;
-    for (int64_t i = threadIdx.x; i < ne0; i += blockDim.x) { const float v = xr[i]; s = fmaf(v, v, s); }
-    s = block_sum(s, red);
-    const float mean = s / (float) ne0;
+    double s = 0.0;   // sum += (ggml_float)(x*x): float product, double accumulation (ops.cpp:3736-3741)
+    for (int64_t i = threadIdx.x; i < ne0; i += blockDim.x) { const float v = xr[i]; s += (double) __fmul_rn(v, v); }
+    s = block_sum_double(s, red);
+    const float mean = (float) (s / (double) ne0);
     const float scale = 1.0f / sqrtf(mean + eps);
     for (int64_t i = threadIdx.x; i < ne0; i += blockDim.x) {
         const float v = xr[i] * scale;
