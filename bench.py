@@ -393,6 +393,7 @@ def main():
     from chatllm_cpp_b200 import sharding
     lo, hi = sharding.plan_layers(cfg.layers, world)[rank]
     sess = S.DecodeSession(cfg, seed=0, layer_lo=lo, layer_hi=hi, first=(rank == 0), last=(rank == world - 1), fused=(3 if use_mk else not a.unfused))
+    sess.device_argmax = True   # every N: a step is "token in -> next token out" (greedy sampling on the device, b200_argmax)
     sess.mk_advance = True   # persistent kernel only: tok <- argmax(logits), pos <- pos + 1 on the device (greedy decoding, growing KV cache)
     sess.fill_kv_random(N_PAST, seed=rank)
     sess.tok.fill_(12345 % cfg.vocab)

@@ -414,13 +414,16 @@ int peer_send(const float * x, float * peer_x, int64_t n, const int32_t * tok, i
 }
 
 // out[0] = index of the FIRST maximum of x[0..n)  (greedy sampling on the device: src/models.cpp:1026-1031 reads 0.5 MB of logits back
-// and scans them on the host every token).  One CTA.
-__global__ void __launch_bounds__(1024) argmax_kernel(const float * x, int64_t n, int32_t * out) {
-    __shared__ unsigned long long red[32];
+// and scans them on the host every token).  64 CTAs fold their slices into one 64-bit key with atomicMax; the last CTA to finish decodes it
+// and re-arms the scratch (per-device module globals; one stream at a time).
+__device__ unsigned long long g_argmax_key = 0ull;
+__device__ unsigned int g_argmax_done = 0u;
+__global__ void __launch_bounds__(256) argmax_kernel(const float * x, int64_t n, int32_t * out) {
+    __shared__ unsigned long long red[8];
     pdl_launch_dependents();
     pdl_wait();
     unsigned long long best = 0ull;
-    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t) gridDim.x * blockDim.x) {
         const uint32_t b = __float_as_uint(x[i]);
         const uint32_t ord = (b & 0x80000000u) ? ~b : (b | 0x80000000u);   // order-preserving float -> uint
         const unsigned long long key = ((unsigned long long) ord << 32) | (unsigned) (0xffffffffu - (unsigned) i);   // ties: the smaller index wins
@@ -430,16 +433,22 @@ __global__ void __launch_bounds__(1024) argmax_kernel(const float * x, int64_t n
     for (int o = 16; o > 0; o >>= 1) { const unsigned long long v = __shfl_xor_sync(0xffffffffu, best, o); best = v > best ? v : best; }
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = best;
     __syncthreads();
-    if (threadIdx.x < 32) {
-        unsigned long long v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0ull;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { const unsigned long long w = __shfl_xor_sync(0xffffffffu, v, o); v = w > v ? w : v; }
-        if (threadIdx.x == 0) out[0] = (int32_t) (0xffffffffu - (unsigned) (v & 0xffffffffu));
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int) (blockDim.x >> 5); ++w) best = red[w] > best ? red[w] : best;
+        atomicMax(&g_argmax_key, best);
+        __threadfence();
+        if (atomicAdd(&g_argmax_done, 1u) == gridDim.x - 1) {   // last CTA: every key has been folded in
+            __threadfence();
+            const unsigned long long v = atomicExch(&g_argmax_key, 0ull);
+            out[0] = (int32_t) (0xffffffffu - (unsigned) (v & 0xffffffffu));
+            g_argmax_done = 0u;
+        }
     }
 }
 int argmax_f32(const float * x, int64_t n, int32_t * out, cudaStream_t st) {
     if (n <= 0 || n > 0x7fffffff) return B200_ERR_ARG;
-    launch_pdl(argmax_kernel, dim3(1), dim3(1024), 0, st, x, n, out);
+    const int grid = (int) (n >= 65536 ? 64 : (n >= 4096 ? 8 : 1));
+    launch_pdl(argmax_kernel, dim3(grid), dim3(256), 0, st, x, n, out);
     return (int) cudaGetLastError();
 }
 

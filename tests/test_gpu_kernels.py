@@ -472,3 +472,26 @@ def test_moe_experts_swiglu_vs_reference_golden(K):
     dg, du = K.upload_weights(qf.Q4_K, wg, hidden, n_expert * ffn), K.upload_weights(qf.Q4_K, wu, hidden, n_expert * ffn)
     y = K.mul_mat_id(qf.Q4_K, dg, hidden, ffn, n_expert, _t(sel.astype(np.int32)), _t(x), w1_dev=du).cpu().numpy()
     assert np.abs(y - ref).max() <= 3e-5 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("n", [1, 1000, 32000, 128256, 152064])
+def test_argmax_first_maximum(n):
+    """b200_argmax = the host's greedy pick (src/models.cpp:1026-1031: first maximum), ties and negative values included"""
+    import torch
+    import __graft_entry__ as ge
+    pkg = ge.load_package()
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal(n).astype(np.float32)
+    if n > 10:
+        x[rng.integers(0, n, 3)] = x.max()          # ties: the first one must win
+    out = torch.full((1,), -1, dtype=torch.int32, device="cuda")
+    xd = torch.from_numpy(x).cuda()
+    for _ in range(2):                                # twice: the scratch re-arms itself
+        assert pkg.lib().b200_argmax(xd.data_ptr(), n, out.data_ptr(), torch.cuda.current_stream().cuda_stream) == 0
+        torch.cuda.synchronize()
+        assert int(out.item()) == int(np.argmax(x))
+    xn = -np.abs(x) - 1.0
+    xnd = torch.from_numpy(xn).cuda()
+    assert pkg.lib().b200_argmax(xnd.data_ptr(), n, out.data_ptr(), torch.cuda.current_stream().cuda_stream) == 0
+    torch.cuda.synchronize()
+    assert int(out.item()) == int(np.argmax(xn))
