@@ -615,11 +615,11 @@ static int try_fuse_bias(b200_backend_ctx * bc, ggml_cgraph * g, int i, int * rc
 }
 
 static const ggml_tensor * view_root(const ggml_tensor * t);
-// The cluster V.P kernel wins under CUDA-graph replay (bench `value`: 9.45 vs 12.1 us per layer) but measured r02 it made the plugin's
-// stream-launched decode step 2x slower end to end (5.17 vs 2.49 ms per token): cluster launches from the host are expensive, so the
-// plugin keeps the three-launch attention unless B200_ATTN_CLUSTER=1 is set explicitly.
+// Thread-block-cluster V.P (2 launches per attention) vs split V.P + tail (3 launches): measured r02 through the unmodified host on the B200
+// (B200_PROFILE): 2.02 vs 2.16 ms of GPU time and 0.59 vs 0.95 ms of host enqueue per token -> on by default; B200_ATTN_CLUSTER=0 selects the
+// three-launch form.
 static int plugin_attn_cluster() {
-    static const int v = getenv("B200_ATTN_CLUSTER") ? (atoi(getenv("B200_ATTN_CLUSTER")) != 0) : 0;
+    static const int v = getenv("B200_ATTN_CLUSTER") ? (atoi(getenv("B200_ATTN_CLUSTER")) != 0) : 1;
     return v;
 }
 // decode attention: MUL_MAT(K,Q) -> SCALE -> DIAG_MASK_INF -> SOFT_MAX -> MUL_MAT(V,P) -> PERMUTE -> CONT, one query token
