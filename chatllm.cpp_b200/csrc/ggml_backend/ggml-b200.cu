@@ -965,13 +965,12 @@ static bool b200_cpy_tensor_async(ggml_backend_t backend_src, ggml_backend_t bac
     b200_backend_ctx * bs = (b200_backend_ctx *) backend_src->context;
     static const bool off = getenv("B200_SYNC_P2P") != nullptr;
     if (off) return false;
+    // recoverable by contract: on any failure below the scheduler falls back to synchronize + blocking copy
     if (!bs->p2p_ev) {
-        CUDA_OK(cudaSetDevice(bs->device));
-        CUDA_OK(cudaEventCreateWithFlags(&bs->p2p_ev, cudaEventDisableTiming));
+        if (cudaSetDevice(bs->device) != cudaSuccess || cudaEventCreateWithFlags(&bs->p2p_ev, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); bs->p2p_ev = nullptr; return false; }
     }
-    CUDA_OK(cudaSetDevice(bs->device));
-    CUDA_OK(cudaEventRecord(bs->p2p_ev, bs->stream));
-    CUDA_OK(cudaSetDevice(bd->device));
+    if (cudaSetDevice(bs->device) != cudaSuccess || cudaEventRecord(bs->p2p_ev, bs->stream) != cudaSuccess) { cudaGetLastError(); cudaSetDevice(bd->device); return false; }
+    if (cudaSetDevice(bd->device) != cudaSuccess) { cudaGetLastError(); return false; }
     if (bs->device != bd->device) {  // direct NVLink path for the peer copy (without it the copy is staged through host memory)
         static bool tried[B200_MAX_DEVICES][B200_MAX_DEVICES] = {};
         bool & t = tried[bd->device % B200_MAX_DEVICES][bs->device % B200_MAX_DEVICES];
@@ -985,9 +984,10 @@ static bool b200_cpy_tensor_async(ggml_backend_t backend_src, ggml_backend_t bac
             }
         }
     }
-    CUDA_OK(cudaStreamWaitEvent(bd->stream, bs->p2p_ev, 0));
-    if (bs->device == bd->device) CUDA_OK(cudaMemcpyAsync(dst->data, src->data, nb, cudaMemcpyDeviceToDevice, bd->stream));
-    else CUDA_OK(cudaMemcpyPeerAsync(dst->data, bd->device, src->data, bs->device, nb, bd->stream));
+    if (cudaStreamWaitEvent(bd->stream, bs->p2p_ev, 0) != cudaSuccess) { cudaGetLastError(); return false; }
+    const cudaError_t ce = (bs->device == bd->device) ? cudaMemcpyAsync(dst->data, src->data, nb, cudaMemcpyDeviceToDevice, bd->stream)
+                                                      : cudaMemcpyPeerAsync(dst->data, bd->device, src->data, bs->device, nb, bd->stream);
+    if (ce != cudaSuccess) { cudaGetLastError(); return false; }
     return true;
 }
 // B200_TRACE=1: after every executed node / fused group print a checksum of each output it produced (debug aid; syncs)

@@ -95,13 +95,13 @@ def test_rope_inplace_on_linear_output(mode, qlen):
     both(build, tol=4e-6)
 
 
-@pytest.mark.parametrize("n_past,qlen", [(0, 5), (37, 1), (300, 3)])
-def test_kv_cache_write_and_attention(n_past, qlen):
+@pytest.mark.parametrize("n_past,qlen,shape", [(0, 5, None), (37, 1, None), (300, 3, None), (4096, 1, (32, 8, 128, 4352))])
+def test_kv_cache_write_and_attention(n_past, qlen, shape):
     """save_to_cache (src/layers.cpp:3044-3123): K via set_rows(F32->F16), V via transpose+cpy into the transposed cache;
     then calc_attn_scores (:2541-2561): permuted K view, mul_mat(prec F32), scale, diag_mask_inf, soft_max, mul_mat(V,P),
     permute, cont."""
     rng = np.random.default_rng(n_past + qlen)
-    heads, kvh, hd, max_len = 8, 2, 64, 512
+    heads, kvh, hd, max_len = shape or (8, 2, 64, 512)   # last case: Llama-3-8B attention at the benchmarked context, against the reference CPU backend
     kv_hidden = kvh * hd
     kc0 = (rng.standard_normal((max_len, kv_hidden))).astype(np.float16)
     vc0 = (rng.standard_normal((kv_hidden, max_len))).astype(np.float16)
@@ -130,7 +130,7 @@ def test_kv_cache_write_and_attention(n_past, qlen):
         ctx = g.mul_mat(V, p)                                                       # [hd, qlen, heads]
         ctx = g.cont(g.permute(ctx, (0, 2, 1, 3)))                                  # [hd, heads, qlen]
         return [(g.cont(vw), np.float16, (kv_hidden, qlen)), (kw, np.float16, (max_len, kv_hidden)), (ctx, np.float32, (qlen, heads, hd))]
-    both(build, tol=3e-5)
+    both(build, tol=3e-5 if shape is None else 1e-4)
 
 
 def test_swiglu_and_embedding():
