@@ -70,7 +70,7 @@ struct GemvParams {
 };
 
 template <class F, int RG, int NC, int MODE>
-__global__ void __launch_bounds__(512) gemv_q_kernel(const GemvParams p) {
+__global__ void __launch_bounds__(256) gemv_q_kernel(const GemvParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     pdl_launch_dependents();  // let the next kernel in the stream become resident and prefetch its own weights
     const int lane = threadIdx.x & 31;
@@ -95,7 +95,8 @@ __global__ void __launch_bounds__(512) gemv_q_kernel(const GemvParams p) {
 
     uint8_t * act_s = smem;
     uint64_t * bars = reinterpret_cast<uint64_t *>(smem + act_bytes) + (size_t) warp * p.stages;
-    uint8_t * ring = smem + act_bytes + al16((int64_t) nwarps * p.stages * 8) + (size_t) warp * p.stages * stage_bytes;
+    uint64_t * act_bar = reinterpret_cast<uint64_t *>(smem + act_bytes) + (size_t) nwarps * p.stages;  // completion of the activation copy
+    uint8_t * ring = smem + act_bytes + al16((int64_t) (nwarps * p.stages + 1) * 8) + (size_t) warp * p.stages * stage_bytes;
 
     // ---- this warp's logical rows (aligned to GROUP so groups never straddle a matrix) and its work items
     const int64_t gw = (int64_t) blockIdx.x * nwarps + warp;
@@ -132,6 +133,7 @@ __global__ void __launch_bounds__(512) gemv_q_kernel(const GemvParams p) {
 
     if (lane == 0) {
         for (int s = 0; s < p.stages; ++s) mbar_init(&bars[s], 1);
+        if (warp == 0) mbar_init(act_bar, 1);
         fence_mbar_init();
     }
     __syncwarp();
@@ -181,15 +183,17 @@ __global__ void __launch_bounds__(512) gemv_q_kernel(const GemvParams p) {
         for (int it = 0; it < pre; ++it) issue(it);
     }
 
-    // ---- activations: wait for the producer kernel (PDL), then stage the quantized columns in smem
+    // ---- activations: wait for the producer kernel (PDL), then stage the quantized columns in smem with ONE bulk copy (a per-thread
+    // copy loop costs one L2 round trip per 4 KB: 4 serial trips for k = 14336)
     if constexpr (!IDX) pdl_wait();
-    {
-        const uint4 * src = reinterpret_cast<const uint4 *>(p.qact);
-        uint4 * dst = reinterpret_cast<uint4 *>(act_s);
-        const int n16 = (int) (((size_t) p.act_col_bytes * stage_cols) >> 4);
-        for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = src[i];
+    if (threadIdx.x == 0) {
+        const uint32_t bytes = (uint32_t) (((size_t) p.act_col_bytes * stage_cols) & ~(size_t) 15);
+        asm volatile("fence.proxy.async.global;" ::: "memory");
+        mbar_arrive_expect_tx(act_bar, bytes);
+        bulk_g2s(act_s, p.qact, bytes, act_bar);
     }
-    __syncthreads();
+    __syncthreads();  // act_bar's initialisation is visible to every warp
+    mbar_wait(act_bar, 0);
 
     const ActLayout L = act_layout(F::Q8K, p.k);
     constexpr int LPU = F::LPU;
@@ -214,22 +218,25 @@ __global__ void __launch_bounds__(512) gemv_q_kernel(const GemvParams p) {
         }
         mbar_wait(&bars[s], parity);
         const uint8_t * st = ring + (size_t) s * stage_bytes;
-        for (int u = ul; u < nu; u += UPS) {
-            if constexpr (NC == 1) {
-                typename F::Act A;
-                const uint8_t * acol = act_s;
-                if constexpr (IDX) { if (p.act_cols > 1) acol += (size_t) (row0 / p.mat[0].m) * p.act_col_bytes; }
-                F::load_act(acol, L, u0 + u, g, A);
+        const uint8_t * acol = act_s;
+        if constexpr (IDX) { if (p.act_cols > 1) acol += (size_t) (row0 / p.mat[0].m) * p.act_col_bytes; }
+        if (nlog == GROUP) {
+            // full group (all but the last group of a warp's range): no per-row branches, so the RG rows' shared-memory loads and
+            // dot-product chains interleave — the per-stage latency of a warp, not the issue rate, is what short GEMVs wait for
+            for (int u = ul; u < nu; u += UPS) {
+                typename F::Wt Wr[RG];
 #pragma unroll
-                for (int r = 0; r < RG; ++r) {
-                    const bool valid = PAIRED ? ((r < HALF ? r : r - HALF) < nlog) : (r < nlog);
-                    if (valid) {
-                        typename F::Wt Wr;
-                        F::load_w(st + (size_t) r * rsA, st + offB + (size_t) r * rsB, u, g, Wr);
-                        acc[r][0] = F::dot(Wr, A, acc[r][0]);
-                    }
+                for (int r = 0; r < RG; ++r) F::load_w(st + (size_t) r * rsA, st + offB + (size_t) r * rsB, u, g, Wr[r]);
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {
+                    typename F::Act A;
+                    F::load_act(acol + (size_t) c * p.act_col_bytes, L, u0 + u, g, A);
+#pragma unroll
+                    for (int r = 0; r < RG; ++r) acc[r][c] = F::dot(Wr[r], A, acc[r][c]);
                 }
-            } else {
+            }
+        } else {
+            for (int u = ul; u < nu; u += UPS) {
 #pragma unroll
                 for (int r = 0; r < RG; ++r) {
                     const bool valid = PAIRED ? ((r < HALF ? r : r - HALF) < nlog) : (r < nlog);
@@ -239,7 +246,7 @@ __global__ void __launch_bounds__(512) gemv_q_kernel(const GemvParams p) {
 #pragma unroll
                         for (int c = 0; c < NC; ++c) {
                             typename F::Act A;
-                            F::load_act(act_s + (size_t) c * p.act_col_bytes, L, u0 + u, g, A);
+                            F::load_act(acol + (size_t) c * p.act_col_bytes, L, u0 + u, g, A);
                             acc[r][c] = F::dot(Wr, A, acc[r][c]);
                         }
                     }
@@ -307,6 +314,7 @@ __global__ void __launch_bounds__(512) gemv_q_kernel(const GemvParams p) {
             }
         }
     }
+
 }
 
 // ======================================================================================================
@@ -408,8 +416,6 @@ static int unit_bytes(int wtype) {
 int mul_mat_q_multi(int wtype, int mode, int nmat, const void * const * W, const int64_t * m, float * const * y, const int64_t * ldy,
                     const float * const * bias, int64_t k, const void * qact, int64_t n, const GemvTuning * tune, cudaStream_t st) {
     if (k <= 0 || n <= 0 || nmat <= 0) return B200_OK;
-    if (k % 256 || nmat > 3) return B200_ERR_UNSUPPORTED;
-    if (mode == 1 && (nmat != 2 || m[0] != m[1])) return B200_ERR_ARG;
     int unit;
     switch (wtype) {
         case B200_TYPE_Q4_K: unit = FmtQ4K::A_UNIT + FmtQ4K::B_UNIT; break;
@@ -433,6 +439,8 @@ int mul_mat_q_multi(int wtype, int mode, int nmat, const void * const * W, const
         GemvTuning t;
         t.rg = tune && tune->rg ? tune->rg : env_tuning().rg;
         t.warps = tune && tune->warps ? tune->warps : env_tuning().warps;
+    if (t.warps > 8) t.warps = 8;
+        if (t.warps > 8) t.warps = 8;  // __launch_bounds__(256): the full-group path keeps RG rows of weights in registers
         t.stages = tune && tune->stages ? tune->stages : env_tuning().stages;
         t.ks = tune && tune->ks ? tune->ks : env_tuning().ks;
         t.grid = tune && tune->grid ? tune->grid : env_tuning().grid;
@@ -453,7 +461,7 @@ int mul_mat_q_multi(int wtype, int mode, int nmat, const void * const * W, const
         }
         const size_t act_bytes = (size_t) al16((int64_t) acb * nc);
         auto smem_for = [&](const GemvTuning & q) {
-            return act_bytes + (size_t) al16((int64_t) q.warps * q.stages * 8) + (size_t) q.warps * q.stages * q.rg * q.ks * unit;
+            return act_bytes + (size_t) al16((int64_t) (q.warps * q.stages + 1) * 8) + (size_t) q.warps * q.stages * q.rg * q.ks * unit;
         };
         const size_t limit = 227 * 1024;
         while (smem_for(t) > limit && t.stages > 3) t.stages--;
@@ -526,7 +534,7 @@ int mul_mat_q_id(int wtype, int paired, const void * W0, const void * W1, int64_
     }
     const size_t act_bytes = (size_t) al16((int64_t) acb * act_cols);
     auto smem_for = [&](const GemvTuning & q) {
-        return act_bytes + (size_t) al16((int64_t) q.warps * q.stages * 8) + (size_t) q.warps * q.stages * q.rg * q.ks * unit;
+        return act_bytes + (size_t) al16((int64_t) (q.warps * q.stages + 1) * 8) + (size_t) q.warps * q.stages * q.rg * q.ks * unit;
     };
     const size_t limit = 227 * 1024;
     while (smem_for(t) > limit && t.stages > 3) t.stages--;
