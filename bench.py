@@ -565,7 +565,8 @@ def main():
             out["e2e"] = {"value": round(1000.0 / e_ms, 2), "unit": "tokens/s", "ms_per_step": round(e_ms, 4),
                           "h2d_bytes_per_step": 4 + 4 * cfg.layers, "d2h_bytes_per_step": 4 * cfg.vocab,
                           "path": "unmodified chatllm host (graph rebuild + ggml sched per token) -> libggml-cuda.so; pageable host buffers of the host app",
-                          "plugin_launches_per_step": r.get("plugin_launches_per_step"),
+                          "plugin_execution": "every one-token graph -> decode plan -> ONE replayed CUDA graph of the per-op kernels, re-parameterised for the next "
+                                              "token while the current one runs (csrc/decode_graph.cu; B200_GRAPH=0 = node-by-node launches)",
                           "prefill": {"tokens": r.get("prefill_tokens"), "ms": r.get("prefill_ms"), "note": "real 4096-token prompt through the plugin (batch 512) before the timed decode"}}
             # parity of the benchmarked FILE: the same short real prompt through the plugin and on the reference's CPU backend, logits of the
             # prompt's last token and of 3 decode steps compared (the 4096-token prompt itself would take the CPU minutes)

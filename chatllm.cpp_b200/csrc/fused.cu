@@ -1129,6 +1129,15 @@ int attn_decode2(const float * q, const void * kc, const void * vc, float * out,
 }
 
 // as attn_decode2, and additionally qact = the output quantized as the activations of a following matmul with weight type wtype
+// the (head_dim, heads per KV head) pairs attn_decode3 is instantiated for
+bool attn_decode3_supported(int n_heads, int kv_heads, int head_dim, int64_t k_row_stride, int64_t v_row_stride) {
+    if (kv_heads <= 0 || n_heads % kv_heads || (k_row_stride % 8) || (v_row_stride % 8)) return false;
+    const int gqa = n_heads / kv_heads;
+    if (head_dim == 128) return gqa == 4 || gqa == 7 || gqa == 1 || gqa == 8 || gqa == 2;
+    if (head_dim == 64) return gqa == 8 || gqa == 4 || gqa == 2 || gqa == 1;
+    return false;
+}
+
 int attn_decode3(const float * q, const void * kc, const void * vc, float * out, float * scratch, int n_heads, int kv_heads, int head_dim, int n_kv,
                  int64_t k_row_stride, int64_t v_row_stride, float scale, int wtype, void * qact, cudaStream_t st, int preload, int cluster) {
     if (n_kv <= 0) return B200_OK;

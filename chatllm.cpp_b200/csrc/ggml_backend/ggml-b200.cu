@@ -104,6 +104,7 @@ struct b200_backend_ctx {
     DecodeModel mk_model{};
     int mk_max_ctx = 0;
     long long mk_tokens = 0;
+    bool mk_is_graph = false;  // the cached plan is a decode_graph (replayed CUDA graph of the per-op kernels), not the persistent kernel
 };
 
 static ggml_backend_device g_devices[B200_MAX_DEVICES];
@@ -928,7 +929,12 @@ static void b200_backend_free(ggml_backend_t backend) {
     if (bc->qact) cudaFree(bc->qact);
     if (bc->attn_scratch) cudaFree(bc->attn_scratch);
     if (bc->kv_scratch) cudaFree(bc->kv_scratch);
-    if (bc->mk_plan) decode_plan_destroy(bc->mk_plan);
+    if (bc->mk_plan && getenv("B200_STATS") && bc->mk_is_graph) {
+        long long a = 0, b = 0, c = 0;
+        decode_graph_stats(bc->mk_plan, &a, &b, &c);
+        fprintf(stderr, "B200STATS device=%d graph_replays=%lld captures=%lld instantiations=%lld\n", bc->device, a, b, c);
+    }
+    if (bc->mk_plan) { if (bc->mk_is_graph) decode_graph_destroy(bc->mk_plan); else decode_plan_destroy(bc->mk_plan); }
     if (bc->p2p_ev) cudaEventDestroy(bc->p2p_ev);
     if (bc->ev0) cudaEventDestroy(bc->ev0);
     if (bc->ev1) cudaEventDestroy(bc->ev1);
@@ -1036,8 +1042,11 @@ static bool try_whole_token(b200_backend_ctx * bc, ggml_cgraph * g, int * rc) {
     // OPT-IN (B200_MK=1): measured on the B200 the persistent kernel is slower than the node-by-node path (88 vs 55 us per
     // layer); it stays available because it is the only path that needs no host work per node and reproduces the CPU's double-precision
     // RMSNorm sum exactly
-    static const bool on = getenv("B200_MK") && atoi(getenv("B200_MK")) != 0;
-    if (!on || !fusion_enabled() || bc->kv_rewritten || g->n_nodes < 20) return false;
+    static const bool mk_on = getenv("B200_MK") && atoi(getenv("B200_MK")) != 0;
+    // DEFAULT (B200_GRAPH=0 disables): the same per-op kernels as the node-by-node path, replayed as one CUDA graph per token (decode_graph.cu)
+    static const bool graph_on = !(getenv("B200_GRAPH") && atoi(getenv("B200_GRAPH")) == 0);
+    if (!(mk_on || graph_on) || !fusion_enabled() || bc->kv_rewritten || g->n_nodes < 20) return false;
+    const bool use_graph = !mk_on;
     const int n = g->n_nodes;
     auto next_real = [&](int from) { while (from < n && (is_view_op(g->nodes[from]->op) || ggml_is_empty(g->nodes[from]))) ++from; return from; };
     int i = next_real(0);
@@ -1170,7 +1179,7 @@ static bool try_whole_token(b200_backend_ctx * bc, ggml_cgraph * g, int * rc) {
     M.layers = nullptr;
     const int max_ctx = (int) M.v_row_stride;
     if (n_kv > max_ctx) return false;
-    bool same = bc->mk_plan && bc->mk_layers.size() == layers.size() && bc->mk_max_ctx == max_ctx;
+    bool same = bc->mk_plan && bc->mk_is_graph == use_graph && bc->mk_layers.size() == layers.size() && bc->mk_max_ctx == max_ctx;
     if (same) {
         DecodeModel a = bc->mk_model, b = M;
         a.layers = b.layers = nullptr;
@@ -1179,21 +1188,36 @@ static bool try_whole_token(b200_backend_ctx * bc, ggml_cgraph * g, int * rc) {
     if (same) {
         for (size_t l = 0; l < layers.size() && same; ++l) {
             DecodeLayer a = bc->mk_layers[l], b = layers[l];
-            if (a.k_cache != b.k_cache || a.v_cache != b.v_cache) { decode_plan_set_kv(bc->mk_plan, (int) l, b.k_cache, b.v_cache); bc->mk_layers[l].k_cache = b.k_cache; bc->mk_layers[l].v_cache = b.v_cache; a = bc->mk_layers[l]; }
+            if (a.k_cache != b.k_cache || a.v_cache != b.v_cache) { if (use_graph) decode_graph_set_kv(bc->mk_plan, (int) l, b.k_cache, b.v_cache); else decode_plan_set_kv(bc->mk_plan, (int) l, b.k_cache, b.v_cache); bc->mk_layers[l].k_cache = b.k_cache; bc->mk_layers[l].v_cache = b.v_cache; a = bc->mk_layers[l]; }
             same = memcmp(&a, &b, sizeof(DecodeLayer)) == 0;
         }
     }
     if (!same) {
-        if (bc->mk_plan) { CUDA_OK(cudaStreamSynchronize(bc->stream)); decode_plan_destroy(bc->mk_plan); bc->mk_plan = nullptr; }
+        if (bc->mk_plan) {
+            CUDA_OK(cudaStreamSynchronize(bc->stream));
+            if (bc->mk_is_graph) decode_graph_destroy(bc->mk_plan); else decode_plan_destroy(bc->mk_plan);
+            bc->mk_plan = nullptr;
+        }
         M.layers = layers.data();
         int err = 0;
-        bc->mk_plan = decode_plan_create(M, max_ctx, &err);
+        bc->mk_plan = use_graph ? decode_graph_create(M, max_ctx, plugin_attn_cluster(), &err) : decode_plan_create(M, max_ctx, &err);
+        bc->mk_is_graph = use_graph;
         if (!bc->mk_plan) {
             static bool warned = false;
-            if (!warned) { GGML_LOG_INFO("b200: persistent decode kernel declined this model (err %d): per-node path\n", err); warned = true; }
+            if (!warned) { GGML_LOG_INFO("b200: whole-token plan declined this model (err %d): per-node path\n", err); warned = true; }
             return false;
         }
         bc->mk_layers = layers; bc->mk_model = M; bc->mk_model.layers = nullptr; bc->mk_max_ctx = max_ctx;
+    }
+    if (use_graph) {
+        // ---- one graph launch between three small copies; then, while it runs, the executable graph is re-parameterised for the next token
+        *rc = decode_graph_step(bc->mk_plan, tok ? (const int32_t *) tok->data : nullptr, (const int32_t *) pos->data, x_in ? (const float *) x_in->data : nullptr,
+                                logits ? nullptr : (float *) x_out->data, logits ? (float *) logits->data : nullptr, (int) n_kv, bc->stream);
+        bc->launches += 4;
+        bc->fused += n;
+        bc->mk_tokens++;
+        if (*rc == 0) decode_graph_prepare(bc->mk_plan, (int) n_kv + 1, bc->stream);  // best effort: a failure only means the next step captures itself
+        return true;
     }
     // ---- one launch.  The residual stream lives in the tensor a later split / the host reads (layer-split models), else in the plan.
     DecodeIO io{};

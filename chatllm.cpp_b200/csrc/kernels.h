@@ -74,6 +74,14 @@ int decode_plan_info(void * plan, int * grid, int * smem_bytes, int * n_steps, i
 int decode_step(void * plan, const DecodeIO & io, cudaStream_t st);
 int decode_plan_times(void * plan, long long * out, int cap, cudaStream_t st);
 
+// ---- decode_graph.cu: the same token as ONE replayed CUDA graph of the per-op kernels (the plugin's default decode path)
+void * decode_graph_create(const DecodeModel & m, int max_ctx, int attn_cluster, int * err);
+void decode_graph_destroy(void * plan);
+int decode_graph_set_kv(void * plan, int layer, void * k_cache, void * v_cache);
+int decode_graph_step(void * plan, const int32_t * tok, const int32_t * pos, const float * x_in, float * x_out, float * logits, int n_kv, cudaStream_t st);
+int decode_graph_prepare(void * plan, int n_kv_next, cudaStream_t live);
+void decode_graph_stats(void * plan, long long * replays, long long * recaptures, long long * reinstantiations);
+
 // ---- prefill.cu: batched (n > 8) quantized matmul on the int8 tensor cores, plain activation layout
 size_t pact_col_bytes(int wtype, int64_t k);
 int quantize_plain(int wtype, const float * x, int64_t x_col_stride, int64_t k, int64_t n, void * pact, cudaStream_t st);
@@ -120,6 +128,7 @@ int attn_decode2(const float * q, const void * kc, const void * vc, float * out,
 // EARLIER decode steps), 0 = a launch just before this call may have rewritten them (cache shift), -1 = library default
 int attn_decode3(const float * q, const void * kc, const void * vc, float * out, float * scratch, int n_heads, int kv_heads, int head_dim, int n_kv,
                  int64_t k_row_stride, int64_t v_row_stride, float scale, int wtype, void * qact, cudaStream_t st, int preload = -1, int cluster = -1);
+bool attn_decode3_supported(int n_heads, int kv_heads, int head_dim, int64_t k_row_stride, int64_t v_row_stride);
 // cluster: 1 = thread-block-cluster V.P (2 launches), 0 = split V.P + tail launch (3 launches), -1 = library default (B200_ATTN_CLUSTER, on)
 
 // ---- ops_generic.cu: strided / broadcasting ops as ggml graphs present them (ne[0] fastest, nb in bytes)

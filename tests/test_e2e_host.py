@@ -215,7 +215,7 @@ def test_decode_graphs_run_as_one_persistent_launch(tmp_path, arch, quant):
     d = str(tmp_path)
     decode = 12
     r1, e1 = run_host(model, "all", os.path.join(d, "mk.bin"), 5, decode, extra_env={"B200_STATS": "1", "B200_MK": "1"})
-    r0, e0 = run_host(model, "all", os.path.join(d, "nomk.bin"), 5, decode, extra_env={"B200_STATS": "1"})
+    r0, e0 = run_host(model, "all", os.path.join(d, "nomk.bin"), 5, decode, extra_env={"B200_STATS": "1", "B200_GRAPH": "0"})
     run_host(model, "0", os.path.join(d, "cpu.bin"), 5, decode)
     s1, s0 = _stats(e1), _stats(e0)
     assert s1["whole_token_graphs"] >= decode, s1          # (the harness' 1-token probe call is one more)
@@ -226,3 +226,28 @@ def test_decode_graphs_run_as_one_persistent_launch(tmp_path, arch, quant):
     print(arch, quant, "persistent kernel vs CPU", rel_cpu, "vs node-by-node", rel_nomk)
     assert np.median(rel_cpu) <= 1e-3 and rel_cpu.max() <= 3e-2, rel_cpu
     assert np.median(rel_nomk) <= 1e-3 and rel_nomk.max() <= 3e-2, rel_nomk
+
+
+@pytest.mark.parametrize("arch,quant", [("tiny-test", "q4_K"), ("tiny-test", "q8_0"), ("qwen2-test", "q4_0")])
+def test_decode_graphs_replay_one_cuda_graph_per_token(tmp_path, arch, quant):
+    """SURVEY.md §8 f1, the DEFAULT decode path: every one-token graph of a dense Llama-family model is reduced to a decode plan and executed as one
+    replayed CUDA graph of the per-op kernels (csrc/decode_graph.cu), re-parameterised for the next token while the current one runs.  Same kernels
+    in the same order as the node-by-node path (B200_GRAPH=0): the logits must be BIT-equal to it, and within the usual bounds of the CPU."""
+    model = make_model(str(tmp_path), arch, quant)
+    d = str(tmp_path)
+    decode = 12
+    r1, e1 = run_host(model, "all", os.path.join(d, "graph.bin"), 5, decode, extra_env={"B200_STATS": "1"})
+    r0, e0 = run_host(model, "all", os.path.join(d, "nodes.bin"), 5, decode, extra_env={"B200_STATS": "1", "B200_GRAPH": "0"})
+    run_host(model, "0", os.path.join(d, "cpu.bin"), 5, decode)
+    s1, s0 = _stats(e1), _stats(e0)
+    assert s1["whole_token_graphs"] >= decode and s0["whole_token_graphs"] == 0, (s0, s1)
+    g = [l for l in e1.splitlines() if l.startswith("B200STATS") and "graph_replays" in l]
+    assert g, e1[-1500:]
+    gs = {k: int(v) for k, v in (kv.split("=") for kv in g[0].split()[1:])}
+    # the first token runs eagerly; from then on one replay per token, each prepared (captured + applied) while its predecessor ran
+    assert gs["graph_replays"] >= decode - 2 and gs["instantiations"] <= 2, gs
+    a, b, c = _logits(os.path.join(d, "graph.bin"), 512), _logits(os.path.join(d, "nodes.bin"), 512), _logits(os.path.join(d, "cpu.bin"), 512)
+    assert np.isfinite(a).all()
+    assert np.array_equal(a, b), float(_rel(b, a).max())
+    rel_cpu = _rel(c, a)
+    assert np.median(rel_cpu) <= 1e-3 and rel_cpu.max() <= 3e-2, rel_cpu
