@@ -552,25 +552,35 @@ def main():
     if a.layers:
         out["config"]["workload"] += f" [DEBUG: {cfg.layers} layers only]"
 
-    # ---- e2e through the drop-in boundary (N=1 only: the reference host is a single process)
-    if not a.no_e2e and world == 1 and os.path.exists(HARNESS):
+    # ---- e2e through the drop-in boundary.  The reference host is ONE process that drives every device itself (-ngl "0:16,prolog;1:16,epilog",
+    # docs/gpu.md): at N > 1 rank 0 runs it over all N GPUs after the other ranks have left (their memory is released with them).
+    if not a.no_e2e and os.path.exists(HARNESS):
         try:
             if use_mk and sess.mk_status() != 0:
                 raise SystemExit("persistent kernel reported a grid-barrier timeout")
             del sess, graph, gg
             torch.cuda.empty_cache()
             model = ensure_model_file(a.layers)
-            r = run_harness(model, "all", a.warmup + a.steps, 16, ["--skip", str(a.warmup)], real_prefill=True)
+            ngl = "all"
+            if world > 1:
+                from chatllm_cpp_b200 import sharding as _sh
+                spans = _sh.plan_layers(cfg.layers, world)
+                ngl = ";".join(f"{d}:{hi_ - lo_}" + (",prolog" if d == 0 else "") + (",epilog" if d == world - 1 else "") for d, (lo_, hi_) in enumerate(spans))
+                time.sleep(3.0)   # the other ranks are exiting
+            r = run_harness(model, ngl, a.warmup + a.steps, 16, ["--skip", str(a.warmup)], real_prefill=True)
             e_ms = r["decode_ms_mean_after_skip"]
             out["e2e"] = {"value": round(1000.0 / e_ms, 2), "unit": "tokens/s", "ms_per_step": round(e_ms, 4),
                           "h2d_bytes_per_step": 4 + 4 * cfg.layers, "d2h_bytes_per_step": 4 * cfg.vocab,
-                          "path": "unmodified chatllm host (graph rebuild + ggml sched per token) -> libggml-cuda.so; pageable host buffers of the host app",
+                          "path": "unmodified chatllm host (graph rebuild + ggml sched per token) -> libggml-cuda.so; pageable host buffers of the host app"
+                                  + (f"; layers split over {world} devices with -ngl {ngl}" if world > 1 else ""),
                           "plugin_execution": "every one-token graph -> decode plan -> ONE replayed CUDA graph of the per-op kernels, re-parameterised for the next "
                                               "token while the current one runs (csrc/decode_graph.cu; B200_GRAPH=0 = node-by-node launches)",
                           "prefill": {"tokens": r.get("prefill_tokens"), "ms": r.get("prefill_ms"), "note": "real 4096-token prompt through the plugin (batch 512) before the timed decode"}}
             # parity of the benchmarked FILE: the same short real prompt through the plugin and on the reference's CPU backend, logits of the
             # prompt's last token and of 3 decode steps compared (the 4096-token prompt itself would take the CPU minutes)
             try:
+                if world > 1:
+                    raise RuntimeError("reported at N = 1 only")
                 import numpy as np
                 dumps = {}
                 for tag, ngl, rd in (("gpu", "all", RUNDIR), ("cpu", "0", RUNDIR + "_avx512"), ("cpu_avx2", "0", RUNDIR + "_avx2")):
