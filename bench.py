@@ -523,8 +523,8 @@ def main():
                 "frac_of_nominal_8TBps": round(achieved / 8000.0, 4), "launches": len(shapes), "avg_launch_us": round(gemv_ms * 1e3 / len(shapes), 2),
                 "algorithmic_MB_per_token_shard": round(gemv_bytes / 1e6, 1),
                 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` capture of this kernel on the gate shape
-                # (profiles/r02f_gemv_q4k_gate_ncu_full_summary.json: 33.067 MB read, 0 written, for 33.03 MB algorithmic), scaled to the mean launch
-                "traffic": round(gemv_bytes / len(shapes) * 33.067008 / 33.030144),
+                # (profiles/r02i_gemv_q4k_gate_ncu_full_summary.json: 33.074 MB read, 0 written, for 33.03 MB algorithmic), scaled to the mean launch
+                "traffic": round(gemv_bytes / len(shapes) * 33.074176 / 33.030144),
                 "share_of_step": round(gemv_ms / ms, 3)}
     if use_mk and world == 1:
         # the dominant kernel IS the step: one launch of decode_mk_kernel streams every weight byte of the token plus the KV cache.

@@ -201,6 +201,14 @@ class DecodeSession:
         if hasattr(self, "_tables"):
             del self._tables
 
+    def attn_launches(self, n_kv):
+        """kernels b200_attn_decode_quant launches for this shape (the predicate of csrc/fused.cu attn_decode_mma_t): tensor-core scores + the
+        thread-block-cluster V.P (2), or scores + split V.P + the tail that sums the partials (3)"""
+        import os
+        c = self.cfg
+        cluster = os.environ.get("B200_ATTN_CLUSTER", "1") != "0" and os.environ.get("B200_ATTN_NO_MMA", "0") == "0"
+        return 2 if cluster and (c.heads // c.kv_heads * c.head_dim) % 256 == 0 and (n_kv + 511) // 512 <= 16 else 3
+
     def enqueue_step_fused(self, n_past):
         c = self.cfg
         L = lib()
@@ -227,7 +235,7 @@ class DecodeSession:
                                        c.heads, c.kv_heads, hd, c.rope_mode, c.rope_theta, c.kv_hidden, c.max_len, st); n += 1
             # scores, split V.P, and the tail that sums the partials AND quantizes the result for the o-projection
             rc |= L.b200_attn_decode_quant(self.q.data_ptr(), W.kc.data_ptr(), W.vc.data_ptr(), self.att.data_ptr(), self.scratch.data_ptr(), c.heads,
-                                           c.kv_heads, hd, n_kv, c.kv_hidden, c.max_len, 1.0 / math.sqrt(hd), c.wtype, q, st); n += 3
+                                           c.kv_heads, hd, n_kv, c.kv_hidden, c.max_len, 1.0 / math.sqrt(hd), c.wtype, q, st); n += self.attn_launches(n_kv)
             rc |= L.b200_mul_mat_q(c.wtype, W.wo.data_ptr(), c.hidden, c.hidden, q, 1, self.o.data_ptr(), c.hidden, 0, st); n += 1
             rc |= L.b200_add_rmsnorm_quant(c.wtype, self.x.data_ptr(), self.o.data_ptr(), W.ffn_norm.data_ptr(), self.x.data_ptr(), 0, q, c.hidden, 1, c.eps, st); n += 1
             t = W.gu

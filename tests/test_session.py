@@ -95,4 +95,4 @@ def test_graph_replay_equals_eager():
     sess.logits.zero_()
     g.replay(); torch.cuda.synchronize()
     assert torch.equal(eager, sess.logits)
-    assert sess.launches_per_step == 1 + 3 * 11 + 2   # get_rows + 11 per layer + final norm + lm_head
+    assert sess.launches_per_step == 1 + 3 * 10 + 2   # get_rows + 10 per layer (2 of them the attention: scores + cluster V.P) + final norm + lm_head
