@@ -84,13 +84,13 @@ def ensure_model_file(layers=0):
     return path
 
 
-def run_harness(model, ngl, decode, threads, extra=(), real_prefill=False):
+def run_harness(model, ngl, decode, threads, extra=(), real_prefill=False, timeout=3000):
     # real_prefill: the 4096-token prompt is actually evaluated (plugin arm: prompt GEMM path, ~6 s); otherwise the host is
     # told 4096 positions are cached (KV buffers zero-filled) — decode cost does not depend on the cached VALUES
     pf = ["--prefill", str(N_PAST), "--batch", "512"] if real_prefill else ["--prefill", "0", "--fake_prefill", str(N_PAST)]
     cmd = [HARNESS, "--model", model, "--ggml_dir", RUNDIR, "--ngl", ngl, "--threads", str(threads)] + pf + [
            "--decode", str(decode), "--max_length", str(N_PAST + 256)] + list(extra)
-    p = subprocess.run(cmd, capture_output=True, text=True, timeout=3000)
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
     if p.returncode != 0:
         raise RuntimeError("host_harness failed: " + p.stderr[-1500:])
     return json.loads(p.stdout.strip().splitlines()[-1])
@@ -567,7 +567,7 @@ def main():
                 spans = _sh.plan_layers(cfg.layers, world)
                 ngl = ";".join(f"{d}:{hi_ - lo_}" + (",prolog" if d == 0 else "") + (",epilog" if d == world - 1 else "") for d, (lo_, hi_) in enumerate(spans))
                 time.sleep(3.0)   # the other ranks are exiting
-            r = run_harness(model, ngl, a.warmup + a.steps, 16, ["--skip", str(a.warmup)], real_prefill=True)
+            r = run_harness(model, ngl, a.warmup + a.steps, 16, ["--skip", str(a.warmup)], real_prefill=True, timeout=600)
             e_ms = r["decode_ms_mean_after_skip"]
             out["e2e"] = {"value": round(1000.0 / e_ms, 2), "unit": "tokens/s", "ms_per_step": round(e_ms, 4),
                           "h2d_bytes_per_step": 4 + 4 * cfg.layers, "d2h_bytes_per_step": 4 * cfg.vocab,
@@ -609,7 +609,7 @@ def main():
             out["e2e"] = {"value": None, "error": str(ex)[-300:]}
     if not a.no_cpu and world == 1 and os.path.exists(HARNESS):
         try:
-            r = cpu_reference_arm(4, 1, probe=(8, 32, 64))
+            r = cpu_reference_arm(4, 1, probe=(8, 16, 32, 64))
             out["cpu_baseline"] = {"value": round(r["value"], 3), "unit": "tokens/s", "cores": r["cores"], "host_cores": r["host_cores"], "kind": "reference",
                                    "sample": r["sample"], "threads_probed_ms_per_token": r["threads_probed_ms_per_token"]}
         except Exception as ex:  # noqa: BLE001
