@@ -205,6 +205,14 @@ int decode_graph_step(void * plan, const int32_t * tok, const int32_t * pos, con
     return (int) e;
 }
 
+// Is the executable graph already parameterised for n_kv (or is this the eager first token)?  The plugin sends a token whose n_kv was not
+// predicted down its node-by-node path when that keeps happening (interleaved sequences): a synchronous capture before the launch would leave
+// the GPU idle, while node-by-node launches overlap their own enqueue.
+bool decode_graph_ready(void * plan, int n_kv) {
+    DecodeGraph * P = (DecodeGraph *) plan;
+    return P && (!P->warmed || P->exec_n_kv == n_kv);
+}
+
 // Host-only: parameterise the executable graph for the NEXT token while the current one runs.
 int decode_graph_prepare(void * plan, int n_kv_next, cudaStream_t live) {
     DecodeGraph * P = (DecodeGraph *) plan;

@@ -104,6 +104,8 @@ struct b200_backend_ctx {
     DecodeModel mk_model{};
     int mk_max_ctx = 0;
     long long mk_tokens = 0;
+    int graph_prepare_n = 0;   // != 0: prepare the CUDA graph for this n_kv once the current token's nodes are enqueued
+    int graph_misses = 0;      // consecutive one-token graphs whose n_kv the prepared CUDA graph did not predict
     bool mk_is_graph = false;  // the cached plan is a decode_graph (replayed CUDA graph of the per-op kernels), not the persistent kernel
 };
 
@@ -1210,6 +1212,17 @@ static bool try_whole_token(b200_backend_ctx * bc, ggml_cgraph * g, int * rc) {
         bc->mk_layers = layers; bc->mk_model = M; bc->mk_model.layers = nullptr; bc->mk_max_ctx = max_ctx;
     }
     if (use_graph) {
+        // a token whose n_kv was not the predicted one needs a synchronous re-capture (GPU idle meanwhile): fine once (new prompt, context
+        // shift), but when it keeps happening (the host interleaves sequences) the node-by-node path — whose enqueue overlaps execution — is
+        // the faster one; the prediction is still refreshed so that a regular decode loop finds its graph again
+        if (!decode_graph_ready(bc->mk_plan, (int) n_kv)) {
+            if (++bc->graph_misses >= 2) {
+                bc->graph_prepare_n = (int) n_kv + 1;   // graph_compute refreshes the prediction AFTER it has enqueued this token's nodes
+                return false;
+            }
+        } else {
+            bc->graph_misses = 0;
+        }
         // ---- one graph launch between three small copies; then, while it runs, the executable graph is re-parameterised for the next token
         *rc = decode_graph_step(bc->mk_plan, tok ? (const int32_t *) tok->data : nullptr, (const int32_t *) pos->data, x_in ? (const float *) x_in->data : nullptr,
                                 logits ? nullptr : (float *) x_out->data, logits ? (float *) logits->data : nullptr, (int) n_kv, bc->stream);
@@ -1291,6 +1304,10 @@ static enum ggml_status b200_graph_compute(ggml_backend_t backend, ggml_cgraph *
                            rc > 0 ? cudaGetErrorString((cudaError_t) rc) : "");
             return GGML_STATUS_FAILED;
         }
+    }
+    if (bc->graph_prepare_n) {
+        if (bc->mk_plan && bc->mk_is_graph) decode_graph_prepare(bc->mk_plan, bc->graph_prepare_n, bc->stream);
+        bc->graph_prepare_n = 0;
     }
     if (prof) {
         cudaEventRecord(bc->ev1, bc->stream);

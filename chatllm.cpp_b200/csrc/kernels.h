@@ -79,6 +79,7 @@ void * decode_graph_create(const DecodeModel & m, int max_ctx, int attn_cluster,
 void decode_graph_destroy(void * plan);
 int decode_graph_set_kv(void * plan, int layer, void * k_cache, void * v_cache);
 int decode_graph_step(void * plan, const int32_t * tok, const int32_t * pos, const float * x_in, float * x_out, float * logits, int n_kv, cudaStream_t st);
+bool decode_graph_ready(void * plan, int n_kv);
 int decode_graph_prepare(void * plan, int n_kv_next, cudaStream_t live);
 void decode_graph_stats(void * plan, long long * replays, long long * recaptures, long long * reinstantiations);
 
