@@ -177,7 +177,7 @@ class DecodeSession:
             self._mm(self.lm_head, c.hidden, c.vocab, self.xn, self.logits)
         self.launches_per_step = self._n
 
-    # ---- fused step: 11 launches per layer ------------------------------------------------------------------------
+    # ---- fused step: 10 launches per layer ------------------------------------------------------------------------
     def _ptr_arrays(self):
         """host-side pointer tables for b200_mul_mat_q_multi (kept alive for the lifetime of the session / graph)"""
         import ctypes as C
