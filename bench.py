@@ -564,8 +564,7 @@ def main():
             ngl = "all"
             if world > 1:
                 from chatllm_cpp_b200 import sharding as _sh
-                spans = _sh.plan_layers(cfg.layers, world)
-                ngl = ";".join(f"{d}:{hi_ - lo_}" + (",prolog" if d == 0 else "") + (",epilog" if d == world - 1 else "") for d, (lo_, hi_) in enumerate(spans))
+                ngl = _sh.ngl_spec(cfg.layers, world)
                 time.sleep(3.0)   # the other ranks are exiting
             r = run_harness(model, ngl, a.warmup + a.steps, 16, ["--skip", str(a.warmup)], real_prefill=True, timeout=600)
             e_ms = r["decode_ms_mean_after_skip"]

@@ -21,6 +21,23 @@ def plan_layers(n_layers, world):
     return out
 
 
+def ngl_spec(n_layers, world):
+    """the reference host's `-ngl` argument (docs/gpu.md:36-52: `[id:]layer_specs[;id:layer_specs]..`) that places the layers on `world` devices
+    exactly as plan_layers() shards them: the embedding ("prolog") with the first range, final norm + lm_head ("epilog") with the last"""
+    if world <= 1:
+        return "all"
+    parts = []
+    for d, (lo, hi) in enumerate(plan_layers(n_layers, world)):
+        spec = [str(hi - lo)] if hi > lo else []
+        if d == 0:
+            spec.append("prolog")
+        if d == world - 1:
+            spec.append("epilog")
+        if spec:
+            parts.append(f"{d}:" + ",".join(spec))
+    return ";".join(parts)
+
+
 class Pipeline:
     """run_shard(x) -> x for this rank's layers; step() moves ONE token through all ranks.
 

@@ -93,3 +93,27 @@ def test_ring_io_flags_are_consistent():
                 assert ios[r]["send_tok"] == bases[0] + L["tok"] and ios[r]["send_x"] == 0
         # rank 0 starts step t when the token of step t-1 has arrived (offset 0); rank r > 0 needs the hidden row of step t itself (offset 1)
         assert [io["wait_offset"] for io in ios] == [0] + [1] * (world - 1)
+
+
+def test_ngl_spec_places_layers_like_the_rank_plan():
+    """bench.py's e2e leg at N > 1 hands the ONE host process the same layer placement the ranks of the device-resident arm use"""
+    import re
+    import __graft_entry__ as ge
+    ge.load_package()
+    from chatllm_cpp_b200 import sharding
+    assert sharding.ngl_spec(32, 1) == "all"
+    assert sharding.ngl_spec(32, 2) == "0:16,prolog;1:16,epilog"
+    assert sharding.ngl_spec(32, 4) == "0:8,prolog;1:8;2:8;3:8,epilog"
+    for n, w in [(32, 8), (28, 8), (22, 4), (2, 2), (3, 8)]:
+        spec = sharding.ngl_spec(n, w)
+        plan = sharding.plan_layers(n, w)
+        seen = 0
+        for part in spec.split(";"):
+            m = re.fullmatch(r"(\d+):(.*)", part)
+            assert m, spec
+            d, items = int(m.group(1)), m.group(2).split(",")
+            cnt = sum(int(i) for i in items if i.isdigit())
+            assert cnt == plan[d][1] - plan[d][0], (spec, plan)
+            assert ("prolog" in items) == (d == 0) and ("epilog" in items) == (d == w - 1), spec
+            seen += cnt
+        assert seen == n, spec
